@@ -1,0 +1,208 @@
+// C-ABI entry points for the tensor-core path: conv3x3 / conv1x1 (+BN+ReLU+pool) and the
+// column classifier. Declared in include/hctr_b200.h.
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "igemm_tcgen05.cuh"
+#include "../../include/hctr_b200.h"
+
+namespace hctr {
+
+// ---------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return HCTR_OK;
+    set_error("CUDA error %s (%d) in %s", cudaGetErrorString(e), static_cast<int>(e), what);
+    return HCTR_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// NHWC bf16 activation [B,H,W,C] -> 4-D map (C, W, H, B), box (64, 128, 1, 1), 128B swizzle, zero OOB fill.
+static int make_act_map(CUtensorMap* m, const void* x, int B, int H, int W, int C) {
+    EncodeTiledFn enc = get_encode_fn();
+    HCTR_CHECK(enc != nullptr, HCTR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileM, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HCTR_CHECK(r == CUDA_SUCCESS, HCTR_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", B, H, W, C,
+               (int)r);
+    return HCTR_OK;
+}
+
+// Packed weights [N][K] bf16 (K-major) -> 2-D map (K, N), box (64, block_n).
+static int make_weight_map(CUtensorMap* m, const void* w, int N, int K, int block_n) {
+    EncodeTiledFn enc = get_encode_fn();
+    HCTR_CHECK(enc != nullptr, HCTR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    HCTR_CHECK(r == CUDA_SUCCESS, HCTR_ERR_CUDA, "cuTensorMapEncodeTiled(weights %dx%d) failed: %d", N, K, (int)r);
+    return HCTR_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
+    using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES>;
+    auto kern = igemm_tcgen05_kernel<BLOCK_N, NUM_SUB, STAGES, ACC_STAGES, EPI>;
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+        configured = true;
+    }
+    int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    kern<<<grid, kIgemmThreads, L::kTotal, stream>>>(tmA, tmB, p);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace hctr
+
+using namespace hctr;
+
+extern "C" {
+
+const char* hctr_last_error(void) { return g_err; }
+
+int hctr_abi_version(void) { return HCTR_ABI_VERSION; }
+
+int hctr_device_supported(int device) {
+    cudaDeviceProp prop;
+    HCTR_CUDA(cudaGetDeviceProperties(&prop, device));
+    HCTR_CHECK(prop.major == 10, HCTR_ERR_UNSUPPORTED,
+               "hctr_b200 kernels need an sm_100a device (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    return HCTR_OK;
+}
+
+int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,
+                         int H, int W, int Cin, int Cout, int ksize, int relu, int pool, void* stream) {
+    HCTR_CHECK(x && w_packed && scale && shift && y, HCTR_ERR_INVALID, "conv: null pointer");
+    HCTR_CHECK(ksize == 1 || ksize == 3, HCTR_ERR_INVALID, "conv: ksize must be 1 or 3 (got %d)", ksize);
+    HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "conv: empty tensor %dx%dx%d", B, H, W);
+    HCTR_CHECK(Cin % 64 == 0 && Cin >= 64, HCTR_ERR_INVALID, "conv: Cin must be a multiple of 64 (got %d)", Cin);
+    HCTR_CHECK(Cout == 64 || Cout == 128 || Cout % 256 == 0, HCTR_ERR_INVALID,
+               "conv: Cout must be 64, 128 or a multiple of 256 (got %d)", Cout);
+    HCTR_CHECK(!pool || (H % 2 == 0), HCTR_ERR_INVALID, "conv: (2,1) pooling needs an even height (got %d)", H);
+    HCTR_CHECK(aligned16(x) && aligned16(w_packed) && aligned16(y) && aligned16(scale) && aligned16(shift),
+               HCTR_ERR_INVALID, "conv: pointers must be 16-byte aligned");
+
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = H; p.W = W;
+    p.cin_chunks = Cin / 64;
+    if (ksize == 3) {
+        p.ntaps = 9;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) { p.tap_dh[kh * 3 + kw] = (int8_t)(kh - 1); p.tap_dw[kh * 3 + kw] = (int8_t)(kw - 1); }
+    } else {
+        p.ntaps = 1;
+    }
+    p.sub_dh = 1; p.sub_dw = 0;
+    p.N = Cout;
+    p.w_tiles = (W + kTileM - 1) / kTileM;
+    p.h_tiles = (H + 1) / 2;
+    p.scale = scale; p.shift = shift; p.out = y;
+    p.relu = relu; p.pool = pool;
+    p.out_H = pool ? H / 2 : H;
+
+    const int block_n = Cout >= 256 ? 256 : Cout;
+    p.n_tiles = Cout / block_n;
+    const long long total = (long long)B * p.h_tiles * p.w_tiles * p.n_tiles;
+    HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "conv: too many tiles");
+    p.total_tiles = (int)total;
+
+    CUtensorMap tmA, tmB;
+    int rc = make_act_map(&tmA, x, B, H, W, Cin);
+    if (rc) return rc;
+    rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, block_n);
+    if (rc) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (block_n) {
+        case 64:  return launch_igemm<64, 2, 4, 2, EPI_CONV>(tmA, tmB, p, s);
+        case 128: return launch_igemm<128, 2, 4, 2, EPI_CONV>(tmA, tmB, p, s);
+        default:  return launch_igemm<256, 2, 3, 1, EPI_CONV>(tmA, tmB, p, s);
+    }
+}
+
+int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                        long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, void* stream) {
+    HCTR_CHECK(feat && w_packed && bias && logits, HCTR_ERR_INVALID, "classifier: null pointer");
+    HCTR_CHECK(B > 0 && W > 0 && Hf > 0 && Hf <= kMaxTaps, HCTR_ERR_INVALID, "classifier: bad shape B=%d Hf=%d W=%d", B, Hf, W);
+    HCTR_CHECK(Cf % 64 == 0 && Cf >= 64, HCTR_ERR_INVALID, "classifier: feature channels must be a multiple of 64 (got %d)", Cf);
+    HCTR_CHECK(num_classes > 0 && out_pitch >= num_classes, HCTR_ERR_INVALID, "classifier: pitch %lld < classes %d", out_pitch, num_classes);
+    HCTR_CHECK(out_dtype == HCTR_F32 || out_dtype == HCTR_BF16, HCTR_ERR_INVALID, "classifier: bad out dtype %d", out_dtype);
+    HCTR_CHECK(aligned16(feat) && aligned16(w_packed) && aligned16(bias), HCTR_ERR_INVALID, "classifier: pointers must be 16-byte aligned");
+
+    IgemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.H = Hf; p.W = W;
+    p.cin_chunks = Cf / 64;
+    p.ntaps = Hf;                               // one "tap" per feature row: K index = h*Cf + c
+    for (int h = 0; h < Hf; ++h) { p.tap_dh[h] = (int8_t)h; p.tap_dw[h] = 0; }
+    p.sub_dh = 0; p.sub_dw = 1;
+    p.N = num_classes;
+    p.w_tiles = (W + 2 * kTileM - 1) / (2 * kTileM);
+    p.h_tiles = 1;
+    p.n_tiles = (num_classes + 255) / 256;
+    p.shift = bias; p.out = logits;
+    p.out_H = 1;
+    p.out_dtype = out_dtype; p.out_pitch = out_pitch;
+    const long long total = (long long)B * p.w_tiles * p.n_tiles;
+    HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "classifier: too many tiles");
+    p.total_tiles = (int)total;
+
+    CUtensorMap tmA, tmB;
+    int rc = make_act_map(&tmA, feat, B, Hf, W, Cf);
+    if (rc) return rc;
+    rc = make_weight_map(&tmB, w_packed, num_classes, Hf * Cf, 256);
+    if (rc) return rc;
+    return launch_igemm<256, 2, 3, 1, EPI_LINEAR>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// HBM-bound parts of the backbone: the 1->64 stem conv (CUDA cores, 9 FLOP/B), the SE squeeze /
+// excite / scale+residual+ReLU passes. All activations are NHWC bf16; loads/stores are 16-byte
+// vectors over the channel dimension so that a warp always touches whole 128-byte lines.
+#include "common.cuh"
+#include "../../include/hctr_b200.h"
+
+namespace hctr {
+
+// ---------------------------------------------------------------- stem: conv0_1 + bn0_1 + relu
+// reference: models/handwritten_ctr_model.py:116-118. One thread = one pixel x 8 output channels;
+// 8 consecutive lanes cover the 64 channels of a pixel (one 128-byte line), a warp covers 4 pixels.
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B, int H, int W) {
+    __shared__ float sw[64 * 9];
+    __shared__ float ssc[64], ssh[64];
+    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
+    if (threadIdx.x < 64) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
+    __syncthreads();
+
+    const int cg = threadIdx.x & 7;                       // channel group: channels cg*8 .. cg*8+7
+    float wr[8][9], sc[8], sh[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[c][t] = sw[(cg * 8 + c) * 9 + t];
+        sc[c] = ssc[cg * 8 + c];
+        sh[c] = ssh[cg * 8 + c];
+    }
+    const long long npix = (long long)B * H * W;
+    const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+    for (long long pix = (long long)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); pix < npix; pix += stride) {
+        const int wq = (int)(pix % W);
+        const long long bh = pix / W;
+        const int h = (int)(bh % H);
+        const float* img = x + (bh - h) * W;              // start of line b (single input channel)
+        float in[9];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hh = h + kh - 1;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ww = wq + kw - 1;
+                in[kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (long long)hh * W + ww) : 0.f;
+            }
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { a0 = fmaf(in[t], wr[c][t], a0); a1 = fmaf(in[t], wr[c + 1][t], a1); }
+            a0 = fmaxf(fmaf(a0, sc[c], sh[c]), 0.f);
+            a1 = fmaxf(fmaf(a1, sc[c + 1], sh[c + 1]), 0.f);
+            pk[c >> 1] = pack_bf16x2(a0, a1);
+        }
+        *reinterpret_cast<uint4*>(y + pix * 64 + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+// ---------------------------------------------------------------- SE squeeze (stage 1 of 2)
+// reference: SELayer.forward avg_pool (models/handwritten_ctr_model.py:27-28). Grid (slices, B); every block
+// sums a contiguous pixel range of one line for all channels in a fixed order -> partial[b][slice][c].
+constexpr int kSePixPerSlice = 2048;
+
+__global__ void __launch_bounds__(256)
+se_squeeze_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C, int slices) {
+    extern __shared__ float red[];                         // [groups][C]
+    const int b = blockIdx.y, slice = blockIdx.x;
+    const int vec_per_pix = C >> 3;                        // 16-byte vectors per pixel
+    const int groups = blockDim.x / vec_per_pix;           // pixels processed in parallel
+    const int g = threadIdx.x / vec_per_pix;
+    const int v = threadIdx.x - g * vec_per_pix;
+    const int p0 = slice * kSePixPerSlice;
+    const int p1 = min(p0 + kSePixPerSlice, HW);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (g < groups) {
+        const __nv_bfloat16* base = x + ((size_t)b * HW) * C + v * 8;
+        for (int p = p0 + g; p < p1; p += groups) {
+            const uint4 q = ld_nc_v4(base + (size_t)p * C);
+            acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x);
+            acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+            acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z);
+            acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[g * C + v * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int gg = 0; gg < groups; ++gg) s += red[gg * C + c];     // fixed order: deterministic
+        partial[((size_t)b * slices + slice) * C + c] = s;
+    }
+}
+
+// ---------------------------------------------------------------- SE excite (stage 2 + the two FCs)
+// reference: SELayer.fc (models/handwritten_ctr_model.py:19-24,29). One block per line.
+__global__ void __launch_bounds__(512)
+se_excite_kernel(const float* __restrict__ partial, int slices, const float* __restrict__ w1,
+                 const float* __restrict__ w2, float* __restrict__ gate, int C, int Cr, float inv_hw) {
+    extern __shared__ float sm[];                          // mean[C] + hidden[Cr]
+    float* mean = sm;
+    float* hidden = sm + C;
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int i = 0; i < slices; ++i) s += partial[((size_t)b * slices + i) * C + c];
+        mean[c] = s * inv_hw;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < Cr; r += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(w1[(size_t)r * C + c], mean[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hidden[r] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < Cr; ++r) s = fmaf(w2[(size_t)c * Cr + r], hidden[r], s);
+        gate[(size_t)b * C + c] = 1.f / (1.f + expf(-s));
+    }
+}
+
+// ---------------------------------------------------------------- SE scale + residual + ReLU
+// reference: BasicBlock.forward tail (models/handwritten_ctr_model.py:30,54-58); dropout is identity in eval().
+__global__ void __launch_bounds__(256)
+se_scale_residual_relu_kernel(const uint4* __restrict__ x, const float* __restrict__ gate,
+                              const uint4* __restrict__ res, uint4* __restrict__ y, long long nvec, int vec_per_line,
+                              int vec_per_pix, int C) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const int b = (int)(i / vec_per_line);
+        const int c0 = (int)(i % vec_per_pix) * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * C + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * C + c0 + 4));
+        const uint4 a = ld_nc_v4(x + i);
+        const uint4 r = ld_nc_v4(res + i);
+        uint4 o;
+        o.x = pack_bf16x2(fmaxf(fmaf(bf16_lo(a.x), g0.x, bf16_lo(r.x)), 0.f), fmaxf(fmaf(bf16_hi(a.x), g0.y, bf16_hi(r.x)), 0.f));
+        o.y = pack_bf16x2(fmaxf(fmaf(bf16_lo(a.y), g0.z, bf16_lo(r.y)), 0.f), fmaxf(fmaf(bf16_hi(a.y), g0.w, bf16_hi(r.y)), 0.f));
+        o.z = pack_bf16x2(fmaxf(fmaf(bf16_lo(a.z), g1.x, bf16_lo(r.z)), 0.f), fmaxf(fmaf(bf16_hi(a.z), g1.y, bf16_hi(r.z)), 0.f));
+        o.w = pack_bf16x2(fmaxf(fmaf(bf16_lo(a.w), g1.z, bf16_lo(r.w)), 0.f), fmaxf(fmaf(bf16_hi(a.w), g1.w, bf16_hi(r.w)), 0.f));
+        y[i] = o;
+    }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace hctr
+
+using namespace hctr;
+
+extern "C" {
+
+int hctr_stem_conv_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int B, int H,
+                       int W, void* stream) {
+    HCTR_CHECK(x && w && scale && shift && y, HCTR_ERR_INVALID, "stem: null pointer");
+    HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "stem: empty tensor");
+    HCTR_CHECK(al16(y), HCTR_ERR_INVALID, "stem: output must be 16-byte aligned");
+    const long long npix = (long long)B * H * W;
+    long long blocks = (npix + 31) / 32;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    stem_conv_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, scale, shift, static_cast<__nv_bfloat16*>(y), B, H, W);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_se_slices(int H, int W) {
+    const long long hw = (long long)H * W;
+    return (int)((hw + kSePixPerSlice - 1) / kSePixPerSlice);
+}
+
+int hctr_se_squeeze(const void* x, float* partial, int B, int H, int W, int C, void* stream) {
+    HCTR_CHECK(x && partial, HCTR_ERR_INVALID, "se_squeeze: null pointer");
+    HCTR_CHECK(C % 8 == 0 && C >= 8 && C <= 2048 && 256 % (C / 8) == 0, HCTR_ERR_INVALID,
+               "se_squeeze: C/8 must divide 256 (got C=%d)", C);
+    HCTR_CHECK(al16(x), HCTR_ERR_INVALID, "se_squeeze: x must be 16-byte aligned");
+    const int slices = hctr_se_slices(H, W);
+    const int groups = 256 / (C / 8);
+    const size_t smem = (size_t)groups * C * sizeof(float);
+    dim3 grid(slices, B);
+    se_squeeze_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), partial, H * W, C, slices);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_se_excite(const float* partial, int slices, const float* w1, const float* w2, float* gate, int B, int C,
+                   int Cr, int HW, void* stream) {
+    HCTR_CHECK(partial && w1 && w2 && gate, HCTR_ERR_INVALID, "se_excite: null pointer");
+    HCTR_CHECK(C > 0 && Cr > 0 && slices > 0 && HW > 0, HCTR_ERR_INVALID, "se_excite: bad shape");
+    const size_t smem = (size_t)(C + Cr) * sizeof(float);
+    se_excite_kernel<<<B, 512, smem, static_cast<cudaStream_t>(stream)>>>(partial, slices, w1, w2, gate, C, Cr,
+                                                                           1.0f / (float)HW);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_se_scale_residual_relu(const void* x, const float* gate, const void* residual, void* y, int B, int H, int W,
+                                int C, void* stream) {
+    HCTR_CHECK(x && gate && residual && y, HCTR_ERR_INVALID, "se_scale: null pointer");
+    HCTR_CHECK(C % 8 == 0, HCTR_ERR_INVALID, "se_scale: C must be a multiple of 8");
+    HCTR_CHECK(al16(x) && al16(residual) && al16(y) && al16(gate), HCTR_ERR_INVALID, "se_scale: 16-byte alignment");
+    const long long vec_per_line = (long long)H * W * C / 8;
+    HCTR_CHECK(vec_per_line < (1ll << 31), HCTR_ERR_INVALID, "se_scale: line too large");
+    const long long nvec = vec_per_line * B;
+    long long blocks = (nvec + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    se_scale_residual_relu_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), gate, static_cast<const uint4*>(residual), static_cast<uint4*>(y), nvec,
+        (int)vec_per_line, C / 8, C);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// Implicit-GEMM on tcgen05 / TMEM, fed by TMA, for the HCTR backbone and classifier.
+//
+//   D[pixel, n] = sum_{tap, c} X[b, h + dh(tap), w + dw(tap), c] * Wt[n, tap, c]
+//
+// X is an NHWC bf16 activation tensor seen through a 4-D TMA tensor map (C, W, H, B); a box of
+// (64 ch, 128 px, 1 row, 1 line) lands in shared memory as a K-major SWIZZLE_128B operand tile
+// (128 rows x 128 B), and out-of-bounds coordinates are zero-filled by the TMA unit, which is
+// exactly the conv's zero padding (reference: nn.Conv2d(.., 3, 1, 1),
+// models/handwritten_ctr_model.py:37-41,73-92). Wt is the packed weight matrix [N][taps*Cin]
+// (K-major) seen through a 2-D map. One CTA owns NUM_SUB accumulators of 128 pixels x BLOCK_N
+// channels in TMEM; the two sub-tiles are either the two rows of a (2,1) max-pool pair
+// (:123,129,136,143,150) or two adjacent 128-pixel spans of a line (classifier, :172-176).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> BN/ReLU/pool or bias -> global).
+#pragma once
+#include "common.cuh"
+
+namespace hctr {
+
+constexpr int kTileM = 128;          // pixels per accumulator (UMMA M)
+constexpr int kBlockK = 64;          // bf16 elements per K block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kIgemmThreads = 192;
+constexpr int kMaxTaps = 9;
+
+enum : int { EPI_CONV = 0, EPI_LINEAR = 1 };
+
+struct IgemmParams {
+    // problem
+    int B, H, W;              // input activation dims (NHWC)
+    int cin_chunks;           // Cin / 64
+    int ntaps;
+    int8_t tap_dh[kMaxTaps];
+    int8_t tap_dw[kMaxTaps];
+    int sub_dh, sub_dw;       // offset of sub-tile s relative to sub-tile 0: (s*sub_dh rows, s*sub_dw*128 px)
+    int N;                    // output channels / classes
+    // tiling (derived on host)
+    int w_tiles, h_tiles, n_tiles, total_tiles;
+    // epilogue
+    const float* scale;       // [N] (EPI_CONV) or nullptr
+    const float* shift;       // [N] BN shift (EPI_CONV) / bias (EPI_LINEAR)
+    void* out;
+    int relu, pool;
+    int out_H;                // output rows (H or H/2 when pooled)
+    int out_dtype;            // EPI_LINEAR: HCTR_F32 | HCTR_BF16
+    long long out_pitch;      // EPI_LINEAR: elements between consecutive (b,w) rows
+};
+
+template <int BLOCK_N, int NUM_SUB, int STAGES>
+struct IgemmSmem {
+    static constexpr int kABytes = kTileM * kBlockK * 2;      // 16 KB per sub-tile
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = NUM_SUB * kABytes + kBBytes;
+    static constexpr int kBarBytes = 1024;
+    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
+};
+
+template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI>
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmB,
+                     const IgemmParams p) {
+    using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES>;
+    constexpr int kAccCols = NUM_SUB * BLOCK_N;
+    constexpr int kTmemCols = ACC_STAGES * kAccCols;
+    static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32,
+                  "TMEM allocation must be a power of two in [32, 512]");
+    static_assert(BLOCK_N % 32 == 0 && BLOCK_N <= 256, "BLOCK_N");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* bar_base = smem + STAGES * L::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);            // [STAGES]
+    uint64_t* empty_bar = full_bar + STAGES;                               // [STAGES]
+    uint64_t* acc_full = empty_bar + STAGES;                               // [ACC_STAGES]
+    uint64_t* acc_empty = acc_full + ACC_STAGES;                           // [ACC_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kblocks = p.ntaps * p.cin_chunks;
+    const int sub_rows = p.sub_dh ? NUM_SUB : 1;     // input rows covered by one tile
+    const int sub_cols = p.sub_dw ? NUM_SUB : 1;     // 128-px spans covered by one tile
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                int m = tile / p.n_tiles;
+                const int w_tile = m % p.w_tiles; m /= p.w_tiles;
+                const int h_tile = m % p.h_tiles;
+                const int b = m / p.h_tiles;
+                const int h0 = h_tile * sub_rows;
+                const int w0 = w_tile * sub_cols * kTileM;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    const int tap = kb / p.cin_chunks;
+                    const int ch = kb - tap * p.cin_chunks;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+                    uint8_t* st = smem + stage * L::kStageBytes;
+#pragma unroll
+                    for (int s = 0; s < NUM_SUB; ++s) {
+                        tma_load_4d(st + s * L::kABytes, &tmA, &full_bar[stage],
+                                    ch * kBlockK,
+                                    w0 + s * p.sub_dw * kTileM + p.tap_dw[tap],
+                                    h0 + s * p.sub_dh + p.tap_dh[tap],
+                                    b);
+                    }
+                    tma_load_2d(st + NUM_SUB * L::kABytes, &tmB, &full_bar[stage],
+                                kb * kBlockK, n_tile * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_base = tmem_base + acc * kAccCols;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t b_addr = a_addr + NUM_SUB * L::kABytes;
+#pragma unroll
+                    for (int s = 0; s < NUM_SUB; ++s) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            const uint64_t da = make_sw128_kmajor_desc(a_addr + s * L::kABytes + k * kUmmaK * 2);
+                            const uint64_t db = make_sw128_kmajor_desc(b_addr + k * kUmmaK * 2);
+                            umma_bf16(d_base + s * BLOCK_N, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+                    if (kb == kblocks - 1) umma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int quad = warp & 3;                      // TMEM lane quarter this warp may read
+        const int pix = quad * 32 + lane;               // pixel within the 128-px sub-tile
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            int m = tile / p.n_tiles;
+            const int w_tile = m % p.w_tiles; m /= p.w_tiles;
+            const int h_tile = m % p.h_tiles;
+            const int b = m / p.h_tiles;
+            const int h0 = h_tile * sub_rows;
+            const int w0 = w_tile * sub_cols * kTileM;
+
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
+
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                const int n0 = n_tile * BLOCK_N + c0;
+                if (n0 >= p.N) break;                    // warp-uniform
+                float v[NUM_SUB][32];
+#pragma unroll
+                for (int s = 0; s < NUM_SUB; ++s) tmem_ld_32x32(t_base + s * BLOCK_N + c0, v[s]);
+
+                if constexpr (EPI == EPI_CONV) {
+                    // y = acc*scale + shift  (conv bias and eval-mode BN folded, fp32), ReLU, H-pair max
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + j));
+#pragma unroll
+                        for (int s = 0; s < NUM_SUB; ++s) {
+                            v[s][j + 0] = fmaf(v[s][j + 0], sc.x, sh.x);
+                            v[s][j + 1] = fmaf(v[s][j + 1], sc.y, sh.y);
+                            v[s][j + 2] = fmaf(v[s][j + 2], sc.z, sh.z);
+                            v[s][j + 3] = fmaf(v[s][j + 3], sc.w, sh.w);
+                        }
+                    }
+                    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+                    if (p.pool) {
+                        const int w = w0 + pix;
+                        const int ho = h_tile;
+                        if (w < p.W && ho < p.out_H) {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                float a0 = fmaxf(v[0][j], v[NUM_SUB - 1][j]);
+                                float a1 = fmaxf(v[0][j + 1], v[NUM_SUB - 1][j + 1]);
+                                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                                pk[j >> 1] = pack_bf16x2(a0, a1);
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(
+                                out + ((static_cast<size_t>(b) * p.out_H + ho) * p.W + w) * p.N + n0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NUM_SUB; ++s) {
+                            const int w = w0 + s * p.sub_dw * kTileM + pix;
+                            const int h = h0 + s * p.sub_dh;
+                            if (w < p.W && h < p.out_H) {
+                                uint32_t pk[16];
+#pragma unroll
+                                for (int j = 0; j < 32; j += 2) {
+                                    float a0 = v[s][j], a1 = v[s][j + 1];
+                                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                                    pk[j >> 1] = pack_bf16x2(a0, a1);
+                                }
+                                uint4* dst = reinterpret_cast<uint4*>(
+                                    out + ((static_cast<size_t>(b) * p.out_H + h) * p.W + w) * p.N + n0);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            }
+                        }
+                    }
+                } else {
+                    // logits[b, w, n] = acc + bias[n]   (reference: nn.Linear, handwritten_ctr_model.py:169,175)
+#pragma unroll
+                    for (int s = 0; s < NUM_SUB; ++s) {
+                        const int w = w0 + s * p.sub_dw * kTileM + pix;
+                        if (w >= p.W) continue;
+                        const size_t row = static_cast<size_t>(b) * p.W + w;
+                        if (p.out_dtype == HCTR_F32) {
+                            float* dst = static_cast<float*>(p.out) + row * p.out_pitch + n0;
+                            if (n0 + 32 <= p.N && (p.out_pitch & 3) == 0) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 bs = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + j));
+                                    *reinterpret_cast<float4*>(dst + j) =
+                                        make_float4(v[s][j] + bs.x, v[s][j + 1] + bs.y, v[s][j + 2] + bs.z, v[s][j + 3] + bs.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (n0 + j < p.N) dst[j] = v[s][j] + __ldg(p.shift + n0 + j);
+                            }
+                        } else {
+                            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + row * p.out_pitch + n0;
+                            if (n0 + 32 <= p.N && (p.out_pitch & 7) == 0) {
+                                uint32_t pk[16];
+#pragma unroll
+                                for (int j = 0; j < 32; j += 2)
+                                    pk[j >> 1] = pack_bf16x2(v[s][j] + __ldg(p.shift + n0 + j),
+                                                             v[s][j + 1] + __ldg(p.shift + n0 + j + 1));
+                                uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    d4[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[s][j] + __ldg(p.shift + n0 + j));
+                            }
+                        }
+                    }
+                }
+            }
+            // release this accumulator stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace hctr

@@ -1,0 +1,252 @@
+"""B200-native drop-in for the reference recognition model.
+
+Mirrors `models/handwritten_ctr_model.py` of the reference (file:line cited per item):
+  * `hctr_model(num_classes=7375)` with attributes img_height/PAD/optimizer/pred/noutput (:156-169)
+  * `forward(input[B,1,128,W]) -> [W,B,num_classes]` (:171-178)
+  * the exact 254-entry `state_dict` (names, shapes, registration order) and the same
+    construction order, so `torch.manual_seed(s); hctr_model()` yields bit-identical parameters.
+
+The nn.Modules below only *hold* parameters; no torch op runs in `forward`. The arithmetic is the
+hand-written sm_100a path behind include/hctr_b200.h: a CUDA-core stem, tcgen05 implicit-GEMM
+convolutions with bias/BN/ReLU/(2,1)-max-pool folded into the epilogue, SE squeeze/excite/apply
+passes and the tcgen05 classifier GEMM. There is no CPU fallback.
+"""
+import importlib.util
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _core():
+    """Return the `hctr_b200` package even when this file was imported as top-level `models.*`
+    (i.e. with the package directory itself on PYTHONPATH, the drop-in arrangement)."""
+    pkg = sys.modules.get("hctr_b200")
+    if pkg is None:
+        spec = importlib.util.spec_from_file_location(
+            "hctr_b200", os.path.join(_PKG_DIR, "__init__.py"), submodule_search_locations=[_PKG_DIR])
+        pkg = importlib.util.module_from_spec(spec)
+        sys.modules["hctr_b200"] = pkg
+        spec.loader.exec_module(pkg)
+    return pkg
+
+
+_STAGE_PLANES = (128, 256, 512, 512)      # reference: ResNet.__init__ inout_channels (:66-70)
+_STAGE_BLOCKS = (2, 4, 5, 1)              # reference: hctr_model.__init__ (:166)
+_SE_REDUCTION = 16                        # reference: SELayer default (:16)
+_FEATURE_ROWS = 4                         # 128 / 2**5 after five (2,1) pools (:123-150)
+
+
+class _SqueezeExcite(nn.Module):
+    """Parameter holder for SELayer (:11-24): fc.0 = Linear(C, C/16), fc.2 = Linear(C/16, C), no biases."""
+
+    def __init__(self, channels):
+        super().__init__()
+        hidden = channels // _SE_REDUCTION
+        self.fc = nn.Sequential(
+            nn.Linear(channels, hidden, bias=False), nn.ReLU(inplace=True),
+            nn.Linear(hidden, channels, bias=False), nn.Sigmoid())
+
+
+class _ResidualUnit(nn.Module):
+    """Parameter holder for BasicBlock (:33-45); registration order conv1,bn1,conv2,bn2,se,downsample."""
+
+    def __init__(self, cin, cout, shortcut):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, 1, 1)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.se = _SqueezeExcite(cout)
+        self.downsample = shortcut
+
+
+class _Backbone(nn.Module):
+    """Parameter holder for ResNet(1, 512, BasicBlock, [2,4,5,1]) (:63-99)."""
+
+    def __init__(self):
+        super().__init__()
+        width = 64
+        self.conv0_1 = nn.Conv2d(1, width, 3, 1, 1)
+        self.bn0_1 = nn.BatchNorm2d(width)
+        self.conv0_2 = nn.Conv2d(width, width, 3, 1, 1)
+        self.bn0_2 = nn.BatchNorm2d(width)
+        for stage, (planes, count) in enumerate(zip(_STAGE_PLANES, _STAGE_BLOCKS), start=1):
+            # the reference builds the projection shortcut *before* the block's own convs
+            # (_make_block, :101-113) - the RNG draw order matters for seed-identical parameters
+            shortcut = None
+            if width != planes:
+                shortcut = nn.Sequential(nn.Conv2d(width, planes, kernel_size=1, stride=1, bias=False),
+                                         nn.BatchNorm2d(planes))
+            units = [_ResidualUnit(width, planes, shortcut)]
+            width = planes
+            units += [_ResidualUnit(width, planes, None) for _ in range(1, count)]
+            setattr(self, "block%d" % stage, nn.Sequential(*units))
+            setattr(self, "conv%d" % stage, nn.Conv2d(planes, planes, 3, 1, 1))
+            setattr(self, "bn%d" % stage, nn.BatchNorm2d(planes))
+
+
+def _fold_bn(bn, conv_bias):
+    """Eval-mode BN as an fp32 epilogue: y = acc*scale + shift."""
+    scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    bias = conv_bias.detach().float() if conv_bias is not None else torch.zeros_like(scale)
+    shift = (bias - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
+    return scale.contiguous(), shift.contiguous()
+
+
+def _pack_conv(conv):
+    """OIHW fp32 -> [Cout][kh][kw][Cin] bf16 (K-major rows for the implicit GEMM's B operand)."""
+    return conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+class _ConvSpec(object):
+    __slots__ = ("w", "scale", "shift", "cin", "cout", "ksize")
+
+    def __init__(self, conv, bn):
+        self.w = _pack_conv(conv)
+        self.scale, self.shift = _fold_bn(bn, conv.bias)
+        self.cout, self.cin = conv.weight.shape[0], conv.weight.shape[1]
+        self.ksize = conv.weight.shape[2]
+
+
+class _InferencePlan(object):
+    """Device-resident packed parameters for the eval-mode forward (rebuilt when parameters change)."""
+
+    def __init__(self, model):
+        cnn = model.cnn
+        dev = model.linear.weight.device
+        self.device = dev
+        self.stem_w = cnn.conv0_1.weight.detach().float().reshape(64, 9).contiguous()
+        self.stem_scale, self.stem_shift = _fold_bn(cnn.bn0_1, cnn.conv0_1.bias)
+        self.conv0_2 = _ConvSpec(cnn.conv0_2, cnn.bn0_2)
+        self.stages = []
+        for stage in range(1, 5):
+            units = []
+            for unit in getattr(cnn, "block%d" % stage):
+                units.append({
+                    "conv1": _ConvSpec(unit.conv1, unit.bn1),
+                    "conv2": _ConvSpec(unit.conv2, unit.bn2),
+                    "se_w1": unit.se.fc[0].weight.detach().float().contiguous(),
+                    "se_w2": unit.se.fc[2].weight.detach().float().contiguous(),
+                    "shortcut": None if unit.downsample is None else _ConvSpec(unit.downsample[0], unit.downsample[1]),
+                })
+            tail = _ConvSpec(getattr(cnn, "conv%d" % stage), getattr(cnn, "bn%d" % stage))
+            self.stages.append((units, tail))
+        lin = model.linear
+        n, d = lin.weight.shape
+        cf = d // _FEATURE_ROWS
+        # reference flatten(1,2) gives d = c*4 + h (:173); our features are NHWC so k = h*512 + c
+        self.cls_w = (lin.weight.detach().reshape(n, cf, _FEATURE_ROWS).permute(0, 2, 1)
+                      .contiguous().to(torch.bfloat16).reshape(n, d))
+        self.cls_b = lin.bias.detach().float().contiguous()
+        self.cf = cf
+
+
+class hctr_model(nn.Module):
+    """Drop-in for the reference `hctr_model` (models/handwritten_ctr_model.py:156-178)."""
+
+    def __init__(self, num_classes=7375):
+        super().__init__()
+        self.img_height = 128
+        self.PAD = 'NormalizePAD'
+        self.optimizer = 'SGD'
+        self.pred = 'CTC'
+        self.noutput = num_classes          # 1 blank + characters + 1 unknown
+        self.cnn = _Backbone()
+        self.linear = nn.Linear(512 * _FEATURE_ROWS, self.noutput)
+        # element type of the logits tensor handed back by forward(); the reference returns fp32
+        self.logits_dtype = torch.float32
+        self._plan = None
+        self._plan_key = None
+
+    # -------------------------------------------------------------------------------- plan cache
+    def _current_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _get_plan(self):
+        key = self._current_key()
+        if self._plan is None or key != self._plan_key:
+            self._plan = _InferencePlan(self)
+            self._plan_key = key
+        return self._plan
+
+    # -------------------------------------------------------------------------------- forward
+    def forward(self, input):
+        if self.training:
+            raise NotImplementedError(
+                "hctr_b200: train-mode forward (batch-stat BN, dropout, autograd) is not built yet; "
+                "call .eval() - there is no PyTorch fallback on this path")
+        if not input.is_cuda:
+            raise RuntimeError("hctr_b200: input must be a CUDA tensor on an sm_100a device (no CPU fallback)")
+        if input.dim() != 4 or input.shape[1] != 1:
+            raise RuntimeError("hctr_b200: expected input [B,1,%d,W], got %s" % (self.img_height, tuple(input.shape)))
+        if input.shape[2] != self.img_height:
+            # the reference fails in nn.Linear: (H/32)*512 features != 2048
+            raise RuntimeError("mat1 and mat2 shapes cannot be multiplied: input height %d gives %d features, "
+                               "linear expects %d" % (input.shape[2], (input.shape[2] // 32) * 512,
+                                                      self.linear.in_features))
+        if self.linear.weight.device != input.device:
+            raise RuntimeError("hctr_b200: input is on %s but parameters are on %s" % (input.device, self.linear.weight.device))
+        with torch.cuda.device(input.device):
+            return self._forward_eval(input.detach().float().contiguous())
+
+    def _conv(self, nat, x, spec, B, H, W, relu, pool):
+        ho = H // 2 if pool else H
+        y = torch.empty((B, ho, W, spec.cout), dtype=torch.bfloat16, device=x.device)
+        nat.check(nat.lib().hctr_conv_bn_act_fwd(
+            nat.ptr(x), nat.ptr(spec.w), nat.ptr(spec.scale), nat.ptr(spec.shift), nat.ptr(y),
+            B, H, W, spec.cin, spec.cout, spec.ksize, int(relu), int(pool), nat.stream_ptr()), "conv_bn_act")
+        return y
+
+    def _forward_eval(self, x):
+        nat = _core().native
+        lib = nat.lib()
+        plan = self._get_plan()
+        B, _, H, W = x.shape
+        st = nat.stream_ptr()
+        dev = x.device
+
+        a = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=dev)
+        nat.check(lib.hctr_stem_conv_fwd(nat.ptr(x), nat.ptr(plan.stem_w), nat.ptr(plan.stem_scale),
+                                         nat.ptr(plan.stem_shift), nat.ptr(a), B, H, W, st), "stem")
+        a = self._conv(nat, a, plan.conv0_2, B, H, W, relu=True, pool=True)
+        H //= 2
+        for units, tail in plan.stages:
+            for u in units:
+                t = self._conv(nat, a, u["conv1"], B, H, W, relu=True, pool=False)
+                v = self._conv(nat, t, u["conv2"], B, H, W, relu=False, pool=False)
+                del t
+                C = u["conv2"].cout
+                slices = lib.hctr_se_slices(H, W)
+                partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
+                gate = torch.empty((B, C), dtype=torch.float32, device=dev)
+                nat.check(lib.hctr_se_squeeze(nat.ptr(v), nat.ptr(partial), B, H, W, C, st), "se_squeeze")
+                nat.check(lib.hctr_se_excite(nat.ptr(partial), slices, nat.ptr(u["se_w1"]), nat.ptr(u["se_w2"]),
+                                             nat.ptr(gate), B, C, u["se_w1"].shape[0], H * W, st), "se_excite")
+                res = a if u["shortcut"] is None else self._conv(nat, a, u["shortcut"], B, H, W, relu=False, pool=False)
+                out = torch.empty_like(v)
+                nat.check(lib.hctr_se_scale_residual_relu(nat.ptr(v), nat.ptr(gate), nat.ptr(res), nat.ptr(out),
+                                                          B, H, W, C, st), "se_scale_residual_relu")
+                a = out
+                del v, res
+            a = self._conv(nat, a, tail, B, H, W, relu=True, pool=True)
+            H //= 2
+        return self._classify(nat, a, plan, B, H, W)
+
+    def _classify(self, nat, feat, plan, B, Hf, W):
+        n = self.noutput
+        if self.logits_dtype == torch.bfloat16:
+            code, pitch = nat.HCTR_BF16, (n + 7) // 8 * 8        # 16-byte aligned rows
+        elif self.logits_dtype == torch.float32:
+            code, pitch = nat.HCTR_F32, (n + 3) // 4 * 4
+        else:
+            raise ValueError("logits_dtype must be torch.float32 or torch.bfloat16")
+        logits = torch.empty((B, W, pitch), dtype=self.logits_dtype, device=feat.device)
+        nat.check(nat.lib().hctr_classifier_fwd(nat.ptr(feat), nat.ptr(plan.cls_w), nat.ptr(plan.cls_b),
+                                                nat.ptr(logits), code, pitch, B, Hf, W, plan.cf, n,
+                                                nat.stream_ptr()), "classifier")
+        # reference: x.permute(1, 0, 2) of the contiguous [B,W,C] linear output (:176)
+        return logits[:, :, :n].permute(1, 0, 2)

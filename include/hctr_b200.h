@@ -1,0 +1,124 @@
+/*
+ * hctr_b200 — C ABI of the B200-native (sm_100a) HCTR recognition hot path.
+ *
+ * The reference (AndrewCullacino/handwritten-chinese-ocr-samples) has no FFI layer: its boundary is
+ * the Python surface models/handwritten_ctr_model.py (hctr_model), utils/ctc_codec.py (ctc_codec) and
+ * the CTCLoss call in main.py. Each entry point below names the reference call it stands in for
+ * (file:line under /root/reference). The host-side Python mirrors of those objects live in
+ * handwritten-chinese-ocr-samples_b200/{models,utils}/ and bind this library through ctypes;
+ * INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; hctr_last_error() gives a thread-local message.
+ *   - all pointers are DEVICE pointers unless the name says host_; the library borrows them for the
+ *     duration of the call and allocates nothing persistent.
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); launches are async.
+ *   - activations are NHWC bf16 ([B][H][W][C], C innermost); parameters are fp32 unless packed.
+ *   - there is no CPU fallback: without an sm_100a device the calls fail.
+ */
+#ifndef HCTR_B200_H_
+#define HCTR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCTR_ABI_VERSION 1
+
+/* error codes */
+#define HCTR_OK 0
+#define HCTR_ERR_INVALID (-1)      /* bad argument: maps to ValueError / RuntimeError(shape) */
+#define HCTR_ERR_CUDA (-2)         /* CUDA failure: RuntimeError */
+#define HCTR_ERR_UNSUPPORTED (-3)  /* not an sm_100a device */
+#define HCTR_ERR_INDEX (-4)        /* reference raises IndexError (utils/ctc_codec.py:139,198) */
+
+/* element types of logit tensors */
+#define HCTR_F32 0
+#define HCTR_BF16 1
+
+const char* hctr_last_error(void);
+int hctr_abi_version(void);
+/* 0 iff `device` can run these kernels (compute capability 10.x). */
+int hctr_device_supported(int device);
+
+/* ---- backbone ------------------------------------------------------------------------------- */
+
+/* cnn.conv0_1 + bn0_1 + relu (models/handwritten_ctr_model.py:116-118).
+ * x: fp32 [B][1][H][W] (the reference input, [-1,1]); w: fp32 [64][9] (OIHW flattened);
+ * scale/shift: fp32 [64], y = relu(conv(x)*scale + shift) with the conv bias and eval-mode BN folded in;
+ * y: bf16 NHWC [B][H][W][64]. */
+int hctr_stem_conv_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int B, int H,
+                       int W, void* stream);
+
+/* 3x3 (pad 1) or 1x1 convolution + per-channel fp32 scale/shift (+ReLU) (+(2,1) max-pool over H pairs):
+ * conv0_2/bn0_2 (:119-123), BasicBlock conv1/bn1/relu and conv2/bn2 (:49-53), downsample (:55-57, :104-107),
+ * cnn.convS/bnS/relu/max_pool2d (:126-129,133-136,140-143,147-150).
+ * x: bf16 NHWC [B][H][W][Cin]; w_packed: bf16 [Cout][ksize*ksize][Cin]; y: bf16 NHWC [B][H or H/2][W][Cout].
+ * tcgen05 implicit GEMM, TMA-fed; Cin % 64 == 0; Cout in {64,128} or a multiple of 256. */
+int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,
+                         int H, int W, int Cin, int Cout, int ksize, int relu, int pool, void* stream);
+
+/* SELayer squeeze (:27-28): deterministic two-stage mean over (H,W) incl. padded columns.
+ * x: bf16 NHWC; partial: fp32 workspace [B][slices][C]; the second stage runs inside hctr_se_excite.
+ * `slices` must equal hctr_se_slices(H, W). */
+int hctr_se_slices(int H, int W);
+int hctr_se_squeeze(const void* x, float* partial, int B, int H, int W, int C, void* stream);
+/* SELayer excite (:19-24,29): gate = sigmoid(W2 . relu(W1 . mean)); w1: fp32 [C/r][C]; w2: fp32 [C][C/r];
+ * gate: fp32 [B][C]. */
+int hctr_se_excite(const float* partial, int slices, const float* w1, const float* w2, float* gate, int B, int C,
+                   int Cr, int HW, void* stream);
+/* BasicBlock tail (:30,54-58): y = relu(x * gate[b,c] + residual); all bf16 NHWC, same shape. */
+int hctr_se_scale_residual_relu(const void* x, const float* gate, const void* residual, void* y, int B, int H, int W,
+                                int C, void* stream);
+
+/* Column classifier, hctr_model.forward (:172-176): feat: bf16 NHWC [B][Hf][W][Cf] (Hf*Cf = 2048);
+ * w_packed: bf16 [num_classes][Hf*Cf] with k = h*Cf + c (the reference's flatten gives d = c*Hf + h);
+ * logits: [B][W][out_pitch] of out_dtype, only the first num_classes columns of a row are written. The
+ * reference's [W,B,C] result is the (1,0,2) permuted view of it. */
+int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                        long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, void* stream);
+
+/* ---- CTC codec ------------------------------------------------------------------------------ */
+
+/* ctc_codec.__greedy_search__ (utils/ctc_codec.py:70-99): per (t,b) argmax over C (ties -> lowest index,
+ * NaN -> first NaN, as numpy.argmax), then drop blank (0), unknown (C-1) and repeats of the raw previous index.
+ * logits element (t,b,c) is at logits[t*stride_t + b*stride_b + c] (elements of `dtype`).
+ * argmax_out: int32 [B][T] raw per-step argmax (may be NULL); out_idx: int32 [B][T] compacted label indices;
+ * out_len: int32 [B]. */
+int hctr_ctc_greedy_decode(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
+                           int32_t* argmax_out, int32_t* out_idx, int32_t* out_len, void* stream);
+
+/* log_softmax over C (scipy.special.log_softmax, utils/ctc_codec.py:65) fused with the per-step top-k
+ * (np.argsort flip, :186). topk_idx: int32 [T][B][k] descending by log-prob (ties -> lower index first);
+ * topk_logp: fp32 [T][B][k]; lse: fp32 [T][B] (logp = logit - lse). k <= 32. */
+int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C, long long stride_t,
+                             long long stride_b, int k, int32_t* topk_idx, float* topk_logp, float* lse, void* stream);
+
+/* ctc_codec.__cbs_full__ + __context_beam_search__ + Beam (utils/ctc_codec.py:183-285,288-307) without a
+ * transformer; the language model is a per-class unigram table (lm_table[c], fp64, may be NULL = zero LM),
+ * scored over prefix + look-ahead suffix exactly as `ngram.score(' '.join(prefix+suffix))` would for a
+ * unigram model. float64 accumulators, stable ordering by insertion. One CTA per sequence.
+ * Inputs are the outputs of hctr_ctc_topk_logsoftmax. out_idx: int32 [B][T]; out_len: int32 [B];
+ * status: int32 [B], 0 ok, HCTR_ERR_INDEX if the greedy path is empty (the reference raises IndexError). */
+int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp, int T, int B, int C, int k,
+                                int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                int32_t* out_idx, int32_t* out_len, int32_t* status, void* stream);
+
+/* CTCLoss(blank=0, reduction='mean', zero_infinity=True) on log_softmax(logits) and its gradient wrt the
+ * logits (main.py:205,406-409,426). logits element (t,b,c) at logits[t*stride_t + b*stride_b + c];
+ * targets: int32 concatenated [sum L]; target_lengths/input_lengths: int32 [B].
+ * nll: fp32 [B] per-sequence negative log-likelihood (inf -> 0 when zero_infinity); loss: fp32 [1] =
+ * mean_b(nll_b / max(L_b,1)); grad (may be NULL): same dtype/strides as logits, d loss / d logits scaled by
+ * grad_scale. */
+int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
+                          const int32_t* targets, const int32_t* target_lengths, const int32_t* input_lengths,
+                          int max_target_len, float* nll, float* loss, void* grad, float grad_scale, void* workspace,
+                          long long workspace_bytes, void* stream);
+long long hctr_ctc_loss_workspace_bytes(int T, int B, int max_target_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCTR_B200_H_ */
