@@ -1,0 +1,440 @@
+// CTC prefix beam search on device (reference: ctc_codec.decode beam branch, utils/ctc_codec.py:63-67,
+// __cbs_full__ :183-210, __context_beam_search__ :212-285, Beam :288-307).
+//   kernel 1 (HBM-bound): per (t,b) row, one warp: online log-sum-exp + per-lane sorted top-k in registers,
+//                         merged across the warp; emits candidates in descending log-prob order.
+//   kernel 2 (latency-bound): one warp per sequence walks the time steps; float64 accumulators,
+//                         np.logaddexp semantics, insertion-ordered stable ranking exactly as the
+//                         reference's dict + sorted(reverse=True).
+#include <cfloat>
+
+#include "common.cuh"
+#include "../../include/hctr_b200.h"
+
+namespace hctr {
+
+constexpr int kMaxK = 16;        // search_depth limit
+constexpr int kMaxBeam = 16;     // beam_size limit
+constexpr int kMaxGen = kMaxBeam * (kMaxK + 1);
+constexpr int kTopkWarps = 4;
+
+// ---------------------------------------------------------------------------------------------- top-k
+__device__ __forceinline__ bool cand_better(float v, int i, float w, int j) {
+    return v > w || (v == w && i < j);
+}
+
+template <typename T> struct LoadVec;
+template <> struct LoadVec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&o)[4]) {
+        const uint4 q = ld_nc_v4(p);
+        o[0] = __uint_as_float(q.x); o[1] = __uint_as_float(q.y); o[2] = __uint_as_float(q.z); o[3] = __uint_as_float(q.w);
+    }
+    static __device__ __forceinline__ float one(const float* p) { return __ldg(p); }
+};
+template <> struct LoadVec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+        const uint4 q = ld_nc_v4(p);
+        o[0] = bf16_lo(q.x); o[1] = bf16_hi(q.x); o[2] = bf16_lo(q.y); o[3] = bf16_hi(q.y);
+        o[4] = bf16_lo(q.z); o[5] = bf16_hi(q.z); o[6] = bf16_lo(q.w); o[7] = bf16_hi(q.w);
+    }
+    static __device__ __forceinline__ float one(const __nv_bfloat16* p) {
+        return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(p)) << 16);
+    }
+};
+
+struct LaneTopK {
+    float v[kMaxK];
+    int i[kMaxK];
+    float m, s;      // running max / sum of exp(x - m)
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j) { v[j] = -INFINITY; i[j] = 0x7fffffff; }
+        m = -FLT_MAX; s = 0.f;
+    }
+    __device__ __forceinline__ void push(float x, int idx) {
+        // sorted insert, descending, equal values keep the lower index first
+        if (!cand_better(x, idx, v[kMaxK - 1], i[kMaxK - 1])) return;
+        bool placed = false;
+        float cv = x; int ci = idx;
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j) {
+            if (placed || cand_better(cv, ci, v[j], i[j])) {
+                const float tv = v[j]; const int ti = i[j];
+                v[j] = cv; i[j] = ci; cv = tv; ci = ti; placed = true;
+            }
+        }
+    }
+};
+
+// online log-sum-exp + top-k update with N consecutive elements starting at class index `base`
+template <int N>
+__device__ __forceinline__ void visit_vec(LaneTopK& st, const float (&x)[N], int base) {
+    float vm = x[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) vm = fmaxf(vm, x[j]);
+    if (vm > st.m) { st.s *= __expf(st.m - vm); st.m = vm; }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { st.s += __expf(x[j] - st.m); st.push(x[j], base + j); }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTopkWarps * 32)
+ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
+                           int k, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp,
+                           float* __restrict__ lse_out) {
+    constexpr int V = LoadVec<T>::N;
+    __shared__ float sv[kTopkWarps][32][kMaxK + 1];
+    __shared__ int si[kTopkWarps][32][kMaxK + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * kTopkWarps + warp;          // row = t*B + b
+    if (row >= (long long)Tn * Bn) return;
+    const int t = (int)(row / Bn), b = (int)(row - (long long)t * Bn);
+    const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+
+    LaneTopK st; st.init();
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > C) head = C;
+    if (lane < head) { float x1[1] = {LoadVec<T>::one(p + lane)}; visit_vec<1>(st, x1, lane); }
+    const int nvec = (C - head) / V;
+    const T* pv = p + head;
+    int vi = lane;
+    for (; vi + 32 < nvec; vi += 64) {
+        float x0[V], x1[V];
+        LoadVec<T>::load(pv + (long long)vi * V, x0);
+        LoadVec<T>::load(pv + (long long)(vi + 32) * V, x1);
+        visit_vec<V>(st, x0, head + vi * V);
+        visit_vec<V>(st, x1, head + (vi + 32) * V);
+    }
+    for (; vi < nvec; vi += 32) {
+        float x0[V];
+        LoadVec<T>::load(pv + (long long)vi * V, x0);
+        visit_vec<V>(st, x0, head + vi * V);
+    }
+    const int tail0 = head + nvec * V;
+    if (tail0 + lane < C) { float x1[1] = {LoadVec<T>::one(p + tail0 + lane)}; visit_vec<1>(st, x1, tail0 + lane); }
+
+    // row max / sum
+    float m = st.m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = st.s * __expf(st.m - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float logs = logf(s);
+    if (lane == 0) lse_out[row] = m + logs;
+
+    // merge the 32 sorted lane lists: k rounds of warp arg-best over the list heads
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) { sv[warp][lane][j] = st.v[j]; si[warp][lane][j] = st.i[j]; }
+    sv[warp][lane][kMaxK] = -INFINITY; si[warp][lane][kMaxK] = 0x7fffffff;
+    __syncwarp();
+    int hd = 0;
+    for (int r = 0; r < k; ++r) {
+        float bv = sv[warp][lane][hd]; int bi = si[warp][lane][hd];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        }
+        if (si[warp][lane][hd] == bi && hd < kMaxK) ++hd;                    // the winning lane advances
+        if (lane == 0) {
+            topk_idx[row * k + r] = bi;
+            topk_logp[row * k + r] = (bv - m) - logs;                         // scipy: (x - max) - log(sum(exp(x - max)))
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- beam search
+__device__ __forceinline__ double logaddexp_np(double x, double y) {
+    // numpy npy_logaddexp for doubles
+    if (x == y) return __dadd_rn(x, 0.693147180559945309417232121458176568);
+    const double tmp = __dsub_rn(x, y);
+    if (tmp > 0) return __dadd_rn(x, log1p(exp(-tmp)));
+    if (tmp <= 0) return __dadd_rn(y, log1p(exp(tmp)));
+    return tmp;
+}
+
+struct KeptState {
+    int node[kMaxBeam];
+    int len[kMaxBeam];
+    int last[kMaxBeam];
+    unsigned long long hash[kMaxBeam];
+    double pb[kMaxBeam], pnb[kMaxBeam], lmsum[kMaxBeam];
+};
+
+__device__ __forceinline__ unsigned long long mix_hash(unsigned long long h, int c) {
+    h ^= (unsigned long long)(c + 1) * 0x9E3779B97F4A7C15ull;
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 29;
+    return h;
+}
+
+// exact string equality of two trie nodes known to have equal length
+__device__ bool same_string(const int* parent, const int* chr, int a, int b) {
+    while (a != b) {
+        if (chr[a] != chr[b]) return false;
+        a = parent[a]; b = parent[b];
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32)
+ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __restrict__ topk_logp, int Tn, int Bn, int C,
+                       int k, int beam_size, double lm_penalty, double len_bonus, const double* __restrict__ lm_table,
+                       int32_t* __restrict__ out_idx, int32_t* __restrict__ out_len, int32_t* __restrict__ status,
+                       unsigned char* __restrict__ workspace, long long ws_per_seq) {
+    __shared__ KeptState kept[2];
+    __shared__ double Pj[kMaxBeam];
+    __shared__ int parentk[kMaxBeam];
+    __shared__ int cand[kMaxK];
+    __shared__ double candp[kMaxK];
+    __shared__ int ent_of_kept[kMaxBeam];
+    __shared__ int e_kind[kMaxGen];                 // >=0: kept index j''; <0: NEW
+    __shared__ int e_src[kMaxGen], e_chr[kMaxGen];
+    __shared__ double e_pb[kMaxGen], e_pnb[kMaxGen], e_tot[kMaxGen], e_lm[kMaxGen];
+    __shared__ int s_ngen;
+
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int unknown = C - 1;
+    unsigned char* ws = workspace + (long long)b * ws_per_seq;
+    int* g_char = reinterpret_cast<int*>(ws);
+    int* g_time = g_char + Tn;
+    const int cap = Tn * beam_size + 1;
+    int* n_parent = g_time + Tn;
+    int* n_chr = n_parent + cap;
+    unsigned long long* n_hash = reinterpret_cast<unsigned long long*>(
+        (reinterpret_cast<uintptr_t>(n_chr + cap) + 7) & ~uintptr_t(7));
+
+    // ---- top_line: greedy (char, t) list from the top-1 candidates (:188-195), warp compaction
+    int ng = 0;
+    for (int base = 0; base < Tn; base += 32) {
+        const int t = base + lane;
+        int cur = 0, keep = 0;
+        if (t < Tn) {
+            cur = topk_idx[((long long)t * Bn + b) * k];
+            const int prev = t > 0 ? topk_idx[((long long)(t - 1) * Bn + b) * k] : -1;
+            keep = (cur != 0) && (cur != unknown) && !(t > 0 && prev == cur);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = ng + __popc(bal & ((1u << lane) - 1));
+            g_char[pos] = cur; g_time[pos] = t;
+        }
+        ng += __popc(bal);
+    }
+    __syncwarp();
+    if (ng == 0) {                                   // reference: top_line[-1] -> IndexError (:198)
+        if (lane == 0) { status[b] = HCTR_ERR_INDEX; out_len[b] = 0; }
+        return;
+    }
+    int end_step = g_time[ng - 1] + 4;               // :198-199
+    if (end_step >= Tn) end_step = Tn;
+
+    if (lane == 0) {
+        n_parent[0] = 0; n_chr[0] = -1; n_hash[0] = 0x243F6A8885A308D3ull;
+        kept[0].node[0] = 0; kept[0].len[0] = 0; kept[0].last[0] = -1; kept[0].hash[0] = n_hash[0];
+        kept[0].pb[0] = 0.0; kept[0].pnb[0] = -INFINITY; kept[0].lmsum[0] = 0.0;       // Beam() :289-297
+    }
+    int nkept = 1, cur_buf = 0, gptr = 0;
+    __syncwarp();
+
+    for (int t = 0; t < end_step; ++t) {
+        KeptState& K = kept[cur_buf];
+        KeptState& Kn = kept[cur_buf ^ 1];
+        while (gptr < ng && g_time[gptr] <= t) ++gptr;                 // suffix = next <=4 greedy chars after t (:202-203)
+        int nsuf = ng - gptr; if (nsuf > 4) nsuf = 4;
+
+        if (lane < k) {
+            const long long o = ((long long)t * Bn + b) * k + lane;
+            cand[lane] = topk_idx[o];
+            candp[lane] = (double)topk_logp[o];                        // fp32 log-prob promoted on addition
+        }
+        if (lane < nkept) {
+            Pj[lane] = logaddexp_np(K.pb[lane], K.pnb[lane]);          // Beam.prob() of the INPUT beam (:299-300)
+            // which kept beam (if any) is this beam's prefix minus its last character?
+            int pk = -1;
+            if (K.len[lane] > 0) {
+                const int par = n_parent[K.node[lane]];
+                for (int j = 0; j < nkept; ++j) {
+                    if (K.len[j] != K.len[lane] - 1) continue;
+                    if (K.node[j] == par || (K.hash[j] == n_hash[par] && same_string(n_parent, n_chr, K.node[j], par))) {
+                        pk = j; break;
+                    }
+                }
+            }
+            parentk[lane] = pk;
+            ent_of_kept[lane] = -1;
+        }
+        __syncwarp();
+
+        // ---- insertion order of the reference's gen_beams dict (:235-255), simulated sequentially
+        if (lane == 0) {
+            int ngen = 0;
+            for (int j = 0; j < nkept; ++j) {
+                for (int q = 0; q < k; ++q) {
+                    const int idx = cand[q];
+                    if (idx >= unknown) continue;                                  // :238-239
+                    if (ent_of_kept[j] < 0) { ent_of_kept[j] = ngen; e_kind[ngen] = j; ++ngen; }   // :243-244
+                    if (idx == 0) continue;
+                    int tgt = -1;                                                  // prefix_j + idx equals a kept prefix?
+                    for (int j2 = 0; j2 < nkept; ++j2)
+                        if (parentk[j2] == j && K.last[j2] == idx) { tgt = j2; break; }
+                    if (tgt >= 0) {
+                        if (ent_of_kept[tgt] < 0) { ent_of_kept[tgt] = ngen; e_kind[ngen] = tgt; ++ngen; }
+                    } else {
+                        e_kind[ngen] = -1; e_src[ngen] = j; e_chr[ngen] = idx;    // :253-255
+                        ++ngen;
+                    }
+                }
+            }
+            s_ngen = ngen;
+        }
+        __syncwarp();
+        const int ngen = s_ngen;
+
+        // ---- scores: every entry gathers its (at most two) contributions; np.logaddexp is symmetric and
+        //      logaddexp(-inf, a) == a, so the result is bit-identical to the reference's accumulation order.
+        for (int e = lane; e < ngen; e += 32) {
+            double pb = -INFINITY, pnb = -INFINITY, lm, plen;
+            if (e_kind[e] >= 0) {
+                const int j2 = e_kind[e];
+                for (int q = 0; q < k; ++q) {
+                    const int idx = cand[q];
+                    if (idx >= unknown) continue;
+                    if (idx == 0) pb = logaddexp_np(pb, __dadd_rn(Pj[j2], candp[q]));                  // :246-249
+                    else if (idx == K.last[j2]) pnb = logaddexp_np(pnb, __dadd_rn(K.pnb[j2], candp[q])); // :264-265
+                }
+                const int j = parentk[j2];
+                if (j >= 0) {
+                    for (int q = 0; q < k; ++q) {
+                        if (cand[q] != K.last[j2] || cand[q] >= unknown || cand[q] == 0) continue;
+                        const double add = (cand[q] != K.last[j]) ? __dadd_rn(Pj[j], candp[q])        // :256-258
+                                                                   : __dadd_rn(K.pb[j], candp[q]);    // :261-262
+                        pnb = logaddexp_np(pnb, add);
+                    }
+                }
+                lm = K.lmsum[j2]; plen = (double)K.len[j2];
+            } else {
+                const int j = e_src[e], idx = e_chr[e];
+                double p = 0.0;
+                for (int q = 0; q < k; ++q) if (cand[q] == idx) p = candp[q];
+                pnb = (idx != K.last[j]) ? __dadd_rn(Pj[j], p) : __dadd_rn(K.pb[j], p);
+                lm = lm_table ? __dadd_rn(K.lmsum[j], lm_table[idx]) : 0.0;
+                plen = (double)(K.len[j] + 1);
+            }
+            e_lm[e] = lm;                                                       // LM sum over the prefix only
+            double lmt = lm;
+            if (lm_table) for (int c = 0; c < nsuf; ++c) lmt = __dadd_rn(lmt, lm_table[g_char[gptr + c]]);
+            const double pt = __dadd_rn(__dmul_rn(lmt, lm_penalty), __dmul_rn(plen, len_bonus));   // :277-281
+            e_pb[e] = pb; e_pnb[e] = pnb;
+            e_tot[e] = __dadd_rn(logaddexp_np(pb, pnb), pt);                     // Beam.total() :302-303
+        }
+        __syncwarp();
+
+        // ---- sorted(..., key=total, reverse=True)[:beam_size]: stable, ties keep insertion order (:283-285)
+        const int keep_n = ngen < beam_size ? ngen : beam_size;
+        for (int e = lane; e < ngen; e += 32) {
+            const double te = e_tot[e];
+            int rank = 0;
+            for (int f = 0; f < ngen; ++f) rank += (e_tot[f] > te) || (e_tot[f] == te && f < e);
+            if (rank < keep_n) {
+                Kn.pb[rank] = e_pb[e]; Kn.pnb[rank] = e_pnb[e]; Kn.lmsum[rank] = e_lm[e];
+                if (e_kind[e] >= 0) {
+                    const int j2 = e_kind[e];
+                    Kn.node[rank] = K.node[j2]; Kn.len[rank] = K.len[j2]; Kn.last[rank] = K.last[j2]; Kn.hash[rank] = K.hash[j2];
+                } else {
+                    const int j = e_src[e], idx = e_chr[e];
+                    const int id = 1 + t * beam_size + rank;
+                    const unsigned long long h = mix_hash(K.hash[j], idx);
+                    n_parent[id] = K.node[j]; n_chr[id] = idx; n_hash[id] = h;
+                    Kn.node[rank] = id; Kn.len[rank] = K.len[j] + 1; Kn.last[rank] = idx; Kn.hash[rank] = h;
+                }
+            }
+        }
+        __threadfence_block();
+        __syncwarp();
+        nkept = keep_n;
+        cur_buf ^= 1;
+    }
+
+    // ---- texts.append(kept_beams[0].prefix) (:208)
+    if (lane == 0) {
+        const KeptState& K = kept[cur_buf];
+        const int L = K.len[0];
+        int node = K.node[0];
+        for (int c = L - 1; c >= 0; --c) { out_idx[(long long)b * Tn + c] = n_chr[node]; node = n_parent[node]; }
+        out_len[b] = L;
+        status[b] = 0;
+    }
+}
+
+}  // namespace hctr
+
+using namespace hctr;
+
+extern "C" {
+
+int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C, long long stride_t,
+                             long long stride_b, int k, int32_t* topk_idx, float* topk_logp, float* lse, void* stream) {
+    HCTR_CHECK(topk_idx && topk_logp && lse, HCTR_ERR_INVALID, "topk: null output");
+    HCTR_CHECK(T >= 0 && B >= 0 && C > 0, HCTR_ERR_INVALID, "topk: bad shape");
+    HCTR_CHECK(k >= 1 && k <= kMaxK && k <= C, HCTR_ERR_INVALID, "topk: search depth must be in [1,%d] and <= C (got %d)", kMaxK, k);
+    HCTR_CHECK(dtype == HCTR_F32 || dtype == HCTR_BF16, HCTR_ERR_INVALID, "topk: bad dtype");
+    if (T == 0 || B == 0) return HCTR_OK;
+    HCTR_CHECK(logits != nullptr, HCTR_ERR_INVALID, "topk: null logits");
+    const long long rows = (long long)T * B;
+    const long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
+    HCTR_CHECK(blocks < (1ll << 31), HCTR_ERR_INVALID, "topk: too many rows");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == HCTR_F32)
+        ctc_topk_logsoftmax_kernel<float><<<(int)blocks, kTopkWarps * 32, 0, s>>>(
+            static_cast<const float*>(logits), T, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
+    else
+        ctc_topk_logsoftmax_kernel<__nv_bfloat16><<<(int)blocks, kTopkWarps * 32, 0, s>>>(
+            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+static long long beam_ws_per_seq(int T, int beam) {
+    const long long cap = (long long)T * beam + 1;
+    long long bytes = 8ll * T + 8ll * cap + 8 /*align*/ + 8ll * cap;
+    return (bytes + 15) & ~15ll;
+}
+
+long long hctr_ctc_beam_workspace_bytes(int T, int B, int beam_size) {
+    if (T <= 0 || B <= 0 || beam_size <= 0) return 0;
+    return beam_ws_per_seq(T, beam_size) * B;
+}
+
+int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp, int T, int B, int C, int k,
+                                int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                int32_t* out_idx, int32_t* out_len, int32_t* status, void* workspace,
+                                long long workspace_bytes, void* stream) {
+    HCTR_CHECK(out_idx && out_len && status, HCTR_ERR_INVALID, "beam: null output");
+    HCTR_CHECK(k >= 1 && k <= kMaxK, HCTR_ERR_INVALID, "beam: search depth must be in [1,%d] (got %d)", kMaxK, k);
+    HCTR_CHECK(beam_size >= 1 && beam_size <= kMaxBeam, HCTR_ERR_INVALID, "beam: beam size must be in [1,%d] (got %d)", kMaxBeam, beam_size);
+    HCTR_CHECK(T >= 0 && B >= 0 && C > 1, HCTR_ERR_INVALID, "beam: bad shape");
+    if (B == 0) return HCTR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (T == 0) {        // no frames: the greedy path is empty for every sequence
+        HCTR_CUDA(cudaMemsetAsync(out_len, 0, sizeof(int32_t) * B, s));
+        HCTR_CUDA(cudaMemsetAsync(status, 0xff, sizeof(int32_t) * B, s));
+        return HCTR_OK;
+    }
+    HCTR_CHECK(topk_idx && topk_logp, HCTR_ERR_INVALID, "beam: null input");
+    HCTR_CHECK((long long)T * beam_size + 1 < (1ll << 31), HCTR_ERR_INVALID, "beam: sequence too long");
+    const long long need = hctr_ctc_beam_workspace_bytes(T, B, beam_size);
+    HCTR_CHECK(workspace && workspace_bytes >= need, HCTR_ERR_INVALID, "beam: workspace too small (%lld < %lld)", workspace_bytes, need);
+    HCTR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, HCTR_ERR_INVALID, "beam: workspace must be 16-byte aligned");
+    ctc_prefix_beam_kernel<<<B, 32, 0, s>>>(topk_idx, topk_logp, T, B, C, k, beam_size, lm_penalty, len_bonus, lm_table,
+                                            out_idx, out_len, status, static_cast<unsigned char*>(workspace),
+                                            beam_ws_per_seq(T, beam_size));
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+}  // extern "C"

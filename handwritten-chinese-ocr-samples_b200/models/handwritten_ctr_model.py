@@ -161,6 +161,9 @@ class hctr_model(nn.Module):
         self.logits_dtype = torch.float32
         self._plan = None
         self._plan_key = None
+        # optional per-kernel trace: a list that receives (tag, flops, bytes, start_event, end_event) per launch
+        self.kernel_trace = None
+        self.launch_count = 0
 
     # -------------------------------------------------------------------------------- plan cache
     def _current_key(self):
@@ -193,12 +196,30 @@ class hctr_model(nn.Module):
         with torch.cuda.device(input.device):
             return self._forward_eval(input.detach().float().contiguous())
 
+    def _launch(self, nat, tag, flops, nbytes, fn, *args):
+        """One C-ABI call = one kernel launch on the current stream; optionally bracketed by CUDA events."""
+        self.launch_count += 1
+        trace = self.kernel_trace
+        if trace is None:
+            nat.check(fn(*args), tag)
+            return
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        nat.check(fn(*args), tag)
+        e1.record()
+        trace.append((tag, flops, nbytes, e0, e1))
+
     def _conv(self, nat, x, spec, B, H, W, relu, pool):
         ho = H // 2 if pool else H
         y = torch.empty((B, ho, W, spec.cout), dtype=torch.bfloat16, device=x.device)
-        nat.check(nat.lib().hctr_conv_bn_act_fwd(
-            nat.ptr(x), nat.ptr(spec.w), nat.ptr(spec.scale), nat.ptr(spec.shift), nat.ptr(y),
-            B, H, W, spec.cin, spec.cout, spec.ksize, int(relu), int(pool), nat.stream_ptr()), "conv_bn_act")
+        taps = spec.ksize * spec.ksize
+        flops = 2.0 * B * H * W * spec.cout * spec.cin * taps
+        nbytes = 2.0 * (x.numel() + y.numel() + spec.w.numel())
+        tag = "conv%dx%d_%d_%d%s" % (spec.ksize, spec.ksize, spec.cin, spec.cout, "_pool" if pool else "")
+        self._launch(nat, tag, flops, nbytes, nat.lib().hctr_conv_bn_act_fwd,
+                     nat.ptr(x), nat.ptr(spec.w), nat.ptr(spec.scale), nat.ptr(spec.shift), nat.ptr(y),
+                     B, H, W, spec.cin, spec.cout, spec.ksize, int(relu), int(pool), nat.stream_ptr())
         return y
 
     def _forward_eval(self, x):
@@ -210,8 +231,9 @@ class hctr_model(nn.Module):
         dev = x.device
 
         a = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=dev)
-        nat.check(lib.hctr_stem_conv_fwd(nat.ptr(x), nat.ptr(plan.stem_w), nat.ptr(plan.stem_scale),
-                                         nat.ptr(plan.stem_shift), nat.ptr(a), B, H, W, st), "stem")
+        self._launch(nat, "stem", 2.0 * B * H * W * 64 * 9, 4.0 * x.numel() + 2.0 * a.numel(), lib.hctr_stem_conv_fwd,
+                     nat.ptr(x), nat.ptr(plan.stem_w), nat.ptr(plan.stem_scale), nat.ptr(plan.stem_shift), nat.ptr(a),
+                     B, H, W, st)
         a = self._conv(nat, a, plan.conv0_2, B, H, W, relu=True, pool=True)
         H //= 2
         for units, tail in plan.stages:
@@ -223,13 +245,15 @@ class hctr_model(nn.Module):
                 slices = lib.hctr_se_slices(H, W)
                 partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
                 gate = torch.empty((B, C), dtype=torch.float32, device=dev)
-                nat.check(lib.hctr_se_squeeze(nat.ptr(v), nat.ptr(partial), B, H, W, C, st), "se_squeeze")
-                nat.check(lib.hctr_se_excite(nat.ptr(partial), slices, nat.ptr(u["se_w1"]), nat.ptr(u["se_w2"]),
-                                             nat.ptr(gate), B, C, u["se_w1"].shape[0], H * W, st), "se_excite")
+                self._launch(nat, "se_squeeze", 0.0, 2.0 * v.numel(), lib.hctr_se_squeeze,
+                             nat.ptr(v), nat.ptr(partial), B, H, W, C, st)
+                self._launch(nat, "se_excite", 0.0, 4.0 * partial.numel(), lib.hctr_se_excite,
+                             nat.ptr(partial), slices, nat.ptr(u["se_w1"]), nat.ptr(u["se_w2"]), nat.ptr(gate),
+                             B, C, u["se_w1"].shape[0], H * W, st)
                 res = a if u["shortcut"] is None else self._conv(nat, a, u["shortcut"], B, H, W, relu=False, pool=False)
                 out = torch.empty_like(v)
-                nat.check(lib.hctr_se_scale_residual_relu(nat.ptr(v), nat.ptr(gate), nat.ptr(res), nat.ptr(out),
-                                                          B, H, W, C, st), "se_scale_residual_relu")
+                self._launch(nat, "se_scale_residual_relu", 0.0, 6.0 * v.numel(), lib.hctr_se_scale_residual_relu,
+                             nat.ptr(v), nat.ptr(gate), nat.ptr(res), nat.ptr(out), B, H, W, C, st)
                 a = out
                 del v, res
             a = self._conv(nat, a, tail, B, H, W, relu=True, pool=True)
@@ -245,8 +269,9 @@ class hctr_model(nn.Module):
         else:
             raise ValueError("logits_dtype must be torch.float32 or torch.bfloat16")
         logits = torch.empty((B, W, pitch), dtype=self.logits_dtype, device=feat.device)
-        nat.check(nat.lib().hctr_classifier_fwd(nat.ptr(feat), nat.ptr(plan.cls_w), nat.ptr(plan.cls_b),
-                                                nat.ptr(logits), code, pitch, B, Hf, W, plan.cf, n,
-                                                nat.stream_ptr()), "classifier")
+        self._launch(nat, "classifier", 2.0 * B * W * n * Hf * plan.cf,
+                     2.0 * feat.numel() + logits.numel() * logits.element_size() + 2.0 * plan.cls_w.numel(),
+                     nat.lib().hctr_classifier_fwd, nat.ptr(feat), nat.ptr(plan.cls_w), nat.ptr(plan.cls_b),
+                     nat.ptr(logits), code, pitch, B, Hf, W, plan.cf, n, nat.stream_ptr())
         # reference: x.permute(1, 0, 2) of the contiguous [B,W,C] linear output (:176)
         return logits[:, :, :n].permute(1, 0, 2)

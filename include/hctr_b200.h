@@ -92,7 +92,7 @@ int hctr_ctc_greedy_decode(const void* logits, int dtype, int T, int B, int C, l
 
 /* log_softmax over C (scipy.special.log_softmax, utils/ctc_codec.py:65) fused with the per-step top-k
  * (np.argsort flip, :186). topk_idx: int32 [T][B][k] descending by log-prob (ties -> lower index first);
- * topk_logp: fp32 [T][B][k]; lse: fp32 [T][B] (logp = logit - lse). k <= 32. */
+ * topk_logp: fp32 [T][B][k]; lse: fp32 [T][B] (logp = logit - lse). k <= 16. */
 int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C, long long stride_t,
                              long long stride_b, int k, int32_t* topk_idx, float* topk_logp, float* lse, void* stream);
 
@@ -100,11 +100,14 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
  * transformer; the language model is a per-class unigram table (lm_table[c], fp64, may be NULL = zero LM),
  * scored over prefix + look-ahead suffix exactly as `ngram.score(' '.join(prefix+suffix))` would for a
  * unigram model. float64 accumulators, stable ordering by insertion. One CTA per sequence.
- * Inputs are the outputs of hctr_ctc_topk_logsoftmax. out_idx: int32 [B][T]; out_len: int32 [B];
+ * Inputs are the outputs of hctr_ctc_topk_logsoftmax (k <= 16, beam_size <= 16). out_idx: int32 [B][T]; out_len: int32 [B];
  * status: int32 [B], 0 ok, HCTR_ERR_INDEX if the greedy path is empty (the reference raises IndexError). */
 int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp, int T, int B, int C, int k,
                                 int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
-                                int32_t* out_idx, int32_t* out_len, int32_t* status, void* stream);
+                                int32_t* out_idx, int32_t* out_len, int32_t* status, void* workspace,
+                                long long workspace_bytes, void* stream);
+/* bytes of caller-owned device scratch (greedy look-ahead list + prefix trie) for the call above */
+long long hctr_ctc_beam_workspace_bytes(int T, int B, int beam_size);
 
 /* CTCLoss(blank=0, reduction='mean', zero_infinity=True) on log_softmax(logits) and its gradient wrt the
  * logits (main.py:205,406-409,426). logits element (t,b,c) at logits[t*stride_t + b*stride_b + c];

@@ -1,0 +1,88 @@
+"""Seeded synthetic inputs shared by tests/golden/make_golden.py, the tests and bench.py.
+Everything uses numpy's legacy RandomState (bit-stable across numpy versions), so fixtures only need to
+store the reference's OUTPUTS; the inputs are regenerated from the seed on any box."""
+import numpy as np
+
+
+def charset(n):
+    """Synthetic charset of n distinct CJK characters (BASELINE config 1: chr(0x4E00+i))."""
+    return ''.join(chr(0x4E00 + i) for i in range(n))
+
+
+def ctc_like_logits(T, B, C, seed, peak=12.0, period=3, noise=2.0):
+    """Peaky CTC-like logits [T,B,C] fp32: a planted path that emits a random class every `period` steps
+    (blank otherwise) on top of noise*randn; includes forced repeats and unknown-class hits."""
+    rs = np.random.RandomState(seed)
+    x = (noise * rs.randn(T, B, C)).astype(np.float32)
+    for b in range(B):
+        last = 0
+        for t in range(T):
+            r = rs.rand()
+            if t % period == 0:
+                if r < 0.15 and last not in (0,):
+                    c = last                          # forced repeat of the previous emission
+                elif r < 0.25:
+                    c = C - 1                         # unknown-class hit
+                else:
+                    c = 1 + rs.randint(C - 2)
+                last = c
+            elif r < 0.2 and last != 0:
+                c = last                              # run of the same class (collapsed by the decoder)
+            else:
+                c = 0
+            x[t, b, c] += peak
+    return x
+
+
+def beam_logits(T, B, C, seed, period=8):
+    """BASELINE config 5 input: 2*randn with +12 on a random class at t%period==0 and on blank otherwise
+    (guarantees a non-empty greedy path and no ties inside the top 11)."""
+    rs = np.random.RandomState(seed)
+    x = (2.0 * rs.randn(T, B, C)).astype(np.float32)
+    for b in range(B):
+        for t in range(T):
+            c = 1 + rs.randint(C - 2) if t % period == 0 else 0
+            x[t, b, c] += 12.0
+    return x
+
+
+def lm_table(C, seed):
+    """Deterministic per-class unigram 'log10 probabilities' for the table LM stub."""
+    rs = np.random.RandomState(seed)
+    t = -(0.5 + 3.0 * rs.rand(C))
+    t[0] = 0.0
+    return t.astype(np.float64)
+
+
+def ctc_targets(B, C, Lmin, Lmax, seed, repeat_frac=0.1):
+    """Random label sequences over classes 1..C-2 with forced repeats -> (targets int32 [sum L], lengths int32 [B])."""
+    rs = np.random.RandomState(seed)
+    lens = rs.randint(Lmin, Lmax + 1, size=B).astype(np.int32)
+    out = []
+    for L in lens:
+        seq = []
+        for i in range(L):
+            if i > 0 and rs.rand() < repeat_frac:
+                seq.append(seq[-1])
+            else:
+                seq.append(1 + rs.randint(C - 2))
+        out.extend(seq)
+    return np.array(out, dtype=np.int32), lens
+
+
+def text_lines(B, W, seed, H=128):
+    """Synthetic 'ink on paper' text lines [B,1,H,W] fp32 in [-1,1]: background +1, random dark strokes."""
+    rs = np.random.RandomState(seed)
+    x = np.ones((B, 1, H, W), np.float32)
+    for b in range(B):
+        n = max(4, W // 6)
+        cx = rs.randint(0, W, size=n); cy = rs.randint(16, H - 16, size=n)
+        ln = rs.randint(4, 28, size=n); th = rs.randint(1, 4, size=n); hor = rs.rand(n) < 0.5
+        val = -1.0 + 0.6 * rs.rand(n)
+        for i in range(n):
+            if hor[i]:
+                x[b, 0, cy[i]:cy[i] + th[i], max(0, cx[i] - ln[i]):cx[i] + ln[i]] = val[i]
+            else:
+                x[b, 0, max(0, cy[i] - ln[i]):cy[i] + ln[i], cx[i]:cx[i] + th[i]] = val[i]
+    x += (0.05 * rs.randn(B, 1, H, W)).astype(np.float32)
+    return np.clip(x, -1.0, 1.0).astype(np.float32)

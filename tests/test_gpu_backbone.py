@@ -1,0 +1,256 @@
+"""GPU parity of the backbone + classifier kernels (through the C ABI) against torch fp32 ops / the fp32 oracle.
+
+Tolerances (floating point, stated per test):
+  * single kernels see bf16-rounded inputs and weights and accumulate in fp32, so only the final bf16 rounding of the
+    output differs from an fp32 evaluation of the same rounded operands: |err| <= 2^-7 * max|ref| (half a bf16 ulp at
+    the output scale, plus accumulation-order noise);
+  * end-to-end logits: <= 2e-2 max-abs vs the fp32 reference in the default-init regime (north star); with
+    BN-calibrated weights the reference's own bf16-autocast path is 0.27 max-abs / 0.035 mean-abs away from its fp32
+    path, so the gate there is 0.35 max-abs and 0.05 mean-abs plus argmax agreement.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+from oracle import hctr_forward
+
+pytestmark = pytest.mark.gpu
+
+BF16_GATE = 2.0 ** -7
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = a, b
+
+
+def _nat():
+    from hctr_b200 import native
+    return native
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, relu, pool      (every channel configuration of the network, ragged widths)
+    (2, 16, 256, 64, 64, 3, 1, 1),            # conv0_2 + pool
+    (1, 8, 488, 64, 128, 3, 1, 0),            # block1.0.conv1
+    (2, 8, 200, 128, 128, 3, 0, 0),           # block1.x.conv2 (no relu)
+    (1, 8, 130, 128, 128, 3, 1, 1),           # cnn.conv1 + pool
+    (1, 6, 96, 128, 256, 3, 1, 0),            # block2.0.conv1, W < one tile
+    (2, 4, 384, 256, 256, 3, 1, 1),           # cnn.conv2 + pool
+    (1, 4, 257, 256, 512, 3, 1, 0),           # block3.0.conv1
+    (1, 4, 256, 512, 512, 3, 0, 0),           # block3/4 conv2
+    (1, 8, 300, 512, 512, 3, 1, 1),           # cnn.conv3/4 + pool
+    (2, 8, 256, 64, 128, 1, 0, 0),            # block1.0.downsample
+    (1, 4, 100, 128, 256, 1, 0, 0),           # block2.0.downsample
+    (1, 4, 129, 256, 512, 1, 0, 0),           # block3.0.downsample
+    (3, 2, 1, 64, 64, 3, 1, 1),               # degenerate width
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,relu,pool", CONV_CASES)
+def test_conv_bn_act_kernel(B, H, W, Cin, Cout, k, relu, pool):
+    nat = _nat()
+    g = torch.Generator().manual_seed(B * 1000 + W + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda().to(torch.bfloat16)
+    scale = ((torch.rand(Cout, generator=g) + 0.5) * torch.where(torch.rand(Cout, generator=g) < 0.25, -1.0, 1.0)).cuda()
+    shift = (0.2 * torch.randn(Cout, generator=g)).cuda()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wp = w.permute(0, 2, 3, 1).contiguous()
+    Ho = H // 2 if pool else H
+    y = torch.full((B, Ho, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    nat.check(nat.lib().hctr_conv_bn_act_fwd(nat.ptr(xn), nat.ptr(wp), nat.ptr(scale), nat.ptr(shift), nat.ptr(y),
+                                             B, H, W, Cin, Cout, k, relu, pool, nat.stream_ptr()))
+    ref = F.conv2d(x.float(), w.float(), padding=k // 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if relu:
+        ref = ref.relu()
+    if pool:
+        ref = F.max_pool2d(ref, (2, 1), (2, 1))
+    got = y.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= BF16_GATE * ref.abs().max().item()
+
+
+def test_conv_rejects_bad_shapes():
+    nat = _nat()
+    t = torch.zeros(64, device="cuda")
+    rc = nat.lib().hctr_conv_bn_act_fwd(nat.ptr(t), nat.ptr(t), nat.ptr(t), nat.ptr(t), nat.ptr(t), 1, 4, 8, 48, 64, 3, 1, 0, None)
+    assert rc == nat.HCTR_ERR_INVALID and "Cin" in nat.last_error()
+    rc = nat.lib().hctr_conv_bn_act_fwd(nat.ptr(t), nat.ptr(t), nat.ptr(t), nat.ptr(t), nat.ptr(t), 1, 3, 8, 64, 64, 3, 1, 1, None)
+    assert rc == nat.HCTR_ERR_INVALID and "even" in nat.last_error()
+
+
+@pytest.mark.parametrize("B,W,N,dtype", [(2, 256, 7375, torch.float32), (1, 200, 7375, torch.bfloat16),
+                                         (3, 31, 37, torch.float32), (1, 513, 1000, torch.bfloat16)])
+def test_classifier_kernel(B, W, N, dtype):
+    nat = _nat()
+    g = torch.Generator().manual_seed(W + N)
+    feat = torch.randn(B, 4, W, 512, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(N, 2048, generator=g) / 45).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    pitch = (N + 7) // 8 * 8
+    out = torch.full((B, W, pitch), float("nan"), dtype=dtype, device="cuda")
+    nat.check(nat.lib().hctr_classifier_fwd(nat.ptr(feat), nat.ptr(w), nat.ptr(bias), nat.ptr(out),
+                                            nat.HCTR_F32 if dtype == torch.float32 else nat.HCTR_BF16, pitch, B, 4, W, 512,
+                                            N, nat.stream_ptr()))
+    ref = (feat.float().permute(0, 2, 1, 3).reshape(B * W, 2048) @ w.float().t() + bias).reshape(B, W, N)
+    got = out[:, :, :N].float()
+    tol = 1e-4 * ref.abs().max().item() if dtype == torch.float32 else BF16_GATE * ref.abs().max().item()   # fp32: <=1e-4 rel
+    assert (got - ref).abs().max().item() <= tol
+    assert torch.isnan(out[:, :, N:].float()).all()                     # pitch padding is never written
+
+
+def test_stem_and_se_kernels():
+    nat = _nat()
+    lib = nat.lib()
+    g = torch.Generator().manual_seed(2)
+    B, H, W = 2, 128, 200
+    x = (torch.rand(B, 1, H, W, generator=g) * 2 - 1).cuda()
+    w = (torch.randn(64, 1, 3, 3, generator=g) / 3).cuda()
+    scale = (torch.rand(64, generator=g) + 0.5).cuda()
+    shift = (0.1 * torch.randn(64, generator=g)).cuda()
+    y = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device="cuda")
+    nat.check(lib.hctr_stem_conv_fwd(nat.ptr(x), nat.ptr(w.reshape(64, 9).contiguous()), nat.ptr(scale), nat.ptr(shift),
+                                     nat.ptr(y), B, H, W, nat.stream_ptr()))
+    ref = (F.conv2d(x, w, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
+    assert (y.permute(0, 3, 1, 2).float() - ref).abs().max().item() <= BF16_GATE * ref.abs().max().item()
+    for C, H2, W2 in ((128, 64, 200), (256, 32, 130), (512, 8, 513)):
+        v = torch.randn(B, H2, W2, C, generator=g).cuda().to(torch.bfloat16)
+        r = torch.randn(B, H2, W2, C, generator=g).cuda().to(torch.bfloat16)
+        w1 = (torch.randn(C // 16, C, generator=g) / 16).cuda()
+        w2 = (torch.randn(C, C // 16, generator=g) / 4).cuda()
+        slices = lib.hctr_se_slices(H2, W2)
+        partial = torch.empty(B, slices, C, device="cuda")
+        gate = torch.empty(B, C, device="cuda")
+        out = torch.empty_like(v)
+        nat.check(lib.hctr_se_squeeze(nat.ptr(v), nat.ptr(partial), B, H2, W2, C, nat.stream_ptr()))
+        nat.check(lib.hctr_se_excite(nat.ptr(partial), slices, nat.ptr(w1), nat.ptr(w2), nat.ptr(gate), B, C, C // 16,
+                                     H2 * W2, nat.stream_ptr()))
+        nat.check(lib.hctr_se_scale_residual_relu(nat.ptr(v), nat.ptr(gate), nat.ptr(r), nat.ptr(out), B, H2, W2, C,
+                                                  nat.stream_ptr()))
+        gref = torch.sigmoid(torch.relu(v.float().mean(dim=(1, 2)) @ w1.t()) @ w2.t())
+        assert (gate - gref).abs().max().item() <= 1e-5                 # fp32 reduction-order noise only
+        oref = (v.float() * gref.view(B, 1, 1, C) + r.float()).relu()
+        assert (out.float() - oref).abs().max().item() <= BF16_GATE * oref.abs().max().item()
+        # deterministic: a second run is bit-identical
+        gate2 = torch.empty_like(gate)
+        nat.check(lib.hctr_se_squeeze(nat.ptr(v), nat.ptr(partial), B, H2, W2, C, nat.stream_ptr()))
+        nat.check(lib.hctr_se_excite(nat.ptr(partial), slices, nat.ptr(w1), nat.ptr(w2), nat.ptr(gate2), B, C, C // 16,
+                                     H2 * W2, nat.stream_ptr()))
+        assert torch.equal(gate, gate2)
+
+
+# ------------------------------------------------------------------------------------------ end to end
+def _model(num_classes, seed):
+    from hctr_b200.models.handwritten_ctr_model import hctr_model
+    torch.manual_seed(seed)
+    return hctr_model(num_classes)
+
+
+def test_logits_default_init_small_model(golden):
+    g = golden("model")
+    m = _model(37, 4321).cuda().eval()
+    x = torch.from_numpy(synth.text_lines(2, 72, 51)).cuda()
+    y = m(x)
+    assert tuple(y.shape) == (72, 2, 37) and y.dtype == torch.float32
+    assert y.stride() == (40, 72 * 40, 1)                               # a permuted view of [B,W,pitch], like the reference
+    ref = torch.from_numpy(g["small_default_logits"])
+    assert (y.cpu() - ref).abs().max().item() <= 2e-2                   # north-star bf16 tolerance
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    orc = hctr_forward.forward(x.cpu(), sd)
+    assert (orc - ref).abs().max().item() <= 1e-5                       # the fp32 oracle restates the reference
+    assert (y.cpu() - orc).abs().max().item() <= 2e-2
+
+
+def test_logits_bn_calibrated_small_model(golden):
+    g = golden("model")
+    m = _model(37, 4321)
+    sd = m.state_dict()
+    for k in list(sd.keys()):
+        if "small_cal." + k in g:
+            sd[k] = torch.from_numpy(g["small_cal." + k])
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    x = torch.from_numpy(synth.text_lines(2, 72, 51)).cuda()
+    y = m(x).cpu()
+    ref = torch.from_numpy(g["small_cal_logits"])
+    orc = hctr_forward.forward(x.cpu(), {k: v.cpu() for k, v in m.state_dict().items()})
+    assert (orc - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+    err = (y - ref).abs()
+    assert err.max().item() <= 0.35 and err.mean().item() <= 0.05
+    agree = (y.argmax(2) == ref.argmax(2)).float().mean().item()
+    assert agree >= 0.80                                                # reference bf16-autocast itself agrees 84 %
+
+
+def test_config1_bundled_images_greedy_text(golden):
+    """BASELINE config 1: the 5 bundled lines (preprocessed by the reference's test.py, stored as uint8), random-init
+    weights (seed 1234), synthetic 7373-char charset, batch 1, greedy decode -> same strings as the reference on CPU."""
+    from hctr_b200.utils.ctc_codec import ctc_codec
+    g = golden("config1")
+    m = _model(7375, 1234).cuda().eval()
+    codec = ctc_codec(synth.charset(7373))
+    texts = []
+    for i in range(5):
+        img = torch.from_numpy(g["img%d" % i]).float().div(255.0).sub(0.5).div(0.5)        # NormalizePAD, no padding at b=1
+        logits = m(img.view(1, 1, 128, -1).cuda())
+        assert logits.shape[0] == int(g["widths"][i])
+        texts.append(codec.decode(logits)[0])
+    assert texts == list(g["text"])
+
+
+def test_full_charset_default_init_line(golden):
+    from hctr_b200.utils.ctc_codec import ctc_codec
+    g = golden("model")
+    m = _model(7375, 1234).cuda().eval()
+    x = torch.from_numpy(synth.text_lines(1, 136, 53)).cuda()
+    y = m(x)
+    assert (y[0, 0].cpu() - torch.from_numpy(g["full_default_logits_t0"])).abs().max().item() <= 2e-2
+    assert ctc_codec(synth.charset(7373)).decode(y) == list(g["full_default_text"])
+    m.logits_dtype = torch.bfloat16
+    yb = m(x)
+    assert yb.dtype == torch.bfloat16 and (yb.float() - y).abs().max().item() <= 2e-2
+
+
+def test_batch_mates_do_not_interact_and_ragged_width():
+    """Lines are independent given the padded width: a line's logits are bit-identical whatever shares
+    its batch, which is what makes batch-sharding across GPUs collective-free."""
+    m = _model(37, 7).cuda().eval()
+    x = torch.from_numpy(synth.text_lines(3, 200, 61)).cuda()
+    y3 = m(x)
+    y1 = m(x[1:2])
+    assert torch.equal(y3[:, 1], y1[:, 0])
+    xs = x.clone(); xs[0] = -xs[0]
+    assert torch.equal(m(xs)[:, 1], y1[:, 0])
+
+
+def test_full_size_batch_properties():
+    """BASELINE config 2 size (B=64, 128x2048, bf16 logits): duplicate lines give identical rows, and equal a B=1 run."""
+    from hctr_b200.utils.ctc_codec import ctc_codec
+    m = _model(7375, 1234).cuda().eval()
+    m.logits_dtype = torch.bfloat16
+    base = torch.from_numpy(synth.text_lines(2, 2048, 62)).cuda()
+    x = base[[0, 1] * 32].contiguous()
+    y = m(x)
+    assert tuple(y.shape) == (2048, 64, 7375)
+    assert torch.equal(y[:, 0], y[:, 62]) and torch.equal(y[:, 1], y[:, 63])
+    y1 = m(base[0:1])
+    assert torch.equal(y1[:, 0], y[:, 0])
+    texts = ctc_codec(synth.charset(7373)).decode(y)
+    assert len(texts) == 64 and texts[0] == texts[2]
+
+
+def test_model_errors():
+    m = _model(37, 1).cuda()
+    with pytest.raises(NotImplementedError):
+        m.train()(torch.zeros(1, 1, 128, 64, device="cuda"))
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 96, 64, device="cuda"))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 128, 64, device="cuda"))
