@@ -54,7 +54,34 @@ template <> struct Vec<__nv_bfloat16> {
 };
 
 constexpr int kArgmaxWarps = 8;
-constexpr int kUnroll = 4;
+constexpr int kUnroll = 8;
+
+// ---- exact (slow) row scan: numpy.argmax semantics incl. NaN; used for the unaligned head/tail and for
+//      rows in which the fast path saw a NaN.
+template <typename T>
+__device__ __noinline__ Best row_argmax_exact(const T* __restrict__ p, int C, int lane) {
+    Best best; best.v = 0.f; best.i = -1; best.nan = 0;
+    for (int c = lane; c < C; c += 32) consider(best, Vec<T>::one(p + c), c);
+    return best;
+}
+
+// ---- fast per-thread scan of the 16-byte-aligned body: only a running maximum and the index of the VECTOR
+//      that produced it (strict '>' keeps the earliest); the element is located afterwards. ~1 instruction per
+//      element, which is what lets the kernel run at HBM speed (the budget is ~8 issue slots per bf16 element).
+__device__ __forceinline__ float vec_max_nanprop(const uint4& q, __nv_bfloat16*) {
+    // packed bf16x2 NaN-propagating max tree
+    const __nv_bfloat162 a = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&q.x), *reinterpret_cast<const __nv_bfloat162*>(&q.y));
+    const __nv_bfloat162 b = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&q.z), *reinterpret_cast<const __nv_bfloat162*>(&q.w));
+    const __nv_bfloat162 c = __hmax2_nan(a, b);
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&c);
+    const float lo = bf16_lo(u), hi = bf16_hi(u);
+    return (lo != lo || hi != hi) ? __int_as_float(0x7fc00000) : fmaxf(lo, hi);
+}
+__device__ __forceinline__ float vec_max_nanprop(const uint4& q, float*) {
+    const float x0 = __uint_as_float(q.x), x1 = __uint_as_float(q.y), x2 = __uint_as_float(q.z), x3 = __uint_as_float(q.w);
+    const float m = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+    return (x0 != x0 || x1 != x1 || x2 != x2 || x3 != x3) ? __int_as_float(0x7fc00000) : m;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kArgmaxWarps * 32)
@@ -67,36 +94,53 @@ ctc_argmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long
     const int b = (int)(row / Tn), t = (int)(row - (long long)b * Tn);
     const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
 
-    Best best; best.v = 0.f; best.i = -1; best.nan = 0;
-    // scalar head up to the first 16-byte boundary
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
     int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
     if (head > C) head = C;
-    if (lane < head) consider(best, Vec<T>::one(p + lane), lane);
     const int nvec = (C - head) / V;
     const T* pv = p + head;
+    const int tail0 = head + nvec * V;
+
+    float bm = -INFINITY;       // running max over this thread's vectors
+    int bvi = -1;               // vector index that produced it
+    bool saw_nan = false;
     int vi = lane;
     for (; vi + (kUnroll - 1) * 32 < nvec; vi += kUnroll * 32) {
-        float x[kUnroll][V];
+        uint4 q[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) Vec<T>::load(pv + (long long)(vi + u * 32) * V, x[u]);
+        for (int u = 0; u < kUnroll; ++u) q[u] = ld_nc_v4(pv + (long long)(vi + u * 32) * V);
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-#pragma unroll
-            for (int j = 0; j < V; ++j) consider(best, x[u][j], head + (vi + u * 32) * V + j);
+        for (int u = 0; u < kUnroll; ++u) {
+            const float m = vec_max_nanprop(q[u], static_cast<T*>(nullptr));
+            if (!(m <= bm)) {                       // greater, or NaN
+                if (m != m) saw_nan = true; else { bm = m; bvi = vi + u * 32; }
+            }
+        }
     }
     for (; vi < nvec; vi += 32) {
-        float x[V];
-        Vec<T>::load(pv + (long long)vi * V, x);
+        const uint4 q = ld_nc_v4(pv + (long long)vi * V);
+        const float m = vec_max_nanprop(q, static_cast<T*>(nullptr));
+        if (!(m <= bm)) {
+            if (m != m) saw_nan = true; else { bm = m; bvi = vi; }
+        }
+    }
+    Best best; best.v = 0.f; best.i = -1; best.nan = 0;
+    if (__any_sync(0xffffffffu, saw_nan)) {
+        best = row_argmax_exact<T>(p, C, lane);      // rare: exact NaN-aware scan of the whole row
+    } else {
+        // head elements (lowest indices) first, then the located body element, then the tail: increasing index order
+        if (lane < head) consider(best, Vec<T>::one(p + lane), lane);
+        if (bvi >= 0) {
+            float x[V];
+            Vec<T>::load(pv + (long long)bvi * V, x);
 #pragma unroll
-        for (int j = 0; j < V; ++j) consider(best, x[j], head + vi * V + j);
+            for (int j = 0; j < V; ++j) consider(best, x[j], head + bvi * V + j);
+        } else if (nvec > 0 && lane < nvec) {
+            // every vector of this thread was all -inf: the first of them holds the thread's first maximum
+            consider(best, -INFINITY, head + lane * V);
+        }
+        if (tail0 + lane < C) consider(best, Vec<T>::one(p + tail0 + lane), tail0 + lane);
     }
-    const int tail0 = head + nvec * V;
-    if (tail0 + lane < C) {
-        // per-thread visiting order must stay increasing: the tail index is larger than all vector indices
-        consider(best, Vec<T>::one(p + tail0 + lane), tail0 + lane);
-    }
-    // NB: the head element (index < head) was visited first, so per-thread order is increasing throughout.
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         Best other;
@@ -152,17 +196,17 @@ using namespace hctr;
 extern "C" int hctr_ctc_greedy_decode(const void* logits, int dtype, int T, int B, int C, long long stride_t,
                                       long long stride_b, int32_t* argmax_out, int32_t* out_idx, int32_t* out_len,
                                       void* stream) {
-    HCTR_CHECK(out_idx && out_len, HCTR_ERR_INVALID, "greedy: null output");
     HCTR_CHECK(T >= 0 && B >= 0 && C > 0, HCTR_ERR_INVALID, "greedy: bad shape T=%d B=%d C=%d", T, B, C);
     HCTR_CHECK(dtype == HCTR_F32 || dtype == HCTR_BF16, HCTR_ERR_INVALID, "greedy: bad dtype %d", dtype);
-    HCTR_CHECK(argmax_out != nullptr, HCTR_ERR_INVALID, "greedy: argmax workspace [B][T] is required");
     if (B == 0) return HCTR_OK;
+    HCTR_CHECK(out_len != nullptr, HCTR_ERR_INVALID, "greedy: null output");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (T == 0) {   // reference: a zero-length sample yields no text (utils/ctc_codec.py:85-86)
         HCTR_CUDA(cudaMemsetAsync(out_len, 0, sizeof(int32_t) * B, s));
         return HCTR_OK;
     }
-    HCTR_CHECK(logits != nullptr, HCTR_ERR_INVALID, "greedy: null logits");
+    HCTR_CHECK(logits != nullptr && out_idx != nullptr, HCTR_ERR_INVALID, "greedy: null logits / output");
+    HCTR_CHECK(argmax_out != nullptr, HCTR_ERR_INVALID, "greedy: argmax workspace [B][T] is required");
     const long long rows = (long long)T * B;
     const long long blocks = (rows + kArgmaxWarps - 1) / kArgmaxWarps;
     HCTR_CHECK(blocks < (1ll << 31), HCTR_ERR_INVALID, "greedy: too many rows");

@@ -4,7 +4,8 @@
 //   A (HBM-bound): one warp per (t,b) row -> log-sum-exp, and the gathered log-probs of the blank-interleaved
 //                  label sequence l' (S = 2L+1) for the recursion.
 //   B (latency-bound): one CTA per sequence, alpha then beta over time with the state in shared memory
-//                  (ping-pong, one barrier per step), fp32 log-space, 3-way log-sum-exp as ATen's ctc_loss.
+//                  (ping-pong, one barrier per step), 3-way log-sum-exp as ATen's ctc_loss but with the state in
+//                  fp64: |log alpha| reaches ~2e4 at T=2048, C=7375, where fp32 log-space has only ~2e-3 resolution.
 //   C (HBM-bound): one CTA per row: grad = (softmax - occupancy) * scale written in one pass, where
 //                  occupancy_c = sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - ll - lp[t, l'_s]).
 // Logits are read twice and the gradient written once: (2*s_in + s_out) * T*B*C bytes.
@@ -18,8 +19,8 @@ namespace hctr {
 struct CtcWs {
     float* lse;        // [B][T]
     float* lpg;        // [B][T][Smax]   log-prob of l'_s at (t,b)
-    float* alpha;      // [B][T][Smax]   alpha, later overwritten by alpha+beta-lp (log occupancy + ll)
-    float* ll;         // [B]            log-likelihood (may be -inf)
+    double* alpha;     // [B][T][Smax]   alpha, later overwritten by alpha+beta-lp (log occupancy + ll), fp64
+    double* ll;        // [B]            log-likelihood (may be -inf), fp64
     int* canon;        // [B][Smax]      first s' with the same class as s
     int* toff;         // [B]            offset of sequence b in the concatenated targets
 };
@@ -31,8 +32,8 @@ static CtcWs carve(void* base, int T, int B, int Smax, long long* total) {
     auto take = [&](long long bytes) { long long o = off; off = align_up(off + bytes, 256); return o; };
     const long long o_lse = take(4ll * B * T);
     const long long o_lpg = take(4ll * B * T * Smax);
-    const long long o_alpha = take(4ll * B * T * Smax);
-    const long long o_ll = take(4ll * B);
+    const long long o_alpha = take(8ll * B * T * Smax);
+    const long long o_ll = take(8ll * B);
     const long long o_canon = take(4ll * B * Smax);
     const long long o_toff = take(4ll * B);
     if (total) *total = off;
@@ -40,8 +41,8 @@ static CtcWs carve(void* base, int T, int B, int Smax, long long* total) {
     char* p = static_cast<char*>(base);
     w.lse = reinterpret_cast<float*>(p + o_lse);
     w.lpg = reinterpret_cast<float*>(p + o_lpg);
-    w.alpha = reinterpret_cast<float*>(p + o_alpha);
-    w.ll = reinterpret_cast<float*>(p + o_ll);
+    w.alpha = reinterpret_cast<double*>(p + o_alpha);
+    w.ll = reinterpret_cast<double*>(p + o_ll);
     w.canon = reinterpret_cast<int*>(p + o_canon);
     w.toff = reinterpret_cast<int*>(p + o_toff);
     return w;
@@ -167,69 +168,68 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
 }
 
 // ---------------------------------------------------------------- pass B: alpha / beta recursion
-__device__ __forceinline__ float lse3(float a, float b, float c) {
-    const float mx = fmaxf(a, fmaxf(b, c));
+__device__ __forceinline__ double lse3(double a, double b, double c) {
+    const double mx = fmax(a, fmax(b, c));
     if (mx == -INFINITY) return -INFINITY;
-    return mx + logf(expf(a - mx) + expf(b - mx) + expf(c - mx));
+    return mx + log(exp(a - mx) + exp(b - mx) + exp(c - mx));
 }
 
 __global__ void __launch_bounds__(1024)
 ctc_alpha_beta_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen,
                       const int32_t* __restrict__ ilen, int Tn, int Smax, int need_beta, float* __restrict__ nll_out,
                       CtcWs w) {
-    extern __shared__ float sm[];                 // 2 x (S + 2) ping-pong state with -inf guards
+    extern __shared__ double smd[];               // 2 x (Smax + 4) ping-pong state with -inf guards, + 1 scratch
     const int b = blockIdx.x, s = threadIdx.x;
     const int L = tlen[b], S = 2 * L + 1, Tb = ilen[b];
     const int32_t* tg = targets + w.toff[b];
     const int W = Smax + 4;
-    float* bufA = sm;            // index s+2 ; two guard cells on the left
-    float* bufB = sm + W;
+    double* bufA = smd;          // alpha: state s lives at index s+2 (two guard cells on the left)
+    double* bufB = smd + W;      // beta:  state s lives at index s   (guard cells on the right)
     const bool act = s < S;
     const int cls = act ? ((s & 1) ? tg[s >> 1] : 0) : 0;
     const bool skip_in = act && s > 1 && cls != 0 && cls != ((s & 1) ? tg[(s >> 1) - 1] : 0);      // s-2 -> s allowed
     const bool skip_out = act && (s + 2 < S) && (((s + 2) & 1) ? tg[(s + 2) >> 1] : 0) != 0 &&
                           ((((s + 2) & 1) ? tg[(s + 2) >> 1] : 0) != cls);                              // s -> s+2 allowed
     const float* lp = w.lpg + (long long)b * Tn * Smax;
-    float* al = w.alpha + (long long)b * Tn * Smax;
+    double* al = w.alpha + (long long)b * Tn * Smax;
 
-    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) sm[i] = -INFINITY;
+    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) smd[i] = -INFINITY;
     __syncthreads();
-    float ll = -INFINITY;
+    double ll = -INFINITY;
     if (Tb > 0) {
         // ---- alpha
-        float a = -INFINITY;
-        if (act && s < 2) a = lp[s];
+        double a = -INFINITY;
+        if (act && s < 2) a = (double)lp[s];
         if (act) { bufA[s + 2] = a; al[s] = a; }
         __syncthreads();
-        float* cur = bufA; float* nxt = bufB;
+        double* cur = bufA; double* nxt = bufB;
         float lp_next = (act && Tb > 1) ? lp[(long long)Smax + s] : 0.f;
         for (int t = 1; t < Tb; ++t) {
-            const float lpt = lp_next;
+            const double lpt = (double)lp_next;
             if (act && t + 1 < Tb) lp_next = lp[(long long)(t + 1) * Smax + s];
             if (act) {
-                const float a0 = cur[s + 2], a1 = cur[s + 1], a2 = skip_in ? cur[s] : -INFINITY;
-                const float v = lse3(a0, a1, a2);
+                const double a0 = cur[s + 2], a1 = cur[s + 1], a2 = skip_in ? cur[s] : -INFINITY;
+                const double v = lse3(a0, a1, a2);
                 a = (v == -INFINITY) ? -INFINITY : v + lpt;
                 nxt[s + 2] = a;
                 al[(long long)t * Smax + s] = a;
             }
             __syncthreads();
-            float* tmp = cur; cur = nxt; nxt = tmp;
+            double* tmp = cur; cur = nxt; nxt = tmp;
         }
         if (threadIdx.x == 0) {
-            const float l1 = cur[S - 1 + 2], l2 = (S > 1) ? cur[S - 2 + 2] : -INFINITY;
-            const float mx = fmaxf(l1, l2);
-            const float v = (mx == -INFINITY) ? -INFINITY : mx + logf(expf(l1 - mx) + expf(l2 - mx));
-            sm[2 * W] = v;
+            const double l1 = cur[S - 1 + 2], l2 = (S > 1) ? cur[S - 2 + 2] : -INFINITY;
+            const double mx = fmax(l1, l2);
+            smd[2 * W] = (mx == -INFINITY) ? -INFINITY : mx + log(exp(l1 - mx) + exp(l2 - mx));
         }
         __syncthreads();
-        ll = sm[2 * W];
+        ll = smd[2 * W];
     } else if (L == 0) {
-        ll = 0.f;
+        ll = 0.0;
     }
     if (threadIdx.x == 0) {
         w.ll[b] = ll;
-        float n = -ll;
+        float n = (float)(-ll);
         if (!(n < INFINITY)) n = 0.f;           // zero_infinity=True (main.py:205)
         nll_out[b] = n;
     }
@@ -237,31 +237,35 @@ ctc_alpha_beta_kernel(const int32_t* __restrict__ targets, const int32_t* __rest
 
     // ---- beta (same ping-pong, guards on the right), fused: al[t][s] <- alpha + beta - lp
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) sm[i] = -INFINITY;
+    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) smd[i] = -INFINITY;
     __syncthreads();
-    float* cur = bufA; float* nxt = bufB;
+    double* cur = bufA; double* nxt = bufB;
     {
         const long long o = (long long)(Tb - 1) * Smax + s;
-        float bt = -INFINITY;
-        if (act && s >= S - 2) bt = lp[o];
-        if (act) { cur[s] = bt; al[o] = al[o] + bt - lp[o]; }
+        double bt = -INFINITY;
+        if (act && s >= S - 2) bt = (double)lp[o];
+        if (act) {
+            cur[s] = bt;
+            const double av = al[o];
+            al[o] = (av == -INFINITY || bt == -INFINITY) ? -INFINITY : av + bt - (double)lp[o];
+        }
     }
     __syncthreads();
     float lp_next = (act && Tb > 1) ? lp[(long long)(Tb - 2) * Smax + s] : 0.f;
     for (int t = Tb - 2; t >= 0; --t) {
-        const float lpt = lp_next;
+        const double lpt = (double)lp_next;
         if (act && t > 0) lp_next = lp[(long long)(t - 1) * Smax + s];
         if (act) {
-            const float b0 = cur[s], b1 = cur[s + 1], b2 = skip_out ? cur[s + 2] : -INFINITY;
-            const float v = lse3(b0, b1, b2);
-            const float bt = (v == -INFINITY) ? -INFINITY : v + lpt;
+            const double b0 = cur[s], b1 = cur[s + 1], b2 = skip_out ? cur[s + 2] : -INFINITY;
+            const double v = lse3(b0, b1, b2);
+            const double bt = (v == -INFINITY) ? -INFINITY : v + lpt;
             nxt[s] = bt;
             const long long o = (long long)t * Smax + s;
-            const float av = al[o];
+            const double av = al[o];
             al[o] = (av == -INFINITY || bt == -INFINITY) ? -INFINITY : av + bt - lpt;
         }
         __syncthreads();
-        float* tmp = cur; cur = nxt; nxt = tmp;
+        double* tmp = cur; cur = nxt; nxt = tmp;
     }
 }
 
@@ -290,14 +294,14 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
     T* g = grad + (long long)t * stride_t + (long long)b * stride_b;
     const int L = tlen[b], S = 2 * L + 1;
-    const float ll = w.ll[b];
+    const double ll = w.ll[b];
     const bool dead = (t >= ilen[b]) || (ll == -INFINITY);          // beyond the input length / zero_infinity
     const float scale = dead ? 0.f : grad_scale / ((float)max(L, 1) * (float)Bn);
     const float lse = dead ? 0.f : w.lse[row];
 
     if (!dead) {
-        const float* ab = w.alpha + row * Smax;
-        for (int s = threadIdx.x; s < S; s += blockDim.x) occ[s] = __expf(ab[s] - ll);
+        const double* ab = w.alpha + row * Smax;
+        for (int s = threadIdx.x; s < S; s += blockDim.x) occ[s] = (float)exp(ab[s] - ll);
     }
     // dense part: softmax * scale
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
@@ -384,7 +388,7 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
             static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Smax, w);
     HCTR_CUDA(cudaGetLastError());
     int threads = (Smax + 31) / 32 * 32;
-    const size_t smB = (size_t)(2 * (Smax + 4) + 4) * sizeof(float);
+    const size_t smB = (size_t)(2 * (Smax + 4) + 2) * sizeof(double);
     ctc_alpha_beta_kernel<<<B, threads, smB, s>>>(targets, target_lengths, input_lengths, T, Smax, grad != nullptr, nll, w);
     HCTR_CUDA(cudaGetLastError());
     ctc_mean_loss_kernel<<<1, 32, 0, s>>>(nll, target_lengths, B, loss);

@@ -67,6 +67,8 @@ class ctc_codec(object):
 
     # ------------------------------------------------------------------ decode (reference :63-68)
     def decode(self, preds):
+        if preds.shape[0] == 0 and not self.use_beam_search:
+            return []               # reference: zero-length samples are skipped (utils/ctc_codec.py:85-86)
         logits = self._as_device_logits(preds)
         if self.use_beam_search:
             if self.skip_search:

@@ -85,7 +85,7 @@ int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bia
 /* ctc_codec.__greedy_search__ (utils/ctc_codec.py:70-99): per (t,b) argmax over C (ties -> lowest index,
  * NaN -> first NaN, as numpy.argmax), then drop blank (0), unknown (C-1) and repeats of the raw previous index.
  * logits element (t,b,c) is at logits[t*stride_t + b*stride_b + c] (elements of `dtype`).
- * argmax_out: int32 [B][T] raw per-step argmax (may be NULL); out_idx: int32 [B][T] compacted label indices;
+ * argmax_out: int32 [B][T] raw per-step argmax (required scratch/result); out_idx: int32 [B][T] compacted label indices;
  * out_len: int32 [B]. */
 int hctr_ctc_greedy_decode(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                            int32_t* argmax_out, int32_t* out_idx, int32_t* out_len, void* stream);

@@ -76,7 +76,7 @@ def test_greedy_full_size_properties():
 
 def test_greedy_empty_inputs():
     c = _codec(30)
-    assert c.decode(np.zeros((0, 3, 30), np.float32)) == ["", "", ""]
+    assert c.decode(np.zeros((0, 3, 30), np.float32)) == []          # T == 0: the reference appends nothing (:85-86)
     assert c.decode(np.zeros((4, 0, 30), np.float32)) == []
 
 
