@@ -202,6 +202,8 @@ def main():
     dev = torch.device("cuda", local)
     native.check(native.lib().hctr_device_supported(local), "device")
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(1234)
