@@ -7,6 +7,7 @@ Drop-in mirrors of the reference's Python surface (AndrewCullacino/handwritten-c
 All arithmetic runs in hand-written CUDA kernels behind the C ABI in include/hctr_b200.h.
 """
 from . import native  # noqa: F401
+from . import train_engine  # noqa: F401
 
 __all__ = ["native", "hctr_model", "ctc_codec", "CTCLoss"]
 

@@ -44,11 +44,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 activation [B,H,W,C] -> 4-D map (C, W, H, B), box (64, 128, 1, 1), 128B swizzle, zero OOB fill.
-static int make_act_map(CUtensorMap* m, const void* x, int B, int H, int W, int C) {
+static int make_act_map(CUtensorMap* m, const void* x, int B, int H, int W, int C, long long pitch = 0) {
     EncodeTiledFn enc = get_encode_fn();
     HCTR_CHECK(enc != nullptr, HCTR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    if (pitch <= 0) pitch = C;                    // elements between consecutive pixels
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileM, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
@@ -60,11 +61,12 @@ static int make_act_map(CUtensorMap* m, const void* x, int B, int H, int W, int 
 }
 
 // Packed weights [N][K] bf16 (K-major) -> 2-D map (K, N), box (64, block_n).
-static int make_weight_map(CUtensorMap* m, const void* w, int N, int K, int block_n) {
+static int make_weight_map(CUtensorMap* m, const void* w, int N, int K, int block_n, long long pitch = 0) {
     EncodeTiledFn enc = get_encode_fn();
     HCTR_CHECK(enc != nullptr, HCTR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    if (pitch <= 0) pitch = K;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
@@ -120,8 +122,9 @@ int hctr_device_supported(int device) {
     return HCTR_OK;
 }
 
-int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,
-                         int H, int W, int Cin, int Cout, int ksize, int relu, int pool, void* stream) {
+static int conv_launch(const void* x, const void* w_packed, const float* scale, const float* shift, const void* add,
+                       void* y, int B, int H, int W, int Cin, int Cout, int ksize, int relu, int pool, int flip,
+                       void* stream) {
     HCTR_CHECK(x && w_packed && scale && shift && y, HCTR_ERR_INVALID, "conv: null pointer");
     HCTR_CHECK(ksize == 1 || ksize == 3, HCTR_ERR_INVALID, "conv: ksize must be 1 or 3 (got %d)", ksize);
     HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "conv: empty tensor %dx%dx%d", B, H, W);
@@ -139,11 +142,16 @@ int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale
     if (ksize == 3) {
         p.ntaps = 9;
         for (int kh = 0; kh < 3; ++kh)
-            for (int kw = 0; kw < 3; ++kw) { p.tap_dh[kh * 3 + kw] = (int8_t)(kh - 1); p.tap_dw[kh * 3 + kw] = (int8_t)(kw - 1); }
+            for (int kw = 0; kw < 3; ++kw) {
+                // flip: transposed convolution for the data gradient reads dz at (h - (kh-1), w - (kw-1))
+                p.tap_dh[kh * 3 + kw] = (int8_t)(flip ? 1 - kh : kh - 1);
+                p.tap_dw[kh * 3 + kw] = (int8_t)(flip ? 1 - kw : kw - 1);
+            }
     } else {
         p.ntaps = 1;
     }
     p.sub_dh = 1; p.sub_dw = 0;
+    p.add = add;
     p.N = Cout;
     p.w_tiles = (W + kTileM - 1) / kTileM;
     p.h_tiles = (H + 1) / 2;
@@ -168,6 +176,60 @@ int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale
         case 128: return launch_igemm<128, 2, 4, 2, EPI_CONV>(tmA, tmB, p, s);
         default:  return launch_igemm<256, 2, 3, 1, EPI_CONV>(tmA, tmB, p, s);
     }
+}
+
+int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,
+                         int H, int W, int Cin, int Cout, int ksize, int relu, int pool, void* stream) {
+    return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, relu, pool, 0, stream);
+}
+
+int hctr_conv_dgrad(const void* dz, const void* w_packed_t, const float* ones, const float* zeros, const void* add,
+                    void* dx, int B, int H, int W, int Cout, int Cin, int ksize, void* stream) {
+    HCTR_CHECK(!add || aligned16(add), HCTR_ERR_INVALID, "dgrad: add tensor must be 16-byte aligned");
+    // the data gradient is the same implicit GEMM with the roles of Cin/Cout swapped and mirrored taps
+    return conv_launch(dz, w_packed_t, ones, zeros, add, dx, B, H, W, Cout, Cin, ksize, 0, 0, 1, stream);
+}
+
+int hctr_classifier_dgrad(const void* dlogits, long long pitch, const void* w_t, const float* ones, const float* zeros,
+                          void* dfeat, int B, int Hf, int W, int Cf, int num_classes, void* stream) {
+    HCTR_CHECK(dlogits && w_t && ones && zeros && dfeat, HCTR_ERR_INVALID, "classifier_dgrad: null pointer");
+    HCTR_CHECK(pitch % 8 == 0 && pitch >= num_classes, HCTR_ERR_INVALID, "classifier_dgrad: pitch must be a multiple of 8");
+    HCTR_CHECK(Cf == 64 || Cf == 128 || Cf % 256 == 0, HCTR_ERR_INVALID, "classifier_dgrad: bad Cf %d", Cf);
+    HCTR_CHECK(aligned16(dlogits) && aligned16(w_t) && aligned16(dfeat), HCTR_ERR_INVALID, "classifier_dgrad: alignment");
+    // dfeat[b, h, w, c] = sum_n dlogits[b, w, n] * Wt[h*Cf + c, n]   (bf16 in, fp32 accumulate, bf16 out)
+    const int kchunks = (num_classes + 63) / 64;
+    const int block_n = Cf >= 256 ? 256 : Cf;
+    for (int h = 0; h < Hf; ++h) {
+        IgemmParams p;
+        memset(&p, 0, sizeof(p));
+        p.B = B; p.H = 1; p.W = W;
+        p.cin_chunks = kchunks; p.ntaps = 1;
+        p.sub_dh = 0; p.sub_dw = 1;
+        p.N = Cf;
+        p.w_tiles = (W + 2 * kTileM - 1) / (2 * kTileM);
+        p.h_tiles = 1;
+        p.n_tiles = Cf / block_n;
+        p.scale = ones; p.shift = zeros;
+        p.out = static_cast<__nv_bfloat16*>(dfeat) + (size_t)h * W * Cf;      // row h of every line; line pitch = Hf*W*Cf
+        p.out_H = 1;
+        // out index = ((b*out_H + 0)*W + w)*N + n  -> we need a line pitch of Hf*W*Cf: fold Hf into W of the output
+        // by treating the output as [B][Hf*W][Cf] with w offset h*W (pointer offset above) and out_H = 1, W_out = Hf*W.
+        p.total_tiles = B * p.w_tiles * p.n_tiles;
+        p.out_line_pitch = (long long)Hf * W * Cf;
+        CUtensorMap tmA, tmB;
+        int rc = make_act_map(&tmA, dlogits, B, 1, W, num_classes, pitch);
+        if (rc) return rc;
+        rc = make_weight_map(&tmB, static_cast<const __nv_bfloat16*>(w_t) + (size_t)h * Cf * pitch, Cf, num_classes, block_n, pitch);
+        if (rc) return rc;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        switch (block_n) {
+            case 64:  rc = launch_igemm<64, 2, 4, 2, EPI_CONV>(tmA, tmB, p, s); break;
+            case 128: rc = launch_igemm<128, 2, 4, 2, EPI_CONV>(tmA, tmB, p, s); break;
+            default:  rc = launch_igemm<256, 2, 3, 1, EPI_CONV>(tmA, tmB, p, s); break;
+        }
+        if (rc) return rc;
+    }
+    return HCTR_OK;
 }
 
 int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,

@@ -11,7 +11,7 @@ namespace hctr {
 // 8 consecutive lanes cover the 64 channels of a pixel (one 128-byte line), a warp covers 4 pixels.
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
-                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B, int H, int W) {
+                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B, int H, int W, int relu) {
     __shared__ float sw[64 * 9];
     __shared__ float ssc[64], ssh[64];
     for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
@@ -50,8 +50,9 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int t = 0; t < 9; ++t) { a0 = fmaf(in[t], wr[c][t], a0); a1 = fmaf(in[t], wr[c + 1][t], a1); }
-            a0 = fmaxf(fmaf(a0, sc[c], sh[c]), 0.f);
-            a1 = fmaxf(fmaf(a1, sc[c + 1], sh[c + 1]), 0.f);
+            a0 = fmaf(a0, sc[c], sh[c]);
+            a1 = fmaf(a1, sc[c + 1], sh[c + 1]);
+            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
             pk[c >> 1] = pack_bf16x2(a0, a1);
         }
         *reinterpret_cast<uint4*>(y + pix * 64 + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -157,7 +158,7 @@ using namespace hctr;
 extern "C" {
 
 int hctr_stem_conv_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int B, int H,
-                       int W, void* stream) {
+                       int W, int relu, void* stream) {
     HCTR_CHECK(x && w && scale && shift && y, HCTR_ERR_INVALID, "stem: null pointer");
     HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "stem: empty tensor");
     HCTR_CHECK(al16(y), HCTR_ERR_INVALID, "stem: output must be 16-byte aligned");
@@ -165,7 +166,7 @@ int hctr_stem_conv_fwd(const float* x, const float* w, const float* scale, const
     long long blocks = (npix + 31) / 32;
     if (blocks > 148 * 64) blocks = 148 * 64;
     stem_conv_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, w, scale, shift, static_cast<__nv_bfloat16*>(y), B, H, W);
+        x, w, scale, shift, static_cast<__nv_bfloat16*>(y), B, H, W, relu);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }

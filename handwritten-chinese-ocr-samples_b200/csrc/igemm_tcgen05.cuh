@@ -41,8 +41,10 @@ struct IgemmParams {
     const float* scale;       // [N] (EPI_CONV) or nullptr
     const float* shift;       // [N] BN shift (EPI_CONV) / bias (EPI_LINEAR)
     void* out;
+    const void* add;          // EPI_CONV: optional bf16 tensor (same layout as out) added before the store (dgrad + residual)
     int relu, pool;
     int out_H;                // output rows (H or H/2 when pooled)
+    long long out_line_pitch; // EPI_CONV: elements between consecutive lines b of the output (0 = out_H*W*N)
     int out_dtype;            // EPI_LINEAR: HCTR_F32 | HCTR_BF16
     long long out_pitch;      // EPI_LINEAR: elements between consecutive (b,w) rows
 };
@@ -226,6 +228,20 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             const int w = w0 + s * p.sub_dw * kTileM + pix;
                             const int h = h0 + s * p.sub_dh;
                             if (w < p.W && h < p.out_H) {
+                                const size_t off = p.out_line_pitch
+                                    ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N + n0
+                                    : ((static_cast<size_t>(b) * p.out_H + h) * p.W + w) * p.N + n0;
+                                if (p.add) {
+                                    const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.add) + off);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const uint4 a = ld_nc_v4(src + q);
+                                        v[s][8 * q + 0] += bf16_lo(a.x); v[s][8 * q + 1] += bf16_hi(a.x);
+                                        v[s][8 * q + 2] += bf16_lo(a.y); v[s][8 * q + 3] += bf16_hi(a.y);
+                                        v[s][8 * q + 4] += bf16_lo(a.z); v[s][8 * q + 5] += bf16_hi(a.z);
+                                        v[s][8 * q + 6] += bf16_lo(a.w); v[s][8 * q + 7] += bf16_hi(a.w);
+                                    }
+                                }
                                 uint32_t pk[16];
 #pragma unroll
                                 for (int j = 0; j < 32; j += 2) {
@@ -233,8 +249,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                     if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
                                     pk[j >> 1] = pack_bf16x2(a0, a1);
                                 }
-                                uint4* dst = reinterpret_cast<uint4*>(
-                                    out + ((static_cast<size_t>(b) * p.out_H + h) * p.W + w) * p.N + n0);
+                                uint4* dst = reinterpret_cast<uint4*>(out + off);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q)
                                     dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);

@@ -1,0 +1,168 @@
+// Small training-side kernels: column sums (classifier bias gradient), the stem's weight gradient, and the fused
+// optimizer tail (global grad-norm clip + SGD with momentum / weight decay; reference main.py:210-213,430-438).
+#include "common.cuh"
+#include "../../include/hctr_b200.h"
+
+namespace hctr {
+
+// ---------------------------------------------------------------- column sums of a bf16 [rows][pitch] matrix
+constexpr int kColRows = 512;     // rows per slice
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int cols, long long pitch, float* __restrict__ partial) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * kColRows;
+    const long long r1 = r0 + kColRows < rows ? r0 + kColRows : rows;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += __bfloat162float(x[r * pitch + c]);
+    partial[(size_t)blockIdx.y * cols + c] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int slices, int cols, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int i = 0; i < slices; ++i) s += partial[(size_t)i * cols + c];
+    out[c] = s;
+}
+
+// ---------------------------------------------------------------- stem weight gradient (Cin = 1)
+// dW[co][tap] = sum_pix dz[pix][co] * x[pix + tap]; dz is NHWC bf16 [B][H][W][64], x fp32 [B][1][H][W].
+constexpr int kStemPix = 4096;
+__global__ void __launch_bounds__(256)
+stem_wgrad_partial_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ x, int B, int H, int W,
+                          float* __restrict__ partial) {
+    __shared__ float red[4][64][9];
+    const int co = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const long long npix = (long long)B * H * W;
+    const long long p0 = (long long)blockIdx.x * kStemPix;
+    const long long p1 = p0 + kStemPix < npix ? p0 + kStemPix : npix;
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long pix = p0 + g; pix < p1; pix += 4) {
+        const int w = (int)(pix % W);
+        const long long bh = pix / W;
+        const int h = (int)(bh % H);
+        const float* img = x + (bh - h) * W;
+        const float d = __bfloat162float(dz[pix * 64 + co]);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hh = h + kh - 1;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ww = w + kw - 1;
+                const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (long long)hh * W + ww) : 0.f;
+                acc[kh * 3 + kw] = fmaf(d, v, acc[kh * 3 + kw]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) red[g][co][t] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) {
+        const int c = i / 9, t = i - c * 9;
+        partial[(size_t)blockIdx.x * 576 + i] = red[0][c][t] + red[1][c][t] + red[2][c][t] + red[3][c][t];
+    }
+}
+
+// ---------------------------------------------------------------- optimizer tail
+// stage 1: per-block partial sums of g^2 over a flat fp32 gradient buffer
+__global__ void __launch_bounds__(256)
+sqnorm_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = g[i];
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+// stage 2: total norm (fixed order) -> clip coefficient (torch.nn.utils.clip_grad_norm_: max_norm / (norm + 1e-6), <= 1)
+__global__ void clip_coef_kernel(const float* __restrict__ partial, int n, float grad_scale, float max_norm,
+                                 float* __restrict__ out /* [0]=total_norm, [1]=coef */) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += (double)partial[i];
+        const float norm = sqrtf((float)s) * grad_scale;
+        float coef = max_norm / (norm + 1e-6f);
+        if (coef > 1.f) coef = 1.f;
+        out[0] = norm; out[1] = max_norm > 0.f ? coef : 1.f;
+    }
+}
+// stage 3: SGD(momentum, weight_decay) exactly as torch.optim.SGD (dampening 0, no nesterov):
+//   g = grad*grad_scale*coef + wd*p ; buf = first ? g : momentum*buf + g ; p -= lr*buf
+__global__ void __launch_bounds__(256)
+sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+                const float* __restrict__ coef, float grad_scale, float lr, float momentum, float wd, int first) {
+    const float c = coef[1] * grad_scale;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float w = p[i];
+        const float gv = fmaf(wd, w, g[i] * c);
+        const float b = first ? gv : fmaf(momentum, buf[i], gv);
+        buf[i] = b;
+        p[i] = w - lr * b;
+    }
+}
+
+}  // namespace hctr
+
+using namespace hctr;
+
+extern "C" {
+
+int hctr_colsum_bf16(const void* x, long long rows, int cols, long long pitch, float* out, float* workspace,
+                     long long workspace_bytes, void* stream) {
+    HCTR_CHECK(x && out && workspace, HCTR_ERR_INVALID, "colsum: null pointer");
+    const long long slices = (rows + kColRows - 1) / kColRows;
+    HCTR_CHECK(workspace_bytes >= slices * cols * 4, HCTR_ERR_INVALID, "colsum: workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid((cols + 255) / 256, (unsigned)slices);
+    colsum_partial_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, cols, pitch, workspace);
+    HCTR_CUDA(cudaGetLastError());
+    colsum_final_kernel<<<(cols + 255) / 256, 256, 0, s>>>(workspace, (int)slices, cols, out);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+long long hctr_colsum_workspace_bytes(long long rows, int cols) { return ((rows + kColRows - 1) / kColRows) * cols * 4; }
+
+int hctr_stem_wgrad(const void* dz, const float* x, float* dw, int B, int H, int W, float* workspace,
+                    long long workspace_bytes, void* stream) {
+    HCTR_CHECK(dz && x && dw && workspace, HCTR_ERR_INVALID, "stem_wgrad: null pointer");
+    const long long npix = (long long)B * H * W;
+    const long long blocks = (npix + kStemPix - 1) / kStemPix;
+    HCTR_CHECK(workspace_bytes >= blocks * 576 * 4, HCTR_ERR_INVALID, "stem_wgrad: workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    stem_wgrad_partial_kernel<<<(int)blocks, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dz), x, B, H, W, workspace);
+    HCTR_CUDA(cudaGetLastError());
+    colsum_final_kernel<<<(576 + 255) / 256, 256, 0, s>>>(workspace, (int)blocks, 576, dw);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+long long hctr_stem_wgrad_workspace_bytes(int B, int H, int W) {
+    return (((long long)B * H * W + kStemPix - 1) / kStemPix) * 576 * 4;
+}
+
+int hctr_sgd_clip_step(float* params, const float* grads, float* momentum_buf, long long n, float grad_scale,
+                       float max_norm, float lr, float momentum, float weight_decay, int first_step, float* norm_out,
+                       float* workspace, void* stream) {
+    HCTR_CHECK(params && grads && momentum_buf && norm_out && workspace, HCTR_ERR_INVALID, "sgd: null pointer");
+    HCTR_CHECK(n > 0, HCTR_ERR_INVALID, "sgd: empty parameter buffer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int blocks = 148 * 8;
+    sqnorm_partial_kernel<<<blocks, 256, 0, s>>>(grads, n, workspace);
+    HCTR_CUDA(cudaGetLastError());
+    clip_coef_kernel<<<1, 32, 0, s>>>(workspace, blocks, grad_scale, max_norm, norm_out);
+    HCTR_CUDA(cudaGetLastError());
+    sgd_step_kernel<<<blocks, 256, 0, s>>>(params, grads, momentum_buf, n, norm_out, grad_scale, lr, momentum, weight_decay, first_step);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+long long hctr_sgd_workspace_bytes(void) { return 148 * 8 * 4; }
+
+}  // extern "C"

@@ -1,0 +1,577 @@
+// Train-mode pointwise passes of the backbone (HBM-bound), forward and backward.
+//
+// Reference semantics (models/handwritten_ctr_model.py, train()):
+//   conv -> BatchNorm2d with batch statistics (:38,40,74-92) -> [SE gate (:26-30)] -> [+ residual (:57)] -> ReLU ->
+//   [max_pool2d((2,1)) (:123-150)] -> Dropout (:45,96-99,59,130,...)
+// Forward per layer:  z = conv(x)+bias (tcgen05 kernel, bf16)  ->  chan_stats(z)  ->  bn_finalize  ->  apply.
+// Backward per layer: bwd_reduce(dout, z, ...) -> bwd_finalize (BN / SE-FC backward on [B,C] data) -> bwd_apply.
+// With d_pre = gradient at the output of the affine (+gate, +residual) stage after the ReLU/pool/dropout masks,
+//   dz = P[b,c]*d_pre + Q[b,c] + R[c]*z,   dres = d_pre
+// where P,Q,R fold the BatchNorm backward (and the SE squeeze path) computed from per-(b,c) partial sums, so each
+// direction touches every activation tensor exactly twice. All reductions are fixed-order (deterministic).
+#include "common.cuh"
+#include "../../include/hctr_b200.h"
+
+namespace hctr {
+
+constexpr int kStatPix = 2048;      // pixels per reduction slice (same slicing as the SE squeeze)
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {       // lowbias32
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// keep-mask of the dropout for output element `idx` (counter-based: forward and backward regenerate it)
+__device__ __forceinline__ bool drop_keep(unsigned long long idx, uint32_t seed, uint32_t thresh) {
+    const uint32_t h = hash32(static_cast<uint32_t>(idx) ^ hash32(seed + static_cast<uint32_t>(idx >> 32) * 0x9E3779B9u));
+    return h >= thresh;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&o)[8]) {
+    o[0] = bf16_lo(q.x); o[1] = bf16_hi(q.x); o[2] = bf16_lo(q.y); o[3] = bf16_hi(q.y);
+    o[4] = bf16_lo(q.z); o[5] = bf16_hi(q.z); o[6] = bf16_lo(q.w); o[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// ---------------------------------------------------------------- per-(b, slice, c) sum and sum of squares
+__global__ void __launch_bounds__(256)
+chan_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ psum, float* __restrict__ psq, int HW, int C,
+                  int slices) {
+    extern __shared__ float red[];                         // [2][groups][C]
+    const int b = blockIdx.y, slice = blockIdx.x;
+    const int vpp = C >> 3, groups = blockDim.x / vpp;
+    const int g = threadIdx.x / vpp, v = threadIdx.x - g * vpp;
+    const int p0 = slice * kStatPix, p1 = min(p0 + kStatPix, HW);
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __nv_bfloat16* base = x + ((size_t)b * HW) * C + v * 8;
+    for (int p = p0 + g; p < p1; p += groups) {
+        float e[8];
+        unpack8(ld_nc_v4(base + (size_t)p * C), e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += e[i]; q[i] = fmaf(e[i], e[i], q[i]); }
+    }
+    float* rs = red; float* rq = red + groups * C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { rs[g * C + v * 8 + i] = s[i]; rq[g * C + v * 8 + i] = q[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, d = 0.f;
+        for (int gg = 0; gg < groups; ++gg) { a += rs[gg * C + c]; d += rq[gg * C + c]; }
+        const size_t o = ((size_t)b * slices + slice) * C + c;
+        psum[o] = a;
+        if (psq) psq[o] = d;
+    }
+}
+
+// ---------------------------------------------------------------- BN batch statistics -> scale/shift (+running stats)
+// One thread per channel. line_sum[b][c] = sum over (h,w) of z (used by the SE squeeze and by the backward).
+__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int B, int slices,
+                                   int C, int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, float* __restrict__ scale_out,
+                                   float* __restrict__ shift_out, float* __restrict__ line_sum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < B; ++b) {
+        float ls = 0.f;
+        for (int i = 0; i < slices; ++i) {
+            const size_t o = ((size_t)b * slices + i) * C + c;
+            ls += psum[o];
+            q += (double)psq[o];
+        }
+        if (line_sum) line_sum[(size_t)b * C + c] = ls;
+        s += (double)ls;
+    }
+    const double n = (double)B * (double)HW;
+    const double mean = s / n;
+    double var = q / n - mean * mean;                      // biased variance (normalisation)
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    mean_out[c] = (float)mean;
+    invstd_out[c] = invstd;
+    scale_out[c] = sc;
+    shift_out[c] = beta[c] - (float)mean * sc;
+    if (running_mean) {                                    // nn.BatchNorm2d: momentum update, unbiased variance
+        const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// ---------------------------------------------------------------- forward apply
+struct ApplyParams {
+    const __nv_bfloat16* z;      // [B][H][W][C]
+    const float* scale;          // [C]
+    const float* shift;          // [C]
+    const float* gate;           // [B][C] or null
+    const __nv_bfloat16* res;    // [B][H][W][C] or null
+    int B, H, W, C;
+    int relu, pool;
+    float drop_p;                // 0 = off
+    uint32_t seed;
+};
+
+template <bool POOL>
+__device__ __forceinline__ void apply_pre(const ApplyParams& p, size_t zoff, int b, int c0, float (&v)[8], const float (&sc)[8],
+                                          const float (&sh)[8]) {
+    float e[8];
+    unpack8(ld_nc_v4(p.z + zoff), e);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(e[i], sc[i], sh[i]);
+    if (p.gate) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)b * p.C + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)b * p.C + c0 + 4));
+        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+    }
+    if (p.res) {
+        float r[8];
+        unpack8(ld_nc_v4(p.res + zoff), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+train_apply_fwd_kernel(ApplyParams p, __nv_bfloat16* __restrict__ out) {
+    const int vpp = p.C >> 3;
+    const int Ho = p.pool ? p.H / 2 : p.H;
+    const long long nvec = (long long)p.B * Ho * p.W * vpp;
+    const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const int cv = (int)(i % vpp);
+        long long pix = i / vpp;
+        const int w = (int)(pix % p.W); pix /= p.W;
+        const int ho = (int)(pix % Ho);
+        const int b = (int)(pix / Ho);
+        const int c0 = cv * 8;
+        float sc[8], sh[8];
+        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+        *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+        *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+        float v[8];
+        if (p.pool) {
+            float v1[8];
+            const size_t o0 = (((size_t)b * p.H + 2 * ho) * p.W + w) * p.C + c0;
+            apply_pre<true>(p, o0, b, c0, v, sc, sh);
+            apply_pre<true>(p, o0 + (size_t)p.W * p.C, b, c0, v1, sc, sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v1[j]);
+        } else {
+            apply_pre<false>(p, (((size_t)b * p.H + ho) * p.W + w) * p.C + c0, b, c0, v, sc, sh);
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.drop_p > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = drop_keep((unsigned long long)i * 8 + j, p.seed, thresh) ? v[j] * keep_scale : 0.f;
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)i * 8) = pack8(v);
+    }
+}
+
+// ---------------------------------------------------------------- backward: recompute masks, d_pre
+// Returns d_pre for the 8 channels of one INPUT-resolution pixel (row h of the z tensor).
+__device__ __forceinline__ void bwd_dpre(const ApplyParams& p, const __nv_bfloat16* __restrict__ dout, int b, int h, int w,
+                                         int c0, uint32_t thresh, float keep_scale, const float (&sc)[8],
+                                         const float (&sh)[8], float (&zv)[8], float (&d)[8]) {
+    const int vpp = p.C >> 3;
+    const size_t zoff = (((size_t)b * p.H + h) * p.W + w) * p.C + c0;
+    unpack8(ld_nc_v4(p.z + zoff), zv);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(zv[i], sc[i], sh[i]);
+    if (p.gate) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)b * p.C + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)b * p.C + c0 + 4));
+        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+    }
+    if (p.res) {
+        float r[8];
+        unpack8(ld_nc_v4(p.res + zoff), r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
+    }
+    bool sel[8];
+    int ho = h;
+    if (p.pool) {
+        // the (2,1) window: gradient goes to the first maximum of the ReLU'd pair (torch max_pool2d backward)
+        ho = h >> 1;
+        const int other = h ^ 1;
+        const size_t ooff = (((size_t)b * p.H + other) * p.W + w) * p.C + c0;
+        float e[8], u[8];
+        unpack8(ld_nc_v4(p.z + ooff), e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = fmaf(e[i], sc[i], sh[i]);
+        // (pool layers have no gate / residual in this network)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float mine = p.relu ? fmaxf(v[i], 0.f) : v[i];
+            const float oth = p.relu ? fmaxf(u[i], 0.f) : u[i];
+            sel[i] = (h & 1) ? (mine > oth) : (mine >= oth);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sel[i] = true;
+    }
+    const int Ho = p.pool ? p.H / 2 : p.H;
+    const size_t oidx = ((((size_t)b * Ho + ho) * p.W + w) * vpp + (c0 >> 3)) * 8;
+    float g[8];
+    unpack8(ld_nc_v4(dout + oidx), g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float t = g[i];
+        if (p.drop_p > 0.f) t = drop_keep((unsigned long long)oidx + i, p.seed, thresh) ? t * keep_scale : 0.f;
+        if (p.relu && !(v[i] > 0.f)) t = 0.f;
+        d[i] = sel[i] ? t : 0.f;
+    }
+}
+
+// per-(b, slice, c): A2 = sum d_pre, A3 = sum d_pre * z
+__global__ void __launch_bounds__(256)
+train_bwd_reduce_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, float* __restrict__ pA2,
+                        float* __restrict__ pA3, int slices) {
+    extern __shared__ float red[];
+    const int b = blockIdx.y, slice = blockIdx.x;
+    const int vpp = p.C >> 3, groups = blockDim.x / vpp;
+    const int g = threadIdx.x / vpp, cv = threadIdx.x - g * vpp;
+    const int HW = p.H * p.W;
+    const int p0 = slice * kStatPix, p1 = min(p0 + kStatPix, HW);
+    const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const int c0 = cv * 8;
+    float sc[8], sh[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    float a2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a3[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int px = p0 + g; px < p1; px += groups) {
+        const int h = px / p.W, w = px - h * p.W;
+        float zv[8], d[8];
+        bwd_dpre(p, dout, b, h, w, c0, thresh, keep_scale, sc, sh, zv, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a2[i] += d[i]; a3[i] = fmaf(d[i], zv[i], a3[i]); }
+    }
+    float* r2 = red; float* r3 = red + groups * p.C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r2[g * p.C + c0 + i] = a2[i]; r3[g * p.C + c0 + i] = a3[i]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+        float x = 0.f, y = 0.f;
+        for (int gg = 0; gg < groups; ++gg) { x += r2[gg * p.C + c]; y += r3[gg * p.C + c]; }
+        const size_t o = ((size_t)b * slices + slice) * p.C + c;
+        pA2[o] = x; pA3[o] = y;
+    }
+}
+
+// BN (+SE) backward on [B,C]-sized data. One block, threads over channels; the SE FC backward is done by the
+// same block (C <= 512, Cr <= 32).
+struct BwdFinalizeParams {
+    const float* pA2; const float* pA3; int slices;
+    int B, C, HW;
+    const float* gamma; const float* mean; const float* invstd; const float* scale; const float* shift;
+    const float* line_sum;       // [B][C] sum_hw z (forward)
+    // SE (all null when the layer has no gate)
+    const float* gate;           // [B][C] sigmoid output
+    const float* se_hidden;      // [B][Cr] relu(W1 m)
+    const float* se_mean;        // [B][C] m = mean_hw(bn(z))
+    const float* w1; const float* w2; int Cr;
+    float* dw1; float* dw2;      // [Cr][C], [C][Cr]
+    // outputs
+    float* dgamma; float* dbeta; float* dbias;     // [C]; dbias = sum dz (conv bias gradient)
+    float* P; float* Q;          // [B][C]
+    float* R;                    // [C]
+};
+
+__global__ void __launch_bounds__(512)
+train_bwd_finalize_kernel(BwdFinalizeParams p) {
+    extern __shared__ float sm[];
+    // layout: A2[B*C], A3[B*C], dm[B*C], du[B*C], da[B*Cr]
+    float* A2 = sm; float* A3 = A2 + p.B * p.C; float* dm = A3 + p.B * p.C; float* du = dm + p.B * p.C;
+    float* da = du + p.B * p.C;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < p.B * p.C; i += nt) {
+        const int b = i / p.C, c = i - b * p.C;
+        float x = 0.f, y = 0.f;
+        for (int s = 0; s < p.slices; ++s) {
+            const size_t o = ((size_t)b * p.slices + s) * p.C + c;
+            x += p.pA2[o]; y += p.pA3[o];
+        }
+        A2[i] = x; A3[i] = y; dm[i] = 0.f;
+    }
+    __syncthreads();
+    if (p.gate) {
+        // dgate[b,c] = sum_hw d_pre * bn(z) = scale*A3 + shift*A2 ; du = dgate * g (1-g)
+        for (int i = tid; i < p.B * p.C; i += nt) {
+            const int c = i % p.C;
+            const float dg = p.scale[c] * A3[i] + p.shift[c] * A2[i];
+            const float g = p.gate[i];
+            du[i] = dg * g * (1.f - g);
+        }
+        __syncthreads();
+        // dW2[c][r] = sum_b du[b,c] * hidden[b,r]
+        for (int i = tid; i < p.C * p.Cr; i += nt) {
+            const int c = i / p.Cr, r = i - c * p.Cr;
+            float s = 0.f;
+            for (int b = 0; b < p.B; ++b) s = fmaf(du[b * p.C + c], p.se_hidden[b * p.Cr + r], s);
+            p.dw2[i] = s;
+        }
+        // da[b,r] = [hidden>0] * sum_c W2[c][r] du[b,c]
+        for (int i = tid; i < p.B * p.Cr; i += nt) {
+            const int b = i / p.Cr, r = i - b * p.Cr;
+            float s = 0.f;
+            for (int c = 0; c < p.C; ++c) s = fmaf(p.w2[c * p.Cr + r], du[b * p.C + c], s);
+            da[i] = p.se_hidden[i] > 0.f ? s : 0.f;
+        }
+        __syncthreads();
+        // dW1[r][c] = sum_b da[b,r] m[b,c] ; dm[b,c] = sum_r W1[r][c] da[b,r]
+        for (int i = tid; i < p.Cr * p.C; i += nt) {
+            const int r = i / p.C, c = i - r * p.C;
+            float s = 0.f;
+            for (int b = 0; b < p.B; ++b) s = fmaf(da[b * p.Cr + r], p.se_mean[b * p.C + c], s);
+            p.dw1[i] = s;
+        }
+        for (int i = tid; i < p.B * p.C; i += nt) {
+            const int b = i / p.C, c = i - b * p.C;
+            float s = 0.f;
+            for (int r = 0; r < p.Cr; ++r) s = fmaf(p.w1[r * p.C + c], da[b * p.Cr + r], s);
+            dm[i] = s;
+        }
+        __syncthreads();
+    }
+    const double n = (double)p.B * (double)p.HW;
+    for (int c = tid; c < p.C; c += nt) {
+        const double mu = p.mean[c], is = p.invstd[c];
+        double S1 = 0.0, S2 = 0.0;
+        for (int b = 0; b < p.B; ++b) {
+            const int i = b * p.C + c;
+            const double g = p.gate ? (double)p.gate[i] : 1.0;
+            const double a2 = A2[i], a3 = A3[i];
+            const double dmb = dm[i];
+            const double x1 = ((double)p.line_sum[i] - (double)p.HW * mu) * is;     // sum_hw xhat
+            S1 += g * a2 + dmb;
+            S2 += g * (a3 - mu * a2) * is + dmb / (double)p.HW * x1;
+        }
+        p.dgamma[c] = (float)S2;
+        p.dbeta[c] = (float)S1;
+        const double gi = (double)p.gamma[c] * is;
+        const double R = -gi * is * S2 / n;
+        p.R[c] = (float)R;
+        double dbias = 0.0;
+        for (int b = 0; b < p.B; ++b) {
+            const int i = b * p.C + c;
+            const double g = p.gate ? (double)p.gate[i] : 1.0;
+            const double Pv = gi * g;
+            const double Qv = gi * ((double)dm[i] / (double)p.HW - S1 / n) - R * mu;
+            p.P[i] = (float)Pv;
+            p.Q[i] = (float)Qv;
+            dbias += Pv * (double)A2[i] + Qv * (double)p.HW + R * (double)p.line_sum[i];
+        }
+        if (p.dbias) p.dbias[c] = (float)dbias;
+    }
+}
+
+// dz = P*d_pre + Q + R*z ; dres = d_pre
+__global__ void __launch_bounds__(256)
+train_bwd_apply_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ P,
+                       const float* __restrict__ Q, const float* __restrict__ R, __nv_bfloat16* __restrict__ dz,
+                       __nv_bfloat16* __restrict__ dres) {
+    const int vpp = p.C >> 3;
+    const long long nvec = (long long)p.B * p.H * p.W * vpp;
+    const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
+    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        const int cv = (int)(i % vpp);
+        long long pix = i / vpp;
+        const int w = (int)(pix % p.W); pix /= p.W;
+        const int h = (int)(pix % p.H);
+        const int b = (int)(pix / p.H);
+        const int c0 = cv * 8;
+        float sc[8], sh[8], Pv[8], Qv[8], Rv[8];
+        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+        *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+        *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+        *reinterpret_cast<float4*>(Pv) = __ldg(reinterpret_cast<const float4*>(P + (size_t)b * p.C + c0));
+        *reinterpret_cast<float4*>(Pv + 4) = __ldg(reinterpret_cast<const float4*>(P + (size_t)b * p.C + c0 + 4));
+        *reinterpret_cast<float4*>(Qv) = __ldg(reinterpret_cast<const float4*>(Q + (size_t)b * p.C + c0));
+        *reinterpret_cast<float4*>(Qv + 4) = __ldg(reinterpret_cast<const float4*>(Q + (size_t)b * p.C + c0 + 4));
+        *reinterpret_cast<float4*>(Rv) = __ldg(reinterpret_cast<const float4*>(R + c0));
+        *reinterpret_cast<float4*>(Rv + 4) = __ldg(reinterpret_cast<const float4*>(R + c0 + 4));
+        float zv[8], d[8], o[8];
+        bwd_dpre(p, dout, b, h, w, c0, thresh, keep_scale, sc, sh, zv, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(Pv[j], d[j], fmaf(Rv[j], zv[j], Qv[j]));
+        *reinterpret_cast<uint4*>(dz + (size_t)i * 8) = pack8(o);
+        if (dres) *reinterpret_cast<uint4*>(dres + (size_t)i * 8) = pack8(d);
+    }
+}
+
+// SE gate from the BN-folded line means: m = scale*mean_hw(z)+shift ; hidden = relu(W1 m) ; gate = sigmoid(W2 hidden)
+__global__ void __launch_bounds__(512)
+se_excite_train_kernel(const float* __restrict__ line_sum, const float* __restrict__ scale, const float* __restrict__ shift,
+                       const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ se_mean,
+                       float* __restrict__ hidden_out, float* __restrict__ gate, int C, int Cr, float inv_hw) {
+    extern __shared__ float sm[];
+    float* mean = sm; float* hidden = sm + C;
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float m = fmaf(line_sum[(size_t)b * C + c] * inv_hw, scale[c], shift[c]);
+        mean[c] = m; se_mean[(size_t)b * C + c] = m;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < Cr; r += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(w1[(size_t)r * C + c], mean[c], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) { hidden[r] = fmaxf(s, 0.f); hidden_out[(size_t)b * Cr + r] = fmaxf(s, 0.f); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < Cr; ++r) s = fmaf(w2[(size_t)c * Cr + r], hidden[r], s);
+        gate[(size_t)b * C + c] = 1.f / (1.f + expf(-s));
+    }
+}
+
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int grid_for(long long nvec) {
+    long long blocks = (nvec + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace hctr
+
+using namespace hctr;
+
+extern "C" {
+
+int hctr_chan_stats(const void* x, float* psum, float* psq, int B, int H, int W, int C, void* stream) {
+    HCTR_CHECK(x && psum, HCTR_ERR_INVALID, "chan_stats: null pointer");
+    HCTR_CHECK(C % 8 == 0 && C >= 8 && C <= 2048 && 256 % (C / 8) == 0, HCTR_ERR_INVALID, "chan_stats: C/8 must divide 256 (C=%d)", C);
+    HCTR_CHECK(al16(x), HCTR_ERR_INVALID, "chan_stats: x must be 16-byte aligned");
+    const int slices = hctr_se_slices(H, W);
+    const int groups = 256 / (C / 8);
+    dim3 grid(slices, B);
+    chan_stats_kernel<<<grid, 256, 2 * (size_t)groups * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), psum, psq, H * W, C, slices);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_bn_finalize_train(const float* psum, const float* psq, int B, int slices, int C, int HW, const float* gamma,
+                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                           float* mean, float* invstd, float* scale, float* shift, float* line_sum, void* stream) {
+    HCTR_CHECK(psum && psq && gamma && beta && mean && invstd && scale && shift, HCTR_ERR_INVALID, "bn_finalize: null pointer");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        psum, psq, B, slices, C, HW, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, line_sum);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_se_excite_train(const float* line_sum, const float* scale, const float* shift, const float* w1, const float* w2,
+                         float* se_mean, float* hidden, float* gate, int B, int C, int Cr, int HW, void* stream) {
+    HCTR_CHECK(line_sum && scale && shift && w1 && w2 && se_mean && hidden && gate, HCTR_ERR_INVALID, "se_excite_train: null pointer");
+    se_excite_train_kernel<<<B, 512, (size_t)(C + Cr) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        line_sum, scale, shift, w1, w2, se_mean, hidden, gate, C, Cr, 1.0f / (float)HW);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+static int fill_apply(ApplyParams& p, const void* z, const float* scale, const float* shift, const float* gate,
+                      const void* res, int B, int H, int W, int C, int relu, int pool, float drop_p, unsigned seed) {
+    HCTR_CHECK(z && scale && shift, HCTR_ERR_INVALID, "train_apply: null pointer");
+    HCTR_CHECK(C % 8 == 0 && C >= 8 && 256 % (C / 8) == 0, HCTR_ERR_INVALID, "train_apply: bad channel count %d", C);
+    HCTR_CHECK(!pool || (H % 2 == 0 && !gate && !res), HCTR_ERR_INVALID, "train_apply: pooling needs even H and no gate/residual");
+    HCTR_CHECK(drop_p >= 0.f && drop_p < 1.f, HCTR_ERR_INVALID, "train_apply: dropout p must be in [0,1)");
+    HCTR_CHECK(al16(z) && al16(scale) && al16(shift) && al16(gate) && al16(res), HCTR_ERR_INVALID, "train_apply: 16-byte alignment");
+    p.z = static_cast<const __nv_bfloat16*>(z); p.scale = scale; p.shift = shift; p.gate = gate;
+    p.res = static_cast<const __nv_bfloat16*>(res);
+    p.B = B; p.H = H; p.W = W; p.C = C; p.relu = relu; p.pool = pool; p.drop_p = drop_p; p.seed = seed;
+    return HCTR_OK;
+}
+
+int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, const float* gate, const void* res,
+                         void* out, int B, int H, int W, int C, int relu, int pool, float drop_p, unsigned seed,
+                         void* stream) {
+    ApplyParams p;
+    int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
+    if (rc) return rc;
+    HCTR_CHECK(out && al16(out), HCTR_ERR_INVALID, "train_apply_fwd: bad output");
+    const long long nvec = (long long)B * (pool ? H / 2 : H) * W * (C / 8);
+    train_apply_fwd_kernel<<<grid_for(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<__nv_bfloat16*>(out));
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_train_bwd_reduce(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
+                          const void* res, float* pA2, float* pA3, int B, int H, int W, int C, int relu, int pool,
+                          float drop_p, unsigned seed, void* stream) {
+    ApplyParams p;
+    int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
+    if (rc) return rc;
+    HCTR_CHECK(dout && pA2 && pA3 && al16(dout), HCTR_ERR_INVALID, "train_bwd_reduce: null pointer");
+    const int slices = hctr_se_slices(H, W);
+    const int groups = 256 / (C / 8);
+    dim3 grid(slices, B);
+    train_bwd_reduce_kernel<<<grid, 256, 2 * (size_t)groups * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        p, static_cast<const __nv_bfloat16*>(dout), pA2, pA3, slices);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int B, int C, int HW, const float* gamma,
+                            const float* mean, const float* invstd, const float* scale, const float* shift,
+                            const float* line_sum, const float* gate, const float* se_hidden, const float* se_mean,
+                            const float* w1, const float* w2, int Cr, float* dw1, float* dw2, float* dgamma,
+                            float* dbeta, float* dbias, float* P, float* Q, float* R, void* stream) {
+    HCTR_CHECK(pA2 && pA3 && gamma && mean && invstd && scale && shift && line_sum && dgamma && dbeta && P && Q && R,
+               HCTR_ERR_INVALID, "train_bwd_finalize: null pointer");
+    HCTR_CHECK(!gate || (se_hidden && se_mean && w1 && w2 && dw1 && dw2 && Cr > 0), HCTR_ERR_INVALID, "train_bwd_finalize: SE arguments");
+    BwdFinalizeParams p;
+    p.pA2 = pA2; p.pA3 = pA3; p.slices = slices; p.B = B; p.C = C; p.HW = HW;
+    p.gamma = gamma; p.mean = mean; p.invstd = invstd; p.scale = scale; p.shift = shift; p.line_sum = line_sum;
+    p.gate = gate; p.se_hidden = se_hidden; p.se_mean = se_mean; p.w1 = w1; p.w2 = w2; p.Cr = gate ? Cr : 0;
+    p.dw1 = dw1; p.dw2 = dw2; p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.P = P; p.Q = Q; p.R = R;
+    const size_t smem = ((size_t)4 * B * C + (size_t)B * (gate ? Cr : 0)) * sizeof(float);
+    HCTR_CHECK(smem <= 200 * 1024, HCTR_ERR_INVALID, "train_bwd_finalize: B*C too large for one block (%zu bytes)", smem);
+    static bool configured = false;
+    if (!configured) {
+        HCTR_CUDA(cudaFuncSetAttribute(train_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    train_bwd_finalize_kernel<<<1, 512, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+int hctr_train_bwd_apply(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
+                         const void* res, const float* P, const float* Q, const float* R, void* dz, void* dres, int B,
+                         int H, int W, int C, int relu, int pool, float drop_p, unsigned seed, void* stream) {
+    ApplyParams p;
+    int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
+    if (rc) return rc;
+    HCTR_CHECK(dout && P && Q && R && dz && al16(dout) && al16(dz) && al16(dres) && al16(P) && al16(Q) && al16(R),
+               HCTR_ERR_INVALID, "train_bwd_apply: bad pointer");
+    const long long nvec = (long long)B * H * W * (C / 8);
+    train_bwd_apply_kernel<<<grid_for(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, static_cast<const __nv_bfloat16*>(dout), P, Q, R, static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dres));
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
+}  // extern "C"

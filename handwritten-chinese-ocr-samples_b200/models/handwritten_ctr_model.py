@@ -178,10 +178,6 @@ class hctr_model(nn.Module):
 
     # -------------------------------------------------------------------------------- forward
     def forward(self, input):
-        if self.training:
-            raise NotImplementedError(
-                "hctr_b200: train-mode forward (batch-stat BN, dropout, autograd) is not built yet; "
-                "call .eval() - there is no PyTorch fallback on this path")
         if not input.is_cuda:
             raise RuntimeError("hctr_b200: input must be a CUDA tensor on an sm_100a device (no CPU fallback)")
         if input.dim() != 4 or input.shape[1] != 1:
@@ -194,7 +190,34 @@ class hctr_model(nn.Module):
         if self.linear.weight.device != input.device:
             raise RuntimeError("hctr_b200: input is on %s but parameters are on %s" % (input.device, self.linear.weight.device))
         with torch.cuda.device(input.device):
-            return self._forward_eval(input.detach().float().contiguous())
+            x = input.detach().float().contiguous()
+            if self.training:
+                return self._forward_train(x)
+            return self._forward_eval(x)
+
+    # -------------------------------------------------------------------------------- train mode
+    def _engine(self):
+        eng = self.__dict__.get("_train_engine")
+        if eng is None:
+            eng = _core().train_engine.TrainEngine(self)
+            self.__dict__["_train_engine"] = eng
+        return eng
+
+    def _forward_train(self, x):
+        """train(): batch-statistics BN (running stats updated), dropout, autograd to the parameters
+        (reference: main.py:367,384 with models/handwritten_ctr_model.py in training mode)."""
+        eng = self._engine()
+        eng.dropout_enabled = bool(getattr(self, "dropout_enabled", True))
+        # one seed per step from torch's CPU generator: reproducible under torch.manual_seed
+        base_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        params = [p for _, p in self.named_parameters()]
+        fn = _core().train_engine._TrainFunction
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            out = fn.apply(eng, x, base_seed, *params)
+        else:
+            logits, _ = eng.forward(x, base_seed)
+            out = logits[:, :, :self.noutput].permute(1, 0, 2)
+        return out if self.logits_dtype == torch.bfloat16 else out.float()
 
     def _launch(self, nat, tag, flops, nbytes, fn, *args):
         """One C-ABI call = one kernel launch on the current stream; optionally bracketed by CUDA events."""
@@ -233,7 +256,7 @@ class hctr_model(nn.Module):
         a = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=dev)
         self._launch(nat, "stem", 2.0 * B * H * W * 64 * 9, 4.0 * x.numel() + 2.0 * a.numel(), lib.hctr_stem_conv_fwd,
                      nat.ptr(x), nat.ptr(plan.stem_w), nat.ptr(plan.stem_scale), nat.ptr(plan.stem_shift), nat.ptr(a),
-                     B, H, W, st)
+                     B, H, W, 1, st)
         a = self._conv(nat, a, plan.conv0_2, B, H, W, relu=True, pool=True)
         H //= 2
         for units, tail in plan.stages:

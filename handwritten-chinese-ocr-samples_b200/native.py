@@ -5,7 +5,7 @@ calls raise.  PyTorch is used only for device memory and streams.
 """
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_uint, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libhctr_b200.so")
@@ -27,7 +27,7 @@ SIGNATURES = {
     "hctr_last_error": (c_char_p, []),
     "hctr_abi_version": (_I, []),
     "hctr_device_supported": (_I, [_I]),
-    "hctr_stem_conv_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "hctr_stem_conv_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "hctr_conv_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "hctr_se_slices": (_I, [_I, _I]),
     "hctr_se_squeeze": (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -40,6 +40,26 @@ SIGNATURES = {
     "hctr_ctc_beam_workspace_bytes": (_L, [_I, _I, _I]),
     "hctr_ctc_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _I, _P, _P, _P, c_float, _P, _L, _P]),
     "hctr_ctc_loss_workspace_bytes": (_L, [_I, _I, _I]),
+    "hctr_chan_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "hctr_bn_finalize_train": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hctr_se_excite_train": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "hctr_train_apply_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, c_float, c_uint, _P]),
+    "hctr_train_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, c_float, c_uint, _P]),
+    "hctr_train_bwd_finalize": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P,
+                                     _P, _P, _P, _P, _P, _P, _P]),
+    "hctr_train_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, c_float, c_uint, _P]),
+    "hctr_conv_dgrad": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "hctr_conv_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "hctr_wgrad_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
+    "hctr_classifier_dgrad": (_I, [_P, _L, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "hctr_linear_wgrad": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
+    "hctr_linear_wgrad_workspace_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "hctr_colsum_bf16": (_I, [_P, _L, _I, _L, _P, _P, _L, _P]),
+    "hctr_colsum_workspace_bytes": (_L, [_L, _I]),
+    "hctr_stem_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _P, _L, _P]),
+    "hctr_stem_wgrad_workspace_bytes": (_L, [_I, _I, _I]),
+    "hctr_sgd_clip_step": (_I, [_P, _P, _P, _L, c_float, c_float, c_float, c_float, c_float, _I, _P, _P, _P]),
+    "hctr_sgd_workspace_bytes": (_L, []),
 }
 
 _lib = None

@@ -47,10 +47,10 @@ int hctr_device_supported(int device);
 
 /* cnn.conv0_1 + bn0_1 + relu (models/handwritten_ctr_model.py:116-118).
  * x: fp32 [B][1][H][W] (the reference input, [-1,1]); w: fp32 [64][9] (OIHW flattened);
- * scale/shift: fp32 [64], y = relu(conv(x)*scale + shift) with the conv bias and eval-mode BN folded in;
- * y: bf16 NHWC [B][H][W][64]. */
+ * scale/shift: fp32 [64], y = relu(conv(x)*scale + shift) with the conv bias and eval-mode BN folded in
+ * (relu=0, scale=1, shift=bias gives the raw conv output the train-mode BN needs); y: bf16 NHWC [B][H][W][64]. */
 int hctr_stem_conv_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int B, int H,
-                       int W, void* stream);
+                       int W, int relu, void* stream);
 
 /* 3x3 (pad 1) or 1x1 convolution + per-channel fp32 scale/shift (+ReLU) (+(2,1) max-pool over H pairs):
  * conv0_2/bn0_2 (:119-123), BasicBlock conv1/bn1/relu and conv2/bn2 (:49-53), downsample (:55-57, :104-107),
@@ -120,6 +120,74 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
                           int max_target_len, float* nll, float* loss, void* grad, float grad_scale, void* workspace,
                           long long workspace_bytes, void* stream);
 long long hctr_ctc_loss_workspace_bytes(int T, int B, int max_target_len);
+
+/* ---- training (train()-mode forward and the backward pass; reference: main.py:367,383-438) -------------------- */
+
+/* Per-(line, slice, channel) sum and sum of squares of an NHWC bf16 tensor (fixed order, deterministic): the batch
+ * statistics of nn.BatchNorm2d in train() (models/handwritten_ctr_model.py:38,40,74-92) and the SE squeeze (:27-28)
+ * come from the same pass. psum/psq: fp32 [B][hctr_se_slices(H,W)][C]; psq may be NULL. */
+int hctr_chan_stats(const void* x, float* psum, float* psq, int B, int H, int W, int C, void* stream);
+/* Batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale; updates running stats with
+ * `momentum` and the unbiased variance (pass NULL to skip); line_sum: fp32 [B][C] = sum over (h,w) (may be NULL). */
+int hctr_bn_finalize_train(const float* psum, const float* psq, int B, int slices, int C, int HW, const float* gamma,
+                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                           float* mean, float* invstd, float* scale, float* shift, float* line_sum, void* stream);
+/* SE gate from BN-folded line means (train mode): m = scale*mean_hw(z)+shift, hidden = relu(W1 m), gate = sigmoid(W2 hidden);
+ * se_mean [B][C], hidden [B][Cr], gate [B][C] are kept for the backward. */
+int hctr_se_excite_train(const float* line_sum, const float* scale, const float* shift, const float* w1, const float* w2,
+                         float* se_mean, float* hidden, float* gate, int B, int C, int Cr, int HW, void* stream);
+/* out = dropout(pool(relu((z*scale+shift) [*gate] [+res]))) - BN apply, SE scale, residual, ReLU, (2,1) max-pool and
+ * counter-based dropout (keep-scale 1/(1-p)) in one pass. z/res: bf16 NHWC [B][H][W][C]; out: [B][H or H/2][W][C]. */
+int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, const float* gate, const void* res,
+                         void* out, int B, int H, int W, int C, int relu, int pool, float drop_p, unsigned seed,
+                         void* stream);
+/* Backward of the pass above + BatchNorm (+SE) backward in three steps; with d_pre the gradient behind the
+ * dropout/pool/ReLU masks: reduce -> per-(b,slice,c) sums of d_pre and d_pre*z; finalize -> dgamma, dbeta, conv-bias
+ * gradient, SE FC gradients and the coefficients P[B][C], Q[B][C], R[C]; apply -> dz = P*d_pre + Q + R*z, dres = d_pre. */
+int hctr_train_bwd_reduce(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
+                          const void* res, float* pA2, float* pA3, int B, int H, int W, int C, int relu, int pool,
+                          float drop_p, unsigned seed, void* stream);
+int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int B, int C, int HW, const float* gamma,
+                            const float* mean, const float* invstd, const float* scale, const float* shift,
+                            const float* line_sum, const float* gate, const float* se_hidden, const float* se_mean,
+                            const float* w1, const float* w2, int Cr, float* dw1, float* dw2, float* dgamma,
+                            float* dbeta, float* dbias, float* P, float* Q, float* R, void* stream);
+int hctr_train_bwd_apply(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
+                         const void* res, const float* P, const float* Q, const float* R, void* dz, void* dres, int B,
+                         int H, int W, int C, int relu, int pool, float drop_p, unsigned seed, void* stream);
+
+/* Data gradient of a 3x3/1x1 convolution: the same tcgen05 implicit GEMM with mirrored taps. dz: bf16 NHWC
+ * [B][H][W][Cout]; w_packed_t: bf16 [Cin][k*k][Cout]; ones/zeros: fp32 [Cin]; add: optional bf16 [B][H][W][Cin]
+ * accumulated into the result (residual branch); dx: bf16 [B][H][W][Cin]. */
+int hctr_conv_dgrad(const void* dz, const void* w_packed_t, const float* ones, const float* zeros, const void* add,
+                    void* dx, int B, int H, int W, int Cout, int Cin, int ksize, void* stream);
+/* Weight gradient on tcgen05 (K = pixels, MN-major operands straight from the NHWC tensors, split-K with a
+ * fixed-order reduction). dw: fp32 [Cout][Cin][k][k] (the reference's OIHW parameter layout). */
+int hctr_conv_wgrad(const void* dz, const void* x, float* dw, int B, int H, int W, int Cout, int Cin, int ksize,
+                    void* workspace, long long workspace_bytes, void* stream);
+long long hctr_wgrad_workspace_bytes(int B, int H, int W, int M, int N, int ntaps);
+/* Classifier backward: dfeat[b,h,w,c] = sum_n dlogits[b,w,n]*W[n, c*Hf+h] (w_t: bf16 [Hf*Cf][pitch], row k = h*Cf+c,
+ * zero padded) and dW[n][c*Hf+h] (fp32, reference layout); dlogits: bf16 [B][W][pitch]. */
+int hctr_classifier_dgrad(const void* dlogits, long long pitch, const void* w_t, const float* ones, const float* zeros,
+                          void* dfeat, int B, int Hf, int W, int Cf, int num_classes, void* stream);
+int hctr_linear_wgrad(const void* dlogits, long long pitch, const void* feat, float* dw, int B, int Hf, int W, int Cf,
+                      int num_classes, void* workspace, long long workspace_bytes, void* stream);
+long long hctr_linear_wgrad_workspace_bytes(int B, int Hf, int W, int Cf, int num_classes);
+/* Column sums of a bf16 [rows][pitch] matrix (classifier bias gradient), two-stage fixed order. */
+int hctr_colsum_bf16(const void* x, long long rows, int cols, long long pitch, float* out, float* workspace,
+                     long long workspace_bytes, void* stream);
+long long hctr_colsum_workspace_bytes(long long rows, int cols);
+/* Stem (Cin=1) weight gradient: dw fp32 [64][9] from dz bf16 [B][H][W][64] and the fp32 input image. */
+int hctr_stem_wgrad(const void* dz, const float* x, float* dw, int B, int H, int W, float* workspace,
+                    long long workspace_bytes, void* stream);
+long long hctr_stem_wgrad_workspace_bytes(int B, int H, int W);
+/* Optimizer tail over flat fp32 buffers (main.py:210-213,430-438): total_norm = ||grad*grad_scale||_2,
+ * coef = min(1, max_norm/(total_norm+1e-6)) (clip_grad_norm_), then SGD with momentum and weight decay as
+ * torch.optim.SGD. norm_out: fp32 [2] = {total_norm, coef}; workspace: hctr_sgd_workspace_bytes(). */
+int hctr_sgd_clip_step(float* params, const float* grads, float* momentum_buf, long long n, float grad_scale,
+                       float max_norm, float lr, float momentum, float weight_decay, int first_step, float* norm_out,
+                       float* workspace, void* stream);
+long long hctr_sgd_workspace_bytes(void);
 
 #ifdef __cplusplus
 }

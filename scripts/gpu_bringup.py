@@ -79,7 +79,7 @@ try:
     scale = (torch.rand(64, generator=g) + 0.5).to(dev); shift = torch.randn(64, generator=g).to(dev) * 0.1
     y = torch.empty(B, H, W, 64, dtype=torch.bfloat16, device=dev)
     nat.check(lib.hctr_stem_conv_fwd(nat.ptr(x), nat.ptr(w.reshape(64, 9).contiguous()), nat.ptr(scale), nat.ptr(shift),
-                                     nat.ptr(y), B, H, W, nat.stream_ptr()), "stem")
+                                     nat.ptr(y), B, H, W, 1, nat.stream_ptr()), "stem")
     ref = (F.conv2d(x, w, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
     report("stem", y.permute(0, 3, 1, 2), ref)
     # SE
