@@ -9,7 +9,7 @@ All arithmetic runs in hand-written CUDA kernels behind the C ABI in include/hct
 from . import native  # noqa: F401
 from . import train_engine  # noqa: F401
 
-__all__ = ["native", "hctr_model", "ctc_codec", "CTCLoss"]
+__all__ = ["native", "hctr_model", "ctc_codec", "CTCLoss", "TrainStep"]
 
 
 def __getattr__(name):
@@ -22,4 +22,7 @@ def __getattr__(name):
     if name == "CTCLoss":
         from .ctc_loss import CTCLoss
         return CTCLoss
+    if name == "TrainStep":
+        from .train_step import TrainStep
+        return TrainStep
     raise AttributeError(name)

@@ -62,7 +62,9 @@ class _CtcFromLogits(torch.autograd.Function):
         g = ctx.grad
         if g is None:
             return None, None, None, None, None
-        return g * grad_out.to(g.dtype), None, None, None, None
+        ctx.grad = None
+        # in place: keeps the [B,W,pitch] kernel layout so the model's backward can consume the buffer without a copy
+        return g.mul_(grad_out.to(g.dtype)), None, None, None, None
 
 
 class CTCLoss(nn.Module):

@@ -103,6 +103,9 @@ def check(rc, what=""):
     raise RuntimeError(msg)
 
 
+c_void_p = c_void_p  # re-exported for callers that offset raw pointers
+
+
 def ptr(t):
     """Raw device pointer of a torch tensor (or None)."""
     return None if t is None else c_void_p(t.data_ptr())

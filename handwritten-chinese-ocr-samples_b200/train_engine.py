@@ -205,8 +205,11 @@ class TrainEngine(object):
         ctx["feat"], ctx["Hf"], ctx["cf"], ctx["pitch"], ctx["wk"] = a, H, cf, pitch, wk
         return logits, ctx
 
-    def backward(self, ctx, dlogits, grads):
-        """dlogits: bf16 [B,W,pitch] gradient buffer; grads: dict name -> fp32 tensor (reference layouts), filled here."""
+    def backward(self, ctx, dlogits, grads, on_stage_done=None):
+        """dlogits: bf16 [B,W,pitch] gradient buffer; grads: dict name -> fp32 tensor (reference layouts), filled here.
+        on_stage_done(name) is called after the kernels producing the last gradient of each parameter group
+        (linear, stage4..stage1, stage0) have been enqueued - the hook the bucketed all-reduce hangs on."""
+        notify = on_stage_done if on_stage_done is not None else (lambda name: None)
         m = self.model
         cnn = m.cnn
         lib, st = self.lib, nat.stream_ptr()
@@ -227,6 +230,7 @@ class TrainEngine(object):
         d = torch.empty((B, Hf, W, cf), dtype=torch.bfloat16, device=dev)
         nat.check(lib.hctr_classifier_dgrad(nat.ptr(dlogits), pitch, nat.ptr(wt), nat.ptr(self.ones(cf, dev)),
                                             nat.ptr(self.zeros(cf, dev)), nat.ptr(d), B, Hf, W, cf, n, st), "classifier_dgrad")
+        notify("linear")
         # ---- backbone, last stage first
         for stage in range(4, 0, -1):
             s = ctx["units"]["tail%d" % stage]
@@ -242,8 +246,10 @@ class TrainEngine(object):
                     d, _ = self.unit_backward(s1, dt, unit.conv1, unit.bn1, grads, add=dsc)
                 else:
                     d, _ = self.unit_backward(s1, dt, unit.conv1, unit.bn1, grads, add=dres)
+            notify("stage%d" % stage)
         d, _ = self.unit_backward(ctx["units"]["0_2"], d, cnn.conv0_2, cnn.bn0_2, grads)
         self.unit_backward(ctx["units"]["0_1"], d, cnn.conv0_1, cnn.bn0_1, grads, need_dx=False)
+        notify("stage0")
 
 
 class _TrainFunction(torch.autograd.Function):
