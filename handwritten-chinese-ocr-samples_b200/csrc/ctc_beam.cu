@@ -15,7 +15,6 @@ namespace hctr {
 constexpr int kMaxK = 16;        // search_depth limit
 constexpr int kMaxBeam = 16;     // beam_size limit
 constexpr int kMaxGen = kMaxBeam * (kMaxK + 1);
-constexpr int kTopkWarps = 4;
 
 // ---------------------------------------------------------------------------------------------- top-k
 __device__ __forceinline__ bool cand_better(float v, int i, float w, int j) {
@@ -43,106 +42,150 @@ template <> struct LoadVec<__nv_bfloat16> {
     }
 };
 
-struct LaneTopK {
-    float v[kMaxK];
-    int i[kMaxK];
-    float m, s;      // running max / sum of exp(x - m)
-    __device__ __forceinline__ void init() {
+// One CTA (256 threads) per (t,b) row; the row is staged once in shared memory as fp32:
+//   pass 1  global -> smem (16-byte loads), per-thread maximum
+//   bound   every warp sorts its 32 lane maxima (bitonic, shuffles); the k-th largest of one warp's lane maxima is a
+//           valid lower bound for the k-th largest of the row (k distinct elements are >= it); tau = best warp's bound
+//   pass 2  smem: sum exp(x - max) and collect the few elements >= tau into a candidate list
+//   rank    candidates ranked by counting (value desc, index asc) -> the top k in order; exact for any input.
+// If more than kMaxCand elements reach tau (e.g. constant rows) an exact k-round arg-max fallback runs instead.
+constexpr int kTopkThreads = 256;
+constexpr int kMaxCand = 512;
+
+__device__ __forceinline__ float warp_kth_largest(float v, int k, int lane) {
+    // bitonic sort of 32 lane values, descending; returns the value that ends up in lane k-1
 #pragma unroll
-        for (int j = 0; j < kMaxK; ++j) { v[j] = -INFINITY; i[j] = 0x7fffffff; }
-        m = -FLT_MAX; s = 0.f;
-    }
-    __device__ __forceinline__ void push(float x, int idx) {
-        // sorted insert, descending, equal values keep the lower index first
-        if (!cand_better(x, idx, v[kMaxK - 1], i[kMaxK - 1])) return;
-        bool placed = false;
-        float cv = x; int ci = idx;
+    for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
-        for (int j = 0; j < kMaxK; ++j) {
-            if (placed || cand_better(cv, ci, v[j], i[j])) {
-                const float tv = v[j]; const int ti = i[j];
-                v[j] = cv; i[j] = ci; cv = tv; ci = ti; placed = true;
-            }
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v, stride);
+            const bool up = ((lane & size) == 0);                 // this block sorts descending if 'up'
+            const bool lower = ((lane & stride) == 0);
+            const float hi = fmaxf(v, o), lo = fminf(v, o);
+            v = (lower == up) ? hi : lo;
         }
     }
-};
-
-// online log-sum-exp + top-k update with N consecutive elements starting at class index `base`
-template <int N>
-__device__ __forceinline__ void visit_vec(LaneTopK& st, const float (&x)[N], int base) {
-    float vm = x[0];
-#pragma unroll
-    for (int j = 1; j < N; ++j) vm = fmaxf(vm, x[j]);
-    if (vm > st.m) { st.s *= __expf(st.m - vm); st.m = vm; }
-#pragma unroll
-    for (int j = 0; j < N; ++j) { st.s += __expf(x[j] - st.m); st.push(x[j], base + j); }
+    return __shfl_sync(0xffffffffu, v, k - 1);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kTopkWarps * 32)
+__global__ void __launch_bounds__(kTopkThreads)
 ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
                            int k, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp,
                            float* __restrict__ lse_out) {
     constexpr int V = LoadVec<T>::N;
-    __shared__ float sv[kTopkWarps][32][kMaxK + 1];
-    __shared__ int si[kTopkWarps][32][kMaxK + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long row = (long long)blockIdx.x * kTopkWarps + warp;          // row = t*B + b
-    if (row >= (long long)Tn * Bn) return;
+    extern __shared__ float rowbuf[];                              // [C] the row as fp32
+    __shared__ float red[8];
+    __shared__ float s_max, s_tau, s_logs;
+    __shared__ int s_ncand;
+    __shared__ float cand_v[kMaxCand];
+    __shared__ int cand_i[kMaxCand];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row = blockIdx.x;                              // row = t*B + b
     const int t = (int)(row / Bn), b = (int)(row - (long long)t * Bn);
     const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
 
-    LaneTopK st; st.init();
+    // ---- pass 1: stage the row, per-thread max
+    float tmax = -INFINITY;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
     int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
     if (head > C) head = C;
-    if (lane < head) { float x1[1] = {LoadVec<T>::one(p + lane)}; visit_vec<1>(st, x1, lane); }
+    if (tid < head) { const float x = LoadVec<T>::one(p + tid); rowbuf[tid] = x; tmax = fmaxf(tmax, x); }
     const int nvec = (C - head) / V;
     const T* pv = p + head;
-    int vi = lane;
-    for (; vi + 32 < nvec; vi += 64) {
-        float x0[V], x1[V];
-        LoadVec<T>::load(pv + (long long)vi * V, x0);
-        LoadVec<T>::load(pv + (long long)(vi + 32) * V, x1);
-        visit_vec<V>(st, x0, head + vi * V);
-        visit_vec<V>(st, x1, head + (vi + 32) * V);
-    }
-    for (; vi < nvec; vi += 32) {
-        float x0[V];
-        LoadVec<T>::load(pv + (long long)vi * V, x0);
-        visit_vec<V>(st, x0, head + vi * V);
+    for (int vi = tid; vi < nvec; vi += kTopkThreads) {
+        float x[V];
+        LoadVec<T>::load(pv + (long long)vi * V, x);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { rowbuf[head + vi * V + j] = x[j]; tmax = fmaxf(tmax, x[j]); }
     }
     const int tail0 = head + nvec * V;
-    if (tail0 + lane < C) { float x1[1] = {LoadVec<T>::one(p + tail0 + lane)}; visit_vec<1>(st, x1, tail0 + lane); }
-
-    // row max / sum
-    float m = st.m;
+    if (tail0 + tid < C) { const float x = LoadVec<T>::one(p + tail0 + tid); rowbuf[tail0 + tid] = x; tmax = fmaxf(tmax, x); }
+    if (tid == 0) s_ncand = 0;
+    // ---- bound: k-th largest lane maximum of each warp, block max
+    const float kth = warp_kth_largest(tmax, k < 32 ? k : 32, lane);
+    float wmax = tmax;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float s = st.s * __expf(st.m - m);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float logs = logf(s);
-    if (lane == 0) lse_out[row] = m + logs;
-
-    // merge the 32 sorted lane lists: k rounds of warp arg-best over the list heads
-#pragma unroll
-    for (int j = 0; j < kMaxK; ++j) { sv[warp][lane][j] = st.v[j]; si[warp][lane][j] = st.i[j]; }
-    sv[warp][lane][kMaxK] = -INFINITY; si[warp][lane][kMaxK] = 0x7fffffff;
-    __syncwarp();
-    int hd = 0;
-    for (int r = 0; r < k; ++r) {
-        float bv = sv[warp][lane][hd]; int bi = si[warp][lane][hd];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    __shared__ float red_kth[8];
+    if (lane == 0) { red[warp] = wmax; red_kth[warp] = kth; }
+    __syncthreads();
+    if (tid == 0) {
+        float m = red[0], tau = red_kth[0];
+        for (int i = 1; i < kTopkThreads / 32; ++i) { m = fmaxf(m, red[i]); tau = fmaxf(tau, red_kth[i]); }
+        s_max = m; s_tau = tau;
+    }
+    __syncthreads();
+    const float m = s_max, tau = s_tau;
+    // ---- pass 2: sum of exp and candidate collection
+    float sum = 0.f;
+    for (int c = tid; c < C; c += kTopkThreads) {
+        const float x = rowbuf[c];
+        sum += __expf(x - m);
+        if (x >= tau) {
+            const int slot = atomicAdd(&s_ncand, 1);
+            if (slot < kMaxCand) { cand_v[slot] = x; cand_i[slot] = c; }
         }
-        if (si[warp][lane][hd] == bi && hd < kMaxK) ++hd;                    // the winning lane advances
-        if (lane == 0) {
-            topk_idx[row * k + r] = bi;
-            topk_logp[row * k + r] = (bv - m) - logs;                         // scipy: (x - max) - log(sum(exp(x - max)))
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();                                               // red[] reuse + candidates visible
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float sacc = 0.f;
+        for (int i = 0; i < kTopkThreads / 32; ++i) sacc += red[i];   // fixed order
+        const float logs = logf(sacc);
+        s_logs = logs;
+        lse_out[row] = m + logs;
+    }
+    __syncthreads();
+    const float logs = s_logs;
+    const int ncand = s_ncand;
+    if (ncand <= kMaxCand) {
+        // ---- rank by counting: exact order (value desc, index asc), independent of the collection order
+        for (int e = tid; e < ncand; e += kTopkThreads) {
+            const float v = cand_v[e]; const int ci = cand_i[e];
+            int rank = 0;
+            for (int f = 0; f < ncand; ++f) rank += cand_better(cand_v[f], cand_i[f], v, ci) ? 1 : 0;
+            if (rank < k) {
+                topk_idx[row * k + rank] = ci;
+                topk_logp[row * k + rank] = (v - m) - logs;         // scipy: (x - max) - log(sum(exp(x - max)))
+            }
+        }
+    } else {
+        // ---- exact fallback: k rounds of block arg-best with exclusion of what was already emitted
+        __shared__ float bv_s[8];
+        __shared__ int bi_s[8];
+        __shared__ float last_v;
+        __shared__ int last_i;
+        if (tid == 0) { last_v = INFINITY; last_i = -1; }
+        __syncthreads();
+        for (int r = 0; r < k; ++r) {
+            const float lv = last_v; const int li = last_i;
+            float bv = -INFINITY; int bi = 0x7fffffff;
+            for (int c = tid; c < C; c += kTopkThreads) {
+                const float x = rowbuf[c];
+                // eligible: strictly after (lv, li) in the (value desc, index asc) order
+                const bool elig = (x < lv) || (x == lv && c > li);
+                if (elig && cand_better(x, c, bv, bi)) { bv = x; bi = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { bv_s[warp] = bv; bi_s[warp] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                float v = bv_s[0]; int i2 = bi_s[0];
+                for (int q = 1; q < kTopkThreads / 32; ++q) if (cand_better(bv_s[q], bi_s[q], v, i2)) { v = bv_s[q]; i2 = bi_s[q]; }
+                last_v = v; last_i = i2;
+                topk_idx[row * k + r] = i2;
+                topk_logp[row * k + r] = (v - m) - logs;
+            }
+            __syncthreads();
         }
     }
 }
@@ -386,14 +429,21 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     if (T == 0 || B == 0) return HCTR_OK;
     HCTR_CHECK(logits != nullptr, HCTR_ERR_INVALID, "topk: null logits");
     const long long rows = (long long)T * B;
-    const long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
-    HCTR_CHECK(blocks < (1ll << 31), HCTR_ERR_INVALID, "topk: too many rows");
+    HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "topk: too many rows");
+    const size_t smem = (size_t)C * sizeof(float);
+    HCTR_CHECK(smem <= 160 * 1024, HCTR_ERR_INVALID, "topk: %d classes do not fit the shared-memory row buffer", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    static bool configured = false;
+    if (!configured) {
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
     if (dtype == HCTR_F32)
-        ctc_topk_logsoftmax_kernel<float><<<(int)blocks, kTopkWarps * 32, 0, s>>>(
+        ctc_topk_logsoftmax_kernel<float><<<(int)rows, kTopkThreads, smem, s>>>(
             static_cast<const float*>(logits), T, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
     else
-        ctc_topk_logsoftmax_kernel<__nv_bfloat16><<<(int)blocks, kTopkWarps * 32, 0, s>>>(
+        ctc_topk_logsoftmax_kernel<__nv_bfloat16><<<(int)rows, kTopkThreads, smem, s>>>(
             static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;

@@ -3,9 +3,10 @@
 // Three passes:
 //   A (HBM-bound): one warp per (t,b) row -> log-sum-exp, and the gathered log-probs of the blank-interleaved
 //                  label sequence l' (S = 2L+1) for the recursion.
-//   B (latency-bound): one CTA per sequence, alpha then beta over time with the state in shared memory
-//                  (ping-pong, one barrier per step), 3-way log-sum-exp as ATen's ctc_loss but with the state in
-//                  fp64: |log alpha| reaches ~2e4 at T=2048, C=7375, where fp32 log-space has only ~2e-3 resolution.
+//   B (latency-bound): two CTAs per sequence run the alpha and the beta recursion CONCURRENTLY, state in shared memory
+//                  (ping-pong, one barrier per step), 3-way log-sum-exp as ATen's ctc_loss. The state is fp64 -
+//                  |log alpha| reaches ~2e4 at T=2048, C=7375, where fp32 log-space resolves only ~2e-3 - but the
+//                  exp/log act on O(1) differences and run in fp32 (fast SFU path), which keeps a step at ~0.2 us.
 //   C (HBM-bound): one CTA per row: grad = (softmax - occupancy) * scale written in one pass, where
 //                  occupancy_c = sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - ll - lp[t, l'_s]).
 // Logits are read twice and the gradient written once: (2*s_in + s_out) * T*B*C bytes.
@@ -19,7 +20,8 @@ namespace hctr {
 struct CtcWs {
     float* lse;        // [B][T]
     float* lpg;        // [B][T][Smax]   log-prob of l'_s at (t,b)
-    double* alpha;     // [B][T][Smax]   alpha, later overwritten by alpha+beta-lp (log occupancy + ll), fp64
+    double* alpha;     // [B][T][Smax]   alpha (fp64 state)
+    double* beta;      // [B][T][Smax]   beta (fp64 state); occupancy = exp(alpha + beta - lp - ll)
     double* ll;        // [B]            log-likelihood (may be -inf), fp64
     int* canon;        // [B][Smax]      first s' with the same class as s
     int* toff;         // [B]            offset of sequence b in the concatenated targets
@@ -33,6 +35,7 @@ static CtcWs carve(void* base, int T, int B, int Smax, long long* total) {
     const long long o_lse = take(4ll * B * T);
     const long long o_lpg = take(4ll * B * T * Smax);
     const long long o_alpha = take(8ll * B * T * Smax);
+    const long long o_beta = take(8ll * B * T * Smax);
     const long long o_ll = take(8ll * B);
     const long long o_canon = take(4ll * B * Smax);
     const long long o_toff = take(4ll * B);
@@ -42,6 +45,7 @@ static CtcWs carve(void* base, int T, int B, int Smax, long long* total) {
     w.lse = reinterpret_cast<float*>(p + o_lse);
     w.lpg = reinterpret_cast<float*>(p + o_lpg);
     w.alpha = reinterpret_cast<double*>(p + o_alpha);
+    w.beta = reinterpret_cast<double*>(p + o_beta);
     w.ll = reinterpret_cast<double*>(p + o_ll);
     w.canon = reinterpret_cast<int*>(p + o_canon);
     w.toff = reinterpret_cast<int*>(p + o_toff);
@@ -171,101 +175,94 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
 __device__ __forceinline__ double lse3(double a, double b, double c) {
     const double mx = fmax(a, fmax(b, c));
     if (mx == -INFINITY) return -INFINITY;
-    return mx + log(exp(a - mx) + exp(b - mx) + exp(c - mx));
+    // the differences are <= 0 and O(1): fp32 transcendentals lose nothing that matters, fp64 keeps the large offset
+    const float s = __expf((float)(a - mx)) + __expf((float)(b - mx)) + __expf((float)(c - mx));   // ex2.approx: 2 ulp
+    return mx + (double)logf(s);
 }
 
+// grid (B, 2): blockIdx.y == 0 runs alpha (and the log-likelihood), blockIdx.y == 1 runs beta.
 __global__ void __launch_bounds__(1024)
 ctc_alpha_beta_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen,
-                      const int32_t* __restrict__ ilen, int Tn, int Smax, int need_beta, float* __restrict__ nll_out,
-                      CtcWs w) {
+                      const int32_t* __restrict__ ilen, int Tn, int Smax, float* __restrict__ nll_out, CtcWs w) {
     extern __shared__ double smd[];               // 2 x (Smax + 4) ping-pong state with -inf guards, + 1 scratch
     const int b = blockIdx.x, s = threadIdx.x;
+    const bool is_beta = blockIdx.y == 1;
     const int L = tlen[b], S = 2 * L + 1, Tb = ilen[b];
     const int32_t* tg = targets + w.toff[b];
     const int W = Smax + 4;
-    double* bufA = smd;          // alpha: state s lives at index s+2 (two guard cells on the left)
-    double* bufB = smd + W;      // beta:  state s lives at index s   (guard cells on the right)
+    double* bufA = smd;
+    double* bufB = smd + W;
     const bool act = s < S;
     const int cls = act ? ((s & 1) ? tg[s >> 1] : 0) : 0;
     const bool skip_in = act && s > 1 && cls != 0 && cls != ((s & 1) ? tg[(s >> 1) - 1] : 0);      // s-2 -> s allowed
     const bool skip_out = act && (s + 2 < S) && (((s + 2) & 1) ? tg[(s + 2) >> 1] : 0) != 0 &&
                           ((((s + 2) & 1) ? tg[(s + 2) >> 1] : 0) != cls);                              // s -> s+2 allowed
     const float* lp = w.lpg + (long long)b * Tn * Smax;
-    double* al = w.alpha + (long long)b * Tn * Smax;
 
     for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) smd[i] = -INFINITY;
     __syncthreads();
-    double ll = -INFINITY;
-    if (Tb > 0) {
-        // ---- alpha
-        double a = -INFINITY;
-        if (act && s < 2) a = (double)lp[s];
-        if (act) { bufA[s + 2] = a; al[s] = a; }
-        __syncthreads();
+    if (!is_beta) {
+        // ---- alpha: state s lives at index s+2 (two -inf guard cells on the left)
+        double* al = w.alpha + (long long)b * Tn * Smax;
+        double ll = -INFINITY;
+        if (Tb > 0) {
+            double a = -INFINITY;
+            if (act && s < 2) a = (double)lp[s];
+            if (act) { bufA[s + 2] = a; al[s] = a; }
+            __syncthreads();
+            double* cur = bufA; double* nxt = bufB;
+            float lp_next = (act && Tb > 1) ? lp[(long long)Smax + s] : 0.f;
+            for (int t = 1; t < Tb; ++t) {
+                const double lpt = (double)lp_next;
+                if (act && t + 1 < Tb) lp_next = lp[(long long)(t + 1) * Smax + s];
+                if (act) {
+                    const double v = lse3(cur[s + 2], cur[s + 1], skip_in ? cur[s] : -INFINITY);
+                    a = (v == -INFINITY) ? -INFINITY : v + lpt;
+                    nxt[s + 2] = a;
+                    al[(long long)t * Smax + s] = a;
+                }
+                __syncthreads();
+                double* tmp = cur; cur = nxt; nxt = tmp;
+            }
+            if (threadIdx.x == 0) {
+                const double l1 = cur[S - 1 + 2], l2 = (S > 1) ? cur[S - 2 + 2] : -INFINITY;
+                const double mx = fmax(l1, l2);
+                ll = (mx == -INFINITY) ? -INFINITY : mx + log(exp(l1 - mx) + exp(l2 - mx));
+            }
+        } else if (L == 0) {
+            ll = 0.0;
+        }
+        if (threadIdx.x == 0) {
+            w.ll[b] = ll;
+            float n = (float)(-ll);
+            if (!(n < INFINITY)) n = 0.f;           // zero_infinity=True (main.py:205)
+            nll_out[b] = n;
+        }
+    } else {
+        // ---- beta: state s lives at index s (guard cells on the right)
+        if (Tb <= 0) return;
+        double* be = w.beta + (long long)b * Tn * Smax;
         double* cur = bufA; double* nxt = bufB;
-        float lp_next = (act && Tb > 1) ? lp[(long long)Smax + s] : 0.f;
-        for (int t = 1; t < Tb; ++t) {
+        {
+            const long long o = (long long)(Tb - 1) * Smax + s;
+            double bt = -INFINITY;
+            if (act && s >= S - 2) bt = (double)lp[o];
+            if (act) { cur[s] = bt; be[o] = bt; }
+        }
+        __syncthreads();
+        float lp_next = (act && Tb > 1) ? lp[(long long)(Tb - 2) * Smax + s] : 0.f;
+        for (int t = Tb - 2; t >= 0; --t) {
             const double lpt = (double)lp_next;
-            if (act && t + 1 < Tb) lp_next = lp[(long long)(t + 1) * Smax + s];
+            if (act && t > 0) lp_next = lp[(long long)(t - 1) * Smax + s];
             if (act) {
-                const double a0 = cur[s + 2], a1 = cur[s + 1], a2 = skip_in ? cur[s] : -INFINITY;
-                const double v = lse3(a0, a1, a2);
-                a = (v == -INFINITY) ? -INFINITY : v + lpt;
-                nxt[s + 2] = a;
-                al[(long long)t * Smax + s] = a;
+                const double v = lse3(cur[s], cur[s + 1], skip_out ? cur[s + 2] : -INFINITY);
+                const double bt = (v == -INFINITY) ? -INFINITY : v + lpt;
+                nxt[s] = bt;
+                be[(long long)t * Smax + s] = bt;
             }
             __syncthreads();
             double* tmp = cur; cur = nxt; nxt = tmp;
         }
-        if (threadIdx.x == 0) {
-            const double l1 = cur[S - 1 + 2], l2 = (S > 1) ? cur[S - 2 + 2] : -INFINITY;
-            const double mx = fmax(l1, l2);
-            smd[2 * W] = (mx == -INFINITY) ? -INFINITY : mx + log(exp(l1 - mx) + exp(l2 - mx));
-        }
-        __syncthreads();
-        ll = smd[2 * W];
-    } else if (L == 0) {
-        ll = 0.0;
-    }
-    if (threadIdx.x == 0) {
-        w.ll[b] = ll;
-        float n = (float)(-ll);
-        if (!(n < INFINITY)) n = 0.f;           // zero_infinity=True (main.py:205)
-        nll_out[b] = n;
-    }
-    if (!need_beta || Tb <= 0 || ll == -INFINITY) return;
-
-    // ---- beta (same ping-pong, guards on the right), fused: al[t][s] <- alpha + beta - lp
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) smd[i] = -INFINITY;
-    __syncthreads();
-    double* cur = bufA; double* nxt = bufB;
-    {
-        const long long o = (long long)(Tb - 1) * Smax + s;
-        double bt = -INFINITY;
-        if (act && s >= S - 2) bt = (double)lp[o];
-        if (act) {
-            cur[s] = bt;
-            const double av = al[o];
-            al[o] = (av == -INFINITY || bt == -INFINITY) ? -INFINITY : av + bt - (double)lp[o];
-        }
-    }
-    __syncthreads();
-    float lp_next = (act && Tb > 1) ? lp[(long long)(Tb - 2) * Smax + s] : 0.f;
-    for (int t = Tb - 2; t >= 0; --t) {
-        const double lpt = (double)lp_next;
-        if (act && t > 0) lp_next = lp[(long long)(t - 1) * Smax + s];
-        if (act) {
-            const double b0 = cur[s], b1 = cur[s + 1], b2 = skip_out ? cur[s + 2] : -INFINITY;
-            const double v = lse3(b0, b1, b2);
-            const double bt = (v == -INFINITY) ? -INFINITY : v + lpt;
-            nxt[s] = bt;
-            const long long o = (long long)t * Smax + s;
-            const double av = al[o];
-            al[o] = (av == -INFINITY || bt == -INFINITY) ? -INFINITY : av + bt - lpt;
-        }
-        __syncthreads();
-        double* tmp = cur; cur = nxt; nxt = tmp;
     }
 }
 
@@ -300,8 +297,13 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     const float lse = dead ? 0.f : w.lse[row];
 
     if (!dead) {
-        const double* ab = w.alpha + row * Smax;
-        for (int s = threadIdx.x; s < S; s += blockDim.x) occ[s] = (float)exp(ab[s] - ll);
+        const double* al = w.alpha + row * Smax;
+        const double* be = w.beta + row * Smax;
+        const float* lpr = w.lpg + row * Smax;
+        for (int s = threadIdx.x; s < S; s += blockDim.x) {
+            const double e = al[s] + be[s] - (double)lpr[s] - ll;        // -inf if either side is unreachable
+            occ[s] = (e == e) ? expf((float)e) : 0.f;
+        }
     }
     // dense part: softmax * scale
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
@@ -389,7 +391,7 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     HCTR_CUDA(cudaGetLastError());
     int threads = (Smax + 31) / 32 * 32;
     const size_t smB = (size_t)(2 * (Smax + 4) + 2) * sizeof(double);
-    ctc_alpha_beta_kernel<<<B, threads, smB, s>>>(targets, target_lengths, input_lengths, T, Smax, grad != nullptr, nll, w);
+    ctc_alpha_beta_kernel<<<dim3(B, grad != nullptr ? 2 : 1), threads, smB, s>>>(targets, target_lengths, input_lengths, T, Smax, nll, w);
     HCTR_CUDA(cudaGetLastError());
     ctc_mean_loss_kernel<<<1, 32, 0, s>>>(nll, target_lengths, B, loss);
     HCTR_CUDA(cudaGetLastError());

@@ -272,7 +272,7 @@ class _TrainFunction(torch.autograd.Function):
         n = engine.model.noutput
         if (grad_out.dtype == torch.bfloat16 and tuple(grad_out.stride()) == (pitch, W * pitch, 1)
                 and grad_out.storage_offset() % 8 == 0):
-            buf = grad_out.as_strided((B, W, pitch), (W * pitch, pitch, 1))      # already in the kernel layout (CTCLoss)
+            buf = grad_out.permute(1, 0, 2)           # [B,W,n] view with row pitch `pitch`: already the kernel layout (CTCLoss)
         else:
             buf = torch.zeros((B, W, pitch), dtype=torch.bfloat16, device=grad_out.device)
             buf[:, :, :n] = grad_out.permute(1, 0, 2)
