@@ -189,6 +189,14 @@ int hctr_sgd_clip_step(float* params, const float* grads, float* momentum_buf, l
                        float* workspace, void* stream);
 long long hctr_sgd_workspace_bytes(void);
 
+/* ---- input pipeline (next to the path: utils/dataset.py:78-93 NormalizePAD, test.py:170-186) ----------------- */
+
+/* pixels: uint8 grayscale lines of height H, line b stored row-major [H][widths[b]] at pixels + offsets[b] (device);
+ * out: fp32 [B][1][H][Wb] = ((p/255) - 0.5) / 0.5, columns >= widths[b] replicate the last real column. Bit-exact with
+ * torchvision ToTensor + sub_(0.5).div_(0.5). Requires widths[b] <= Wb. */
+int hctr_normalize_pad(const void* pixels, const long long* offsets, const int32_t* widths, float* out, int B, int H,
+                       int Wb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

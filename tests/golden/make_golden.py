@@ -194,8 +194,22 @@ def make_config1():
     np.savez_compressed(os.path.join(HERE, "config1.npz"), **out)
 
 
+# ------------------------------------------------------------------ NormalizePAD (utils/dataset.py:78-93)
+def make_pad():
+    out = {}
+    rs = np.random.RandomState(61)
+    widths = [37, 64, 50]
+    maxw = 64
+    trans = NormalizePAD((1, 16, maxw))
+    for i, w in enumerate(widths):
+        img = rs.randint(0, 256, size=(16, w, 1)).astype(np.uint8)
+        out["img%d" % i] = img[:, :, 0]
+        out["pad%d" % i] = trans(img).numpy()
+    np.savez_compressed(os.path.join(HERE, "pad.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["greedy", "beam", "ctc_loss", "model", "config1"]
+    which = sys.argv[1:] or ["greedy", "beam", "ctc_loss", "model", "config1", "pad"]
     for w in which:
         print("making", w, flush=True)
         globals()["make_" + w]()
