@@ -124,7 +124,7 @@ int hctr_device_supported(int device) {
 
 static int conv_launch(const void* x, const void* w_packed, const float* scale, const float* shift, const void* add,
                        void* y, int B, int H, int W, int Cin, int Cout, int ksize, int relu, int pool, int flip,
-                       void* stream) {
+                       void* stream, float* se_partial = nullptr) {
     HCTR_CHECK(x && w_packed && scale && shift && y, HCTR_ERR_INVALID, "conv: null pointer");
     HCTR_CHECK(ksize == 1 || ksize == 3, HCTR_ERR_INVALID, "conv: ksize must be 1 or 3 (got %d)", ksize);
     HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "conv: empty tensor %dx%dx%d", B, H, W);
@@ -152,6 +152,7 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     }
     p.sub_dh = 1; p.sub_dw = 0;
     p.add = add;
+    p.se_partial = se_partial;
     p.N = Cout;
     p.w_tiles = (W + kTileM - 1) / kTileM;
     p.h_tiles = (H + 1) / 2;
@@ -181,6 +182,16 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
 int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,
                          int H, int W, int Cin, int Cout, int ksize, int relu, int pool, void* stream) {
     return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, relu, pool, 0, stream);
+}
+
+int hctr_conv_se_slices(int H, int W) {
+    return ((H + 1) / 2) * ((W + kTileM - 1) / kTileM) * 4;
+}
+
+int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
+                        float* se_partial, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {
+    HCTR_CHECK(se_partial != nullptr, HCTR_ERR_INVALID, "conv_bn_se: null partial buffer");
+    return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, 0, 0, 0, stream, se_partial);
 }
 
 int hctr_conv_dgrad(const void* dz, const void* w_packed_t, const float* ones, const float* zeros, const void* add,

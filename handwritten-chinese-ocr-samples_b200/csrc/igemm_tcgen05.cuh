@@ -45,6 +45,8 @@ struct IgemmParams {
     int relu, pool;
     int out_H;                // output rows (H or H/2 when pooled)
     long long out_line_pitch; // EPI_CONV: elements between consecutive lines b of the output (0 = out_H*W*N)
+    float* se_partial;        // EPI_CONV: optional [B][h_tiles*w_tiles][4][N] per-(tile, warp) channel sums of the fp32
+                              // epilogue output (the SE squeeze folded into the producing conv; deterministic)
     int out_dtype;            // EPI_LINEAR: HCTR_F32 | HCTR_BF16
     long long out_pitch;      // EPI_LINEAR: elements between consecutive (b,w) rows
 };
@@ -202,6 +204,35 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             v[s][j + 2] = fmaf(v[s][j + 2], sc.z, sh.z);
                             v[s][j + 3] = fmaf(v[s][j + 3], sc.w, sh.w);
                         }
+                    }
+                    if (p.se_partial) {
+                        // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum over this
+                        // warp's 32 pixels x NUM_SUB rows by a transpose-reduce butterfly (31 shuffles per 32 columns);
+                        // afterwards lane L holds column n0+L. Slots are per (tile, warp): fixed-order final sum.
+                        float tsum[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int s = 0; s < NUM_SUB; ++s) {
+                                const bool ok = (w0 + s * p.sub_dw * kTileM + pix < p.W) && (h0 + s * p.sub_dh < p.out_H);
+                                a += ok ? v[s][j] : 0.f;
+                            }
+                            tsum[j] = a;
+                        }
+#define HCTR_BFLY(O)                                                                          \
+                        {                                                                     \
+                            const bool upper = (lane & (O)) != 0;                             \
+                            _Pragma("unroll") for (int i = 0; i < (O); ++i) {                 \
+                                const float send = upper ? tsum[i] : tsum[i + (O)];           \
+                                const float keep = upper ? tsum[i + (O)] : tsum[i];           \
+                                tsum[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));     \
+                            }                                                                 \
+                        }
+                        HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
+#undef HCTR_BFLY
+                        const size_t slot = ((static_cast<size_t>(b) * p.h_tiles * p.w_tiles + static_cast<size_t>(h_tile) * p.w_tiles + w_tile) * 4 + quad);
+                        p.se_partial[slot * p.N + n0 + lane] = tsum[0];
                     }
                     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
                     if (p.pool) {

@@ -262,14 +262,18 @@ class hctr_model(nn.Module):
         for units, tail in plan.stages:
             for u in units:
                 t = self._conv(nat, a, u["conv1"], B, H, W, relu=True, pool=False)
-                v = self._conv(nat, t, u["conv2"], B, H, W, relu=False, pool=False)
-                del t
-                C = u["conv2"].cout
-                slices = lib.hctr_se_slices(H, W)
+                # conv2 + bn2 with the SE squeeze folded into its epilogue (per-tile channel sums)
+                spec = u["conv2"]
+                C = spec.cout
+                slices = lib.hctr_conv_se_slices(H, W)
                 partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
+                v = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
+                self._launch(nat, "conv3x3_%d_%d_se" % (spec.cin, spec.cout), 2.0 * B * H * W * C * spec.cin * 9,
+                             2.0 * (t.numel() + v.numel() + spec.w.numel()), lib.hctr_conv_bn_se_fwd,
+                             nat.ptr(t), nat.ptr(spec.w), nat.ptr(spec.scale), nat.ptr(spec.shift), nat.ptr(v), nat.ptr(partial),
+                             B, H, W, spec.cin, spec.cout, spec.ksize, st)
+                del t
                 gate = torch.empty((B, C), dtype=torch.float32, device=dev)
-                self._launch(nat, "se_squeeze", 0.0, 2.0 * v.numel(), lib.hctr_se_squeeze,
-                             nat.ptr(v), nat.ptr(partial), B, H, W, C, st)
                 self._launch(nat, "se_excite", 0.0, 4.0 * partial.numel(), lib.hctr_se_excite,
                              nat.ptr(partial), slices, nat.ptr(u["se_w1"]), nat.ptr(u["se_w2"]), nat.ptr(gate),
                              B, C, u["se_w1"].shape[0], H * W, st)

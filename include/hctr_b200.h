@@ -60,6 +60,14 @@ int hctr_stem_conv_fwd(const float* x, const float* w, const float* scale, const
 int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,
                          int H, int W, int Cin, int Cout, int ksize, int relu, int pool, void* stream);
 
+/* BasicBlock conv2 + bn2 (:52-53) with the SELayer squeeze (:27-28) folded into the epilogue: besides y (bf16 NHWC,
+ * no ReLU) the kernel writes per-(tile, warp) channel sums of the fp32 BN output to se_partial
+ * [B][hctr_conv_se_slices(H,W)][Cout]; hctr_se_excite(se_partial, slices = hctr_conv_se_slices(H,W), ...) finishes the
+ * mean in a fixed order (deterministic). Saves one full read of the activation per residual block. */
+int hctr_conv_se_slices(int H, int W);
+int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
+                        float* se_partial, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
+
 /* SELayer squeeze (:27-28): deterministic two-stage mean over (H,W) incl. padded columns.
  * x: bf16 NHWC; partial: fp32 workspace [B][slices][C]; the second stage runs inside hctr_se_excite.
  * `slices` must equal hctr_se_slices(H, W). */
