@@ -7,60 +7,61 @@
 namespace hctr {
 
 // ---------------------------------------------------------------- stem: conv0_1 + bn0_1 + relu
-// reference: models/handwritten_ctr_model.py:116-118. One block = one image row x 256 columns: the 3 x 258 input
-// halo and the 64 x 9 weights sit in shared memory; one thread = one pixel x 8 output channels, 8 consecutive lanes
-// cover the 64 channels of a pixel (one 128-byte line), so a warp writes 512 contiguous bytes per iteration.
+// reference: models/handwritten_ctr_model.py:116-118. One block walks one image row in 256-column segments: the
+// 3 x 258 input halo of a segment sits in shared memory, the thread's 8 x 9 weights stay in registers for the whole row;
+// one thread = one pixel x 8 output channels, 8 consecutive lanes cover the 64 channels of a pixel (one 128-byte
+// line), so a warp writes 512 contiguous bytes per iteration. No integer division in the pixel loop.
 constexpr int kStemSeg = 256;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
                  const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B, int H, int W, int relu) {
-    __shared__ __align__(16) float sw[9][64];               // tap-major: lanes of a pixel read disjoint 32-byte runs
-    __shared__ __align__(16) float ssc[64], ssh[64];
     __shared__ float tile[3][kStemSeg + 2];
-    const int w0 = blockIdx.x * kStemSeg, h = blockIdx.y, b = blockIdx.z;
-    for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i % 9][i / 9] = w[i];
-    if (threadIdx.x < 64) { ssc[threadIdx.x] = scale[threadIdx.x]; ssh[threadIdx.x] = shift[threadIdx.x]; }
-    const float* img = x + (size_t)b * H * W;
-    for (int i = threadIdx.x; i < 3 * (kStemSeg + 2); i += blockDim.x) {
-        const int r = i / (kStemSeg + 2), c = i - r * (kStemSeg + 2);
-        const int hh = h + r - 1, ww = w0 + c - 1;
-        tile[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (size_t)hh * W + ww) : 0.f;
-    }
-    __syncthreads();
     const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
-    float sc[8], sh[8];
-    *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(&ssc[cg * 8]);
-    *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(&ssc[cg * 8 + 4]);
-    *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(&ssh[cg * 8]);
-    *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(&ssh[cg * 8 + 4]);
-    __nv_bfloat16* yrow = y + (((size_t)b * H + h) * W) * 64;
+    float wr[8][9], sc[8], sh[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[c][t] = __ldg(w + (cg * 8 + c) * 9 + t);
+        sc[c] = __ldg(scale + cg * 8 + c);
+        sh[c] = __ldg(shift + cg * 8 + c);
+    }
+    for (int row = blockIdx.x; row < B * H; row += gridDim.x) {
+        const int b = row / H, h = row - b * H;
+        const float* img = x + (size_t)b * H * W;
+        __nv_bfloat16* yrow = y + ((size_t)row * W) * 64;
+        for (int w0 = 0; w0 < W; w0 += kStemSeg) {
+            __syncthreads();                                     // previous segment fully consumed
+            for (int i = threadIdx.x; i < 3 * (kStemSeg + 2); i += blockDim.x) {
+                const int r = i / (kStemSeg + 2), c = i - r * (kStemSeg + 2);
+                const int hh = h + r - 1, ww = w0 + c - 1;
+                tile[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(img + (size_t)hh * W + ww) : 0.f;
+            }
+            __syncthreads();
 #pragma unroll 1
-    for (int it = 0; it < kStemSeg / 32; ++it) {
-        const int px = it * 32 + pl;
-        const int wq = w0 + px;
-        if (wq >= W) break;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int it = 0; it < kStemSeg / 32; ++it) {
+                const int px = it * 32 + pl;
+                const int wq = w0 + px;
+                if (wq >= W) break;
+                float in[9];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
+                for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float v = tile[kh][px + kw];
-                const float4 wa = *reinterpret_cast<const float4*>(&sw[kh * 3 + kw][cg * 8]);
-                const float4 wb = *reinterpret_cast<const float4*>(&sw[kh * 3 + kw][cg * 8 + 4]);
-                acc[0] = fmaf(v, wa.x, acc[0]); acc[1] = fmaf(v, wa.y, acc[1]); acc[2] = fmaf(v, wa.z, acc[2]); acc[3] = fmaf(v, wa.w, acc[3]);
-                acc[4] = fmaf(v, wb.x, acc[4]); acc[5] = fmaf(v, wb.y, acc[5]); acc[6] = fmaf(v, wb.z, acc[6]); acc[7] = fmaf(v, wb.w, acc[7]);
+                    for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = tile[kh][px + kw];
+                uint32_t pk[4];
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) { a0 = fmaf(in[t], wr[c][t], a0); a1 = fmaf(in[t], wr[c + 1][t], a1); }
+                    a0 = fmaf(a0, sc[c], sh[c]);
+                    a1 = fmaf(a1, sc[c + 1], sh[c + 1]);
+                    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                    pk[c >> 1] = pack_bf16x2(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(yrow + (size_t)wq * 64 + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         }
-        uint32_t pk[4];
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-            float a0 = fmaf(acc[c], sc[c], sh[c]);
-            float a1 = fmaf(acc[c + 1], sc[c + 1], sh[c + 1]);
-            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            pk[c >> 1] = pack_bf16x2(a0, a1);
-        }
-        *reinterpret_cast<uint4*>(yrow + (size_t)wq * 64 + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -167,8 +168,9 @@ int hctr_stem_conv_fwd(const float* x, const float* w, const float* scale, const
     HCTR_CHECK(x && w && scale && shift && y, HCTR_ERR_INVALID, "stem: null pointer");
     HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "stem: empty tensor");
     HCTR_CHECK(al16(y), HCTR_ERR_INVALID, "stem: output must be 16-byte aligned");
-    HCTR_CHECK(H <= 65535 && B <= 65535, HCTR_ERR_INVALID, "stem: H and B must be <= 65535");
-    dim3 grid((W + kStemSeg - 1) / kStemSeg, H, B);
+    long long rows = (long long)B * H;
+    HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "stem: too many rows");
+    const int grid = (int)(rows < 148 * 16 ? rows : 148 * 16);
     stem_conv_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, w, scale, shift, static_cast<__nv_bfloat16*>(y), B, H, W, relu);
     HCTR_CUDA(cudaGetLastError());

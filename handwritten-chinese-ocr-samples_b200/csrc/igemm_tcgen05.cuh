@@ -11,8 +11,9 @@
 // channels in TMEM; the two sub-tiles are either the two rows of a (2,1) max-pool pair
 // (:123,129,136,143,150) or two adjacent 128-pixel spans of a line (classifier, :172-176).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> BN/ReLU/pool or bias -> global).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> BN/ReLU/pool or bias -> global); a warp may only read the TMEM lane
+// quarter (warp % 4), so the eight epilogue warps form two groups that split the accumulator columns.
 #pragma once
 #include "common.cuh"
 
@@ -21,7 +22,8 @@ namespace hctr {
 constexpr int kTileM = 128;          // pixels per accumulator (UMMA M)
 constexpr int kBlockK = 64;          // bf16 elements per K block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kIgemmThreads = 192;
+constexpr int kEpiWarps = 8;           // two warps per TMEM lane quarter, each draining half of the columns
+constexpr int kIgemmThreads = 64 + kEpiWarps * 32;
 constexpr int kMaxTaps = 9;
 
 enum : int { EPI_CONV = 0, EPI_LINEAR = 1 };
@@ -88,7 +90,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -166,8 +168,9 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 2..9)
         const int quad = warp & 3;                      // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;               // which half of the accumulator columns this warp drains
         const int pix = quad * 32 + lane;               // pixel within the 128-px sub-tile
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -184,7 +187,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
 
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int c0 = half * (BLOCK_N / 2); c0 < (half + 1) * (BLOCK_N / 2); c0 += 32) {
                 const int n0 = n_tile * BLOCK_N + c0;
                 if (n0 >= p.N) break;                    // warp-uniform
                 float v[NUM_SUB][32];
