@@ -14,7 +14,16 @@
 
 namespace hctr {
 
-constexpr int kStatPix = 2048;      // pixels per reduction slice (same slicing as the SE squeeze)
+constexpr int kStatPixMax = 2048;   // upper bound of pixels per reduction slice
+
+// Pixels per slice so that B*slices gives ~8 blocks per SM even for the 2-lines-per-GPU training shape.
+__host__ __device__ inline int stat_pix_per_slice(int B, int HW) {
+    long long per = ((long long)B * HW + 1183) / 1184;
+    per = (per + 31) / 32 * 32;
+    if (per < 128) per = 128;
+    if (per > kStatPixMax) per = kStatPixMax;
+    return (int)per;
+}
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {       // lowbias32
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -37,12 +46,12 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // ---------------------------------------------------------------- per-(b, slice, c) sum and sum of squares
 __global__ void __launch_bounds__(256)
 chan_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ psum, float* __restrict__ psq, int HW, int C,
-                  int slices) {
+                  int slices, int pix_per_slice) {
     extern __shared__ float red[];                         // [2][groups][C]
     const int b = blockIdx.y, slice = blockIdx.x;
     const int vpp = C >> 3, groups = blockDim.x / vpp;
     const int g = threadIdx.x / vpp, v = threadIdx.x - g * vpp;
-    const int p0 = slice * kStatPix, p1 = min(p0 + kStatPix, HW);
+    const int p0 = slice * pix_per_slice, p1 = min(p0 + pix_per_slice, HW);
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const __nv_bfloat16* base = x + ((size_t)b * HW) * C + v * 8;
     for (int p = p0 + g; p < p1; p += groups) {
@@ -65,26 +74,42 @@ chan_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ psum,
 }
 
 // ---------------------------------------------------------------- BN batch statistics -> scale/shift (+running stats)
-// One thread per channel. line_sum[b][c] = sum over (h,w) of z (used by the SE squeeze and by the backward).
-__global__ void bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int B, int slices,
-                                   int C, int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out, float* __restrict__ scale_out,
-                                   float* __restrict__ shift_out, float* __restrict__ line_sum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// One block = 32 channels x 8 partial workers; the workers split the slices of a line, their partials are combined in a
+// fixed order. line_sum[b][c] = sum over (h,w) of z (used by the SE squeeze and by the backward).
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int B, int slices,
+                   int C, int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, float momentum, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, float* __restrict__ mean_out,
+                   float* __restrict__ invstd_out, float* __restrict__ scale_out,
+                   float* __restrict__ shift_out, float* __restrict__ line_sum) {
+    __shared__ float ps[8][32];
+    __shared__ double pq[8][32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
     double s = 0.0, q = 0.0;
     for (int b = 0; b < B; ++b) {
         float ls = 0.f;
-        for (int i = 0; i < slices; ++i) {
-            const size_t o = ((size_t)b * slices + i) * C + c;
-            ls += psum[o];
-            q += (double)psq[o];
+        double lq = 0.0;
+        if (c < C) {
+            for (int i = part; i < slices; i += 8) {
+                const size_t o = ((size_t)b * slices + i) * C + c;
+                ls += psum[o];
+                lq += (double)psq[o];
+            }
         }
-        if (line_sum) line_sum[(size_t)b * C + c] = ls;
-        s += (double)ls;
+        ps[part][lane] = ls; pq[part][lane] = lq;
+        __syncthreads();
+        if (part == 0 && c < C) {
+            float t = 0.f; double u = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { t += ps[k][lane]; u += pq[k][lane]; }
+            if (line_sum) line_sum[(size_t)b * C + c] = t;
+            s += (double)t; q += u;
+        }
+        __syncthreads();
     }
+    if (part != 0 || c >= C) return;
     const double n = (double)B * (double)HW;
     const double mean = s / n;
     double var = q / n - mean * mean;                      // biased variance (normalisation)
@@ -113,6 +138,7 @@ struct ApplyParams {
     int relu, pool;
     float drop_p;                // 0 = off
     uint32_t seed;
+    int vshift;                  // log2(C/8)
 };
 
 template <bool POOL>
@@ -135,46 +161,53 @@ __device__ __forceinline__ void apply_pre(const ApplyParams& p, size_t zoff, int
     }
 }
 
+// Work decomposition of the apply kernels: blockIdx.y walks the rows (b, h) of the iterated tensor, blockIdx.x splits a
+// row of W * C/8 16-byte vectors into segments. C/8 is a power of two and divides the block size, so a thread keeps the
+// same channel group for its whole life: the per-channel operands are loaded once, and no integer division runs in
+// the element loop.
 __global__ void __launch_bounds__(256)
 train_apply_fwd_kernel(ApplyParams p, __nv_bfloat16* __restrict__ out) {
     const int vpp = p.C >> 3;
     const int Ho = p.pool ? p.H / 2 : p.H;
-    const long long nvec = (long long)p.B * Ho * p.W * vpp;
+    const int rowlen = p.W * vpp;
     const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
     const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const int cv = (int)(i % vpp);
-        long long pix = i / vpp;
-        const int w = (int)(pix % p.W); pix /= p.W;
-        const int ho = (int)(pix % Ho);
-        const int b = (int)(pix / Ho);
-        const int c0 = cv * 8;
-        float sc[8], sh[8];
-        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
-        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-        *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
-        *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
-        float v[8];
-        if (p.pool) {
-            float v1[8];
-            const size_t o0 = (((size_t)b * p.H + 2 * ho) * p.W + w) * p.C + c0;
-            apply_pre<true>(p, o0, b, c0, v, sc, sh);
-            apply_pre<true>(p, o0 + (size_t)p.W * p.C, b, c0, v1, sc, sh);
+    const int cv = threadIdx.x & (vpp - 1);
+    const int c0 = cv * 8;
+    float sc[8], sh[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    const int seg_len = ((rowlen + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+    const int j0 = blockIdx.x * seg_len, j1 = min(rowlen, j0 + seg_len);
+    for (int row = blockIdx.y; row < p.B * Ho; row += gridDim.y) {
+        const int b = row / Ho, ho = row - b * Ho;
+        const size_t obase = (size_t)row * rowlen;                       // output vector index of (row, j=0)
+        for (int j = j0 + threadIdx.x; j < j1; j += 256) {
+            const int w = j >> p.vshift;
+            float v[8];
+            if (p.pool) {
+                float v1[8];
+                const size_t o0 = (((size_t)b * p.H + 2 * ho) * p.W + w) * p.C + c0;
+                apply_pre<true>(p, o0, b, c0, v, sc, sh);
+                apply_pre<true>(p, o0 + (size_t)p.W * p.C, b, c0, v1, sc, sh);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v1[j]);
-        } else {
-            apply_pre<false>(p, (((size_t)b * p.H + ho) * p.W + w) * p.C + c0, b, c0, v, sc, sh);
-        }
-        if (p.relu) {
+                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], v1[q]);
+            } else {
+                apply_pre<false>(p, ((size_t)row * p.W + w) * p.C + c0, b, c0, v, sc, sh);
+            }
+            if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.drop_p > 0.f) {
+                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+            }
+            const size_t i = obase + j;
+            if (p.drop_p > 0.f) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = drop_keep((unsigned long long)i * 8 + j, p.seed, thresh) ? v[j] * keep_scale : 0.f;
+                for (int q = 0; q < 8; ++q) v[q] = drop_keep((unsigned long long)i * 8 + q, p.seed, thresh) ? v[q] * keep_scale : 0.f;
+            }
+            *reinterpret_cast<uint4*>(out + i * 8) = pack8(v);
         }
-        *reinterpret_cast<uint4*>(out + (size_t)i * 8) = pack8(v);
     }
 }
 
@@ -238,13 +271,13 @@ __device__ __forceinline__ void bwd_dpre(const ApplyParams& p, const __nv_bfloat
 // per-(b, slice, c): A2 = sum d_pre, A3 = sum d_pre * z
 __global__ void __launch_bounds__(256)
 train_bwd_reduce_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, float* __restrict__ pA2,
-                        float* __restrict__ pA3, int slices) {
+                        float* __restrict__ pA3, int slices, int pix_per_slice) {
     extern __shared__ float red[];
     const int b = blockIdx.y, slice = blockIdx.x;
     const int vpp = p.C >> 3, groups = blockDim.x / vpp;
     const int g = threadIdx.x / vpp, cv = threadIdx.x - g * vpp;
     const int HW = p.H * p.W;
-    const int p0 = slice * kStatPix, p1 = min(p0 + kStatPix, HW);
+    const int p0 = slice * pix_per_slice, p1 = min(p0 + pix_per_slice, HW);
     const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
     const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const int c0 = cv * 8;
@@ -273,10 +306,32 @@ train_bwd_reduce_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, f
     }
 }
 
+// Combine the per-slice partial sums of every (b,c) item into slice 0, in a fixed order (64 items x 4 workers per block).
+__global__ void __launch_bounds__(256)
+bwd_slice_reduce_kernel(float* __restrict__ pA2, float* __restrict__ pA3, int slices, int B, int C) {
+    __shared__ float s2[4][64], s3[4][64];
+    const int li = threadIdx.x & 63, part = threadIdx.x >> 6;
+    const int item = blockIdx.x * 64 + li;
+    const int items = B * C;
+    float x = 0.f, y = 0.f;
+    size_t o0 = 0;
+    if (item < items) {
+        const int b = item / C, c = item - b * C;
+        o0 = ((size_t)b * slices) * C + c;
+        for (int s = part; s < slices; s += 4) { x += pA2[o0 + (size_t)s * C]; y += pA3[o0 + (size_t)s * C]; }
+    }
+    s2[part][li] = x; s3[part][li] = y;
+    __syncthreads();
+    if (part == 0 && item < items) {
+        pA2[o0] = (s2[0][li] + s2[1][li]) + (s2[2][li] + s2[3][li]);
+        pA3[o0] = (s3[0][li] + s3[1][li]) + (s3[2][li] + s3[3][li]);
+    }
+}
+
 // BN (+SE) backward on [B,C]-sized data. One block, threads over channels; the SE FC backward is done by the
 // same block (C <= 512, Cr <= 32).
 struct BwdFinalizeParams {
-    const float* pA2; const float* pA3; int slices;
+    const float* pA2; const float* pA3; int slices;       // slice 0 holds the totals (bwd_slice_reduce_kernel ran first)
     int B, C, HW;
     const float* gamma; const float* mean; const float* invstd; const float* scale; const float* shift;
     const float* line_sum;       // [B][C] sum_hw z (forward)
@@ -299,14 +354,11 @@ train_bwd_finalize_kernel(BwdFinalizeParams p) {
     float* A2 = sm; float* A3 = A2 + p.B * p.C; float* dm = A3 + p.B * p.C; float* du = dm + p.B * p.C;
     float* da = du + p.B * p.C;
     const int tid = threadIdx.x, nt = blockDim.x;
+    // the per-slice partials were already combined into slice 0 by bwd_slice_reduce_kernel (many blocks)
     for (int i = tid; i < p.B * p.C; i += nt) {
         const int b = i / p.C, c = i - b * p.C;
-        float x = 0.f, y = 0.f;
-        for (int s = 0; s < p.slices; ++s) {
-            const size_t o = ((size_t)b * p.slices + s) * p.C + c;
-            x += p.pA2[o]; y += p.pA3[o];
-        }
-        A2[i] = x; A3[i] = y; dm[i] = 0.f;
+        const size_t o = ((size_t)b * p.slices) * p.C + c;
+        A2[i] = p.pA2[o]; A3[i] = p.pA3[o]; dm[i] = 0.f;
     }
     __syncthreads();
     if (p.gate) {
@@ -386,34 +438,38 @@ train_bwd_apply_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, co
                        const float* __restrict__ Q, const float* __restrict__ R, __nv_bfloat16* __restrict__ dz,
                        __nv_bfloat16* __restrict__ dres) {
     const int vpp = p.C >> 3;
-    const long long nvec = (long long)p.B * p.H * p.W * vpp;
+    const int rowlen = p.W * vpp;
     const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
     const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        const int cv = (int)(i % vpp);
-        long long pix = i / vpp;
-        const int w = (int)(pix % p.W); pix /= p.W;
-        const int h = (int)(pix % p.H);
-        const int b = (int)(pix / p.H);
-        const int c0 = cv * 8;
-        float sc[8], sh[8], Pv[8], Qv[8], Rv[8];
-        *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
-        *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-        *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
-        *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    const int cv = threadIdx.x & (vpp - 1);
+    const int c0 = cv * 8;
+    float sc[8], sh[8], Rv[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    *reinterpret_cast<float4*>(Rv) = __ldg(reinterpret_cast<const float4*>(R + c0));
+    *reinterpret_cast<float4*>(Rv + 4) = __ldg(reinterpret_cast<const float4*>(R + c0 + 4));
+    const int seg_len = ((rowlen + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+    const int j0 = blockIdx.x * seg_len, j1 = min(rowlen, j0 + seg_len);
+    for (int row = blockIdx.y; row < p.B * p.H; row += gridDim.y) {
+        const int b = row / p.H, h = row - b * p.H;
+        float Pv[8], Qv[8];
         *reinterpret_cast<float4*>(Pv) = __ldg(reinterpret_cast<const float4*>(P + (size_t)b * p.C + c0));
         *reinterpret_cast<float4*>(Pv + 4) = __ldg(reinterpret_cast<const float4*>(P + (size_t)b * p.C + c0 + 4));
         *reinterpret_cast<float4*>(Qv) = __ldg(reinterpret_cast<const float4*>(Q + (size_t)b * p.C + c0));
         *reinterpret_cast<float4*>(Qv + 4) = __ldg(reinterpret_cast<const float4*>(Q + (size_t)b * p.C + c0 + 4));
-        *reinterpret_cast<float4*>(Rv) = __ldg(reinterpret_cast<const float4*>(R + c0));
-        *reinterpret_cast<float4*>(Rv + 4) = __ldg(reinterpret_cast<const float4*>(R + c0 + 4));
-        float zv[8], d[8], o[8];
-        bwd_dpre(p, dout, b, h, w, c0, thresh, keep_scale, sc, sh, zv, d);
+        const size_t ibase = (size_t)row * rowlen;
+        for (int j = j0 + threadIdx.x; j < j1; j += 256) {
+            const int w = j >> p.vshift;
+            float zv[8], d[8], o[8];
+            bwd_dpre(p, dout, b, h, w, c0, thresh, keep_scale, sc, sh, zv, d);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(Pv[j], d[j], fmaf(Rv[j], zv[j], Qv[j]));
-        *reinterpret_cast<uint4*>(dz + (size_t)i * 8) = pack8(o);
-        if (dres) *reinterpret_cast<uint4*>(dres + (size_t)i * 8) = pack8(d);
+            for (int q = 0; q < 8; ++q) o[q] = fmaf(Pv[q], d[q], fmaf(Rv[q], zv[q], Qv[q]));
+            const size_t i = ibase + j;
+            *reinterpret_cast<uint4*>(dz + i * 8) = pack8(o);
+            if (dres) *reinterpret_cast<uint4*>(dres + i * 8) = pack8(d);
+        }
     }
 }
 
@@ -447,11 +503,14 @@ se_excite_train_kernel(const float* __restrict__ line_sum, const float* __restri
 }
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-static int grid_for(long long nvec) {
-    long long blocks = (nvec + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
+// grid (segments per row, rows): enough blocks for ~8 per SM, at least 256 vectors per block
+static dim3 grid_rows(long long rows, int rowlen) {
+    long long gy = rows < 32768 ? rows : 32768;
+    long long segs = (1184 + gy - 1) / gy;
+    const long long max_segs = (rowlen + 255) / 256;
+    if (segs > max_segs) segs = max_segs;
+    if (segs < 1) segs = 1;
+    return dim3((unsigned)segs, (unsigned)gy);
 }
 
 }  // namespace hctr
@@ -460,15 +519,20 @@ using namespace hctr;
 
 extern "C" {
 
+int hctr_stat_slices(int B, int H, int W) {
+    const int per = stat_pix_per_slice(B, H * W);
+    return (H * W + per - 1) / per;
+}
+
 int hctr_chan_stats(const void* x, float* psum, float* psq, int B, int H, int W, int C, void* stream) {
     HCTR_CHECK(x && psum, HCTR_ERR_INVALID, "chan_stats: null pointer");
     HCTR_CHECK(C % 8 == 0 && C >= 8 && C <= 2048 && 256 % (C / 8) == 0, HCTR_ERR_INVALID, "chan_stats: C/8 must divide 256 (C=%d)", C);
     HCTR_CHECK(al16(x), HCTR_ERR_INVALID, "chan_stats: x must be 16-byte aligned");
-    const int slices = hctr_se_slices(H, W);
+    const int slices = hctr_stat_slices(B, H, W);
     const int groups = 256 / (C / 8);
     dim3 grid(slices, B);
     chan_stats_kernel<<<grid, 256, 2 * (size_t)groups * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), psum, psq, H * W, C, slices);
+        static_cast<const __nv_bfloat16*>(x), psum, psq, H * W, C, slices, stat_pix_per_slice(B, H * W));
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }
@@ -477,7 +541,7 @@ int hctr_bn_finalize_train(const float* psum, const float* psq, int B, int slice
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                            float* mean, float* invstd, float* scale, float* shift, float* line_sum, void* stream) {
     HCTR_CHECK(psum && psq && gamma && beta && mean && invstd && scale && shift, HCTR_ERR_INVALID, "bn_finalize: null pointer");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         psum, psq, B, slices, C, HW, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, line_sum);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
@@ -502,6 +566,9 @@ static int fill_apply(ApplyParams& p, const void* z, const float* scale, const f
     p.z = static_cast<const __nv_bfloat16*>(z); p.scale = scale; p.shift = shift; p.gate = gate;
     p.res = static_cast<const __nv_bfloat16*>(res);
     p.B = B; p.H = H; p.W = W; p.C = C; p.relu = relu; p.pool = pool; p.drop_p = drop_p; p.seed = seed;
+    p.vshift = 0;
+    while ((1 << p.vshift) < C / 8) ++p.vshift;
+    HCTR_CHECK((1 << p.vshift) == C / 8, HCTR_ERR_INVALID, "train_apply: C/8 must be a power of two (C=%d)", C);
     return HCTR_OK;
 }
 
@@ -512,8 +579,8 @@ int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, 
     int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
     if (rc) return rc;
     HCTR_CHECK(out && al16(out), HCTR_ERR_INVALID, "train_apply_fwd: bad output");
-    const long long nvec = (long long)B * (pool ? H / 2 : H) * W * (C / 8);
-    train_apply_fwd_kernel<<<grid_for(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, static_cast<__nv_bfloat16*>(out));
+    train_apply_fwd_kernel<<<grid_rows((long long)B * (pool ? H / 2 : H), W * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, static_cast<__nv_bfloat16*>(out));
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }
@@ -525,11 +592,11 @@ int hctr_train_bwd_reduce(const void* dout, const void* z, const float* scale, c
     int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
     if (rc) return rc;
     HCTR_CHECK(dout && pA2 && pA3 && al16(dout), HCTR_ERR_INVALID, "train_bwd_reduce: null pointer");
-    const int slices = hctr_se_slices(H, W);
+    const int slices = hctr_stat_slices(B, H, W);
     const int groups = 256 / (C / 8);
     dim3 grid(slices, B);
     train_bwd_reduce_kernel<<<grid, 256, 2 * (size_t)groups * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        p, static_cast<const __nv_bfloat16*>(dout), pA2, pA3, slices);
+        p, static_cast<const __nv_bfloat16*>(dout), pA2, pA3, slices, stat_pix_per_slice(B, H * W));
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }
@@ -554,6 +621,9 @@ int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int 
         HCTR_CUDA(cudaFuncSetAttribute(train_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
+    bwd_slice_reduce_kernel<<<(B * C + 63) / 64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        const_cast<float*>(pA2), const_cast<float*>(pA3), slices, B, C);
+    HCTR_CUDA(cudaGetLastError());
     train_bwd_finalize_kernel<<<1, 512, smem, static_cast<cudaStream_t>(stream)>>>(p);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
@@ -567,8 +637,7 @@ int hctr_train_bwd_apply(const void* dout, const void* z, const float* scale, co
     if (rc) return rc;
     HCTR_CHECK(dout && P && Q && R && dz && al16(dout) && al16(dz) && al16(dres) && al16(P) && al16(Q) && al16(R),
                HCTR_ERR_INVALID, "train_bwd_apply: bad pointer");
-    const long long nvec = (long long)B * H * W * (C / 8);
-    train_bwd_apply_kernel<<<grid_for(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    train_bwd_apply_kernel<<<grid_rows((long long)B * H, W * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         p, static_cast<const __nv_bfloat16*>(dout), P, Q, R, static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dres));
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;

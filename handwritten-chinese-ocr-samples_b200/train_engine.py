@@ -71,7 +71,7 @@ class TrainEngine(object):
             w = conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
             nat.check(lib.hctr_conv_bn_act_fwd(nat.ptr(x), nat.ptr(w), nat.ptr(self.ones(cout, dev)), nat.ptr(bias), nat.ptr(z),
                                                B, H, W, cin, cout, k, 0, 0, st), "conv")
-        slices = lib.hctr_se_slices(H, W)
+        slices = lib.hctr_stat_slices(B, H, W)
         psum = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
         psq = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
         nat.check(lib.hctr_chan_stats(nat.ptr(z), nat.ptr(psum), nat.ptr(psq), B, H, W, cout, st), "chan_stats")
@@ -110,7 +110,7 @@ class TrainEngine(object):
         """dout: gradient wrt the unit's output. Fills grads[...] for conv/bn(/se) and returns (dx, dres)."""
         lib, st, dev = self.lib, nat.stream_ptr(), conv.weight.device
         B, H, W, C = s.B, s.H, s.W, s.cout
-        slices = lib.hctr_se_slices(H, W)
+        slices = lib.hctr_stat_slices(B, H, W)
         a2 = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
         a3 = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
         nat.check(lib.hctr_train_bwd_reduce(nat.ptr(dout), nat.ptr(s.z), nat.ptr(s.scale), nat.ptr(s.shift), nat.ptr(s.gate),

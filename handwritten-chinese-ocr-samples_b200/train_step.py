@@ -69,6 +69,7 @@ class TrainStep(object):
         self.norm = torch.zeros((2,), dtype=torch.float32, device=dev)        # {total_norm, clip coefficient}
         self._ws = torch.empty((nat.lib().hctr_sgd_workspace_bytes(),), dtype=torch.uint8, device=dev)
         self.steps = 0
+        self._pin = None
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
 
     def step(self, x, targets, target_lengths, seed=None):
@@ -86,8 +87,16 @@ class TrainStep(object):
             C = m.noutput
             tl_host = target_lengths.cpu() if isinstance(target_lengths, torch.Tensor) else torch.as_tensor(target_lengths)
             max_l = int(tl_host.max().item())
-            tg = torch.as_tensor(targets).to(device=dev, dtype=torch.int32)
-            tl = tl_host.to(device=dev, dtype=torch.int32)
+            # labels travel through pinned staging buffers with async copies: a pageable H2D would block the host until
+            # every kernel of the previous step has finished and serialise CPU enqueue with GPU execution
+            tg_host = torch.as_tensor(targets).to(torch.int32)
+            n_t = tg_host.numel()
+            if self._pin is None or self._pin.numel() < n_t + B:
+                self._pin = torch.empty((max(4096, 2 * (n_t + B)),), dtype=torch.int32).pin_memory()
+            self._pin[:n_t].copy_(tg_host.reshape(-1))
+            self._pin[n_t:n_t + B].copy_(tl_host.to(torch.int32).reshape(-1))
+            staged = self._pin[:n_t + B].to(dev, non_blocking=True)
+            tg, tl = staged[:n_t], staged[n_t:n_t + B]
             il = torch.full((B,), W, dtype=torch.int32, device=dev)            # preds_sizes = [T]*B (main.py:388)
             nll = torch.empty((B,), dtype=torch.float32, device=dev)
             loss = torch.empty((1,), dtype=torch.float32, device=dev)

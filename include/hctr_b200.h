@@ -133,7 +133,9 @@ long long hctr_ctc_loss_workspace_bytes(int T, int B, int max_target_len);
 
 /* Per-(line, slice, channel) sum and sum of squares of an NHWC bf16 tensor (fixed order, deterministic): the batch
  * statistics of nn.BatchNorm2d in train() (models/handwritten_ctr_model.py:38,40,74-92) and the SE squeeze (:27-28)
- * come from the same pass. psum/psq: fp32 [B][hctr_se_slices(H,W)][C]; psq may be NULL. */
+ * come from the same pass. psum/psq: fp32 [B][hctr_stat_slices(B,H,W)][C]; psq may be NULL. The slice size adapts to B
+ * so that even 2 lines per GPU fill the SMs. */
+int hctr_stat_slices(int B, int H, int W);
 int hctr_chan_stats(const void* x, float* psum, float* psq, int B, int H, int W, int C, void* stream);
 /* Batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale; updates running stats with
  * `momentum` and the unbiased variance (pass NULL to skip); line_sum: fp32 [B][C] = sum over (h,w) (may be NULL). */
@@ -155,6 +157,7 @@ int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, 
 int hctr_train_bwd_reduce(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
                           const void* res, float* pA2, float* pA3, int B, int H, int W, int C, int relu, int pool,
                           float drop_p, unsigned seed, void* stream);
+/* (finalize combines the per-slice partials in place: slice 0 of pA2/pA3 is overwritten with the totals) */
 int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int B, int C, int HW, const float* gamma,
                             const float* mean, const float* invstd, const float* scale, const float* shift,
                             const float* line_sum, const float* gate, const float* se_hidden, const float* se_mean,

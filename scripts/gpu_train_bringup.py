@@ -66,7 +66,7 @@ def pointwise_case(B, H, W, C, gate, res, relu, pool):
     # ours
     zn = z.permute(0, 2, 3, 1).contiguous(); rn = r.permute(0, 2, 3, 1).contiguous() if res else None
     dn = dout.permute(0, 2, 3, 1).contiguous()
-    slices = lib.hctr_se_slices(H, W)
+    slices = lib.hctr_stat_slices(B, H, W)
     ps = torch.empty(B, slices, C, device=dev); pq = torch.empty(B, slices, C, device=dev)
     nat.check(lib.hctr_chan_stats(nat.ptr(zn), nat.ptr(ps), nat.ptr(pq), B, H, W, C, S()))
     mean = torch.empty(C, device=dev); invstd = torch.empty(C, device=dev); scale = torch.empty(C, device=dev); shift = torch.empty(C, device=dev)

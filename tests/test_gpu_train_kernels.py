@@ -91,7 +91,7 @@ def test_bn_se_act_unit_forward_backward(B, H, W, C, gate, res, relu, pool):
     y.backward(dout.float())
     zn = z.permute(0, 2, 3, 1).contiguous(); rn = r.permute(0, 2, 3, 1).contiguous() if res else None
     dn = dout.permute(0, 2, 3, 1).contiguous()
-    slices = lib.hctr_se_slices(H, W)
+    slices = lib.hctr_stat_slices(B, H, W)
     ps = torch.empty(B, slices, C, device=dev); pq = torch.empty(B, slices, C, device=dev)
     nat.check(lib.hctr_chan_stats(nat.ptr(zn), nat.ptr(ps), nat.ptr(pq), B, H, W, C, S()))
     st = torch.empty(4, C, device=dev); line = torch.empty(B, C, device=dev)
