@@ -29,9 +29,17 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {       // lowbias32
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
     return x;
 }
-// keep-mask of the dropout for output element `idx` (counter-based: forward and backward regenerate it)
-__device__ __forceinline__ bool drop_keep(unsigned long long idx, uint32_t seed, uint32_t thresh) {
-    const uint32_t h = hash32(static_cast<uint32_t>(idx) ^ hash32(seed + static_cast<uint32_t>(idx >> 32) * 0x9E3779B9u));
+// Counter-based dropout: the keep-mask of output element (vector index `vec`, lane q in 0..7) is a pure function of
+// (seed, vec, q), so forward and backward regenerate it instead of storing a mask. One full avalanche hash per 16-byte
+// vector, then a 3-instruction finalizer per element.
+__device__ __forceinline__ uint32_t drop_base(unsigned long long vec, uint32_t seed) {
+    return hash32(static_cast<uint32_t>(vec) ^ hash32(seed + static_cast<uint32_t>(vec >> 32) * 0x9E3779B9u));
+}
+__device__ __forceinline__ bool drop_keep(uint32_t base, int q, uint32_t thresh) {
+    uint32_t h = (base ^ (static_cast<uint32_t>(q + 1) * 0x9E3779B9u)) * 0x2C1B3C6Du;
+    h ^= h >> 15;
+    h *= 0x297A2D39u;
+    h ^= h >> 16;
     return h >= thresh;
 }
 
@@ -203,8 +211,9 @@ train_apply_fwd_kernel(ApplyParams p, __nv_bfloat16* __restrict__ out) {
             }
             const size_t i = obase + j;
             if (p.drop_p > 0.f) {
+                const uint32_t base = drop_base(i, p.seed);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = drop_keep((unsigned long long)i * 8 + q, p.seed, thresh) ? v[q] * keep_scale : 0.f;
+                for (int q = 0; q < 8; ++q) v[q] = drop_keep(base, q, thresh) ? v[q] * keep_scale : 0.f;
             }
             *reinterpret_cast<uint4*>(out + i * 8) = pack8(v);
         }
@@ -256,20 +265,21 @@ __device__ __forceinline__ void bwd_dpre(const ApplyParams& p, const __nv_bfloat
         for (int i = 0; i < 8; ++i) sel[i] = true;
     }
     const int Ho = p.pool ? p.H / 2 : p.H;
-    const size_t oidx = ((((size_t)b * Ho + ho) * p.W + w) * vpp + (c0 >> 3)) * 8;
+    const size_t ovec = (((size_t)b * Ho + ho) * p.W + w) * vpp + (c0 >> 3);
     float g[8];
-    unpack8(ld_nc_v4(dout + oidx), g);
+    unpack8(ld_nc_v4(dout + ovec * 8), g);
+    const uint32_t dbase = p.drop_p > 0.f ? drop_base(ovec, p.seed) : 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float t = g[i];
-        if (p.drop_p > 0.f) t = drop_keep((unsigned long long)oidx + i, p.seed, thresh) ? t * keep_scale : 0.f;
+        if (p.drop_p > 0.f) t = drop_keep(dbase, i, thresh) ? t * keep_scale : 0.f;
         if (p.relu && !(v[i] > 0.f)) t = 0.f;
         d[i] = sel[i] ? t : 0.f;
     }
 }
 
 // per-(b, slice, c): A2 = sum d_pre, A3 = sum d_pre * z
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 train_bwd_reduce_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, float* __restrict__ pA2,
                         float* __restrict__ pA3, int slices, int pix_per_slice) {
     extern __shared__ float red[];
@@ -287,8 +297,9 @@ train_bwd_reduce_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, f
     *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
     *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
     float a2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a3[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int px = p0 + g; px < p1; px += groups) {
-        const int h = px / p.W, w = px - h * p.W;
+    int h = (p0 + g) / p.W, w = (p0 + g) - h * p.W;
+    for (int px = p0 + g; px < p1; px += groups, w += groups) {
+        while (w >= p.W) { w -= p.W; ++h; }
         float zv[8], d[8];
         bwd_dpre(p, dout, b, h, w, c0, thresh, keep_scale, sc, sh, zv, d);
 #pragma unroll
@@ -433,7 +444,7 @@ train_bwd_finalize_kernel(BwdFinalizeParams p) {
 }
 
 // dz = P*d_pre + Q + R*z ; dres = d_pre
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 train_bwd_apply_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, const float* __restrict__ P,
                        const float* __restrict__ Q, const float* __restrict__ R, __nv_bfloat16* __restrict__ dz,
                        __nv_bfloat16* __restrict__ dres) {
