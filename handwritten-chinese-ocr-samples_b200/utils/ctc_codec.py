@@ -71,10 +71,7 @@ class ctc_codec(object):
             return []               # reference: zero-length samples are skipped (utils/ctc_codec.py:85-86)
         logits = self._as_device_logits(preds)
         if self.use_beam_search:
-            if self.skip_search:
-                raise NotImplementedError("hctr_b200: __cbs_skip__ (skip_search=True) is not built; "
-                                          "use skip_search=False (reference: utils/ctc_codec.py:124-181)")
-            idx, ln = self.beam_search_indices(logits)
+            idx, ln = self.skip_search_indices(logits) if self.skip_search else self.beam_search_indices(logits)
         else:
             idx, ln = self.greedy_indices(logits)
         return self.indices_to_text(idx, ln)
@@ -156,6 +153,37 @@ class ctc_codec(object):
             self.lm_table = table
         else:
             self.lm_table = None        # zero LM
+
+    def skip_search_indices(self, logits):
+        """__cbs_skip__ on the device (reference: utils/ctc_codec.py:124-181)."""
+        nat = _core().native
+        lib = nat.lib()
+        T, B, C = logits.shape
+        if C != len(self.characters):
+            raise ValueError("logits have %d classes but the codec has %d" % (C, len(self.characters)))
+        dev = logits.device
+        with torch.cuda.device(dev):
+            idx = torch.zeros((B, T), dtype=torch.int32, device=dev)
+            ln = torch.zeros((B,), dtype=torch.int32, device=dev)
+            status = torch.zeros((B,), dtype=torch.int32, device=dev)
+            table = None
+            if self.lm_table is not None:
+                table = torch.from_numpy(np.ascontiguousarray(self.lm_table, dtype=np.float64)).to(dev)
+            nb = lib.hctr_ctc_skip_workspace_bytes(T, B)
+            ws = torch.empty((max(nb, 8) + 256,), dtype=torch.uint8, device=dev)
+            off = (-ws.data_ptr()) % 256
+            nat.check(lib.hctr_ctc_skip_beam_search(
+                nat.ptr(logits), self._dtype_code(nat, logits), T, B, C, logits.stride(0), logits.stride(1),
+                int(self.beam_size), float(self.lm_panelty), float(self.len_bonus), nat.ptr(table), nat.ptr(idx), nat.ptr(ln),
+                nat.ptr(status), nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()), "ctc_skip_beam_search")
+            st = status.cpu()
+            if T == 0 or bool((st == nat.HCTR_ERR_INDEX).any()) or bool((st == -1).any()):
+                raise IndexError("list index out of range")     # reference: utils/ctc_codec.py:139,179
+            if bool((st != 0).any()):
+                raise NotImplementedError("hctr_b200: a time step has more than %d classes above the 0.001 prune "
+                                          "threshold; the device skip-search holds at most that many candidates"
+                                          % lib.hctr_ctc_skip_max_candidates())
+        return idx, ln
 
     def beam_search_indices(self, logits):
         """__cbs_full__ on the device: fused log-softmax + top-k, then one CTA per sequence."""

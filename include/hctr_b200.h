@@ -117,6 +117,17 @@ int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp,
 /* bytes of caller-owned device scratch (greedy look-ahead list + prefix trie) for the call above */
 long long hctr_ctc_beam_workspace_bytes(int T, int B, int beam_size);
 
+/* ctc_codec.__cbs_skip__ (utils/ctc_codec.py:124-181): candidates per step are the classes with log-prob > log(0.001)
+ * in index order; a single candidate takes the reference's in-place fast path (quirks included), otherwise a
+ * duplicate-aware context beam search runs over the candidates. Fused log-softmax/prune pre-pass + one CTA per sequence.
+ * status[b]: 0 ok; HCTR_ERR_INDEX where the reference raises IndexError (empty greedy path :139, or a step without any
+ * candidate :179); HCTR_ERR_UNSUPPORTED if a step has more than hctr_ctc_skip_max_candidates() candidates. */
+int hctr_ctc_skip_beam_search(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
+                              int beam_size, double lm_penalty, double len_bonus, const double* lm_table, int32_t* out_idx,
+                              int32_t* out_len, int32_t* status, void* workspace, long long workspace_bytes, void* stream);
+long long hctr_ctc_skip_workspace_bytes(int T, int B);
+int hctr_ctc_skip_max_candidates(void);
+
 /* CTCLoss(blank=0, reduction='mean', zero_infinity=True) on log_softmax(logits) and its gradient wrt the
  * logits (main.py:205,406-409,426). logits element (t,b,c) at logits[t*stride_t + b*stride_b + c];
  * targets: int32 concatenated [sum L]; target_lengths/input_lengths: int32 [B].

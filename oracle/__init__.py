@@ -53,6 +53,8 @@ def _c():
         L.oracle_topk_row.restype = None
         L.oracle_ctc_beam_search.argtypes = [P, P, I, I, I, I, I, D, D, P, P, P, P]
         L.oracle_ctc_beam_search.restype = I
+        L.oracle_ctc_beam_search_skip.argtypes = [P, P, I, I, I, I, D, D, P, P, P, P]
+        L.oracle_ctc_beam_search_skip.restype = I
         L.oracle_ctc_loss.argtypes = [P, I, I, I, P, P, P, P, P]
         L.oracle_ctc_loss.restype = D
         _lib = L
@@ -108,6 +110,21 @@ def beam_search(logits, beam_size=10, search_depth=10, lm_penalty=2.0, len_bonus
     tab = None if lm_table is None else np.ascontiguousarray(lm_table, dtype=np.float64)
     _c().oracle_ctc_beam_search(_p(logp), _p(tk), T, B, C, search_depth, beam_size, float(lm_penalty), float(len_bonus),
                                 _p(tab), _p(idx), _p(ln), _p(st))
+    return idx, ln, st
+
+
+def beam_search_skip(logits, beam_size=10, lm_penalty=2.0, len_bonus=5.8, lm_table=None):
+    """decode() with skip_search=True: log_softmax -> __cbs_skip__. Returns (idx [B,T], length [B], status [B])."""
+    logits = np.ascontiguousarray(logits, dtype=np.float32)
+    T, B, C = logits.shape
+    logp = log_softmax(logits)
+    top1 = np.ascontiguousarray(np.argmax(logp, axis=2).astype(np.int32))
+    idx = np.zeros((B, T), np.int32)
+    ln = np.zeros((B,), np.int32)
+    st = np.zeros((B,), np.int32)
+    tab = None if lm_table is None else np.ascontiguousarray(lm_table, dtype=np.float64)
+    _c().oracle_ctc_beam_search_skip(_p(logp), _p(top1), T, B, C, beam_size, float(lm_penalty), float(len_bonus), _p(tab),
+                                     _p(idx), _p(ln), _p(st))
     return idx, ln, st
 
 

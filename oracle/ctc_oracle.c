@@ -223,6 +223,131 @@ int oracle_ctc_beam_search(const float* logp, const int32_t* topk, int T, int B,
     return rc;
 }
 
+/* One __context_beam_search__ step (utils/ctc_codec.py:212-285) over an explicit candidate list (shared by the full and
+ * the skip search). kept/nkept are replaced by the surviving beams. */
+static void context_step(Beam* kept, int* nkept_io, Beam* gen, int* order, const float* lp, const int32_t* cand, int ncand,
+                         int unknown, int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                         const int32_t* suffix, int nsuf, int cap) {
+    int nkept = *nkept_io, ngen = 0;
+    for (int j = 0; j < nkept; ++j) {
+        const Beam* in = &kept[j];
+        const double P = beam_prob(in);
+        const int tail = in->len ? in->prefix[in->len - 1] : -1;
+        for (int q = 0; q < ncand; ++q) {
+            const int idx = cand[q];
+            if (idx >= unknown) continue;
+            const double p = (double)lp[idx];
+            int self = find_beam(gen, ngen, in->prefix, in->len, -1);
+            if (self < 0) { self = new_beam(gen, ngen, in->prefix, in->len, -1, cap); ++ngen; }
+            if (idx == 0) { gen[self].pb = logaddexp_d(gen[self].pb, P + p); continue; }
+            int ext = find_beam(gen, ngen, in->prefix, in->len, idx);
+            if (ext < 0) { ext = new_beam(gen, ngen, in->prefix, in->len, idx, cap); ++ngen; }
+            if (idx != tail) {
+                gen[ext].pnb = logaddexp_d(gen[ext].pnb, P + p);
+            } else {
+                gen[ext].pnb = logaddexp_d(gen[ext].pnb, in->pb + p);
+                gen[self].pnb = logaddexp_d(gen[self].pnb, in->pnb + p);
+            }
+        }
+    }
+    for (int i = 0; i < ngen; ++i) {
+        double lm = 0.0;
+        if (lm_table) {
+            for (int c = 0; c < gen[i].len; ++c) lm += lm_table[gen[i].prefix[c]];
+            for (int c = 0; c < nsuf; ++c) lm += lm_table[suffix[c]];
+        }
+        gen[i].pt = lm * lm_penalty + (double)gen[i].len * len_bonus;
+    }
+    for (int i = 0; i < ngen; ++i) order[i] = i;
+    for (int i = 1; i < ngen; ++i) {
+        const int cur = order[i];
+        const double tv = beam_total(&gen[cur]);
+        int j2 = i - 1;
+        while (j2 >= 0 && beam_total(&gen[order[j2]]) < tv) { order[j2 + 1] = order[j2]; --j2; }
+        order[j2 + 1] = cur;
+    }
+    for (int j = 0; j < nkept; ++j) { free(kept[j].prefix); kept[j].prefix = NULL; }
+    const int keep = ngen < beam_size ? ngen : beam_size;
+    for (int j = 0; j < keep; ++j) { kept[j] = gen[order[j]]; gen[order[j]].prefix = NULL; }
+    for (int i = 0; i < ngen; ++i) if (gen[i].prefix) { free(gen[i].prefix); gen[i].prefix = NULL; }
+    *nkept_io = keep;
+}
+
+/* ctc_codec.__cbs_skip__ (utils/ctc_codec.py:124-181): candidates at step t are ALL classes with log-prob > log(0.001)
+ * in index order (:144); exactly one candidate -> the in-place fast path (:147-171, with its quirks: a blank step leaves
+ * pnb untouched, no merging of equal prefixes); otherwise the normal context beam search over those candidates. A step
+ * without any candidate empties the beam list and the reference ends in IndexError (:179) -> status -4.
+ * top1: [T][B] arg-max class per step (the reference takes it from the arg-sort, :128-134). */
+int oracle_ctc_beam_search_skip(const float* logp, const int32_t* top1, int T, int B, int C, int beam_size,
+                                double lm_penalty, double len_bonus, const double* lm_table, int32_t* out_idx,
+                                int32_t* out_len, int32_t* status) {
+    const int unknown = C - 1;
+    const double thresh = log(0.001);                         /* prune_thresh = np.log(0.001)  :129 */
+    int rc = 0;
+    const int max_gen = beam_size * (C + 1) + 1 < 200000 ? beam_size * (C + 1) + 1 : 200000;
+    int32_t* g_char = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T + 1));
+    int32_t* g_time = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T + 1));
+    int32_t* cand = (int32_t*)malloc(sizeof(int32_t) * (size_t)C);
+    Beam* kept = (Beam*)calloc((size_t)max_gen, sizeof(Beam));
+    Beam* gen = (Beam*)calloc((size_t)max_gen, sizeof(Beam));
+    int* order = (int*)malloc(sizeof(int) * (size_t)max_gen);
+    for (int b = 0; b < B; ++b) {
+        int ng = 0, prev = -1;
+        for (int t = 0; t < T; ++t) {
+            const int cur = top1[(size_t)t * B + b];
+            if (cur != 0 && cur != unknown && !(t > 0 && prev == cur)) { g_char[ng] = cur; g_time[ng] = t; ++ng; }
+            prev = cur;
+        }
+        if (ng == 0) { status[b] = -4; out_len[b] = 0; rc = -4; continue; }
+        status[b] = 0;
+        int end_step = g_time[ng - 1] + 4;
+        if (end_step >= T) end_step = T;
+        int nkept = 1;
+        new_beam(kept, 0, NULL, 0, -1, T);
+        kept[0].pb = 0.0; kept[0].pnb = NEG_INF; kept[0].pt = 0.0;
+        int gptr = 0;
+        for (int t = 0; t < end_step; ++t) {
+            const float* lp = logp + ((size_t)t * B + b) * C;
+            int nc = 0;
+            for (int c = 0; c < C; ++c) if ((double)lp[c] > thresh) cand[nc++] = c;          /* np.where(...)  :144 */
+            if (nc == 1) {                                                                    /* :147 */
+                const int pidx = cand[0];
+                if (pidx >= unknown) continue;                                                /* :150-151 */
+                for (int j = 0; j < nkept; ++j) {
+                    Beam* kb = &kept[j];
+                    const int tail = kb->len ? kb->prefix[kb->len - 1] : -1;
+                    if (pidx == 0) {
+                        kb->pb = beam_prob(kb) + (double)lp[0];                               /* :155-157 */
+                    } else if (pidx != tail) {
+                        const double pr = beam_prob(kb);
+                        kb->prefix[kb->len++] = pidx;
+                        kb->pnb = pr + (double)lp[pidx];
+                        kb->pb = NEG_INF;                                                     /* :158-161 */
+                    } else if (kb->pb != NEG_INF) {
+                        kb->prefix[kb->len++] = pidx;
+                        kb->pnb = kb->pb + (double)lp[pidx];
+                        kb->pb = NEG_INF;                                                     /* :163-167 */
+                    } else {
+                        kb->pb = beam_prob(kb) + (double)lp[0];
+                        kb->pnb = kb->pnb + (double)lp[pidx];                                 /* :168-171 */
+                    }
+                }
+            } else {
+                while (gptr < ng && g_time[gptr] <= t) ++gptr;
+                int nsuf = ng - gptr; if (nsuf > 4) nsuf = 4;
+                context_step(kept, &nkept, gen, order, lp, cand, nc, unknown, beam_size, lm_penalty, len_bonus, lm_table,
+                             g_char + gptr, nsuf, T);
+            }
+        }
+        if (nkept == 0) { status[b] = -4; out_len[b] = 0; rc = -4; continue; }              /* kept_beams[0] -> IndexError :179 */
+        out_len[b] = kept[0].len;
+        for (int c = 0; c < kept[0].len; ++c) out_idx[(size_t)b * T + c] = kept[0].prefix[c];
+        for (int j = 0; j < nkept; ++j) { free(kept[j].prefix); kept[j].prefix = NULL; }
+    }
+    free(g_char); free(g_time); free(cand); free(kept); free(gen); free(order);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * CTC loss forward/backward as called by the reference training loop (main.py:205,406-409):
  *   criterion = CTCLoss(blank=0, reduction='mean', zero_infinity=True)

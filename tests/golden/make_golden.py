@@ -92,6 +92,32 @@ def make_beam():
     np.savez_compressed(os.path.join(HERE, "beam.npz"), **out)
 
 
+def make_beam_skip():
+    """__cbs_skip__ (utils/ctc_codec.py:124-181): pruned candidates + the single-candidate fast path."""
+    out = {}
+    # noise scales chosen so that steps mix the single-candidate fast path with 2..~60-candidate searches
+    # (name, T, B, C, seed, period, scale, boost): boost sharpens the arg-max so that steps mix the single-candidate
+    # fast path with small multi-candidate searches; "big" keeps >64 candidates per step (oracle only).
+    cases = [("small", 48, 3, 40, 21, 4, 2.0, 0.0), ("mid", 96, 2, 300, 22, 8, 2.0, 2.0), ("wide", 64, 2, 7375, 23, 6, 2.0, 3.5),
+             ("flat", 60, 2, 60, 25, 3, 0.7, 0.0), ("big", 40, 2, 7375, 26, 6, 2.0, 0.0)]
+    settings = [("zero_b0", None, 2.0, 0.0), ("zero_b58", None, 2.0, 5.8), ("tab_p2", 31, 2.0, 5.8)]
+    for name, T, B, C, seed, period, noise, boost in cases:
+        x = synth.beam_logits(T, B, C, seed, period)
+        if noise != 2.0:
+            x = (x * (noise / 2.0)).astype(np.float32)          # weaker peaks -> more steps with several candidates
+        x = synth.peakier(x, boost)
+        out[name + "_shape"] = np.array([T, B, C, seed, period]); out[name + "_noise"] = np.array(noise)
+        out[name + "_boost"] = np.array(boost)
+        for sname, tseed, pen, bonus in settings:
+            codec = ctc_codec(synth.charset(C - 2))
+            codec.use_beam_search = True; codec.use_tfm_pred = False; codec.use_tfm_score = False
+            codec.skip_search = True; codec.lm_panelty = pen; codec.len_bonus = bonus
+            codec.ngram = ZeroLM() if tseed is None else TableLM(synth.lm_table(C, tseed), codec.dict)
+            out["%s_%s_text" % (name, sname)] = strs(codec.decode(x))
+            out["%s_%s_cfg" % (name, sname)] = np.array([-1 if tseed is None else tseed, pen, bonus])
+    np.savez_compressed(os.path.join(HERE, "beam_skip.npz"), **out)
+
+
 # ------------------------------------------------------------------ CTC loss (main.py:205,406-409)
 def make_ctc_loss():
     out = {}
@@ -209,7 +235,7 @@ def make_pad():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["greedy", "beam", "ctc_loss", "model", "config1", "pad"]
+    which = sys.argv[1:] or ["greedy", "beam", "beam_skip", "ctc_loss", "model", "config1", "pad"]
     for w in which:
         print("making", w, flush=True)
         globals()["make_" + w]()

@@ -86,3 +86,13 @@ def text_lines(B, W, seed, H=128):
                 x[b, 0, max(0, cy[i] - ln[i]):cy[i] + ln[i], cx[i]:cx[i] + th[i]] = val[i]
     x += (0.05 * rs.randn(B, 1, H, W)).astype(np.float32)
     return np.clip(x, -1.0, 1.0).astype(np.float32)
+
+
+def peakier(x, boost):
+    """Add `boost` to the arg-max class of every (t, b) row of logits [T,B,C] (returns a copy)."""
+    y = np.array(x, copy=True)
+    if boost:
+        am = y.argmax(axis=2)
+        t, b = np.meshgrid(np.arange(y.shape[0]), np.arange(y.shape[1]), indexing="ij")
+        y[t, b, am] += np.float32(boost)
+    return y

@@ -162,3 +162,42 @@ def test_beam_empty_greedy_path_raises_index_error():
     c.set_beam_search(use_tfm_pred=False, search_depth=5)
     with pytest.raises(IndexError):
         c.decode(x)
+
+
+# ------------------------------------------------------------------ __cbs_skip__ (utils/ctc_codec.py:124-181)
+def _skip_inputs(g, case):
+    T, B, C, seed, period = [int(v) for v in g[case + "_shape"]]
+    noise, boost = float(g[case + "_noise"]), float(g[case + "_boost"])
+    x = synth.beam_logits(T, B, C, seed, period)
+    if noise != 2.0:
+        x = (x * (noise / 2.0)).astype(np.float32)
+    return synth.peakier(x, boost), C
+
+
+SKIP_CASES = [(c, s) for c in ("small", "mid", "wide", "flat") for s in ("zero_b0", "zero_b58", "tab_p2")]
+
+
+@pytest.mark.parametrize("case,setting", SKIP_CASES)
+def test_skip_search_golden(golden, case, setting):
+    g = golden("beam_skip")
+    x, C = _skip_inputs(g, case)
+    tseed, pen, bonus = g["%s_%s_cfg" % (case, setting)]
+    c = _codec(C)
+    c.set_beam_search(skip_search=True, use_tfm_pred=False, lm_panelty=float(pen), len_bonus=float(bonus))
+    c.lm_table = None if tseed < 0 else synth.lm_table(C, int(tseed))
+    assert c.decode(x) == list(g["%s_%s_text" % (case, setting)])
+
+
+def test_skip_search_candidate_overflow_and_errors(golden):
+    g = golden("beam_skip")
+    x, C = _skip_inputs(g, "big")                          # up to 144 classes above the prune threshold in one step
+    c = _codec(C)
+    c.set_beam_search(skip_search=True, use_tfm_pred=False)
+    with pytest.raises(NotImplementedError):
+        c.decode(x)
+    flat = np.zeros((6, 1, 2000), np.float32)              # uniform over 2000 classes: nothing above 0.001 -> reference IndexError
+    flat[:, 0, 5] = 0.5
+    c2 = _codec(2000)
+    c2.set_beam_search(skip_search=True, use_tfm_pred=False)
+    with pytest.raises(IndexError):
+        c2.decode(flat)

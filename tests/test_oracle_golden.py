@@ -86,3 +86,22 @@ def test_ctc_loss_matches_torch_reference(golden, name):
         assert np.abs(grad[:, :, g[name + "_grad_tgt_cls"]] - g[name + "_grad_tgt"]).max() <= 1e-5
     if name == "infeasible":
         assert loss == 0.0 and np.abs(grad).max() == 0.0     # zero_infinity=True
+
+
+SKIP_CASES = [(c, s) for c in ("small", "mid", "wide", "flat", "big") for s in ("zero_b0", "zero_b58", "tab_p2")]
+
+
+@pytest.mark.parametrize("case,setting", SKIP_CASES)
+def test_skip_search_matches_reference(golden, case, setting):
+    g = golden("beam_skip")
+    T, B, C, seed, period = [int(v) for v in g[case + "_shape"]]
+    noise, boost = float(g[case + "_noise"]), float(g[case + "_boost"])
+    x = synth.beam_logits(T, B, C, seed, period)
+    if noise != 2.0:
+        x = (x * (noise / 2.0)).astype(np.float32)
+    x = synth.peakier(x, boost)
+    tseed, pen, bonus = g["%s_%s_cfg" % (case, setting)]
+    table = None if tseed < 0 else synth.lm_table(C, int(tseed))
+    idx, ln, st = oracle.beam_search_skip(x, 10, pen, bonus, table)
+    assert (st == 0).all()
+    assert _texts(C, idx, ln) == list(g["%s_%s_text" % (case, setting)])
