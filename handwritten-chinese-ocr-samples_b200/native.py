@@ -66,6 +66,7 @@ SIGNATURES = {
     "hctr_stem_wgrad_workspace_bytes": (_L, [_I, _I, _I]),
     "hctr_sgd_clip_step": (_I, [_P, _P, _P, _L, c_float, c_float, c_float, c_float, c_float, _I, _P, _P, _P]),
     "hctr_sgd_workspace_bytes": (_L, []),
+    "hctr_edit_distance": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "hctr_normalize_pad": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
 }
 

@@ -124,6 +124,22 @@ class ctc_codec(object):
                 nat.ptr(raw), nat.ptr(idx), nat.ptr(ln), nat.stream_ptr()), "ctc_greedy_decode")
         return (idx, ln, raw) if return_argmax else (idx, ln)
 
+    # ------------------------------------------------------------------ CER on device (main.py:497-517)
+    def error_counts(self, idx, ln, truths):
+        """Edit distances between decoded label arrays (device, from greedy_/beam_search_indices) and ground-truth strings.
+        Returns (int32 [B] distances on the device, total characters). CER = dist.sum() / nchars, as main.py:506-517."""
+        nat = _core().native
+        tg, tl = self.encode(list(truths))
+        dev = idx.device
+        B, T = idx.shape
+        with torch.cuda.device(dev):
+            d_tg = torch.from_numpy(tg).to(dev) if tg.size else torch.zeros((1,), dtype=torch.int32, device=dev)
+            d_tl = torch.from_numpy(tl).to(dev)
+            dist = torch.empty((B,), dtype=torch.int32, device=dev)
+            nat.check(nat.lib().hctr_edit_distance(nat.ptr(idx), nat.ptr(ln), T, T, nat.ptr(d_tg), nat.ptr(d_tl), B, nat.ptr(dist),
+                                                   nat.stream_ptr()), "edit_distance")
+        return dist, int(tl.sum())
+
     # ------------------------------------------------------------------ beam search (reference :101-122,183-285)
     def set_beam_search(self, skip_search=False, ngram_path='', tfm_path='',
                         lm_panelty=2, len_bonus=5.8, beam_size=10, search_depth=10,

@@ -219,6 +219,14 @@ long long hctr_sgd_workspace_bytes(void);
 int hctr_normalize_pad(const void* pixels, const long long* offsets, const int32_t* widths, float* out, int B, int H,
                        int Wb, void* stream);
 
+/* ---- evaluation (the step after decode: main.py:497-517, test.py:266-286) -------------------------------------- */
+
+/* Levenshtein distance of each decoded label sequence to its ground truth (editdistance.eval(pre, tru)); CER =
+ * sum(dist) / sum(target_lengths). pred_idx: int32 [B][pred_pitch] (the decode output), pred_len: int32 [B]
+ * (all <= max_pred_len), targets: int32 concatenated labels (ctc_codec.encode), target_lengths: int32 [B]; dist: int32 [B]. */
+int hctr_edit_distance(const int32_t* pred_idx, const int32_t* pred_len, int pred_pitch, int max_pred_len,
+                       const int32_t* targets, const int32_t* target_lengths, int B, int32_t* dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,8 @@ def _c():
         L.oracle_ctc_beam_search.restype = I
         L.oracle_ctc_beam_search_skip.argtypes = [P, P, I, I, I, I, D, D, P, P, P, P]
         L.oracle_ctc_beam_search_skip.restype = I
+        L.oracle_edit_distance.argtypes = [P, I, P, I]
+        L.oracle_edit_distance.restype = I
         L.oracle_ctc_loss.argtypes = [P, I, I, I, P, P, P, P, P]
         L.oracle_ctc_loss.restype = D
         _lib = L
@@ -126,6 +128,17 @@ def beam_search_skip(logits, beam_size=10, lm_penalty=2.0, len_bonus=5.8, lm_tab
     _c().oracle_ctc_beam_search_skip(_p(logp), _p(top1), T, B, C, beam_size, float(lm_penalty), float(len_bonus), _p(tab),
                                      _p(idx), _p(ln), _p(st))
     return idx, ln, st
+
+
+def edit_distance(a, b):
+    """Levenshtein distance between two label sequences (or strings, compared by code point)."""
+    if isinstance(a, str):
+        a = [ord(c) for c in a]
+    if isinstance(b, str):
+        b = [ord(c) for c in b]
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    b = np.ascontiguousarray(b, dtype=np.int32)
+    return int(_c().oracle_edit_distance(_p(a), len(a), _p(b), len(b)))
 
 
 def ctc_loss(logits, targets, input_lengths, target_lengths, need_grad=True):

@@ -437,3 +437,24 @@ double oracle_ctc_loss(const float* logits, int T, int B, int C, const int32_t* 
     }
     return loss / (double)B;
 }
+
+/* editdistance.eval(a, b): plain Levenshtein distance (insert / delete / substitute, unit costs), the metric of the
+ * reference's CER (main.py:506-517, test.py:275-286; the `editdistance` PyPI package, unpinned in requirements.txt:6). */
+int oracle_edit_distance(const int32_t* a, int n, const int32_t* b, int m) {
+    int* prev = (int*)malloc(sizeof(int) * (size_t)(m + 1));
+    int* cur = (int*)malloc(sizeof(int) * (size_t)(m + 1));
+    for (int j = 0; j <= m; ++j) prev[j] = j;
+    for (int i = 1; i <= n; ++i) {
+        cur[0] = i;
+        for (int j = 1; j <= m; ++j) {
+            int v = prev[j - 1] + (a[i - 1] != b[j - 1]);
+            if (prev[j] + 1 < v) v = prev[j] + 1;
+            if (cur[j - 1] + 1 < v) v = cur[j - 1] + 1;
+            cur[j] = v;
+        }
+        int* t = prev; prev = cur; cur = t;
+    }
+    const int d = prev[m];
+    free(prev); free(cur);
+    return d;
+}

@@ -201,3 +201,30 @@ def test_skip_search_candidate_overflow_and_errors(golden):
     c2.set_beam_search(skip_search=True, use_tfm_pred=False)
     with pytest.raises(IndexError):
         c2.decode(flat)
+
+
+def test_edit_distance_and_cer_on_device():
+    """CER of decoded label arrays vs ground-truth strings (main.py:506-517) - bit-exact integer distances."""
+    T, B, C = 700, 9, 300
+    rs = np.random.RandomState(3)
+    c = _codec(C)
+    x = synth.ctc_like_logits(T, B, C, 31, period=2)
+    x[:, 3, :] = 0.0; x[:, 3, 0] = 5.0                      # an empty prediction
+    idx, ln = c.greedy_indices(torch.from_numpy(x).cuda())
+    preds = c.indices_to_text(idx, ln)
+    truths = []
+    for b in range(B):
+        s = list(preds[b])
+        for _ in range(rs.randint(0, 12)):                  # random edits
+            op = rs.randint(3)
+            pos = rs.randint(0, len(s) + 1)
+            if op == 0: s.insert(pos, c.characters[1 + rs.randint(C - 2)])
+            elif op == 1 and s: s.pop(min(pos, len(s) - 1))
+            elif s: s[min(pos, len(s) - 1)] = c.characters[1 + rs.randint(C - 2)]
+        truths.append(''.join(s))
+    truths[5] = ""                                           # an empty ground truth
+    truths[6] = truths[6] + "éx"                        # characters outside the charset
+    dist, nchars = c.error_counts(idx, ln, truths)
+    want = [oracle.edit_distance(p, t) for p, t in zip(preds, truths)]
+    assert dist.cpu().tolist() == want
+    assert nchars == sum(len(t) for t in truths)

@@ -105,3 +105,12 @@ def test_skip_search_matches_reference(golden, case, setting):
     idx, ln, st = oracle.beam_search_skip(x, 10, pen, bonus, table)
     assert (st == 0).all()
     assert _texts(C, idx, ln) == list(g["%s_%s_text" % (case, setting)])
+
+
+def test_edit_distance_known_answers():
+    # classic known answers (the `editdistance` package's own doctest values)
+    assert oracle.edit_distance("kitten", "sitting") == 3
+    assert oracle.edit_distance("flaw", "lawn") == 2
+    assert oracle.edit_distance("", "abc") == 3 and oracle.edit_distance("abc", "") == 3 and oracle.edit_distance("", "") == 0
+    assert oracle.edit_distance("intention", "execution") == 5
+    assert oracle.edit_distance([1, 2, 3], [1, 2, 3]) == 0
