@@ -104,6 +104,18 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// log-sum-exp fix-up of the classifier's per-(row, half-tile) softmax partials (fixed order)
+__global__ void lse_combine_kernel(const float2* __restrict__ partial, long long rows, int slots, float* __restrict__ lse) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float2* p = partial + r * slots;
+    float m = -3.0e38f;
+    for (int i = 0; i < slots; ++i) m = fmaxf(m, p[i].x);
+    float s = 0.f;
+    for (int i = 0; i < slots; ++i) s += p[i].y * __expf(p[i].x - m);
+    lse[r] = m + logf(s);
+}
+
 }  // namespace hctr
 
 using namespace hctr;
@@ -243,8 +255,9 @@ int hctr_classifier_dgrad(const void* dlogits, long long pitch, const void* w_t,
     return HCTR_OK;
 }
 
-int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
-                        long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, void* stream) {
+static int classifier_launch(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                             long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, float2* lse_partial,
+                             void* stream) {
     HCTR_CHECK(feat && w_packed && bias && logits, HCTR_ERR_INVALID, "classifier: null pointer");
     HCTR_CHECK(B > 0 && W > 0 && Hf > 0 && Hf <= kMaxTaps, HCTR_ERR_INVALID, "classifier: bad shape B=%d Hf=%d W=%d", B, Hf, W);
     HCTR_CHECK(Cf % 64 == 0 && Cf >= 64, HCTR_ERR_INVALID, "classifier: feature channels must be a multiple of 64 (got %d)", Cf);
@@ -266,6 +279,7 @@ int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bia
     p.shift = bias; p.out = logits;
     p.out_H = 1;
     p.out_dtype = out_dtype; p.out_pitch = out_pitch;
+    p.lse_partial = lse_partial;
     const long long total = (long long)B * p.w_tiles * p.n_tiles;
     HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "classifier: too many tiles");
     p.total_tiles = (int)total;
@@ -276,6 +290,33 @@ int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bia
     rc = make_weight_map(&tmB, w_packed, num_classes, Hf * Cf, 256);
     if (rc) return rc;
     return launch_igemm<256, 2, 3, 1, EPI_LINEAR>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+
+int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                        long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, void* stream) {
+    return classifier_launch(feat, w_packed, bias, logits, out_dtype, out_pitch, B, Hf, W, Cf, num_classes, nullptr, stream);
+}
+
+long long hctr_classifier_lse_workspace_bytes(int B, int W, int num_classes) {
+    return (long long)B * W * ((num_classes + 255) / 256) * 2 * (long long)sizeof(float2);
+}
+
+int hctr_classifier_lse_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                            long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, float* row_lse,
+                            void* workspace, long long workspace_bytes, void* stream) {
+    HCTR_CHECK(row_lse && workspace, HCTR_ERR_INVALID, "classifier_lse: null pointer");
+    HCTR_CHECK(workspace_bytes >= hctr_classifier_lse_workspace_bytes(B, W, num_classes), HCTR_ERR_INVALID, "classifier_lse: workspace too small");
+    HCTR_CHECK(aligned16(workspace), HCTR_ERR_INVALID, "classifier_lse: workspace alignment");
+    int rc = classifier_launch(feat, w_packed, bias, logits, out_dtype, out_pitch, B, Hf, W, Cf, num_classes,
+                               static_cast<float2*>(workspace), stream);
+    if (rc) return rc;
+    const long long rows = (long long)B * W;
+    const int slots = ((num_classes + 255) / 256) * 2;
+    lse_combine_kernel<<<(int)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2*>(workspace), rows, slots, row_lse);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
 }
 
 }  // extern "C"

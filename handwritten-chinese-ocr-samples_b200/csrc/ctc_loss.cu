@@ -113,7 +113,7 @@ template <typename T>
 __global__ void __launch_bounds__(kLseWarps * 32)
 ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
                       const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen,
-                      const int32_t* __restrict__ ilen, int Smax, CtcWs w) {
+                      const int32_t* __restrict__ ilen, int Smax, const float* __restrict__ lse_in, CtcWs w) {
     constexpr int V = Ld<T>::N;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * kLseWarps + (threadIdx.x >> 5);     // row = b*T + t
@@ -121,46 +121,51 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
     const int b = (int)(row / Tn), t = (int)(row - (long long)b * Tn);
     if (t >= ilen[b]) return;
     const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
-    float m = -FLT_MAX, s = 0.f;
-    auto upd = [&](float x) {
-        if (x > m) { s = s * __expf(m - x) + 1.f; m = x; } else { s += __expf(x - m); }
-    };
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-    int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
-    if (head > C) head = C;
-    if (lane < head) upd(Ld<T>::one(p + lane));
-    const int nvec = (C - head) / V;
-    const T* pv = p + head;
-    int vi = lane;
-    for (; vi + 96 < nvec; vi += 128) {
-        float x[4][V];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) Ld<T>::vec(pv + (long long)(vi + 32 * u) * V, x[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float vm = x[u][0];
-#pragma unroll
-            for (int j = 1; j < V; ++j) vm = fmaxf(vm, x[u][j]);
-            if (vm > m) { s *= __expf(m - vm); m = vm; }
-#pragma unroll
-            for (int j = 0; j < V; ++j) s += __expf(x[u][j] - m);
+    float lse;
+    if (lse_in != nullptr) {
+        lse = lse_in[row];            // log-sum-exp already produced by the classifier epilogue: only gather the labels
+    } else {
+        float m = -FLT_MAX, s = 0.f;
+        auto upd = [&](float x) {
+            if (x > m) { s = s * __expf(m - x) + 1.f; m = x; } else { s += __expf(x - m); }
+        };
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+        int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+        if (head > C) head = C;
+        if (lane < head) upd(Ld<T>::one(p + lane));
+        const int nvec = (C - head) / V;
+        const T* pv = p + head;
+        int vi = lane;
+        for (; vi + 96 < nvec; vi += 128) {
+            float x[4][V];
+    #pragma unroll
+            for (int u = 0; u < 4; ++u) Ld<T>::vec(pv + (long long)(vi + 32 * u) * V, x[u]);
+    #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float vm = x[u][0];
+    #pragma unroll
+                for (int j = 1; j < V; ++j) vm = fmaxf(vm, x[u][j]);
+                if (vm > m) { s *= __expf(m - vm); m = vm; }
+    #pragma unroll
+                for (int j = 0; j < V; ++j) s += __expf(x[u][j] - m);
+            }
         }
+        for (; vi < nvec; vi += 32) {
+            float x[V];
+            Ld<T>::vec(pv + (long long)vi * V, x);
+    #pragma unroll
+            for (int j = 0; j < V; ++j) upd(x[j]);
+        }
+        const int tail0 = head + nvec * V;
+        if (tail0 + lane < C) upd(Ld<T>::one(p + tail0 + lane));
+        float mm = m;
+    #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        float ss = s * __expf(m - mm);
+    #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        lse = mm + logf(ss);
     }
-    for (; vi < nvec; vi += 32) {
-        float x[V];
-        Ld<T>::vec(pv + (long long)vi * V, x);
-#pragma unroll
-        for (int j = 0; j < V; ++j) upd(x[j]);
-    }
-    const int tail0 = head + nvec * V;
-    if (tail0 + lane < C) upd(Ld<T>::one(p + tail0 + lane));
-    float mm = m;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-    float ss = s * __expf(m - mm);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float lse = mm + logf(ss);
     if (lane == 0) w.lse[row] = lse;
     const int L = tlen[b], S = 2 * L + 1;
     const int32_t* tg = targets + w.toff[b];
@@ -362,8 +367,8 @@ long long hctr_ctc_loss_workspace_bytes(int T, int B, int max_target_len) {
 
 int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                           const int32_t* targets, const int32_t* target_lengths, const int32_t* input_lengths,
-                          int max_target_len, float* nll, float* loss, void* grad, float grad_scale, void* workspace,
-                          long long workspace_bytes, void* stream) {
+                          int max_target_len, const float* row_lse, float* nll, float* loss, void* grad, float grad_scale,
+                          void* workspace, long long workspace_bytes, void* stream) {
     HCTR_CHECK(logits && target_lengths && input_lengths && nll && loss, HCTR_ERR_INVALID, "ctc_loss: null pointer");
     HCTR_CHECK(T > 0 && B > 0 && C > 1, HCTR_ERR_INVALID, "ctc_loss: bad shape T=%d B=%d C=%d", T, B, C);
     HCTR_CHECK(dtype == HCTR_F32 || dtype == HCTR_BF16, HCTR_ERR_INVALID, "ctc_loss: bad dtype");
@@ -384,10 +389,10 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "ctc_loss: too many rows");
     if (dtype == HCTR_F32)
         ctc_lse_gather_kernel<float><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
-            static_cast<const float*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Smax, w);
+            static_cast<const float*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Smax, row_lse, w);
     else
         ctc_lse_gather_kernel<__nv_bfloat16><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Smax, w);
+            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Smax, row_lse, w);
     HCTR_CUDA(cudaGetLastError());
     int threads = (Smax + 31) / 32 * 32;
     const size_t smB = (size_t)(2 * (Smax + 4) + 2) * sizeof(double);

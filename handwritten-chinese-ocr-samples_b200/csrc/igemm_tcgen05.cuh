@@ -51,6 +51,8 @@ struct IgemmParams {
                               // epilogue output (the SE squeeze folded into the producing conv; deterministic)
     int out_dtype;            // EPI_LINEAR: HCTR_F32 | HCTR_BF16
     long long out_pitch;      // EPI_LINEAR: elements between consecutive (b,w) rows
+    float2* lse_partial;      // EPI_LINEAR: optional [B*W][n_tiles*2] (max, sum exp(x-max)) per (row, column half-tile) of the
+                              // logits as stored (log_softmax fused into the classifier epilogue; combined by lse_combine)
 };
 
 template <int BLOCK_N, int NUM_SUB, int STAGES>
@@ -186,6 +188,9 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             tc_fence_after();
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
 
+            float run_m[NUM_SUB], run_s[NUM_SUB];
+#pragma unroll
+            for (int s = 0; s < NUM_SUB; ++s) { run_m[s] = -3.0e38f; run_s[s] = 0.f; }
 #pragma unroll 1
             for (int c0 = half * (BLOCK_N / 2); c0 < (half + 1) * (BLOCK_N / 2); c0 += 32) {
                 const int n0 = n_tile * BLOCK_N + c0;
@@ -297,6 +302,25 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                         const int w = w0 + s * p.sub_dw * kTileM + pix;
                         if (w >= p.W) continue;
                         const size_t row = static_cast<size_t>(b) * p.W + w;
+                        if (p.lse_partial) {
+                            // online (max, sum exp) over this thread's row: the row of D lives in one TMEM lane, so the
+                            // softmax statistics need no cross-thread traffic. Values are taken as they will be stored.
+                            float cm = run_m[s];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = v[s][j] + __ldg(p.shift + min(n0 + j, p.N - 1));
+                                if (p.out_dtype != HCTR_F32) x = __bfloat162float(__float2bfloat16_rn(x));
+                                if (n0 + j < p.N) cm = fmaxf(cm, x);
+                            }
+                            float acc = run_s[s] * __expf(run_m[s] - cm);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = v[s][j] + __ldg(p.shift + min(n0 + j, p.N - 1));
+                                if (p.out_dtype != HCTR_F32) x = __bfloat162float(__float2bfloat16_rn(x));
+                                if (n0 + j < p.N) acc += __expf(x - cm);
+                            }
+                            run_m[s] = cm; run_s[s] = acc;
+                        }
                         if (p.out_dtype == HCTR_F32) {
                             float* dst = static_cast<float*>(p.out) + row * p.out_pitch + n0;
                             if (n0 + 32 <= p.N && (p.out_pitch & 3) == 0) {
@@ -329,6 +353,17 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                     if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(v[s][j] + __ldg(p.shift + n0 + j));
                             }
                         }
+                    }
+                }
+            }
+            if constexpr (EPI == EPI_LINEAR) {
+                if (p.lse_partial) {
+#pragma unroll
+                    for (int s = 0; s < NUM_SUB; ++s) {
+                        const int w = w0 + s * p.sub_dw * kTileM + pix;
+                        if (w < p.W)
+                            p.lse_partial[(static_cast<size_t>(b) * p.W + w) * (p.n_tiles * 2) + n_tile * 2 + half] =
+                                make_float2(run_m[s], run_s[s]);
                     }
                 }
             }

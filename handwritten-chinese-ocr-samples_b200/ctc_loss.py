@@ -51,7 +51,7 @@ class _CtcFromLogits(torch.autograd.Function):
             code = nat.HCTR_F32 if logits.dtype == torch.float32 else nat.HCTR_BF16
             nat.check(lib.hctr_ctc_loss_fwd_bwd(
                 nat.ptr(logits), code, T, B, C, logits.stride(0), logits.stride(1), nat.ptr(targets),
-                nat.ptr(target_lengths), nat.ptr(input_lengths), max_target_len, nat.ptr(nll), nat.ptr(loss),
+                nat.ptr(target_lengths), nat.ptr(input_lengths), max_target_len, None, nat.ptr(nll), nat.ptr(loss),
                 nat.ptr(grad), 1.0, nat.ptr(ws), ws_bytes, nat.stream_ptr()), "ctc_loss_fwd_bwd")
         ctx.grad = grad
         ctx.nll = nll

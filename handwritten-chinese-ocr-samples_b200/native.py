@@ -36,6 +36,8 @@ SIGNATURES = {
     "hctr_se_excite": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "hctr_se_scale_residual_relu": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "hctr_classifier_fwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _P]),
+    "hctr_classifier_lse_fwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
+    "hctr_classifier_lse_workspace_bytes": (_L, [_I, _I, _I]),
     "hctr_ctc_greedy_decode": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P]),
     "hctr_ctc_topk_logsoftmax": (_I, [_P, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P]),
     "hctr_ctc_prefix_beam_search": (_I, [_P, _P, _I, _I, _I, _I, _I, c_double, c_double, _P, _P, _P, _P, _P, _L, _P]),
@@ -43,7 +45,7 @@ SIGNATURES = {
     "hctr_ctc_skip_beam_search": (_I, [_P, _I, _I, _I, _I, _L, _L, _I, c_double, c_double, _P, _P, _P, _P, _P, _L, _P]),
     "hctr_ctc_skip_workspace_bytes": (_L, [_I, _I]),
     "hctr_ctc_skip_max_candidates": (_I, []),
-    "hctr_ctc_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _I, _P, _P, _P, c_float, _P, _L, _P]),
+    "hctr_ctc_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _I, _P, _P, _P, _P, c_float, _P, _L, _P]),
     "hctr_ctc_loss_workspace_bytes": (_L, [_I, _I, _I]),
     "hctr_stat_slices": (_I, [_I, _I, _I]),
     "hctr_chan_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

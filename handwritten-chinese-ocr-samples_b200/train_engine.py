@@ -200,9 +200,15 @@ class TrainEngine(object):
         cf = lin.weight.shape[1] // H
         wk = (lin.weight.detach().reshape(n, cf, H).permute(0, 2, 1).contiguous().to(torch.bfloat16).reshape(n, H * cf))
         logits = torch.empty((B, W, pitch), dtype=torch.bfloat16, device=x.device)
-        nat.check(self.lib.hctr_classifier_fwd(nat.ptr(a), nat.ptr(wk), nat.ptr(lin.bias.detach()), nat.ptr(logits), nat.HCTR_BF16,
-                                               pitch, B, H, W, cf, n, nat.stream_ptr()), "classifier")
+        # classifier GEMM fused with log_softmax: the epilogue also yields the row log-sum-exp the CTC loss needs
+        row_lse = torch.empty((B, W), dtype=torch.float32, device=x.device)
+        nb = self.lib.hctr_classifier_lse_workspace_bytes(B, W, n)
+        ws = self._ws(nb, x.device)
+        nat.check(self.lib.hctr_classifier_lse_fwd(nat.ptr(a), nat.ptr(wk), nat.ptr(lin.bias.detach()), nat.ptr(logits),
+                                                   nat.HCTR_BF16, pitch, B, H, W, cf, n, nat.ptr(row_lse), nat.ptr(ws), nb,
+                                                   nat.stream_ptr()), "classifier_lse")
         ctx["feat"], ctx["Hf"], ctx["cf"], ctx["pitch"], ctx["wk"] = a, H, cf, pitch, wk
+        ctx["row_lse"] = row_lse
         return logits, ctx
 
     def backward(self, ctx, dlogits, grads, on_stage_done=None):

@@ -105,7 +105,7 @@ class TrainStep(object):
             ws = torch.empty((nb + 256,), dtype=torch.uint8, device=dev)
             off = (-ws.data_ptr()) % 256
             nat.check(lib.hctr_ctc_loss_fwd_bwd(nat.ptr(logits), nat.HCTR_BF16, W, B, C, pitch, W * pitch, nat.ptr(tg), nat.ptr(tl),
-                                                nat.ptr(il), max_l, nat.ptr(nll), nat.ptr(loss), nat.ptr(dlogits), 1.0,
+                                                nat.ptr(il), max_l, nat.ptr(ctx["row_lse"]), nat.ptr(nll), nat.ptr(loss), nat.ptr(dlogits), 1.0,
                                                 nat.c_void_p(ws.data_ptr() + off), nb, st), "ctc_loss_fwd_bwd")
             works = []
             done = [0]

@@ -88,6 +88,15 @@ int hctr_se_scale_residual_relu(const void* x, const float* gate, const void* re
 int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
                         long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, void* stream);
 
+/* The same classifier GEMM fused with log_softmax: the epilogue keeps an online (max, sum exp) per logits row and
+ * column half-tile (a row of the accumulator lives in one TMEM lane, so no cross-thread traffic), a fix-up kernel combines
+ * them into row_lse fp32 [B][W]; log_softmax(logits)[b,w,c] = logits[b,w,c] - row_lse[b,w] (reference: main.py:406
+ * `preds.log_softmax(2)`). workspace: hctr_classifier_lse_workspace_bytes(B, W, num_classes), 16-byte aligned. */
+int hctr_classifier_lse_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                            long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, float* row_lse,
+                            void* workspace, long long workspace_bytes, void* stream);
+long long hctr_classifier_lse_workspace_bytes(int B, int W, int num_classes);
+
 /* ---- CTC codec ------------------------------------------------------------------------------ */
 
 /* ctc_codec.__greedy_search__ (utils/ctc_codec.py:70-99): per (t,b) argmax over C (ties -> lowest index,
@@ -133,11 +142,12 @@ int hctr_ctc_skip_max_candidates(void);
  * targets: int32 concatenated [sum L]; target_lengths/input_lengths: int32 [B].
  * nll: fp32 [B] per-sequence negative log-likelihood (inf -> 0 when zero_infinity); loss: fp32 [1] =
  * mean_b(nll_b / max(L_b,1)); grad (may be NULL): same dtype/strides as logits, d loss / d logits scaled by
- * grad_scale. */
+ * grad_scale. row_lse (may be NULL): fp32 [B][T] log-sum-exp of every logits row, e.g. from hctr_classifier_lse_fwd -
+ * then the first pass over the logits only gathers the label columns. */
 int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                           const int32_t* targets, const int32_t* target_lengths, const int32_t* input_lengths,
-                          int max_target_len, float* nll, float* loss, void* grad, float grad_scale, void* workspace,
-                          long long workspace_bytes, void* stream);
+                          int max_target_len, const float* row_lse, float* nll, float* loss, void* grad, float grad_scale,
+                          void* workspace, long long workspace_bytes, void* stream);
 long long hctr_ctc_loss_workspace_bytes(int T, int B, int max_target_len);
 
 /* ---- training (train()-mode forward and the backward pass; reference: main.py:367,383-438) -------------------- */

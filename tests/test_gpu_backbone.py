@@ -251,3 +251,31 @@ def test_model_errors():
         m(torch.zeros(1, 1, 96, 64, device="cuda"))
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 128, 64, device="cuda"))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_classifier_fused_log_softmax(dtype):
+    """Classifier GEMM fused with log_softmax (north star item 2): row_lse from the epilogue partials == logsumexp of the
+    logits the kernel stored (<=1e-5 abs), for ragged W and the 7375-class tail tile."""
+    nat = _nat()
+    lib = nat.lib()
+    B, W, N = 2, 300, 7375
+    g = torch.Generator().manual_seed(9)
+    feat = torch.randn(B, 4, W, 512, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(N, 2048, generator=g) / 20).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    pitch = 7376
+    out = torch.zeros((B, W, pitch), dtype=dtype, device="cuda")
+    lse = torch.empty((B, W), device="cuda")
+    nb = lib.hctr_classifier_lse_workspace_bytes(B, W, N)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    nat.check(lib.hctr_classifier_lse_fwd(nat.ptr(feat), nat.ptr(w), nat.ptr(bias), nat.ptr(out),
+                                          nat.HCTR_F32 if dtype == torch.float32 else nat.HCTR_BF16, pitch, B, 4, W, 512, N,
+                                          nat.ptr(lse), nat.ptr(ws), nb, nat.stream_ptr()))
+    ref = torch.logsumexp(out[:, :, :N].double(), dim=2)
+    assert (lse.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    plain = torch.zeros_like(out)
+    nat.check(lib.hctr_classifier_fwd(nat.ptr(feat), nat.ptr(w), nat.ptr(bias), nat.ptr(plain),
+                                      nat.HCTR_F32 if dtype == torch.float32 else nat.HCTR_BF16, pitch, B, 4, W, 512, N,
+                                      nat.stream_ptr()))
+    assert torch.equal(plain, out)                      # the fused epilogue stores the same logits
