@@ -9,6 +9,8 @@
 //   dz = P[b,c]*d_pre + Q[b,c] + R[c]*z,   dres = d_pre
 // where P,Q,R fold the BatchNorm backward (and the SE squeeze path) computed from per-(b,c) partial sums, so each
 // direction touches every activation tensor exactly twice. All reductions are fixed-order (deterministic).
+#include <cstring>
+
 #include "common.cuh"
 #include "../../include/hctr_b200.h"
 
@@ -147,6 +149,7 @@ struct ApplyParams {
     float drop_p;                // 0 = off
     uint32_t seed;
     int vshift;                  // log2(C/8)
+    uint8_t* mask;               // [B][H][W][C/8] one keep-bit per element at INPUT resolution (fwd: written; bwd: read)
 };
 
 template <bool POOL>
@@ -194,88 +197,72 @@ train_apply_fwd_kernel(ApplyParams p, __nv_bfloat16* __restrict__ out) {
         const size_t obase = (size_t)row * rowlen;                       // output vector index of (row, j=0)
         for (int j = j0 + threadIdx.x; j < j1; j += 256) {
             const int w = j >> p.vshift;
+            const size_t i = obase + j;
+            uint32_t keep = 0xffu;                                   // dropout keep bits of the 8 output elements
+            if (p.drop_p > 0.f) {
+                const uint32_t base = drop_base(i, p.seed);
+                keep = 0u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) keep |= drop_keep(base, q, thresh) ? (1u << q) : 0u;
+            }
             float v[8];
             if (p.pool) {
                 float v1[8];
                 const size_t o0 = (((size_t)b * p.H + 2 * ho) * p.W + w) * p.C + c0;
                 apply_pre<true>(p, o0, b, c0, v, sc, sh);
                 apply_pre<true>(p, o0 + (size_t)p.W * p.C, b, c0, v1, sc, sh);
+                uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], v1[q]);
+                for (int q = 0; q < 8; ++q) {
+                    const float r0 = p.relu ? fmaxf(v[q], 0.f) : v[q];
+                    const float r1 = p.relu ? fmaxf(v1[q], 0.f) : v1[q];
+                    const bool first = r0 >= r1;                     // torch max_pool2d: the first maximum takes the gradient
+                    const bool pos = !p.relu || (first ? v[q] : v1[q]) > 0.f;
+                    if (pos && first) m0 |= 1u << q;
+                    if (pos && !first) m1 |= 1u << q;
+                    v[q] = first ? r0 : r1;
+                }
+                if (p.mask) {
+                    const size_t mi = (((size_t)b * p.H + 2 * ho) * p.W + w) * vpp + cv;
+                    p.mask[mi] = (uint8_t)(m0 & keep);
+                    p.mask[mi + (size_t)p.W * vpp] = (uint8_t)(m1 & keep);
+                }
             } else {
                 apply_pre<false>(p, ((size_t)row * p.W + w) * p.C + c0, b, c0, v, sc, sh);
-            }
-            if (p.relu) {
+                uint32_t m0 = 0xffu;
+                if (p.relu) {
+                    m0 = 0u;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+                    for (int q = 0; q < 8; ++q) { if (v[q] > 0.f) m0 |= 1u << q; v[q] = fmaxf(v[q], 0.f); }
+                }
+                if (p.mask) p.mask[((size_t)row * p.W + w) * vpp + cv] = (uint8_t)(m0 & keep);
             }
-            const size_t i = obase + j;
             if (p.drop_p > 0.f) {
-                const uint32_t base = drop_base(i, p.seed);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = drop_keep(base, q, thresh) ? v[q] * keep_scale : 0.f;
+                for (int q = 0; q < 8; ++q) v[q] = ((keep >> q) & 1u) ? v[q] * keep_scale : 0.f;
             }
             *reinterpret_cast<uint4*>(out + i * 8) = pack8(v);
         }
     }
 }
 
-// ---------------------------------------------------------------- backward: recompute masks, d_pre
-// Returns d_pre for the 8 channels of one INPUT-resolution pixel (row h of the z tensor).
+// ---------------------------------------------------------------- backward: d_pre from the stored keep-mask
+// d_pre = gradient behind the dropout / pool / ReLU masks for the 8 channels of one INPUT-resolution pixel. The forward
+// stored one keep-bit per element (ReLU sign, pool winner and dropout keep folded together), so the backward reads
+// 1 byte per 16-byte vector instead of recomputing the affine/gate/residual chain and the dropout hash.
 __device__ __forceinline__ void bwd_dpre(const ApplyParams& p, const __nv_bfloat16* __restrict__ dout, int b, int h, int w,
-                                         int c0, uint32_t thresh, float keep_scale, const float (&sc)[8],
-                                         const float (&sh)[8], float (&zv)[8], float (&d)[8]) {
+                                         int c0, float keep_scale, float (&zv)[8], float (&d)[8]) {
     const int vpp = p.C >> 3;
-    const size_t zoff = (((size_t)b * p.H + h) * p.W + w) * p.C + c0;
-    unpack8(ld_nc_v4(p.z + zoff), zv);
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(zv[i], sc[i], sh[i]);
-    if (p.gate) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)b * p.C + c0));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)b * p.C + c0 + 4));
-        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w; v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-    }
-    if (p.res) {
-        float r[8];
-        unpack8(ld_nc_v4(p.res + zoff), r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
-    }
-    bool sel[8];
-    int ho = h;
-    if (p.pool) {
-        // the (2,1) window: gradient goes to the first maximum of the ReLU'd pair (torch max_pool2d backward)
-        ho = h >> 1;
-        const int other = h ^ 1;
-        const size_t ooff = (((size_t)b * p.H + other) * p.W + w) * p.C + c0;
-        float e[8], u[8];
-        unpack8(ld_nc_v4(p.z + ooff), e);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] = fmaf(e[i], sc[i], sh[i]);
-        // (pool layers have no gate / residual in this network)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float mine = p.relu ? fmaxf(v[i], 0.f) : v[i];
-            const float oth = p.relu ? fmaxf(u[i], 0.f) : u[i];
-            sel[i] = (h & 1) ? (mine > oth) : (mine >= oth);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sel[i] = true;
-    }
+    const size_t ivec = (((size_t)b * p.H + h) * p.W + w) * vpp + (c0 >> 3);
+    unpack8(ld_nc_v4(p.z + ivec * 8), zv);
+    const uint32_t m = p.mask[ivec];
     const int Ho = p.pool ? p.H / 2 : p.H;
+    const int ho = p.pool ? (h >> 1) : h;
     const size_t ovec = (((size_t)b * Ho + ho) * p.W + w) * vpp + (c0 >> 3);
     float g[8];
     unpack8(ld_nc_v4(dout + ovec * 8), g);
-    const uint32_t dbase = p.drop_p > 0.f ? drop_base(ovec, p.seed) : 0u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float t = g[i];
-        if (p.drop_p > 0.f) t = drop_keep(dbase, i, thresh) ? t * keep_scale : 0.f;
-        if (p.relu && !(v[i] > 0.f)) t = 0.f;
-        d[i] = sel[i] ? t : 0.f;
-    }
+    for (int i = 0; i < 8; ++i) d[i] = ((m >> i) & 1u) ? g[i] * keep_scale : 0.f;
 }
 
 // per-(b, slice, c): A2 = sum d_pre, A3 = sum d_pre * z
@@ -288,20 +275,14 @@ train_bwd_reduce_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, f
     const int g = threadIdx.x / vpp, cv = threadIdx.x - g * vpp;
     const int HW = p.H * p.W;
     const int p0 = slice * pix_per_slice, p1 = min(p0 + pix_per_slice, HW);
-    const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
     const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const int c0 = cv * 8;
-    float sc[8], sh[8];
-    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
-    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
-    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
     float a2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a3[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int h = (p0 + g) / p.W, w = (p0 + g) - h * p.W;
     for (int px = p0 + g; px < p1; px += groups, w += groups) {
         while (w >= p.W) { w -= p.W; ++h; }
         float zv[8], d[8];
-        bwd_dpre(p, dout, b, h, w, c0, thresh, keep_scale, sc, sh, zv, d);
+        bwd_dpre(p, dout, b, h, w, c0, keep_scale, zv, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { a2[i] += d[i]; a3[i] = fmaf(d[i], zv[i], a3[i]); }
     }
@@ -450,15 +431,10 @@ train_bwd_apply_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, co
                        __nv_bfloat16* __restrict__ dres) {
     const int vpp = p.C >> 3;
     const int rowlen = p.W * vpp;
-    const uint32_t thresh = p.drop_p > 0.f ? (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967295.f) : 0u;
     const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     const int cv = threadIdx.x & (vpp - 1);
     const int c0 = cv * 8;
-    float sc[8], sh[8], Rv[8];
-    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
-    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
-    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    float Rv[8];
     *reinterpret_cast<float4*>(Rv) = __ldg(reinterpret_cast<const float4*>(R + c0));
     *reinterpret_cast<float4*>(Rv + 4) = __ldg(reinterpret_cast<const float4*>(R + c0 + 4));
     const int seg_len = ((rowlen + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
@@ -474,7 +450,7 @@ train_bwd_apply_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, co
         for (int j = j0 + threadIdx.x; j < j1; j += 256) {
             const int w = j >> p.vshift;
             float zv[8], d[8], o[8];
-            bwd_dpre(p, dout, b, h, w, c0, thresh, keep_scale, sc, sh, zv, d);
+            bwd_dpre(p, dout, b, h, w, c0, keep_scale, zv, d);
 #pragma unroll
             for (int q = 0; q < 8; ++q) o[q] = fmaf(Pv[q], d[q], fmaf(Rv[q], zv[q], Qv[q]));
             const size_t i = ibase + j;
@@ -584,11 +560,12 @@ static int fill_apply(ApplyParams& p, const void* z, const float* scale, const f
 }
 
 int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, const float* gate, const void* res,
-                         void* out, int B, int H, int W, int C, int relu, int pool, float drop_p, unsigned seed,
+                         void* out, void* mask, int B, int H, int W, int C, int relu, int pool, float drop_p, unsigned seed,
                          void* stream) {
     ApplyParams p;
     int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
     if (rc) return rc;
+    p.mask = static_cast<uint8_t*>(mask);
     HCTR_CHECK(out && al16(out), HCTR_ERR_INVALID, "train_apply_fwd: bad output");
     train_apply_fwd_kernel<<<grid_rows((long long)B * (pool ? H / 2 : H), W * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         p, static_cast<__nv_bfloat16*>(out));
@@ -596,11 +573,26 @@ int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, 
     return HCTR_OK;
 }
 
-int hctr_train_bwd_reduce(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
-                          const void* res, float* pA2, float* pA3, int B, int H, int W, int C, int relu, int pool,
-                          float drop_p, unsigned seed, void* stream) {
+static int fill_bwd(ApplyParams& p, const void* z, const void* mask, int B, int H, int W, int C, int pool, float drop_p) {
+    HCTR_CHECK(z && mask, HCTR_ERR_INVALID, "train_bwd: null pointer");
+    HCTR_CHECK(C % 8 == 0 && C >= 8 && 256 % (C / 8) == 0, HCTR_ERR_INVALID, "train_bwd: bad channel count %d", C);
+    HCTR_CHECK(!pool || H % 2 == 0, HCTR_ERR_INVALID, "train_bwd: pooling needs an even H");
+    HCTR_CHECK(drop_p >= 0.f && drop_p < 1.f, HCTR_ERR_INVALID, "train_bwd: dropout p must be in [0,1)");
+    HCTR_CHECK(al16(z), HCTR_ERR_INVALID, "train_bwd: 16-byte alignment");
+    memset(&p, 0, sizeof(p));
+    p.z = static_cast<const __nv_bfloat16*>(z);
+    p.mask = const_cast<uint8_t*>(static_cast<const uint8_t*>(mask));
+    p.B = B; p.H = H; p.W = W; p.C = C; p.pool = pool; p.drop_p = drop_p;
+    p.vshift = 0;
+    while ((1 << p.vshift) < C / 8) ++p.vshift;
+    HCTR_CHECK((1 << p.vshift) == C / 8, HCTR_ERR_INVALID, "train_bwd: C/8 must be a power of two (C=%d)", C);
+    return HCTR_OK;
+}
+
+int hctr_train_bwd_reduce(const void* dout, const void* z, const void* mask, float* pA2, float* pA3, int B, int H, int W,
+                          int C, int pool, float drop_p, void* stream) {
     ApplyParams p;
-    int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
+    int rc = fill_bwd(p, z, mask, B, H, W, C, pool, drop_p);
     if (rc) return rc;
     HCTR_CHECK(dout && pA2 && pA3 && al16(dout), HCTR_ERR_INVALID, "train_bwd_reduce: null pointer");
     const int slices = hctr_stat_slices(B, H, W);
@@ -640,11 +632,10 @@ int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int 
     return HCTR_OK;
 }
 
-int hctr_train_bwd_apply(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
-                         const void* res, const float* P, const float* Q, const float* R, void* dz, void* dres, int B,
-                         int H, int W, int C, int relu, int pool, float drop_p, unsigned seed, void* stream) {
+int hctr_train_bwd_apply(const void* dout, const void* z, const void* mask, const float* P, const float* Q, const float* R,
+                         void* dz, void* dres, int B, int H, int W, int C, int pool, float drop_p, void* stream) {
     ApplyParams p;
-    int rc = fill_apply(p, z, scale, shift, gate, res, B, H, W, C, relu, pool, drop_p, seed);
+    int rc = fill_bwd(p, z, mask, B, H, W, C, pool, drop_p);
     if (rc) return rc;
     HCTR_CHECK(dout && P && Q && R && dz && al16(dout) && al16(dz) && al16(dres) && al16(P) && al16(Q) && al16(R),
                HCTR_ERR_INVALID, "train_bwd_apply: bad pointer");

@@ -213,8 +213,10 @@ class hctr_model(nn.Module):
         params = [p for _, p in self.named_parameters()]
         fn = _core().train_engine._TrainFunction
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            eng.need_backward = True
             out = fn.apply(eng, x, base_seed, *params)
         else:
+            eng.need_backward = False
             logits, _ = eng.forward(x, base_seed)
             out = logits[:, :, :self.noutput].permute(1, 0, 2)
         return out if self.logits_dtype == torch.bfloat16 else out.float()

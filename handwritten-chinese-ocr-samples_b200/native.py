@@ -51,11 +51,11 @@ SIGNATURES = {
     "hctr_chan_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "hctr_bn_finalize_train": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hctr_se_excite_train": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "hctr_train_apply_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, c_float, c_uint, _P]),
-    "hctr_train_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, c_float, c_uint, _P]),
+    "hctr_train_apply_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, c_float, c_uint, _P]),
+    "hctr_train_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float, _P]),
     "hctr_train_bwd_finalize": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P,
                                      _P, _P, _P, _P, _P, _P, _P]),
-    "hctr_train_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, c_float, c_uint, _P]),
+    "hctr_train_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, c_float, _P]),
     "hctr_conv_dgrad": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hctr_conv_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _L, _P]),
     "hctr_wgrad_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),

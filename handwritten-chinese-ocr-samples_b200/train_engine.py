@@ -26,7 +26,7 @@ def _mix_seed(base, k):
 
 class _Saved(object):
     """What one conv+BN unit keeps for its backward."""
-    __slots__ = ("name", "x", "z", "scale", "shift", "mean", "invstd", "line_sum", "gate", "hidden", "se_mean", "res",
+    __slots__ = ("name", "x", "z", "mask", "scale", "shift", "mean", "invstd", "line_sum", "gate", "hidden", "se_mean", "res",
                  "relu", "pool", "drop_p", "seed", "B", "H", "W", "cin", "cout", "ksize", "stem", "se_name")
 
 
@@ -35,6 +35,7 @@ class TrainEngine(object):
         self.model = model
         self.lib = nat.lib()
         self.dropout_enabled = True
+        self.need_backward = True
         self._ones = {}
         self._zeros = {}
 
@@ -102,8 +103,11 @@ class TrainEngine(object):
         s.relu, s.pool, s.drop_p, s.seed = int(relu), int(pool), p, int(seed)
         s.B, s.H, s.W, s.cin, s.cout, s.ksize, s.stem = B, H, W, cin, cout, k, stem
         out = torch.empty((B, H // 2 if pool else H, W, cout), dtype=torch.bfloat16, device=dev)
+        s.mask = torch.empty((B, H, W, cout // 8), dtype=torch.uint8, device=dev) if self.need_backward else None
         nat.check(lib.hctr_train_apply_fwd(nat.ptr(z), nat.ptr(s.scale), nat.ptr(s.shift), nat.ptr(s.gate), nat.ptr(res),
-                                           nat.ptr(out), B, H, W, cout, s.relu, s.pool, p, s.seed, st), "train_apply_fwd")
+                                           nat.ptr(out), nat.ptr(s.mask), B, H, W, cout, s.relu, s.pool, p, s.seed, st),
+                  "train_apply_fwd")
+        s.res = res is not None          # the backward only needs to know whether a residual gradient is wanted
         return out, s
 
     def unit_backward(self, s, dout, conv, bn, grads, se=None, need_dx=True, add=None):
@@ -113,9 +117,8 @@ class TrainEngine(object):
         slices = lib.hctr_stat_slices(B, H, W)
         a2 = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
         a3 = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
-        nat.check(lib.hctr_train_bwd_reduce(nat.ptr(dout), nat.ptr(s.z), nat.ptr(s.scale), nat.ptr(s.shift), nat.ptr(s.gate),
-                                            nat.ptr(s.res), nat.ptr(a2), nat.ptr(a3), B, H, W, C, s.relu, s.pool, s.drop_p,
-                                            s.seed, st), "train_bwd_reduce")
+        nat.check(lib.hctr_train_bwd_reduce(nat.ptr(dout), nat.ptr(s.z), nat.ptr(s.mask), nat.ptr(a2), nat.ptr(a3), B, H, W, C,
+                                            s.pool, s.drop_p, st), "train_bwd_reduce")
         pq = torch.empty((2, B, C), dtype=torch.float32, device=dev)
         r = torch.empty((C,), dtype=torch.float32, device=dev)
         prefix = s.name
@@ -133,10 +136,9 @@ class TrainEngine(object):
             nat.ptr(w1), nat.ptr(w2), cr, nat.ptr(dw1), nat.ptr(dw2), nat.ptr(g_gamma), nat.ptr(g_beta), nat.ptr(g_bias),
             nat.ptr(pq[0]), nat.ptr(pq[1]), nat.ptr(r), st), "train_bwd_finalize")
         dz = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
-        dres = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev) if s.res is not None else None
-        nat.check(lib.hctr_train_bwd_apply(nat.ptr(dout), nat.ptr(s.z), nat.ptr(s.scale), nat.ptr(s.shift), nat.ptr(s.gate),
-                                           nat.ptr(s.res), nat.ptr(pq[0]), nat.ptr(pq[1]), nat.ptr(r), nat.ptr(dz), nat.ptr(dres),
-                                           B, H, W, C, s.relu, s.pool, s.drop_p, s.seed, st), "train_bwd_apply")
+        dres = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev) if s.res else None
+        nat.check(lib.hctr_train_bwd_apply(nat.ptr(dout), nat.ptr(s.z), nat.ptr(s.mask), nat.ptr(pq[0]), nat.ptr(pq[1]), nat.ptr(r),
+                                           nat.ptr(dz), nat.ptr(dres), B, H, W, C, s.pool, s.drop_p, st), "train_bwd_apply")
         g_w = grads[prefix[0] + ".weight"]
         if s.stem:
             nb = lib.hctr_stem_wgrad_workspace_bytes(B, H, W)

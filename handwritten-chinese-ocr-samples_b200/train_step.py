@@ -82,6 +82,7 @@ class TrainStep(object):
             if seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             self.engine.dropout_enabled = bool(getattr(m, "dropout_enabled", True))
+            self.engine.need_backward = True
             logits, ctx = self.engine.forward(x.detach().float().contiguous(), seed)
             B, W, pitch = logits.shape
             C = m.noutput

@@ -168,25 +168,25 @@ int hctr_bn_finalize_train(const float* psum, const float* psq, int B, int slice
 int hctr_se_excite_train(const float* line_sum, const float* scale, const float* shift, const float* w1, const float* w2,
                          float* se_mean, float* hidden, float* gate, int B, int C, int Cr, int HW, void* stream);
 /* out = dropout(pool(relu((z*scale+shift) [*gate] [+res]))) - BN apply, SE scale, residual, ReLU, (2,1) max-pool and
- * counter-based dropout (keep-scale 1/(1-p)) in one pass. z/res: bf16 NHWC [B][H][W][C]; out: [B][H or H/2][W][C]. */
+ * counter-based dropout (keep-scale 1/(1-p)) in one pass. z/res: bf16 NHWC [B][H][W][C]; out: [B][H or H/2][W][C];
+ * mask (may be NULL when no backward follows): uint8 [B][H][W][C/8], one keep-bit per INPUT element with the ReLU sign,
+ * the pool winner and the dropout keep folded together - all the backward needs of this pass. */
 int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, const float* gate, const void* res,
-                         void* out, int B, int H, int W, int C, int relu, int pool, float drop_p, unsigned seed,
+                         void* out, void* mask, int B, int H, int W, int C, int relu, int pool, float drop_p, unsigned seed,
                          void* stream);
-/* Backward of the pass above + BatchNorm (+SE) backward in three steps; with d_pre the gradient behind the
- * dropout/pool/ReLU masks: reduce -> per-(b,slice,c) sums of d_pre and d_pre*z; finalize -> dgamma, dbeta, conv-bias
- * gradient, SE FC gradients and the coefficients P[B][C], Q[B][C], R[C]; apply -> dz = P*d_pre + Q + R*z, dres = d_pre. */
-int hctr_train_bwd_reduce(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
-                          const void* res, float* pA2, float* pA3, int B, int H, int W, int C, int relu, int pool,
-                          float drop_p, unsigned seed, void* stream);
+/* Backward of the pass above + BatchNorm (+SE) backward in three steps; with d_pre = mask ? dout/(1-p) : 0:
+ * reduce -> per-(b,slice,c) sums of d_pre and d_pre*z; finalize -> dgamma, dbeta, conv-bias gradient, SE FC gradients and
+ * the coefficients P[B][C], Q[B][C], R[C]; apply -> dz = P*d_pre + Q + R*z, dres = d_pre. */
+int hctr_train_bwd_reduce(const void* dout, const void* z, const void* mask, float* pA2, float* pA3, int B, int H, int W,
+                          int C, int pool, float drop_p, void* stream);
 /* (finalize combines the per-slice partials in place: slice 0 of pA2/pA3 is overwritten with the totals) */
 int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int B, int C, int HW, const float* gamma,
                             const float* mean, const float* invstd, const float* scale, const float* shift,
                             const float* line_sum, const float* gate, const float* se_hidden, const float* se_mean,
                             const float* w1, const float* w2, int Cr, float* dw1, float* dw2, float* dgamma,
                             float* dbeta, float* dbias, float* P, float* Q, float* R, void* stream);
-int hctr_train_bwd_apply(const void* dout, const void* z, const float* scale, const float* shift, const float* gate,
-                         const void* res, const float* P, const float* Q, const float* R, void* dz, void* dres, int B,
-                         int H, int W, int C, int relu, int pool, float drop_p, unsigned seed, void* stream);
+int hctr_train_bwd_apply(const void* dout, const void* z, const void* mask, const float* P, const float* Q, const float* R,
+                         void* dz, void* dres, int B, int H, int W, int C, int pool, float drop_p, void* stream);
 
 /* Data gradient of a 3x3/1x1 convolution: the same tcgen05 implicit GEMM with mirrored taps. dz: bf16 NHWC
  * [B][H][W][Cout]; w_packed_t: bf16 [Cin][k*k][Cout]; ones/zeros: fp32 [Cin]; add: optional bf16 [B][H][W][Cin]

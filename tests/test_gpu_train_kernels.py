@@ -105,15 +105,15 @@ def test_bn_se_act_unit_forward_backward(B, H, W, C, gate, res, relu, pool):
         nat.check(lib.hctr_se_excite_train(nat.ptr(line), nat.ptr(st[2]), nat.ptr(st[3]), nat.ptr(w1), nat.ptr(w2), nat.ptr(sem),
                                            nat.ptr(hid), nat.ptr(gt_), B, C, Cr, H * W, S()))
     out = torch.empty(B, Ho, W, C, dtype=torch.bfloat16, device=dev)
+    mask = torch.empty(B, H, W, C // 8, dtype=torch.uint8, device=dev)
     nat.check(lib.hctr_train_apply_fwd(nat.ptr(zn), nat.ptr(st[2]), nat.ptr(st[3]), nat.ptr(gt_), nat.ptr(rn), nat.ptr(out),
-                                       B, H, W, C, relu, pool, 0.0, 0, S()))
+                                       nat.ptr(mask), B, H, W, C, relu, pool, 0.0, 0, S()))
     _close(out.permute(0, 3, 1, 2), y.detach(), GATE)
     zf = z.float().transpose(0, 1).reshape(C, -1)
     _close(rm, 0.1 * zf.mean(dim=1), 1e-4)
     _close(rv, 0.9 + 0.1 * zf.var(dim=1, unbiased=True), 1e-4)
     a2 = torch.empty(B, slices, C, device=dev); a3 = torch.empty(B, slices, C, device=dev)
-    nat.check(lib.hctr_train_bwd_reduce(nat.ptr(dn), nat.ptr(zn), nat.ptr(st[2]), nat.ptr(st[3]), nat.ptr(gt_), nat.ptr(rn),
-                                        nat.ptr(a2), nat.ptr(a3), B, H, W, C, relu, pool, 0.0, 0, S()))
+    nat.check(lib.hctr_train_bwd_reduce(nat.ptr(dn), nat.ptr(zn), nat.ptr(mask), nat.ptr(a2), nat.ptr(a3), B, H, W, C, pool, 0.0, S()))
     dgam = torch.empty(C, device=dev); dbet = torch.empty(C, device=dev); dbias = torch.empty(C, device=dev)
     PQ = torch.empty(2, B, C, device=dev); R = torch.empty(C, device=dev)
     dw1 = torch.empty(Cr, C, device=dev) if gate else None; dw2 = torch.empty(C, Cr, device=dev) if gate else None
@@ -123,9 +123,8 @@ def test_bn_se_act_unit_forward_backward(B, H, W, C, gate, res, relu, pool):
                                           nat.ptr(dgam), nat.ptr(dbet), nat.ptr(dbias), nat.ptr(PQ[0]), nat.ptr(PQ[1]), nat.ptr(R), S()))
     dzo = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev)
     dro = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev) if res else None
-    nat.check(lib.hctr_train_bwd_apply(nat.ptr(dn), nat.ptr(zn), nat.ptr(st[2]), nat.ptr(st[3]), nat.ptr(gt_), nat.ptr(rn),
-                                       nat.ptr(PQ[0]), nat.ptr(PQ[1]), nat.ptr(R), nat.ptr(dzo), nat.ptr(dro), B, H, W, C, relu, pool,
-                                       0.0, 0, S()))
+    nat.check(lib.hctr_train_bwd_apply(nat.ptr(dn), nat.ptr(zn), nat.ptr(mask), nat.ptr(PQ[0]), nat.ptr(PQ[1]), nat.ptr(R),
+                                       nat.ptr(dzo), nat.ptr(dro), B, H, W, C, pool, 0.0, S()))
     _close(dzo.permute(0, 3, 1, 2), zr.grad, GATE)
     _close(dgam, gr.grad, 1e-4); _close(dbet, br.grad, 1e-4)
     assert dbias.abs().max().item() <= 1e-3 * max(1.0, dbet.abs().max().item())     # sum dz == 0 behind a train-mode BN
@@ -142,22 +141,25 @@ def test_dropout_mask_statistics_and_backward_consistency():
     one, zero = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
     for p in (0.1, 0.3, 0.9):
         out = torch.empty_like(z)
-        nat.check(lib.hctr_train_apply_fwd(nat.ptr(z), nat.ptr(one), nat.ptr(zero), None, None, nat.ptr(out), B, H, W, C, 0, 0, p, 1234, S()))
+        mask = torch.empty(B, H, W, C // 8, dtype=torch.uint8, device="cuda")
+        nat.check(lib.hctr_train_apply_fwd(nat.ptr(z), nat.ptr(one), nat.ptr(zero), None, None, nat.ptr(out), nat.ptr(mask), B, H, W, C,
+                                           0, 0, p, 1234, S()))
         kept = (out != 0)
         n = kept.numel()
         assert abs(kept.float().mean().item() - (1 - p)) <= 5 * (p * (1 - p) / n) ** 0.5 + 1e-4      # 5 sigma
         assert abs(out.float().max().item() - 1 / (1 - p)) <= 2.0 ** -7 / (1 - p)
         # per-channel keep rates are uniform too
         assert (kept.float().mean(dim=(0, 1, 2)) - (1 - p)).abs().max().item() <= 0.03
-        # the backward regenerates the same mask: with P=1, Q=R=0 -> dz = d_pre = dout * mask / (1-p)
+        # the stored keep-mask drives the backward: with P=1, Q=R=0 -> dz = d_pre = dout * mask / (1-p)
         dout = torch.ones_like(z)
         P = torch.ones(B, C, device="cuda"); Q = torch.zeros(B, C, device="cuda"); R = torch.zeros(C, device="cuda")
         dz = torch.empty_like(z)
-        nat.check(lib.hctr_train_bwd_apply(nat.ptr(dout), nat.ptr(z), nat.ptr(one), nat.ptr(zero), None, None, nat.ptr(P), nat.ptr(Q),
-                                           nat.ptr(R), nat.ptr(dz), None, B, H, W, C, 0, 0, p, 1234, S()))
+        nat.check(lib.hctr_train_bwd_apply(nat.ptr(dout), nat.ptr(z), nat.ptr(mask), nat.ptr(P), nat.ptr(Q), nat.ptr(R), nat.ptr(dz),
+                                           None, B, H, W, C, 0, p, S()))
         assert torch.equal(dz != 0, kept)
+        assert abs(dz.float().max().item() - 1 / (1 - p)) <= 2.0 ** -7 / (1 - p)
         out2 = torch.empty_like(z)
-        nat.check(lib.hctr_train_apply_fwd(nat.ptr(z), nat.ptr(one), nat.ptr(zero), None, None, nat.ptr(out2), B, H, W, C, 0, 0, p, 99, S()))
+        nat.check(lib.hctr_train_apply_fwd(nat.ptr(z), nat.ptr(one), nat.ptr(zero), None, None, nat.ptr(out2), None, B, H, W, C, 0, 0, p, 99, S()))
         assert not torch.equal(out2 != 0, kept)
 
 
