@@ -16,7 +16,9 @@ def _bn(x, sd, name, train_stats=None):
         var = x.var(dim=(0, 2, 3), unbiased=False)
         train_stats[name] = (mean, x.var(dim=(0, 2, 3), unbiased=True))
     else:
-        mean, var = sd[name + ".running_mean"], sd[name + ".running_var"]
+        # eval mode: the same fused op nn.BatchNorm2d dispatches to (keeps the CPU baseline as fast as the reference)
+        return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
+                            False, 0.0, EPS)
     return ((x - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + EPS)
             * sd[name + ".weight"].view(1, -1, 1, 1) + sd[name + ".bias"].view(1, -1, 1, 1))
 
@@ -32,15 +34,20 @@ def _se(x, sd, name):                                                  # SELayer
     return x * y.view(y.shape[0], y.shape[1], 1, 1)
 
 
+def _relu(x):
+    # nn.ReLU(inplace=True) in the reference (:42,94); in place only when autograd is not recording
+    return torch.relu_(x) if not torch.is_grad_enabled() else torch.relu(x)
+
+
 def _block(x, sd, name, train_stats):                                   # BasicBlock.forward :47-60 (dropout = identity)
-    out = torch.relu(_bn(_conv(x, sd, name + ".conv1", 1), sd, name + ".bn1", train_stats))
+    out = _relu(_bn(_conv(x, sd, name + ".conv1", 1), sd, name + ".bn1", train_stats))
     out = _bn(_conv(out, sd, name + ".conv2", 1), sd, name + ".bn2", train_stats)
     out = _se(out, sd, name + ".se")
     if (name + ".downsample.0.weight") in sd:
         res = _bn(_conv(x, sd, name + ".downsample.0", 0), sd, name + ".downsample.1", train_stats)
     else:
         res = x
-    return torch.relu(out + res)
+    return _relu(out.add_(res) if not torch.is_grad_enabled() else out + res)
 
 
 def features(x, sd, train_stats=None, taps=None):
@@ -49,13 +56,13 @@ def features(x, sd, train_stats=None, taps=None):
         if taps is not None:
             taps[name] = v
         return v
-    x = tap("bn0_1", torch.relu(_bn(_conv(x, sd, "cnn.conv0_1", 1), sd, "cnn.bn0_1", train_stats)))
-    x = torch.relu(_bn(_conv(x, sd, "cnn.conv0_2", 1), sd, "cnn.bn0_2", train_stats))
+    x = tap("bn0_1", _relu(_bn(_conv(x, sd, "cnn.conv0_1", 1), sd, "cnn.bn0_1", train_stats)))
+    x = _relu(_bn(_conv(x, sd, "cnn.conv0_2", 1), sd, "cnn.bn0_2", train_stats))
     x = tap("pool0", F.max_pool2d(x, (2, 1), (2, 1)))
     for s, n in enumerate(STAGE_BLOCKS, start=1):
         for i in range(n):
             x = tap("block%d.%d" % (s, i), _block(x, sd, "cnn.block%d.%d" % (s, i), train_stats))
-        x = torch.relu(_bn(_conv(x, sd, "cnn.conv%d" % s, 1), sd, "cnn.bn%d" % s, train_stats))
+        x = _relu(_bn(_conv(x, sd, "cnn.conv%d" % s, 1), sd, "cnn.bn%d" % s, train_stats))
         x = tap("pool%d" % s, F.max_pool2d(x, (2, 1), (2, 1)))
     return x
 
