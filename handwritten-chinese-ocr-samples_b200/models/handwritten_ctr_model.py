@@ -241,7 +241,7 @@ class hctr_model(nn.Module):
         taps = spec.ksize * spec.ksize
         flops = 2.0 * B * H * W * spec.cout * spec.cin * taps
         nbytes = 2.0 * (x.numel() + y.numel() + spec.w.numel())
-        tag = "conv%dx%d_%d_%d%s" % (spec.ksize, spec.ksize, spec.cin, spec.cout, "_pool" if pool else "")
+        tag = "conv%dx%d_%d_%d_h%d%s" % (spec.ksize, spec.ksize, spec.cin, spec.cout, H, "_pool" if pool else "")
         self._launch(nat, tag, flops, nbytes, nat.lib().hctr_conv_bn_act_fwd,
                      nat.ptr(x), nat.ptr(spec.w), nat.ptr(spec.scale), nat.ptr(spec.shift), nat.ptr(y),
                      B, H, W, spec.cin, spec.cout, spec.ksize, int(relu), int(pool), nat.stream_ptr())
@@ -270,7 +270,7 @@ class hctr_model(nn.Module):
                 slices = lib.hctr_conv_se_slices(H, W)
                 partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
                 v = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
-                self._launch(nat, "conv3x3_%d_%d_se" % (spec.cin, spec.cout), 2.0 * B * H * W * C * spec.cin * 9,
+                self._launch(nat, "conv3x3_%d_%d_h%d_se" % (spec.cin, spec.cout, H), 2.0 * B * H * W * C * spec.cin * 9,
                              2.0 * (t.numel() + v.numel() + spec.w.numel()), lib.hctr_conv_bn_se_fwd,
                              nat.ptr(t), nat.ptr(spec.w), nat.ptr(spec.scale), nat.ptr(spec.shift), nat.ptr(v), nat.ptr(partial),
                              B, H, W, spec.cin, spec.cout, spec.ksize, st)
