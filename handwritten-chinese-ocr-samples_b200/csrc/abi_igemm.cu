@@ -44,13 +44,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 activation [B,H,W,C] -> 4-D map (C, W, H, B), box (64, 128, 1, 1), 128B swizzle, zero OOB fill.
-static int make_act_map(CUtensorMap* m, const void* x, int B, int H, int W, int C, long long pitch = 0) {
+static int make_act_map(CUtensorMap* m, const void* x, int B, int H, int W, int C, long long pitch = 0, int box_w = kTileM) {
     EncodeTiledFn enc = get_encode_fn();
     HCTR_CHECK(enc != nullptr, HCTR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     if (pitch <= 0) pitch = C;                    // elements between consecutive pixels
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)kTileM, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)box_w, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -87,10 +87,10 @@ static int sm_count() {
     return n;
 }
 
-template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI>
+template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
-    using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES>;
-    auto kern = igemm_tcgen05_kernel<BLOCK_N, NUM_SUB, STAGES, ACC_STAGES, EPI>;
+    using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES, KWF>;
+    auto kern = igemm_tcgen05_kernel<BLOCK_N, NUM_SUB, STAGES, ACC_STAGES, EPI, KWF>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -101,6 +101,8 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }
+
+static int g_kwf_mode = 2;     // measured on B200: the plain 128-byte start-address shift is what the hardware expects
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -178,17 +180,32 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "conv: too many tiles");
     p.total_tiles = (int)total;
 
+    // thin layers (Cout <= 128) are bound by the L2->SMEM re-reads of the activation tile: fuse the three kw taps
+    const int kwf = (ksize == 3 && block_n <= 128) ? g_kwf_mode : 0;
+    p.kwf_base_offset = (kwf == 1);
     CUtensorMap tmA, tmB;
-    int rc = make_act_map(&tmA, x, B, H, W, Cin);
+    int rc = make_act_map(&tmA, x, B, H, W, Cin, 0, kwf ? kSlabPix : kTileM);
     if (rc) return rc;
     rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, block_n);
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (kwf) {
+        if (block_n == 64) return launch_igemm<64, 2, 3, 2, EPI_CONV, 1>(tmA, tmB, p, s);
+        return launch_igemm<128, 2, 2, 2, EPI_CONV, 1>(tmA, tmB, p, s);
+    }
     switch (block_n) {
         case 64:  return launch_igemm<64, 2, 4, 2, EPI_CONV>(tmA, tmB, p, s);
         case 128: return launch_igemm<128, 2, 4, 2, EPI_CONV>(tmA, tmB, p, s);
         default:  return launch_igemm<256, 2, 3, 1, EPI_CONV>(tmA, tmB, p, s);
     }
+}
+
+// 0 = one TMA box per tap, 2 = kw-fused slab addressed by shifting the descriptor start address by whole 128-byte rows
+// (default; the swizzle XOR is taken from the absolute shared-memory address, so no base_offset is needed), 1 = the same
+// with the row phase also written to the descriptor's base_offset field (measured WRONG on B200 - kept for the record)
+int hctr_debug_set_kwf_mode(int mode) {
+    g_kwf_mode = mode;
+    return HCTR_OK;
 }
 
 int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,

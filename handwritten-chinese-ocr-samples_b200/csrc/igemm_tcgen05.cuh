@@ -35,6 +35,7 @@ struct IgemmParams {
     int ntaps;
     int8_t tap_dh[kMaxTaps];
     int8_t tap_dw[kMaxTaps];
+    int kwf_base_offset;      // KWF: 1 = put the slab row phase into the descriptor's base_offset field
     int sub_dh, sub_dw;       // offset of sub-tile s relative to sub-tile 0: (s*sub_dh rows, s*sub_dw*128 px)
     int N;                    // output channels / classes
     // tiling (derived on host)
@@ -55,21 +56,28 @@ struct IgemmParams {
                               // logits as stored (log_softmax fused into the classifier epilogue; combined by lse_combine)
 };
 
-template <int BLOCK_N, int NUM_SUB, int STAGES>
+// KWF ("kw-fused", 3x3 convs only): one A box of 136 pixels (w0-1 .. w0+134) per (kh, 64-channel chunk) serves the three
+// kw taps - the MMA for tap kw starts (dw+1) rows = (dw+1)*128 B further into the box. The 128-byte swizzle XOR is a
+// function of the absolute shared-memory address (measured: results are exact with base_offset = 0 and wrong with the
+// row phase in base_offset), so a whole-row shift of the start address needs nothing else. The activation tile then
+// crosses L2->SMEM 3 instead of 9 times; a stage holds 3 weight tiles.
+constexpr int kSlabPix = 136;
+
+template <int BLOCK_N, int NUM_SUB, int STAGES, int KWF = 0>
 struct IgemmSmem {
-    static constexpr int kABytes = kTileM * kBlockK * 2;      // 16 KB per sub-tile
+    static constexpr int kABytes = (KWF ? kSlabPix : kTileM) * kBlockK * 2;      // 16 KB (17 KB slab) per sub-tile
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-    static constexpr int kStageBytes = NUM_SUB * kABytes + kBBytes;
+    static constexpr int kStageBytes = NUM_SUB * kABytes + (KWF ? 3 : 1) * kBBytes;
     static constexpr int kBarBytes = 1024;
     static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
 };
 
-template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI>
+template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmB,
                      const IgemmParams p) {
-    using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES>;
+    using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES, KWF>;
     constexpr int kAccCols = NUM_SUB * BLOCK_N;
     constexpr int kTmemCols = ACC_STAGES * kAccCols;
     static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols >= 32,
@@ -101,7 +109,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kblocks = p.ntaps * p.cin_chunks;
+    const int kblocks = (KWF ? 3 : p.ntaps) * p.cin_chunks;      // KWF: one K block = (kh, chunk) = three taps
     const int sub_rows = p.sub_dh ? NUM_SUB : 1;     // input rows covered by one tile
     const int sub_cols = p.sub_dw ? NUM_SUB : 1;     // 128-px spans covered by one tile
 
@@ -118,21 +126,32 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                 const int h0 = h_tile * sub_rows;
                 const int w0 = w_tile * sub_cols * kTileM;
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    const int tap = kb / p.cin_chunks;
+                    const int tap = kb / p.cin_chunks;                 // KWF: this is kh
                     const int ch = kb - tap * p.cin_chunks;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
                     uint8_t* st = smem + stage * L::kStageBytes;
+                    if constexpr (KWF) {
 #pragma unroll
-                    for (int s = 0; s < NUM_SUB; ++s) {
-                        tma_load_4d(st + s * L::kABytes, &tmA, &full_bar[stage],
-                                    ch * kBlockK,
-                                    w0 + s * p.sub_dw * kTileM + p.tap_dw[tap],
-                                    h0 + s * p.sub_dh + p.tap_dh[tap],
-                                    b);
+                        for (int s = 0; s < NUM_SUB; ++s)
+                            tma_load_4d(st + s * L::kABytes, &tmA, &full_bar[stage], ch * kBlockK, w0 - 1,
+                                        h0 + s * p.sub_dh + p.tap_dh[tap * 3], b);
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+                            tma_load_2d(st + NUM_SUB * L::kABytes + kw * L::kBBytes, &tmB, &full_bar[stage],
+                                        ((tap * 3 + kw) * p.cin_chunks + ch) * kBlockK, n_tile * BLOCK_N);
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NUM_SUB; ++s) {
+                            tma_load_4d(st + s * L::kABytes, &tmA, &full_bar[stage],
+                                        ch * kBlockK,
+                                        w0 + s * p.sub_dw * kTileM + p.tap_dw[tap],
+                                        h0 + s * p.sub_dh + p.tap_dh[tap],
+                                        b);
+                        }
+                        tma_load_2d(st + NUM_SUB * L::kABytes, &tmB, &full_bar[stage],
+                                    kb * kBlockK, n_tile * BLOCK_N);
                     }
-                    tma_load_2d(st + NUM_SUB * L::kABytes, &tmB, &full_bar[stage],
-                                kb * kBlockK, n_tile * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -152,13 +171,31 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                 if (lane == 0) {
                     const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t b_addr = a_addr + NUM_SUB * L::kABytes;
+                    if constexpr (KWF) {
+                        const int kh = kb / p.cin_chunks;
 #pragma unroll
-                    for (int s = 0; s < NUM_SUB; ++s) {
+                        for (int s = 0; s < NUM_SUB; ++s) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                            const uint64_t da = make_sw128_kmajor_desc(a_addr + s * L::kABytes + k * kUmmaK * 2);
-                            const uint64_t db = make_sw128_kmajor_desc(b_addr + k * kUmmaK * 2);
-                            umma_bf16(d_base + s * BLOCK_N, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const uint32_t shift = static_cast<uint32_t>(p.tap_dw[kh * 3 + kw] + 1);   // rows into the slab
+#pragma unroll
+                                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                    uint64_t da = make_sw128_kmajor_desc(a_addr + s * L::kABytes + shift * 128 + k * kUmmaK * 2);
+                                    if (p.kwf_base_offset) da |= static_cast<uint64_t>(shift & 7u) << 49;         // swizzle phase of row 0
+                                    const uint64_t db = make_sw128_kmajor_desc(b_addr + kw * L::kBBytes + k * kUmmaK * 2);
+                                    umma_bf16(d_base + s * BLOCK_N, da, db, idesc, (kb | kw | k) != 0 ? 1u : 0u);
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NUM_SUB; ++s) {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                const uint64_t da = make_sw128_kmajor_desc(a_addr + s * L::kABytes + k * kUmmaK * 2);
+                                const uint64_t db = make_sw128_kmajor_desc(b_addr + k * kUmmaK * 2);
+                                umma_bf16(d_base + s * BLOCK_N, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
                         }
                     }
                     umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire

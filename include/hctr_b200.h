@@ -68,6 +68,12 @@ int hctr_conv_se_slices(int H, int W);
 int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
                         float* se_partial, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 
+/* Tuning/debug switch for the thin (Cout <= 128) 3x3 layers: 0 = one TMA box per tap; 2 (default) = kw-fused: one
+ * 136-pixel activation slab per (kh, 64-channel chunk) serves the three kw taps by shifting the UMMA descriptor start
+ * address by whole 128-byte rows (3x fewer L2->SMEM activation bytes, +15 % on those layers); 1 = the same plus the
+ * descriptor base_offset field (measured wrong on B200; kept to document the experiment). */
+int hctr_debug_set_kwf_mode(int mode);
+
 /* SELayer squeeze (:27-28): deterministic two-stage mean over (H,W) incl. padded columns.
  * x: bf16 NHWC; partial: fp32 workspace [B][slices][C]; the second stage runs inside hctr_se_excite.
  * `slices` must equal hctr_se_slices(H, W). */
