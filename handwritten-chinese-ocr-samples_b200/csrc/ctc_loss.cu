@@ -3,14 +3,25 @@
 // Three passes:
 //   A (HBM-bound): one warp per (t,b) row -> log-sum-exp, and the gathered log-probs of the blank-interleaved
 //                  label sequence l' (S = 2L+1) for the recursion.
-//   B (latency-bound): two CTAs per sequence run the alpha and the beta recursion CONCURRENTLY, state in shared memory
-//                  (ping-pong, one barrier per step), 3-way log-sum-exp as ATen's ctc_loss. The state is fp64 -
-//                  |log alpha| reaches ~2e4 at T=2048, C=7375, where fp32 log-space resolves only ~2e-3 - but the
-//                  exp/log act on O(1) differences and run in fp32 (fast SFU path), which keeps a step at ~0.2 us.
+//   B (latency-bound): alpha and beta run CONCURRENTLY (grid (B,2)), each as ONE WARP per sequence holding the state in
+//                  registers (K = 4..32 consecutive states per lane, neighbours by shuffle: no barrier, no shared-memory
+//                  round trip). The recursion is evaluated in SCALED LINEAR space in fp64:
+//                      a_t(s) = (a_{t-1}(s) + a_{t-1}(s-1) + [skip] a_{t-1}(s-2)) * p_t(l'_s) * 2^-d_t
+//                  with an exact power-of-two rescale per step (d_t from the warp-wide maximum exponent two steps back,
+//                  a dead-beat controller, so the reduction is off the dependency chain) and the per-step exponents
+//                  kept as integers. No exp/log on the chain: a step is two shuffles, two adds and a multiply. The
+//                  label probabilities are staged through shared memory with cp.async three chunks deep. beta is the
+//                  same recursion on the reversed label sequence and reversed time.
+//                  Linear space cannot hold states more than ~2^-700 below the row maximum; steps that drop such a
+//                  state are marked, a verify pass proves the dropped paths carry < 2^-260 of the likelihood (the
+//                  opposite recursion is not small where this one peaks) and otherwise - or when a label probability
+//                  is below e^-80 - the sequence is recomputed by the log-space recursion (fp64 state, 3-way
+//                  log-sum-exp as ATen's ctc_loss), which has no such limit.
 //   C (HBM-bound): one CTA per row: grad = (softmax - occupancy) * scale written in one pass, where
 //                  occupancy_c = sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - ll - lp[t, l'_s]).
 // Logits are read twice and the gradient written once: (2*s_in + s_out) * T*B*C bytes.
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "../../include/hctr_b200.h"
@@ -19,34 +30,58 @@ namespace hctr {
 
 struct CtcWs {
     float* lse;        // [B][T]
-    float* lpg;        // [B][T][Smax]   log-prob of l'_s at (t,b)
-    double* alpha;     // [B][T][Smax]   alpha (fp64 state)
-    double* beta;      // [B][T][Smax]   beta (fp64 state); occupancy = exp(alpha + beta - lp - ll)
+    float* lpg;        // [B][T][Sp]     log-prob of l'_s at (t,b) (log-space fallback)
+    double* pg;        // [B][T][Sp]     probability of l'_s at (t,b), zero beyond S (scaled linear recursion)
+    double* alpha;     // [B][T][Sa]     linear mode: alpha_t(s) / 2^ea[t][s/K];  log mode: log alpha_t(s)
+    double* beta;      // [B][T][Sa]     linear mode: MIRRORED, beta[s'] = beta_t(S-1-s') / 2^eb[t][s'/K];  log mode: log beta_t(s)
+    int* ea;           // [B][T][32]     per lane of the scan: (binary exponent << 1) | (a state was dropped at this step)
+    int* eb;           // [B][T][32]     (lanes of the beta scan hold mirrored states s' = S-1-s)
     double* ll;        // [B]            log-likelihood (may be -inf), fp64
-    int* canon;        // [B][Smax]      first s' with the same class as s
+    double* pfin;      // [B]            linear mode: likelihood / 2^efin
+    int* efin;         // [B]
+    int* flag;         // [B]            1 = this sequence takes the log-space recursion
+    int* canon;        // [B][Sp]        first s' with the same class as s
     int* toff;         // [B]            offset of sequence b in the concatenated targets
 };
 
 __host__ __device__ inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
-static CtcWs carve(void* base, int T, int B, int Smax, long long* total) {
+// row pitch of the per-state arrays: S = 2L+1 rounded up to a multiple of 4 (16-byte rows of floats)
+__host__ __device__ inline int state_pitch(int max_target_len) { return (2 * max_target_len + 1 + 3) / 4 * 4; }
+// states per lane of the one-warp scan (0: too many states, log-space recursion only) and the alpha/beta row pitch
+inline int scan_lane_states(int Sp) { return Sp <= 128 ? 4 : Sp <= 256 ? 8 : Sp <= 512 ? 16 : 0; }
+inline int alpha_pitch(int Sp) { const int k = scan_lane_states(Sp); return k ? 32 * k : Sp; }
+
+static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     long long off = 0;
     auto take = [&](long long bytes) { long long o = off; off = align_up(off + bytes, 256); return o; };
     const long long o_lse = take(4ll * B * T);
-    const long long o_lpg = take(4ll * B * T * Smax);
-    const long long o_alpha = take(8ll * B * T * Smax);
-    const long long o_beta = take(8ll * B * T * Smax);
+    const long long o_lpg = take(4ll * B * T * Sp);
+    const long long o_pg = take(8ll * B * T * Sp);
+    const long long o_alpha = take(8ll * B * T * Sa);
+    const long long o_beta = take(8ll * B * T * Sa);
+    const long long o_ea = take(4ll * B * T * 32);
+    const long long o_eb = take(4ll * B * T * 32);
     const long long o_ll = take(8ll * B);
-    const long long o_canon = take(4ll * B * Smax);
+    const long long o_pfin = take(8ll * B);
+    const long long o_efin = take(4ll * B);
+    const long long o_flag = take(4ll * B);
+    const long long o_canon = take(4ll * B * Sp);
     const long long o_toff = take(4ll * B);
     if (total) *total = off;
     CtcWs w;
     char* p = static_cast<char*>(base);
     w.lse = reinterpret_cast<float*>(p + o_lse);
     w.lpg = reinterpret_cast<float*>(p + o_lpg);
+    w.pg = reinterpret_cast<double*>(p + o_pg);
     w.alpha = reinterpret_cast<double*>(p + o_alpha);
     w.beta = reinterpret_cast<double*>(p + o_beta);
+    w.ea = reinterpret_cast<int*>(p + o_ea);
+    w.eb = reinterpret_cast<int*>(p + o_eb);
     w.ll = reinterpret_cast<double*>(p + o_ll);
+    w.pfin = reinterpret_cast<double*>(p + o_pfin);
+    w.efin = reinterpret_cast<int*>(p + o_efin);
+    w.flag = reinterpret_cast<int*>(p + o_flag);
     w.canon = reinterpret_cast<int*>(p + o_canon);
     w.toff = reinterpret_cast<int*>(p + o_toff);
     return w;
@@ -83,14 +118,15 @@ template <> struct Ld<__nv_bfloat16> {
 };
 
 // ---------------------------------------------------------------- prep: target offsets + canonical states
-__global__ void ctc_prep_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen, int B, int Smax,
-                                CtcWs w) {
+__global__ void ctc_prep_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen, int B, int Sp,
+                                int force_log, CtcWs w) {
     __shared__ int s_off;
     const int b = blockIdx.x;
     if (threadIdx.x == 0) {
         int off = 0;
         for (int i = 0; i < b; ++i) off += tlen[i];
         s_off = off; w.toff[b] = off;
+        w.flag[b] = force_log;              // 1: more states than the one-warp scan holds
     }
     __syncthreads();
     const int L = tlen[b], S = 2 * L + 1;
@@ -102,9 +138,13 @@ __global__ void ctc_prep_kernel(const int32_t* __restrict__ targets, const int32
             const int cq = (q & 1) ? tg[q >> 1] : 0;
             if (cq == c) { first = q; break; }
         }
-        w.canon[(long long)b * Smax + s] = first;
+        w.canon[(long long)b * Sp + s] = first;
     }
 }
+
+// label probabilities below this take the sequence to the log-space recursion (keeps p representable in fp32 and bounds
+// the per-step shrink of the scaled recursion by 2^-116)
+constexpr float kMinLinearLogProb = -80.f;
 
 // ---------------------------------------------------------------- pass A: row log-sum-exp + label gather
 constexpr int kLseWarps = 8;
@@ -113,7 +153,7 @@ template <typename T>
 __global__ void __launch_bounds__(kLseWarps * 32)
 ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
                       const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen,
-                      const int32_t* __restrict__ ilen, int Smax, const float* __restrict__ lse_in, CtcWs w) {
+                      const int32_t* __restrict__ ilen, int Sp, const float* __restrict__ lse_in, CtcWs w) {
     constexpr int V = Ld<T>::N;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * kLseWarps + (threadIdx.x >> 5);     // row = b*T + t
@@ -169,14 +209,296 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
     if (lane == 0) w.lse[row] = lse;
     const int L = tlen[b], S = 2 * L + 1;
     const int32_t* tg = targets + w.toff[b];
-    float* dst = w.lpg + row * Smax;
-    for (int q = lane; q < S; q += 32) {
-        const int c = (q & 1) ? tg[q >> 1] : 0;
-        dst[q] = Ld<T>::one(p + c) - lse;
+    float* dst = w.lpg + row * Sp;
+    double* dpr = w.pg + row * Sp;
+    bool small = false;
+    for (int q = lane; q < Sp; q += 32) {
+        float lp = 0.f;
+        double pr = 0.0;
+        if (q < S) {
+            const int c = (q & 1) ? tg[q >> 1] : 0;
+            lp = Ld<T>::one(p + c) - lse;
+            pr = (double)expf(lp);
+            small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);       // exp(-inf) = 0 is exact in linear space
+            small |= !(lp == lp);                                        // NaN: let the log-space path propagate it
+        }
+        dst[q] = lp;
+        dpr[q] = pr;
+    }
+    if (__any_sync(0xffffffffu, small) && lane == 0) w.flag[b] = 1;
+}
+
+// ---------------------------------------------------------------- pass B (fast): scaled linear recursion, one warp
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr int kTinyExp = -760;                       // a state this far below its lane's scale is about to be lost: it
+                                                     // shrinks by at most 2^-240 per pair of steps, so it is still exact
+                                                     // when the exponent step sees it
+constexpr int kTinyHi = (1023 + kTinyExp) << 20;     // high word of 2^kTinyExp
+constexpr int kRebaseDiff = 400;                     // adopt the left neighbour's exponent when it is this far above ours
+constexpr int kScanChunkStates = 32;                 // steps per staged chunk x states per lane
+constexpr int kScanStageDoubles = 3 * kScanChunkStates * 32;     // 3 chunks in flight = 24 KB
+
+__device__ __forceinline__ void cp_async_f64(void* smem_dst, const double* src, bool valid) {
+    const int bytes = valid ? 8 : 0;                                      // 0 source bytes = zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(smem_dst)), "l"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ double pow2_clamped(int x) {          // 2^x, exact, x clamped to the normal range
+    x = max(-1022, min(1023, x));
+    return __hiloint2double((1023 + x) << 20, 0);
+}
+
+// grid (B, 2), 32 threads: blockIdx.y == 0 runs alpha (and the log-likelihood), 1 runs beta as the alpha recursion of
+// the reversed problem (state s' = S-1-s, time i = Tb-1-t; stored mirrored). Lane l owns states l*K .. l*K+K-1 and carries
+// its own binary exponent e (true value = v * 2^e, "block floating point"): neighbouring states stay within a bounded
+// factor of each other, states far apart do not, so the dynamic range across lanes is unlimited like in log space.
+// Steps come in pairs: the first of a pair handles exponents (adopt / compare with the left neighbour, rescale by a
+// power of two, look for dropped states), the second is the bare recursion.
+template <int K>
+__global__ void __launch_bounds__(32)
+ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen, const int32_t* __restrict__ ilen,
+                int Tn, int Sp, float* __restrict__ nll_out, CtcWs w) {
+    constexpr int CH = kScanChunkStates / K;          // steps per staged chunk (even)
+    constexpr int SA = 32 * K;                        // alpha/beta row pitch: every lane's states exist in memory
+    static_assert(CH % 2 == 0 && K % 2 == 0, "pairs of steps, pairs of states");
+    __shared__ __align__(16) double stage[kScanStageDoubles];
+    __shared__ double fin_v[2];
+    __shared__ int fin_e[2];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const bool rev = blockIdx.y == 1;
+    if (w.flag[b]) return;                            // already sent to the log-space recursion
+    const int L = tlen[b], S = 2 * L + 1;
+    const int Tb = min(ilen[b], Tn);
+    if (Tb <= 0) {
+        if (!rev && lane == 0) {
+            const double ll = (L == 0) ? 0.0 : -INFINITY;
+            w.ll[b] = ll; w.pfin[b] = 1.0; w.efin[b] = 0;
+            nll_out[b] = 0.f;                         // -0 or inf -> 0 (zero_infinity)
+        }
+        return;
+    }
+    const int32_t* tg = targets + w.toff[b];
+    const int s0 = lane * K;
+    // transition s'-2 -> s' is allowed iff l''_{s'} is a label different from l''_{s'-2} (same test in either direction);
+    // kept as 0/1 multipliers so that the recursion is fused multiply-adds without selects
+    double skd[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const int sp = s0 + j;
+        skd[j] = 0.0;
+        if (sp >= 2 && sp < S) {
+            const int s = rev ? S - 1 - sp : sp;
+            const int s2 = rev ? s + 2 : s - 2;
+            if ((s & 1) && tg[s >> 1] != tg[s2 >> 1]) skd[j] = 1.0;
+        }
+    }
+    const double* P = w.pg + (long long)b * Tn * Sp;
+    const long long tstep = rev ? -1 : 1;             // rows advance forwards for alpha, backwards for beta
+    const int t_first = rev ? Tb - 1 : 0;
+    double* orow = (rev ? w.beta : w.alpha) + ((long long)b * Tn + t_first) * SA + s0;
+    int* erow = (rev ? w.eb : w.ea) + ((long long)b * Tn + t_first) * 32 + lane;
+
+    const int nsteps = Tb - 1;                        // steps i = 1 .. Tb-1; step i reads row t_first + i*tstep
+    const int nchunks = (nsteps + CH - 1) / CH;
+    // source of this lane's state j in a row (mirrored for beta). States beyond S are zero-filled (0 source bytes; the
+    // address still lies inside the workspace). Rows past the last step are clamped to the last row (copied, unused).
+    const int src_off = rev ? S - 1 - s0 : s0;
+    const double* isrc = P + (long long)t_first * Sp + src_off;          // row of the next step to be staged
+    const long long istride = tstep * Sp;
+    int ileft = nsteps;                                                    // steps not yet staged
+    int nbytes[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) nbytes[j] = (s0 + j < S) ? 8 : 0;
+    const uint32_t stage_u32 = smem_u32(stage) + lane * 8;
+    auto issue = [&](int slot) {
+        const uint32_t dst = stage_u32 + slot * (kScanChunkStates * 32 * 8);
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            if (ileft > 0) { isrc += istride; --ileft; }
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
+                             :: "r"(dst + (u * K + j) * 256), "l"(rev ? isrc - j : isrc + j), "r"(nbytes[j]) : "memory");
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+
+    // ---- i = 0
+    double v[K];
+    bool empty = true;                                // all of this lane's states are exactly zero
+    {
+        const double* src = P + (long long)t_first * Sp + src_off;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int sp = s0 + j;
+            v[j] = (sp < 2 && sp < S) ? (rev ? src[-j] : src[j]) : 0.0;
+            empty &= (v[j] == 0.0);
+        }
+#pragma unroll
+        for (int j = 0; j < K; j += 2) *reinterpret_cast<double2*>(orow + j) = make_double2(v[j], v[j + 1]);
+        *erow = 0;
+    }
+    int e = 0;                                        // true value = v * 2^e
+    int d_next = 0, d_after = 0;                      // rescale exponents for the next two exponent steps
+    int slot = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        issue(slot == 0 ? 2 : slot - 1);
+        cp_async_wait<2>();                           // chunk c has landed (each lane reads only what it copied itself)
+        const double* buf = stage + slot * (kScanChunkStates * 32) + lane;
+        slot = slot == 2 ? 0 : slot + 1;
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int i = 1 + c * CH + u;
+            if (i > nsteps) break;                    // warp-uniform
+            orow += tstep * SA;
+            erow += tstep * 32;
+            // ---- the two states to the left live in lane-1, in its units
+            const double n1 = __shfl_up_sync(0xffffffffu, v[K - 1], 1);
+            const double n2 = __shfl_up_sync(0xffffffffu, v[K - 2], 1);
+            const int pk = __shfl_up_sync(0xffffffffu, (e << 1) | (empty ? 1 : 0), 1);
+            const bool nempty = (pk & 1) != 0 || lane == 0;
+            const int ne = pk >> 1;
+            double nv[K];
+            if ((u & 1) == 0) {
+                // ---- exponent step
+                bool drop = false;
+                if (empty) { e = ne; d_next = 0; d_after = 0; }           // nothing here yet: take the neighbour's units
+                int diff = ne - e;
+                if (!nempty && diff > kRebaseDiff) {
+                    // what arrives is far above what this lane holds: re-express the lane in the neighbour's units
+                    const double rr = pow2_clamped(-diff);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const double nvj = (diff > 1022) ? 0.0 : v[j] * rr;
+                        const int hj = __double2hiint(nvj);
+                        drop |= static_cast<unsigned>(hj - 1) < static_cast<unsigned>(kTinyHi - 1);
+                        if (v[j] != 0.0 && hj < 0x00100000) w.flag[b] = 1;       // lost on the spot (never seen in practice)
+                        v[j] = nvj;
+                    }
+                    e = ne; d_next = 0; d_after = 0; diff = 0;
+                }
+                const double r = nempty ? 0.0 : pow2_clamped(diff);
+                const int d = d_next;
+                const double sc = pow2_clamped(-d);
+                e += d;
+                int mh = 0;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const double ps = buf[(u * K + j) * 32] * sc;
+                    double a;
+                    if (j == 0)      a = fma(fma(n2, skd[0], n1), r, v[0]);
+                    else if (j == 1) a = fma(n1 * skd[1], r, v[1] + v[0]);
+                    else             a = fma(v[j - 2], skd[j], v[j] + v[j - 1]);
+                    nv[j] = a * ps;
+                    const int hi = __double2hiint(nv[j]);
+                    mh = max(mh, hi);
+                    drop |= static_cast<unsigned>(hi - 1) < static_cast<unsigned>(kTinyHi - 1);   // 0 < value < 2^kTinyExp
+                }
+                empty = (mh == 0);
+                // dead-beat rescale with a lag of two exponent steps: the maximum seen now, minus the correction
+                // that is already scheduled
+                const int mexp = mh ? ((mh >> 20) & 0x7ff) - 1023 : 0;
+                d_next = d_after;
+                d_after = max(-1000, min(1000, mexp - d_next));
+                *erow = (e << 1) | (drop ? 1 : 0);
+            } else {
+                // ---- bare step: this lane keeps its units
+                const double r = nempty ? 0.0 : pow2_clamped(ne - e);
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const double ps = buf[(u * K + j) * 32];
+                    double a;
+                    if (j == 0)      a = fma(fma(n2, skd[0], n1), r, v[0]);
+                    else if (j == 1) a = fma(n1 * skd[1], r, v[1] + v[0]);
+                    else             a = fma(v[j - 2], skd[j], v[j] + v[j - 1]);
+                    nv[j] = a * ps;
+                }
+                empty = empty && (nv[0] == 0.0) && (nv[1] == 0.0);      // states >= 2 cannot fill before 0 and 1
+                *erow = e << 1;
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) v[j] = nv[j];
+#pragma unroll
+            for (int j = 0; j < K; j += 2) *reinterpret_cast<double2*>(orow + j) = make_double2(nv[j], nv[j + 1]);
+        }
+    }
+    cp_async_wait<0>();
+    if (!rev) {
+        // likelihood = alpha(S-1) + alpha(S-2) at the last step, each in its lane's units
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int sp = s0 + j;
+            if (sp == S - 1) { fin_v[0] = v[j]; fin_e[0] = e; }
+            if (sp == S - 2) { fin_v[1] = v[j]; fin_e[1] = e; }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const bool two = S > 1;
+            const int em = two ? max(fin_e[0], fin_e[1]) : fin_e[0];
+            const double pf = fin_v[0] * pow2_clamped(fin_e[0] - em) + (two ? fin_v[1] * pow2_clamped(fin_e[1] - em) : 0.0);
+            if (!(pf > 0.0)) {
+                // zero (infeasible alignment, or everything dropped) or NaN: the log-space recursion decides
+                w.flag[b] = 1;
+            } else {
+                const double ll = log(pf) + (double)em * 0.693147180559945309417;
+                w.ll[b] = ll; w.pfin[b] = pf; w.efin[b] = em;
+                float n = (float)(-ll);
+                if (!(n < INFINITY)) n = 0.f;
+                nll_out[b] = n;
+            }
+        }
     }
 }
 
-// ---------------------------------------------------------------- pass B: alpha / beta recursion
+// binary exponent of a positive normal double (others: a very negative number)
+__device__ __forceinline__ int exp2_of(double v) {
+    const int hi = __double2hiint(v);
+    const int ex = (hi >> 20) & 0x7ff;
+    return (hi > 0 && ex != 0) ? ex - 1023 : -(1 << 28);
+}
+
+// One warp per (b,t) row in which some lane saw a state below 2^kTinyExp of its scale (still exact at that moment, gone a
+// few steps later). The paths that will be lost through such a state s weigh alpha(s) beta(s) / p(s) <= 2^116 alpha(s) beta(s);
+// the likelihood is at least M = max_s alpha(s) beta(s). If every such state has alpha(s) beta(s) <= 2^-176 M the loss is
+// below 2^-60 relative; otherwise the sequence goes to the log-space recursion. Exponent arithmetic only. Without a
+// gradient (no beta) any such row sends the sequence there.
+template <int K>
+__global__ void __launch_bounds__(256)
+ctc_scan_verify_kernel(const int32_t* __restrict__ tlen, const int32_t* __restrict__ ilen, int Tn, int Bn,
+                       int have_beta, CtcWs w) {
+    constexpr int SA = 32 * K;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (long long)Tn * Bn) return;
+    const int b = (int)(row / Tn), t = (int)(row - (long long)b * Tn);
+    if (t >= ilen[b] || w.flag[b]) return;
+    const int ea_l = w.ea[row * 32 + lane];
+    const int eb_l = have_beta ? w.eb[row * 32 + lane] : 0;
+    if (!__any_sync(0xffffffffu, ((ea_l | eb_l) & 1) != 0)) return;
+    if (!have_beta) { if (lane == 0) w.flag[b] = 1; return; }
+    const int S = 2 * tlen[b] + 1;
+    const double* al = w.alpha + row * SA;
+    const double* be = w.beta + row * SA;
+    const int NEG = -(1 << 27);
+    int m = NEG, cand = NEG;
+    for (int s = lane; s < S; s += 32) {
+        const int sm = S - 1 - s;                                      // where the beta scan keeps state s
+        const int ma = exp2_of(al[s]), mb = exp2_of(be[sm]);           // relative to the lane scale
+        if (ma <= NEG || mb <= NEG) continue;                          // no path through s survives on both sides
+        const int x = ma + (w.ea[row * 32 + s / K] >> 1) + mb + (w.eb[row * 32 + sm / K] >> 1);
+        m = max(m, x);
+        if (ma < kTinyExp || mb < kTinyExp) cand = max(cand, x);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    cand = __reduce_max_sync(0xffffffffu, cand);
+    if (lane == 0 && (m <= NEG || cand + 116 + 60 > m)) w.flag[b] = 1;
+}
+
+// ---------------------------------------------------------------- pass B (fallback): log-space recursion
 __device__ __forceinline__ double lse3(double a, double b, double c) {
     const double mx = fmax(a, fmax(b, c));
     if (mx == -INFINITY) return -INFINITY;
@@ -185,16 +507,19 @@ __device__ __forceinline__ double lse3(double a, double b, double c) {
     return mx + (double)logf(s);
 }
 
-// grid (B, 2): blockIdx.y == 0 runs alpha (and the log-likelihood), blockIdx.y == 1 runs beta.
+constexpr int kLogPrefetch = 8;
+
+// grid (B, 2): blockIdx.y == 0 runs alpha (and the log-likelihood), blockIdx.y == 1 runs beta. Only flagged sequences.
 __global__ void __launch_bounds__(1024)
-ctc_alpha_beta_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen,
-                      const int32_t* __restrict__ ilen, int Tn, int Smax, float* __restrict__ nll_out, CtcWs w) {
-    extern __shared__ double smd[];               // 2 x (Smax + 4) ping-pong state with -inf guards, + 1 scratch
+ctc_alpha_beta_log_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen,
+                          const int32_t* __restrict__ ilen, int Tn, int Sp, int Sa, float* __restrict__ nll_out, CtcWs w) {
+    extern __shared__ double smd[];               // 2 x (Sp + 4) ping-pong state with -inf guards
     const int b = blockIdx.x, s = threadIdx.x;
+    if (!w.flag[b]) return;
     const bool is_beta = blockIdx.y == 1;
-    const int L = tlen[b], S = 2 * L + 1, Tb = ilen[b];
+    const int L = tlen[b], S = 2 * L + 1, Tb = min(ilen[b], Tn);
     const int32_t* tg = targets + w.toff[b];
-    const int W = Smax + 4;
+    const int W = Sp + 4;
     double* bufA = smd;
     double* bufB = smd + W;
     const bool act = s < S;
@@ -202,13 +527,13 @@ ctc_alpha_beta_kernel(const int32_t* __restrict__ targets, const int32_t* __rest
     const bool skip_in = act && s > 1 && cls != 0 && cls != ((s & 1) ? tg[(s >> 1) - 1] : 0);      // s-2 -> s allowed
     const bool skip_out = act && (s + 2 < S) && (((s + 2) & 1) ? tg[(s + 2) >> 1] : 0) != 0 &&
                           ((((s + 2) & 1) ? tg[(s + 2) >> 1] : 0) != cls);                              // s -> s+2 allowed
-    const float* lp = w.lpg + (long long)b * Tn * Smax;
+    const float* lp = w.lpg + (long long)b * Tn * Sp;
 
     for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) smd[i] = -INFINITY;
     __syncthreads();
     if (!is_beta) {
         // ---- alpha: state s lives at index s+2 (two -inf guard cells on the left)
-        double* al = w.alpha + (long long)b * Tn * Smax;
+        double* al = w.alpha + (long long)b * Tn * Sa;
         double ll = -INFINITY;
         if (Tb > 0) {
             double a = -INFINITY;
@@ -216,18 +541,26 @@ ctc_alpha_beta_kernel(const int32_t* __restrict__ targets, const int32_t* __rest
             if (act) { bufA[s + 2] = a; al[s] = a; }
             __syncthreads();
             double* cur = bufA; double* nxt = bufB;
-            float lp_next = (act && Tb > 1) ? lp[(long long)Smax + s] : 0.f;
-            for (int t = 1; t < Tb; ++t) {
-                const double lpt = (double)lp_next;
-                if (act && t + 1 < Tb) lp_next = lp[(long long)(t + 1) * Smax + s];
-                if (act) {
-                    const double v = lse3(cur[s + 2], cur[s + 1], skip_in ? cur[s] : -INFINITY);
-                    a = (v == -INFINITY) ? -INFINITY : v + lpt;
-                    nxt[s + 2] = a;
-                    al[(long long)t * Smax + s] = a;
+            // the label log-probs are fetched kLogPrefetch steps ahead: a step is shorter than a trip to L2
+            float ring[kLogPrefetch];
+#pragma unroll
+            for (int k = 0; k < kLogPrefetch; ++k) ring[k] = (act && 1 + k < Tb) ? lp[(long long)(1 + k) * Sp + s] : 0.f;
+            for (int t0 = 1; t0 < Tb; t0 += kLogPrefetch) {
+#pragma unroll
+                for (int k = 0; k < kLogPrefetch; ++k) {
+                    const int t = t0 + k;
+                    if (t >= Tb) break;
+                    const double lpt = (double)ring[k];
+                    if (act && t + kLogPrefetch < Tb) ring[k] = lp[(long long)(t + kLogPrefetch) * Sp + s];
+                    if (act) {
+                        const double v = lse3(cur[s + 2], cur[s + 1], skip_in ? cur[s] : -INFINITY);
+                        a = (v == -INFINITY) ? -INFINITY : v + lpt;
+                        nxt[s + 2] = a;
+                        al[(long long)t * Sa + s] = a;
+                    }
+                    __syncthreads();
+                    double* tmp = cur; cur = nxt; nxt = tmp;
                 }
-                __syncthreads();
-                double* tmp = cur; cur = nxt; nxt = tmp;
             }
             if (threadIdx.x == 0) {
                 const double l1 = cur[S - 1 + 2], l2 = (S > 1) ? cur[S - 2 + 2] : -INFINITY;
@@ -246,27 +579,33 @@ ctc_alpha_beta_kernel(const int32_t* __restrict__ targets, const int32_t* __rest
     } else {
         // ---- beta: state s lives at index s (guard cells on the right)
         if (Tb <= 0) return;
-        double* be = w.beta + (long long)b * Tn * Smax;
+        double* be = w.beta + (long long)b * Tn * Sa;
         double* cur = bufA; double* nxt = bufB;
         {
-            const long long o = (long long)(Tb - 1) * Smax + s;
             double bt = -INFINITY;
-            if (act && s >= S - 2) bt = (double)lp[o];
-            if (act) { cur[s] = bt; be[o] = bt; }
+            if (act && s >= S - 2) bt = (double)lp[(long long)(Tb - 1) * Sp + s];
+            if (act) { cur[s] = bt; be[(long long)(Tb - 1) * Sa + s] = bt; }
         }
         __syncthreads();
-        float lp_next = (act && Tb > 1) ? lp[(long long)(Tb - 2) * Smax + s] : 0.f;
-        for (int t = Tb - 2; t >= 0; --t) {
-            const double lpt = (double)lp_next;
-            if (act && t > 0) lp_next = lp[(long long)(t - 1) * Smax + s];
-            if (act) {
-                const double v = lse3(cur[s], cur[s + 1], skip_out ? cur[s + 2] : -INFINITY);
-                const double bt = (v == -INFINITY) ? -INFINITY : v + lpt;
-                nxt[s] = bt;
-                be[(long long)t * Smax + s] = bt;
+        float ring[kLogPrefetch];
+#pragma unroll
+        for (int k = 0; k < kLogPrefetch; ++k) ring[k] = (act && Tb - 2 - k >= 0) ? lp[(long long)(Tb - 2 - k) * Sp + s] : 0.f;
+        for (int t0 = Tb - 2; t0 >= 0; t0 -= kLogPrefetch) {
+#pragma unroll
+            for (int k = 0; k < kLogPrefetch; ++k) {
+                const int t = t0 - k;
+                if (t < 0) break;
+                const double lpt = (double)ring[k];
+                if (act && t - kLogPrefetch >= 0) ring[k] = lp[(long long)(t - kLogPrefetch) * Sp + s];
+                if (act) {
+                    const double v = lse3(cur[s], cur[s + 1], skip_out ? cur[s + 2] : -INFINITY);
+                    const double bt = (v == -INFINITY) ? -INFINITY : v + lpt;
+                    nxt[s] = bt;
+                    be[(long long)t * Sa + s] = bt;
+                }
+                __syncthreads();
+                double* tmp = cur; cur = nxt; nxt = tmp;
             }
-            __syncthreads();
-            double* tmp = cur; cur = nxt; nxt = tmp;
         }
     }
 }
@@ -284,13 +623,22 @@ __global__ void ctc_mean_loss_kernel(const float* __restrict__ nll, const int32_
 // ---------------------------------------------------------------- pass C: gradient wrt logits
 constexpr int kGradThreads = 256;
 
+// value = m * 2^x with m in [1,2); zero / subnormal / non-finite inputs report ok = false
+__device__ __forceinline__ bool split_pow2(double v, double& m, int& x) {
+    const int hi = __double2hiint(v);
+    const int ex = (hi >> 20) & 0x7ff;
+    x = ex - 1023;
+    m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+    return hi > 0 && ex != 0 && ex != 0x7ff;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kGradThreads)
 ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t,
                 long long stride_b, const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen,
-                const int32_t* __restrict__ ilen, int Smax, float grad_scale, CtcWs w) {
+                const int32_t* __restrict__ ilen, int Sp, int Sa, int kscan, float grad_scale, CtcWs w) {
     constexpr int V = Ld<T>::N;
-    extern __shared__ float occ[];                                   // [Smax] exp(alpha+beta-lp-ll) per state
+    extern __shared__ float occ[];                                   // [Sp] state occupancy alpha*beta/(p*likelihood)
     const long long row = blockIdx.x;                                // row = b*T + t
     const int b = (int)(row / Tn), t = (int)(row - (long long)b * Tn);
     const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
@@ -302,12 +650,31 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     const float lse = dead ? 0.f : w.lse[row];
 
     if (!dead) {
-        const double* al = w.alpha + row * Smax;
-        const double* be = w.beta + row * Smax;
-        const float* lpr = w.lpg + row * Smax;
-        for (int s = threadIdx.x; s < S; s += blockDim.x) {
-            const double e = al[s] + be[s] - (double)lpr[s] - ll;        // -inf if either side is unreachable
-            occ[s] = (e == e) ? expf((float)e) : 0.f;
+        const double* al = w.alpha + row * Sa;
+        const double* be = w.beta + row * Sa;
+        if (w.flag[b]) {
+            const float* lpr = w.lpg + row * Sp;
+            for (int s = threadIdx.x; s < S; s += blockDim.x) {
+                const double e = al[s] + be[s] - (double)lpr[s] - ll;        // -inf if either side is unreachable
+                occ[s] = (e == e) ? expf((float)e) : 0.f;
+            }
+        } else {
+            const double* pr = w.pg + row * Sp;
+            const int* ea = w.ea + row * 32;
+            const int* eb = w.eb + row * 32;
+            const int efin = w.efin[b];
+            double mf; int xf;
+            split_pow2(w.pfin[b], mf, xf);
+            for (int s = threadIdx.x; s < S; s += blockDim.x) {
+                double ma, mb, mp; int xa, xb, xp;
+                const bool ok = split_pow2(al[s], ma, xa) & split_pow2(be[S - 1 - s], mb, xb) & split_pow2(pr[s], mp, xp);
+                float o = 0.f;
+                if (ok) {
+                    const int x = xa + xb - xp - xf + (ea[s / kscan] >> 1) + (eb[(S - 1 - s) / kscan] >> 1) - efin;
+                    o = (x < -140) ? 0.f : ldexpf((float)(ma * mb / (mp * mf)), min(x, 8));
+                }
+                occ[s] = o;
+            }
         }
     }
     // dense part: softmax * scale
@@ -340,7 +707,7 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     if (dead) return;
     __syncthreads();
     // label classes: subtract the occupancy, summed over the states that share a class in a fixed order
-    const int* canon = w.canon + (long long)b * Smax;
+    const int* canon = w.canon + (long long)b * Sp;
     const int32_t* tg = targets + w.toff[b];
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         if (canon[s] != s) continue;
@@ -358,10 +725,18 @@ using namespace hctr;
 
 extern "C" {
 
+long long hctr_ctc_loss_flag_offset(int T, int B, int max_target_len) {
+    if (T <= 0 || B <= 0 || max_target_len < 0) return -1;
+    const int Sp = state_pitch(max_target_len);
+    CtcWs w = carve(nullptr, T, B, Sp, alpha_pitch(Sp), nullptr);
+    return static_cast<long long>(reinterpret_cast<intptr_t>(w.flag));
+}
+
 long long hctr_ctc_loss_workspace_bytes(int T, int B, int max_target_len) {
     if (T <= 0 || B <= 0 || max_target_len < 0) return 0;
     long long total = 0;
-    carve(nullptr, T, B, 2 * max_target_len + 1, &total);
+    const int Sp = state_pitch(max_target_len);
+    carve(nullptr, T, B, Sp, alpha_pitch(Sp), &total);
     return total;
 }
 
@@ -375,41 +750,65 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     HCTR_CHECK(max_target_len >= 0 && 2 * max_target_len + 1 <= 1024, HCTR_ERR_INVALID,
                "ctc_loss: target length %d exceeds the 511-label limit of the one-CTA-per-sequence recursion", max_target_len);
     HCTR_CHECK(targets != nullptr || max_target_len == 0, HCTR_ERR_INVALID, "ctc_loss: null targets");
-    const int Smax = 2 * max_target_len + 1;
+    const int Sp = state_pitch(max_target_len);
+    const int kscan = scan_lane_states(Sp);           // states per lane of the one-warp scan; 0 = log-space only
+    const int Sa = alpha_pitch(Sp);
     long long need = 0;
-    CtcWs w = carve(workspace, T, B, Smax, &need);
+    CtcWs w = carve(workspace, T, B, Sp, Sa, &need);
     HCTR_CHECK(workspace && workspace_bytes >= need, HCTR_ERR_INVALID, "ctc_loss: workspace too small (%lld < %lld)", workspace_bytes, need);
     HCTR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, HCTR_ERR_INVALID, "ctc_loss: workspace must be 256-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-    ctc_prep_kernel<<<B, 128, 0, s>>>(targets, target_lengths, B, Smax, w);
+    static const bool debug_force_log = getenv("HCTR_CTC_DEBUG_FORCE_LOG") != nullptr;           // diagnostics only
+    ctc_prep_kernel<<<B, 128, 0, s>>>(targets, target_lengths, B, Sp, (kscan == 0 || debug_force_log) ? 1 : 0, w);
     HCTR_CUDA(cudaGetLastError());
     const long long rows = (long long)T * B;
     const long long blocksA = (rows + kLseWarps - 1) / kLseWarps;
     HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "ctc_loss: too many rows");
     if (dtype == HCTR_F32)
         ctc_lse_gather_kernel<float><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
-            static_cast<const float*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Smax, row_lse, w);
+            static_cast<const float*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Sp, row_lse, w);
     else
         ctc_lse_gather_kernel<__nv_bfloat16><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Smax, row_lse, w);
+            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Sp, row_lse, w);
     HCTR_CUDA(cudaGetLastError());
-    int threads = (Smax + 31) / 32 * 32;
-    const size_t smB = (size_t)(2 * (Smax + 4) + 2) * sizeof(double);
-    ctc_alpha_beta_kernel<<<dim3(B, grad != nullptr ? 2 : 1), threads, smB, s>>>(targets, target_lengths, input_lengths, T, Smax, nll, w);
+
+    // fast path: one warp per (sequence, direction); the beta recursion is only needed for the gradient
+    const dim3 gridB(B, grad != nullptr ? 2 : 1);
+    const int have_beta = grad != nullptr;
+    const int blocksV = (int)((rows + 7) / 8);
+#define HCTR_SCAN(K)                                                                                              \
+    ctc_scan_kernel<K><<<gridB, 32, 0, s>>>(targets, target_lengths, input_lengths, T, Sp, nll, w);               \
+    HCTR_CUDA(cudaGetLastError());                                                                                \
+    ctc_scan_verify_kernel<K><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, have_beta, w);         \
     HCTR_CUDA(cudaGetLastError());
+    switch (kscan) {
+        case 4:  { HCTR_SCAN(4) } break;
+        case 8:  { HCTR_SCAN(8) } break;
+        case 16: { HCTR_SCAN(16) } break;
+        default: break;
+    }
+#undef HCTR_SCAN
+    // log-space recursion for the flagged sequences (exits at once for the others)
+    const int threads = (2 * max_target_len + 1 + 31) / 32 * 32;
+    const size_t smB = (size_t)(2 * (Sp + 4) + 2) * sizeof(double);
+    static const bool debug_no_fallback = getenv("HCTR_CTC_DEBUG_NO_FALLBACK") != nullptr;     // diagnostics only
+    if (!debug_no_fallback) {
+        ctc_alpha_beta_log_kernel<<<gridB, threads, smB, s>>>(targets, target_lengths, input_lengths, T, Sp, Sa, nll, w);
+        HCTR_CUDA(cudaGetLastError());
+    }
     ctc_mean_loss_kernel<<<1, 32, 0, s>>>(nll, target_lengths, B, loss);
     HCTR_CUDA(cudaGetLastError());
     if (grad != nullptr) {
-        const size_t smC = (size_t)Smax * sizeof(float);
+        const size_t smC = (size_t)Sp * sizeof(float);
         if (dtype == HCTR_F32)
             ctc_grad_kernel<float><<<(int)rows, kGradThreads, smC, s>>>(
                 static_cast<const float*>(logits), static_cast<float*>(grad), T, B, C, stride_t, stride_b, targets,
-                target_lengths, input_lengths, Smax, grad_scale, w);
+                target_lengths, input_lengths, Sp, Sa, kscan, grad_scale, w);
         else
             ctc_grad_kernel<__nv_bfloat16><<<(int)rows, kGradThreads, smC, s>>>(
                 static_cast<const __nv_bfloat16*>(logits), static_cast<__nv_bfloat16*>(grad), T, B, C, stride_t, stride_b,
-                targets, target_lengths, input_lengths, Smax, grad_scale, w);
+                targets, target_lengths, input_lengths, Sp, Sa, kscan, grad_scale, w);
         HCTR_CUDA(cudaGetLastError());
     }
     return HCTR_OK;

@@ -26,6 +26,11 @@ def _as_i32(x, device):
 
 
 class _CtcFromLogits(torch.autograd.Function):
+    # diagnostics: when True, `last_fallback` receives the per-sequence int32 flags of the last call (1 = the sequence
+    # was recomputed by the log-space recursion)
+    record_fallback = False
+    last_fallback = None
+
     @staticmethod
     def forward(ctx, logits, targets, input_lengths, target_lengths, max_target_len):
         if not logits.is_cuda:
@@ -53,6 +58,10 @@ class _CtcFromLogits(torch.autograd.Function):
                 nat.ptr(logits), code, T, B, C, logits.stride(0), logits.stride(1), nat.ptr(targets),
                 nat.ptr(target_lengths), nat.ptr(input_lengths), max_target_len, None, nat.ptr(nll), nat.ptr(loss),
                 nat.ptr(grad), 1.0, nat.ptr(ws), ws_bytes, nat.stream_ptr()), "ctc_loss_fwd_bwd")
+            if _CtcFromLogits.record_fallback:
+                foff = lib.hctr_ctc_loss_flag_offset(T, B, max_target_len)
+                _CtcFromLogits.last_fallback = ws[foff:foff + 4 * B].clone().view(torch.int32).cpu()
+                _CtcFromLogits.last_workspace = ws
         ctx.grad = grad
         ctx.nll = nll
         return loss.reshape(())

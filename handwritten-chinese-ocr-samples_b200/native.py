@@ -48,6 +48,7 @@ SIGNATURES = {
     "hctr_ctc_skip_max_candidates": (_I, []),
     "hctr_ctc_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _I, _P, _P, _P, _P, c_float, _P, _L, _P]),
     "hctr_ctc_loss_workspace_bytes": (_L, [_I, _I, _I]),
+    "hctr_ctc_loss_flag_offset": (_L, [_I, _I, _I]),
     "hctr_stat_slices": (_I, [_I, _I, _I]),
     "hctr_chan_stats": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "hctr_bn_finalize_train": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -155,6 +155,9 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
                           int max_target_len, const float* row_lse, float* nll, float* loss, void* grad, float grad_scale,
                           void* workspace, long long workspace_bytes, void* stream);
 long long hctr_ctc_loss_workspace_bytes(int T, int B, int max_target_len);
+/* Byte offset inside that workspace of an int32 [B] array that, after the call, holds 1 for every sequence that was
+ * recomputed by the log-space recursion instead of the scaled linear one (diagnostics / tests). */
+long long hctr_ctc_loss_flag_offset(int T, int B, int max_target_len);
 
 /* ---- training (train()-mode forward and the backward pass; reference: main.py:367,383-438) -------------------- */
 

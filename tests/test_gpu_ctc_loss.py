@@ -89,3 +89,106 @@ def test_ctc_gradient_rows_sum_to_zero_full_width():
     loss, grad = _run(x, tg, tl, [T] * B)
     assert np.isfinite(loss) and loss > 0
     assert np.abs(grad.sum(2)).max() <= 1e-6
+
+
+# ---- the two recursions behind pass B: scaled linear space (one warp per sequence) and the log-space fallback ----------
+
+def _run_flags(x, tg, tl, il, need_grad=True):
+    """-> (loss, grad or None, int32 [B] flags: 1 = sequence recomputed by the log-space recursion)"""
+    from hctr_b200.ctc_loss import CTCLoss, _CtcFromLogits
+    _CtcFromLogits.record_fallback = True
+    try:
+        xt = torch.from_numpy(x).cuda().requires_grad_(need_grad)
+        loss = CTCLoss.from_logits(xt, torch.from_numpy(tg), torch.IntTensor(il), torch.from_numpy(tl))
+        if need_grad:
+            loss.backward()
+        flags = _CtcFromLogits.last_fallback.numpy().copy()
+    finally:
+        _CtcFromLogits.record_fallback = False
+    return float(loss.item()), (xt.grad.cpu().numpy() if need_grad else None), flags
+
+
+def _aligned_logits(T, B, C, tg, tl, peak, seed, noise=1.0):
+    """Logits that follow the labels: every label gets a run of frames, blanks in between."""
+    rs = np.random.RandomState(seed)
+    x = (noise * rs.randn(T, B, C)).astype(np.float32)
+    off = 0
+    for b in range(B):
+        L = int(tl[b])
+        span = T // max(L, 1)
+        for t in range(T):
+            k = min(t // span, L - 1) if L else 0
+            c = int(tg[off + k]) if (L and (t % span) < max(1, span // 2)) else 0
+            x[t, b, c] += peak
+        off += L
+    return x
+
+
+@pytest.mark.parametrize("L,K", [(100, 8), (200, 16), (400, 0)])
+def test_ctc_loss_long_targets_use_wider_lanes(L, K):
+    """S = 2L+1 up to 513 states: K = 8/16 states per lane in the scan kernel; beyond that the log-space recursion."""
+    T, B, C = 900, 3, 40
+    rs = np.random.RandomState(L)
+    x = (1.5 * rs.randn(T, B, C)).astype(np.float32)
+    tg, tl = synth.ctc_targets(B, C, L - 10, L, L + 1, repeat_frac=0.2)
+    il = [T, T - 57, T]
+    oloss, _, ograd = oracle.ctc_loss(x, tg, il, tl)
+    loss, grad, flags = _run_flags(x, tg, tl, il)
+    assert flags.tolist() == ([0, 0, 0] if K else [1, 1, 1])
+    assert abs(loss - oloss) <= 1e-4 * abs(oloss)
+    assert np.abs(grad - ograd).max() <= 1e-5
+
+
+def test_ctc_loss_peaky_aligned_sequences_stay_on_the_linear_path():
+    """A confident model whose frames follow the labels (logit gap 14, label runs of ~9 frames): states left behind decay
+    by ~2^-28 per frame, stay inside the 2^-760 range a lane can hold, or are proven negligible by the verify pass."""
+    T, B, C = 1024, 4, 500
+    tg, tl = synth.ctc_targets(B, C, 40, 60, 21, repeat_frac=0.15)
+    x = _aligned_logits(T, B, C, tg, tl, peak=14.0, seed=22)
+    oloss, _, ograd = oracle.ctc_loss(x, tg, [T] * B, tl)
+    loss, grad, flags = _run_flags(x, tg, tl, [T] * B)
+    assert flags.tolist() == [0] * B
+    assert abs(loss - oloss) <= 1e-4 * max(1.0, abs(oloss))
+    assert np.abs(grad - ograd).max() <= 1e-5
+
+
+def test_ctc_loss_extremely_confident_frames_any_path():
+    """Logit gap 45: neighbouring states drift > 2^760 apart inside one lane while both still matter (alpha huge where beta
+    is tiny); whichever recursion each sequence ends up on, the result must match the oracle."""
+    T, B, C = 1024, 4, 500
+    tg, tl = synth.ctc_targets(B, C, 40, 60, 21, repeat_frac=0.15)
+    x = _aligned_logits(T, B, C, tg, tl, peak=45.0, seed=22)
+    oloss, _, ograd = oracle.ctc_loss(x, tg, [T] * B, tl)
+    loss, grad, flags = _run_flags(x, tg, tl, [T] * B)
+    assert flags.sum() >= 1                                   # the verify pass must have caught at least one of them
+    assert abs(loss - oloss) <= 1e-4 * max(1.0, abs(oloss))
+    assert np.abs(grad - ograd).max() <= 1e-5
+
+
+def test_ctc_loss_falls_back_to_log_space_when_linear_space_cannot_hold_it():
+    """(1) label probabilities below e^-80, (2) confident frames that contradict the labels so that early- and
+    late-emitting paths are > 2^700 apart mid-sequence although they weigh the same in the end."""
+    T, B, C = 400, 3, 60
+    rs = np.random.RandomState(3)
+    x = (0.5 * rs.randn(T, B, C)).astype(np.float32)
+    tg, tl = synth.ctc_targets(B, C, 30, 40, 31, repeat_frac=0.0)
+    x[:, 0, 0] += 120.0                                        # sequence 0: every label at lp ~ -120 -> case (1)
+    x[:, 1, 0] += 60.0                                         # sequence 1: each emission costs e^-60 whenever it happens -> case (2)
+    oloss, _, ograd = oracle.ctc_loss(x, tg, [T] * B, tl)
+    loss, grad, flags = _run_flags(x, tg, tl, [T] * B)
+    assert flags.tolist() == [1, 1, 0]
+    assert abs(loss - oloss) <= 1e-4 * abs(oloss)
+    assert np.abs(grad - ograd).max() <= 1e-5
+
+
+def test_ctc_loss_only_no_gradient():
+    T, B, C = 300, 3, 80
+    x = synth.ctc_like_logits(T, B, C, 41, peak=4.0)
+    tg, tl = synth.ctc_targets(B, C, 10, 30, 42)
+    tl[2] = 0                                                   # an empty target: nll = -sum log p(blank)
+    tg = tg[:int(tl[:2].sum())]
+    oloss, _, _ = oracle.ctc_loss(x, tg, [T] * B, tl, need_grad=False)
+    loss, _, flags = _run_flags(x, tg, tl, [T] * B, need_grad=False)
+    assert abs(loss - oloss) <= 1e-4 * abs(oloss)
+    loss2, grad, _ = _run_flags(x, tg, tl, [T] * B)
+    assert abs(loss2 - loss) <= 1e-6 * abs(loss)
