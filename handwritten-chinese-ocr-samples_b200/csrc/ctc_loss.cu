@@ -236,7 +236,7 @@ constexpr int kTinyExp = -760;                       // a state this far below i
                                                      // shrinks by at most 2^-240 per pair of steps, so it is still exact
                                                      // when the exponent step sees it
 constexpr int kTinyHi = (1023 + kTinyExp) << 20;     // high word of 2^kTinyExp
-constexpr int kRebaseDiff = 400;                     // adopt the left neighbour's exponent when it is this far above ours
+constexpr int kRebaseDiff = 900;                     // adopt the left neighbour's exponent when it is this far above ours
 constexpr int kScanChunkStates = 32;                 // steps per staged chunk x states per lane
 constexpr int kScanStageDoubles = 3 * kScanChunkStates * 32;     // 3 chunks in flight = 24 KB
 
@@ -369,16 +369,13 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
                 if (empty) { e = ne; d_next = 0; d_after = 0; }           // nothing here yet: take the neighbour's units
                 int diff = ne - e;
                 if (!nempty && diff > kRebaseDiff) {
-                    // what arrives is far above what this lane holds: re-express the lane in the neighbour's units
+                    // what arrives is > 2^400 above anything this lane holds (mantissas span 2^-464 .. 2^4): re-express the
+                    // lane in the neighbour's units. What underflows here is old mass of states that receive the arriving
+                    // mass within two steps - same states, same beta - so it is a relative loss below 2^-280 of those
+                    // states' own paths, whatever beta is: no verification needed.
                     const double rr = pow2_clamped(-diff);
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        const double nvj = (diff > 1022) ? 0.0 : v[j] * rr;
-                        const int hj = __double2hiint(nvj);
-                        drop |= static_cast<unsigned>(hj - 1) < static_cast<unsigned>(kTinyHi - 1);
-                        if (v[j] != 0.0 && hj < 0x00100000) w.flag[b] = 1;       // lost on the spot (never seen in practice)
-                        v[j] = nvj;
-                    }
+                    for (int j = 0; j < K; ++j) v[j] = (diff > 1022) ? 0.0 : v[j] * rr;
                     e = ne; d_next = 0; d_after = 0; diff = 0;
                 }
                 const double r = nempty ? 0.0 : pow2_clamped(diff);
@@ -462,13 +459,13 @@ __device__ __forceinline__ int exp2_of(double v) {
 }
 
 // One warp per (b,t) row in which some lane saw a state below 2^kTinyExp of its scale (still exact at that moment, gone a
-// few steps later). The paths that will be lost through such a state s weigh alpha(s) beta(s) / p(s) <= 2^116 alpha(s) beta(s);
-// the likelihood is at least M = max_s alpha(s) beta(s). If every such state has alpha(s) beta(s) <= 2^-176 M the loss is
-// below 2^-60 relative; otherwise the sequence goes to the log-space recursion. Exponent arithmetic only. Without a
-// gradient (no beta) any such row sends the sequence there.
+// few steps later). The paths that will be lost through such a state s weigh w(s) = alpha(s) beta(s) / p(s) - that is the
+// total weight of all paths through (t, s) - and the likelihood is at least max_s w(s). If every such state has
+// w(s) <= 2^-40 max_s w(s) the loss is invisible in fp32 results; otherwise the sequence goes to the log-space recursion.
+// Exponent arithmetic only. Without a gradient (no beta) any such row sends the sequence there.
 template <int K>
 __global__ void __launch_bounds__(256)
-ctc_scan_verify_kernel(const int32_t* __restrict__ tlen, const int32_t* __restrict__ ilen, int Tn, int Bn,
+ctc_scan_verify_kernel(const int32_t* __restrict__ tlen, const int32_t* __restrict__ ilen, int Tn, int Bn, int Sp,
                        int have_beta, CtcWs w) {
     constexpr int SA = 32 * K;
     const int lane = threadIdx.x & 31;
@@ -483,19 +480,20 @@ ctc_scan_verify_kernel(const int32_t* __restrict__ tlen, const int32_t* __restri
     const int S = 2 * tlen[b] + 1;
     const double* al = w.alpha + row * SA;
     const double* be = w.beta + row * SA;
+    const double* pr = w.pg + row * Sp;
     const int NEG = -(1 << 27);
     int m = NEG, cand = NEG;
     for (int s = lane; s < S; s += 32) {
         const int sm = S - 1 - s;                                      // where the beta scan keeps state s
         const int ma = exp2_of(al[s]), mb = exp2_of(be[sm]);           // relative to the lane scale
         if (ma <= NEG || mb <= NEG) continue;                          // no path through s survives on both sides
-        const int x = ma + (w.ea[row * 32 + s / K] >> 1) + mb + (w.eb[row * 32 + sm / K] >> 1);
+        const int x = ma + (w.ea[row * 32 + s / K] >> 1) + mb + (w.eb[row * 32 + sm / K] >> 1) - exp2_of(pr[s]);
         m = max(m, x);
         if (ma < kTinyExp || mb < kTinyExp) cand = max(cand, x);
     }
     m = __reduce_max_sync(0xffffffffu, m);
     cand = __reduce_max_sync(0xffffffffu, cand);
-    if (lane == 0 && (m <= NEG || cand + 116 + 60 > m)) w.flag[b] = 1;
+    if (lane == 0 && (m <= NEG || cand + 40 > m)) w.flag[b] = 1;
 }
 
 // ---------------------------------------------------------------- pass B (fallback): log-space recursion
@@ -780,7 +778,7 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
 #define HCTR_SCAN(K)                                                                                              \
     ctc_scan_kernel<K><<<gridB, 32, 0, s>>>(targets, target_lengths, input_lengths, T, Sp, nll, w);               \
     HCTR_CUDA(cudaGetLastError());                                                                                \
-    ctc_scan_verify_kernel<K><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, have_beta, w);         \
+    ctc_scan_verify_kernel<K><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, Sp, have_beta, w);     \
     HCTR_CUDA(cudaGetLastError());
     switch (kscan) {
         case 4:  { HCTR_SCAN(4) } break;
