@@ -93,31 +93,46 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
                    float* __restrict__ running_var, float* __restrict__ mean_out,
                    float* __restrict__ invstd_out, float* __restrict__ scale_out,
                    float* __restrict__ shift_out, float* __restrict__ line_sum) {
-    __shared__ float ps[8][32];
-    __shared__ double pq[8][32];
+    constexpr int LB = 4;                                  // lines reduced per round: LB*2 independent loads per iteration
+    __shared__ float ps[LB][8][32];
+    __shared__ double pq[LB][8][32];
+    __shared__ float lt[LB][32];
+    __shared__ double lu[LB][32];
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     double s = 0.0, q = 0.0;
-    for (int b = 0; b < B; ++b) {
-        float ls = 0.f;
-        double lq = 0.0;
+    for (int b0 = 0; b0 < B; b0 += LB) {
+        float ls[LB];
+        double lq[LB];
+#pragma unroll
+        for (int k = 0; k < LB; ++k) { ls[k] = 0.f; lq[k] = 0.0; }
         if (c < C) {
+#pragma unroll 2
             for (int i = part; i < slices; i += 8) {
-                const size_t o = ((size_t)b * slices + i) * C + c;
-                ls += psum[o];
-                lq += (double)psq[o];
+#pragma unroll
+                for (int k = 0; k < LB; ++k) {
+                    if (b0 + k < B) {
+                        const size_t o = ((size_t)(b0 + k) * slices + i) * C + c;
+                        ls[k] += psum[o];
+                        lq[k] += (double)psq[o];
+                    }
+                }
             }
         }
-        ps[part][lane] = ls; pq[part][lane] = lq;
+#pragma unroll
+        for (int k = 0; k < LB; ++k) { ps[k][part][lane] = ls[k]; pq[k][part][lane] = lq[k]; }
         __syncthreads();
-        if (part == 0 && c < C) {
+        if (part < LB && b0 + part < B && c < C) {           // warp k combines the 8 partials of line b0+k, fixed order
             float t = 0.f; double u = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { t += ps[k][lane]; u += pq[k][lane]; }
-            if (line_sum) line_sum[(size_t)b * C + c] = t;
-            s += (double)t; q += u;
+            for (int k = 0; k < 8; ++k) { t += ps[part][k][lane]; u += pq[part][k][lane]; }
+            if (line_sum) line_sum[(size_t)(b0 + part) * C + c] = t;
+            lt[part][lane] = t; lu[part][lane] = u;
         }
         __syncthreads();
+        if (part == 0 && c < C) {
+            for (int k = 0; k < LB && b0 + k < B; ++k) { s += (double)lt[k][lane]; q += lu[k][lane]; }
+        }
     }
     if (part != 0 || c >= C) return;
     const double n = (double)B * (double)HW;
