@@ -6,7 +6,7 @@ B=64 synthetic 128x2048 lines per GPU, bf16 logits, greedy CTC decode (forward +
   value     lines/s with the input batch already resident in HBM (CUDA events, max over ranks)
   e2e       the same step through the public API with HOST buffers: pinned fp32 images -> H2D -> hctr_model ->
             ctc_codec.decode -> Python strings (D2H of the compact label arrays inside the timed region)
-  roofline  dominant kernel (tcgen05 implicit-GEMM conv, BLOCK_N=256) vs the measured bf16 peak, timed live with
+  roofline  dominant kernel (tcgen05 implicit-GEMM conv on CTA pairs, 256x256 tiles) vs the measured bf16 peak, timed live with
             CUDA events around each of its launches in an instrumented pass of the same step
   cpu_baseline  the oracle port (torch fp32 restatement + C greedy decode) on the host cores, bounded sample
 `--impl reference` times that CPU implementation as its own arm (rank 0 only).
@@ -300,11 +300,11 @@ def main():
         with open(tpath) as fh:
             traffic = json.load(fh)["igemm_conv3x3_512_512_B64_H16_W2048"]["dram_bytes_per_launch"]
     roofline = {
-        "kernel": "igemm_tcgen05_kernel<BLOCK_N=256,NUM_SUB=2,STAGES=3,ACC=1,EPI_CONV> on the 512->512 3x3 convs (B=64,H=16,W=2048)",
+        "kernel": "igemm_pair_kernel (tcgen05.mma.cta_group::2, M=256 x N=256 per CTA pair, 3 stages x 128 K, 2 TMEM accumulator stages) on the 512->512 3x3 convs (B=64,H=16,W=2048)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops_sustained"], "peak_kind": "bf16_tflops_sustained (%s)" % peaks["source"],
         "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
-        "flops_per_launch": dom_fl / max(dom_n, 1), "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, round 1)",
+        "flops_per_launch": dom_fl / max(dom_n, 1), "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/ncu_traffic.json)",
         "algorithmic_bytes_per_launch": 2.0 * B_PER_GPU * 16 * WIDTH * 512 * 2 + 2.0 * 512 * 4608,
         "launches_per_step": dom_n // trace_steps, "avg_launch_ms": dom_ms / max(dom_n, 1),
         "share_of_forward": dom_ms / total_ms,

@@ -4,7 +4,9 @@
 #include <cstring>
 #include <mutex>
 
-#include "igemm_tcgen05.cuh"
+#include <cstdlib>
+
+#include "igemm2_tcgen05.cuh"
 #include "../../include/hctr_b200.h"
 
 namespace hctr {
@@ -104,6 +106,45 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
 
 static int g_kwf_mode = 2;     // measured on B200: the plain 128-byte start-address shift is what the hardware expects
 
+// CTA-pair kernel (cta_group::2): used for the wide (Cout % 256 == 0), un-pooled convolutions. HCTR_IGEMM_PAIR=0 falls
+// back to the single-CTA kernel (A/B measurements).
+static int g_pair_mode = -1;
+static bool pair_enabled() {
+    if (g_pair_mode < 0) {
+        const char* e = getenv("HCTR_IGEMM_PAIR");
+        g_pair_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pair_mode != 0;
+}
+// (every layer of the model with Cout % 256 == 0 has Cin % 128 == 0, so the K blocks pair up)
+static bool use_pair(int H, int Cin, int Cout, int ksize, int pool) {
+    return pair_enabled() && !pool && Cout % 256 == 0 && H % 2 == 0 && (ksize * ksize * (Cin / 64)) % kPairKSub == 0;
+}
+
+static int launch_igemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        HCTR_CUDA(cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kTotal));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * sm_count());
+        cfg.blockDim = dim3(kIgemmThreads);
+        cfg.dynamicSmemBytes = PairSmem::kTotal;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int n = 0;
+        HCTR_CUDA(cudaOccupancyMaxActiveClusters(&n, igemm_pair_kernel, &cfg));
+        HCTR_CHECK(n > 0, HCTR_ERR_CUDA, "conv: the CTA-pair kernel does not fit this device");
+        max_clusters = n;
+        if (getenv("HCTR_DEBUG")) fprintf(stderr, "hctr_b200: igemm_pair_kernel max active clusters = %d (SMs %d)\n", n, sm_count());
+    }
+    const int pairs = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
+    igemm_pair_kernel<<<2 * pairs, kIgemmThreads, PairSmem::kTotal, stream>>>(tmA, tmB, p);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // log-sum-exp fix-up of the classifier's per-(row, half-tile) softmax partials (fixed order)
@@ -180,6 +221,16 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "conv: too many tiles");
     p.total_tiles = (int)total;
 
+    if (use_pair(H, Cin, Cout, ksize, pool)) {
+        // one tile = rows (2*h_tile, 2*h_tile+1) x 128 pixels x 256 channels on a CTA pair
+        CUtensorMap tmA, tmB;
+        int rc = make_act_map(&tmA, x, B, H, W, Cin);
+        if (rc) return rc;
+        rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, kPairBlockN / 2);
+        if (rc) return rc;
+        return launch_igemm_pair(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+    }
+
     // thin layers (Cout <= 128) are bound by the L2->SMEM re-reads of the activation tile: fuse the three kw taps
     const int kwf = (ksize == 3 && block_n <= 128) ? g_kwf_mode : 0;
     p.kwf_base_offset = (kwf == 1);
@@ -213,13 +264,21 @@ int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale
     return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, relu, pool, 0, stream);
 }
 
-int hctr_conv_se_slices(int H, int W) {
-    return ((H + 1) / 2) * ((W + kTileM - 1) / kTileM) * 4;
+int hctr_debug_set_pair_mode(int mode) {
+    g_pair_mode = mode ? 1 : 0;
+    return HCTR_OK;
+}
+
+int hctr_conv_se_slices(int H, int W, int Cout) {
+    // one slot per (tile row, 128-px span, epilogue warp quarter); the CTA-pair kernel keeps the two rows of a tile apart
+    const int rows = use_pair(H, Cout, Cout, 3, 0) ? H : (H + 1) / 2;        // BasicBlock conv2: 3x3, Cin == Cout
+    return rows * ((W + kTileM - 1) / kTileM) * 4;
 }
 
 int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
                         float* se_partial, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {
     HCTR_CHECK(se_partial != nullptr, HCTR_ERR_INVALID, "conv_bn_se: null partial buffer");
+    HCTR_CHECK(Cin == Cout && ksize == 3, HCTR_ERR_INVALID, "conv_bn_se: BasicBlock conv2 is 3x3 with Cin == Cout (got %d -> %d, k=%d)", Cin, Cout, ksize);
     return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, 0, 0, 0, stream, se_partial);
 }
 

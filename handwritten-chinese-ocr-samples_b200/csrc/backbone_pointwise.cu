@@ -106,13 +106,41 @@ se_squeeze_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ parti
 __global__ void __launch_bounds__(512)
 se_excite_kernel(const float* __restrict__ partial, int slices, const float* __restrict__ w1,
                  const float* __restrict__ w2, float* __restrict__ gate, int C, int Cr, float inv_hw) {
-    extern __shared__ float sm[];                          // mean[C] + hidden[Cr]
+    extern __shared__ float sm[];                          // mean[C] + hidden[Cr] + part[groups][C]
     float* mean = sm;
     float* hidden = sm + C;
+    float* part = sm + ((C + Cr + 3) & ~3);                 // 16-byte aligned rows
     const int b = blockIdx.x;
+    // stage 2 of the squeeze: the block's threads form `groups` workers per float4 column; worker g adds the slices
+    // i = g, g+groups, ... (four loads in flight), the workers' sums are combined in a fixed order
+    const int ncol4 = C >> 2;
+    const int groups = blockDim.x / ncol4;
+    const int col = threadIdx.x % ncol4, g = threadIdx.x / ncol4;
+    if (g < groups) {
+        const float4* src = reinterpret_cast<const float4*>(partial + (size_t)b * slices * C) + col;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        int i = g;
+        for (; i + 3 * groups < slices; i += 4 * groups) {
+            const float4 v0 = __ldg(src + (size_t)i * ncol4), v1 = __ldg(src + (size_t)(i + groups) * ncol4);
+            const float4 v2 = __ldg(src + (size_t)(i + 2 * groups) * ncol4), v3 = __ldg(src + (size_t)(i + 3 * groups) * ncol4);
+            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+            a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+            a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+            a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+        }
+        for (; i < slices; i += groups) {
+            const float4 v0 = __ldg(src + (size_t)i * ncol4);
+            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        }
+        float4 t;
+        t.x = (a0.x + a1.x) + (a2.x + a3.x); t.y = (a0.y + a1.y) + (a2.y + a3.y);
+        t.z = (a0.z + a1.z) + (a2.z + a3.z); t.w = (a0.w + a1.w) + (a2.w + a3.w);
+        reinterpret_cast<float4*>(part + (size_t)g * C)[col] = t;
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float s = 0.f;
-        for (int i = 0; i < slices; ++i) s += partial[((size_t)b * slices + i) * C + c];
+        for (int k = 0; k < groups; ++k) s += part[(size_t)k * C + c];
         mean[c] = s * inv_hw;
     }
     __syncthreads();
@@ -201,7 +229,9 @@ int hctr_se_excite(const float* partial, int slices, const float* w1, const floa
                    int Cr, int HW, void* stream) {
     HCTR_CHECK(partial && w1 && w2 && gate, HCTR_ERR_INVALID, "se_excite: null pointer");
     HCTR_CHECK(C > 0 && Cr > 0 && slices > 0 && HW > 0, HCTR_ERR_INVALID, "se_excite: bad shape");
-    const size_t smem = (size_t)(C + Cr) * sizeof(float);
+    HCTR_CHECK(C % 4 == 0 && C / 4 <= 512 && al16(partial), HCTR_ERR_INVALID, "se_excite: C must be a multiple of 4, <= 2048, partials 16-byte aligned");
+    const int groups = 512 / (C / 4);
+    const size_t smem = ((size_t)((C + Cr + 3) & ~3) + (size_t)groups * C) * sizeof(float);
     se_excite_kernel<<<B, 512, smem, static_cast<cudaStream_t>(stream)>>>(partial, slices, w1, w2, gate, C, Cr,
                                                                            1.0f / (float)HW);
     HCTR_CUDA(cudaGetLastError());

@@ -1,0 +1,298 @@
+// Implicit-GEMM convolution on a CTA PAIR: tcgen05.mma.cta_group::2, M = 256 pixels x N = 256 channels per instruction.
+//
+// Same contraction as igemm_tcgen05.cuh (reference: nn.Conv2d 3x3/1x1 + BN + ReLU, models/handwritten_ctr_model.py:37-45,73-92)
+//   D[pixel, n] = sum_{tap, c} X[b, h + dh(tap), w + dw(tap), c] * Wt[n, tap, c]
+// but one tile is owned by the two SMs of a cluster: CTA r holds the 128 pixels of image row 2*h_tile + r (its half of
+// M) and 128 of the 256 weight rows (its half of N) in its own shared memory; the leader CTA issues every MMA and the
+// tensor cores of both SMs read both halves. Per CTA and K block that is 16 KB of activations + 16 KB of weights for
+// 128 x 256 x 64 MACs - the same L2->SMEM traffic per flop as the single-CTA kernel with two sub-tiles, half the
+// shared-memory operand reads per flop, and a 128-lane x 256-column accumulator per CTA, so TWO accumulator stages fit
+// TMEM and the epilogue of tile i overlaps the main loop of tile i+1 (the single-CTA N=256 kernel has one stage).
+//
+// Barriers (same offsets in both CTAs):
+//   full[s]      leader only, 1 arrival: the leader's producer (arrive.expect_tx of BOTH CTAs' bytes); both CTAs' TMA loads
+//                complete_tx on the leader's barrier (.cta_group::2). The peer needs no arrival of its own: it can only
+//                load into a stage after the multicast commit that freed it, i.e. after the previous phase completed,
+//                and a transaction count may go negative inside a phase.
+//   empty[s]     per CTA, 1 arrival: tcgen05.commit multicast from the leader frees the stage in both CTAs
+//   acc_full[a]  per CTA, 1 arrival: multicast commit after the last K block
+//   acc_empty[a] leader only, 2 x kEpiWarps arrivals: the epilogue warps of both CTAs (the peer's arrive remotely)
+#pragma once
+#include "igemm_tcgen05.cuh"
+
+namespace hctr {
+
+constexpr int kPairStages = 3;
+constexpr int kPairKSub = 2;        // 64-element K blocks per pipeline stage (fewer barrier round trips per flop)
+constexpr int kPairBlockN = 256;
+constexpr int kPairAcc = 2;
+
+struct PairSmem {
+    static constexpr int kABytes = kTileM * kBlockK * 2;               // 16 KB: 128 pixels x 64 channels
+    static constexpr int kBBytes = (kPairBlockN / 2) * kBlockK * 2;    // 16 KB: this CTA's 128 weight rows
+    static constexpr int kStageBytes = kPairKSub * (kABytes + kBBytes);
+    static constexpr int kBarBytes = 1024;
+    static constexpr int kTotal = kPairStages * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope), as CUTLASS does for the 2-SM accumulator release: an explicit
+    // .release.cluster costs a MEMBAR.ALL.GPU per arrive (measured: it halved the kernel when issued per K block)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar,
+                                                 int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar),
+           "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// EPI_CONV only, no pooling (the rows of a pool pair live in different CTAs). p.h_tiles = H/2 pair rows.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1)
+igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+    using L = PairSmem;
+    constexpr int kAccCols = kPairBlockN;
+    constexpr int kTmemCols = kPairAcc * kAccCols;     // 512
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* bar_base = smem + kPairStages * L::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);            // [kPairStages]   (leader's are used)
+    uint64_t* empty_bar = full_bar + kPairStages;                          // [kPairStages]
+    uint64_t* acc_full = empty_bar + kPairStages;                          // [kPairAcc]
+    uint64_t* acc_empty = acc_full + kPairAcc;                             // [kPairAcc]      (leader's are used)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kPairAcc);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < kPairStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < kPairAcc; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * kEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();                       // barriers initialised and TMEM allocated in both CTAs
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int kblocks = p.ntaps * p.cin_chunks / kPairKSub;      // pipeline steps (host guarantees divisibility)
+    const int pair_id = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair_id; tile < p.total_tiles; tile += num_pairs) {
+                const int n_tile = tile % p.n_tiles;
+                int m = tile / p.n_tiles;
+                const int w_tile = m % p.w_tiles; m /= p.w_tiles;
+                const int h_tile = m % p.h_tiles;
+                const int b = m / p.h_tiles;
+                const int h = h_tile * 2 + (int)rank;              // this CTA's image row
+                const int w0 = w_tile * kTileM;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                    uint8_t* st = smem + stage * L::kStageBytes;
+#pragma unroll
+                    for (int q = 0; q < kPairKSub; ++q) {
+                        const int k64 = kb * kPairKSub + q;
+                        const int tap = k64 / p.cin_chunks;
+                        const int ch = k64 - tap * p.cin_chunks;
+                        tma_load_4d_pair(st + q * (L::kABytes + L::kBBytes), &tmA, lbar, ch * kBlockK, w0 + p.tap_dw[tap], h + p.tap_dh[tap], b);
+                        tma_load_2d_pair(st + q * (L::kABytes + L::kBBytes) + L::kABytes, &tmB, lbar, k64 * kBlockK,
+                                         n_tile * kPairBlockN + (int)rank * (kPairBlockN / 2));
+                    }
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * kTileM, kPairBlockN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = pair_id; tile < p.total_tiles; tile += num_pairs) {
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + acc * kAccCols;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < kPairKSub; ++q) {
+                            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes + q * (L::kABytes + L::kBBytes));
+                            const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                const uint64_t da = make_sw128_kmajor_desc(a_addr + k * kUmmaK * 2);
+                                const uint64_t db = make_sw128_kmajor_desc(b_addr + k * kUmmaK * 2);
+                                umma_bf16_pair(d_base, da, db, idesc, (kb | q | k) != 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit_pair(&empty_bar[stage]);             // stage free in both CTAs once these MMAs retire
+                        if (kb == kblocks - 1) umma_commit_pair(&acc_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == kPairStages) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == kPairAcc) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+        const int quad = warp & 3;                      // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;               // which half of the accumulator columns this warp drains
+        const int pix = quad * 32 + lane;               // pixel within the 128-px span
+        const uint32_t lacc_empty0 = mapa_u32(smem_u32(&acc_empty[0]), 0);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = pair_id; tile < p.total_tiles; tile += num_pairs) {
+            const int n_tile = tile % p.n_tiles;
+            int m = tile / p.n_tiles;
+            const int w_tile = m % p.w_tiles; m /= p.w_tiles;
+            const int h_tile = m % p.h_tiles;
+            const int b = m / p.h_tiles;
+            const int h = h_tile * 2 + (int)rank;
+            const int w = w_tile * kTileM + pix;
+
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
+#pragma unroll 1
+            for (int c0 = half * (kPairBlockN / 2); c0 < (half + 1) * (kPairBlockN / 2); c0 += 32) {
+                const int n0 = n_tile * kPairBlockN + c0;
+                float v[32];
+                tmem_ld_32x32(t_base + c0, v);
+                // y = acc*scale + shift  (conv bias and eval-mode BN folded, fp32)
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + j));
+                    v[j + 0] = fmaf(v[j + 0], sc.x, sh.x);
+                    v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
+                    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
+                    v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
+                }
+                const bool ok = (w < p.W) && (h < p.H);
+                if (p.se_partial) {
+                    // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum over this warp's 32
+                    // pixels by a transpose-reduce butterfly; afterwards lane L holds column n0+L. One slot per
+                    // (line, row, 128-px span, warp): fixed-order final sum in se_excite.
+                    float tsum[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tsum[j] = ok ? v[j] : 0.f;
+#define HCTR_BFLY(O)                                                                      \
+                    {                                                                     \
+                        const bool upper = (lane & (O)) != 0;                             \
+                        _Pragma("unroll") for (int i = 0; i < (O); ++i) {                 \
+                            const float send = upper ? tsum[i] : tsum[i + (O)];           \
+                            const float keep = upper ? tsum[i + (O)] : tsum[i];           \
+                            tsum[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));     \
+                        }                                                                 \
+                    }
+                    HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
+#undef HCTR_BFLY
+                    const size_t slot = ((static_cast<size_t>(b) * p.H + h) * p.w_tiles + w_tile) * 4 + quad;
+                    if (h < p.H) p.se_partial[slot * p.N + n0 + lane] = tsum[0];
+                }
+                if (ok) {
+                    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+                    const size_t off = p.out_line_pitch
+                        ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N + n0
+                        : ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.N + n0;
+                    if (p.add) {
+                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.add) + off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 a = ld_nc_v4(src + q);
+                            v[8 * q + 0] += bf16_lo(a.x); v[8 * q + 1] += bf16_hi(a.x);
+                            v[8 * q + 2] += bf16_lo(a.y); v[8 * q + 3] += bf16_hi(a.y);
+                            v[8 * q + 4] += bf16_lo(a.z); v[8 * q + 5] += bf16_hi(a.z);
+                            v[8 * q + 6] += bf16_lo(a.w); v[8 * q + 7] += bf16_hi(a.w);
+                        }
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float a0 = v[j], a1 = v[j + 1];
+                        if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                        pk[j >> 1] = pack_bf16x2(a0, a1);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(out + off);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                }
+            }
+            // release this accumulator stage back to the leader's MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lacc_empty0 + acc * 8);
+            if (++acc == kPairAcc) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                       // nobody may still be reading the peer's shared memory / TMEM
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace hctr

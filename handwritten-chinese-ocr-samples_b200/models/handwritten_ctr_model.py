@@ -267,7 +267,7 @@ class hctr_model(nn.Module):
                 # conv2 + bn2 with the SE squeeze folded into its epilogue (per-tile channel sums)
                 spec = u["conv2"]
                 C = spec.cout
-                slices = lib.hctr_conv_se_slices(H, W)
+                slices = lib.hctr_conv_se_slices(H, W, C)
                 partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
                 v = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
                 self._launch(nat, "conv3x3_%d_%d_h%d_se" % (spec.cin, spec.cout, H), 2.0 * B * H * W * C * spec.cin * 9,

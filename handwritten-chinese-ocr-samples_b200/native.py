@@ -30,7 +30,8 @@ SIGNATURES = {
     "hctr_stem_conv_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "hctr_conv_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "hctr_debug_set_kwf_mode": (_I, [_I]),
-    "hctr_conv_se_slices": (_I, [_I, _I]),
+    "hctr_conv_se_slices": (_I, [_I, _I, _I]),
+    "hctr_debug_set_pair_mode": (_I, [_I]),
     "hctr_conv_bn_se_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hctr_se_slices": (_I, [_I, _I]),
     "hctr_se_squeeze": (_I, [_P, _P, _I, _I, _I, _I, _P]),

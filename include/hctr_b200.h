@@ -62,9 +62,9 @@ int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale
 
 /* BasicBlock conv2 + bn2 (:52-53) with the SELayer squeeze (:27-28) folded into the epilogue: besides y (bf16 NHWC,
  * no ReLU) the kernel writes per-(tile, warp) channel sums of the fp32 BN output to se_partial
- * [B][hctr_conv_se_slices(H,W)][Cout]; hctr_se_excite(se_partial, slices = hctr_conv_se_slices(H,W), ...) finishes the
- * mean in a fixed order (deterministic). Saves one full read of the activation per residual block. */
-int hctr_conv_se_slices(int H, int W);
+ * [B][hctr_conv_se_slices(H,W,Cout)][Cout]; hctr_se_excite(se_partial, slices = hctr_conv_se_slices(H,W,Cout), ...) finishes
+ * the mean in a fixed order (deterministic). Saves one full read of the activation per residual block. */
+int hctr_conv_se_slices(int H, int W, int Cout);
 int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
                         float* se_partial, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 
@@ -73,6 +73,8 @@ int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale,
  * address by whole 128-byte rows (3x fewer L2->SMEM activation bytes, +15 % on those layers); 1 = the same plus the
  * descriptor base_offset field (measured wrong on B200; kept to document the experiment). */
 int hctr_debug_set_kwf_mode(int mode);
+/* 0 = keep the wide convolutions on the single-CTA kernel instead of the CTA-pair (cta_group::2) kernel (measurements) */
+int hctr_debug_set_pair_mode(int mode);
 
 /* SELayer squeeze (:27-28): deterministic two-stage mean over (H,W) incl. padded columns.
  * x: bf16 NHWC; partial: fp32 workspace [B][slices][C]; the second stage runs inside hctr_se_excite.
