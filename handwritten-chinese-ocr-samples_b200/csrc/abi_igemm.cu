@@ -118,29 +118,34 @@ static bool pair_enabled() {
 }
 // (every layer of the model with Cout % 256 == 0 has Cin % 128 == 0, so the K blocks pair up)
 static bool use_pair(int H, int Cin, int Cout, int ksize, int pool) {
+    // (measured: at Cout = 128 the pair kernel without the kw-fused slab is slower than the single-CTA slab kernel,
+    //  763 vs 902 TFLOP/s on 128->128 - the thin layers are bound by L2->SMEM activation traffic, not operand reads)
     return pair_enabled() && !pool && Cout % 256 == 0 && H % 2 == 0 && (ksize * ksize * (Cin / 64)) % kPairKSub == 0;
 }
 
+template <int BLOCK_N, int STAGES>
 static int launch_igemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
-    static int max_clusters = 0;
+    using L = PairSmem<BLOCK_N, STAGES>;
+    auto kern = igemm_pair_kernel<BLOCK_N, STAGES>;
+    static int max_clusters = 0;      // per instantiation
     if (max_clusters == 0) {
-        HCTR_CUDA(cudaFuncSetAttribute(igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::kTotal));
+        HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * sm_count());
         cfg.blockDim = dim3(kIgemmThreads);
-        cfg.dynamicSmemBytes = PairSmem::kTotal;
+        cfg.dynamicSmemBytes = L::kTotal;
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
         int n = 0;
-        HCTR_CUDA(cudaOccupancyMaxActiveClusters(&n, igemm_pair_kernel, &cfg));
+        HCTR_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
         HCTR_CHECK(n > 0, HCTR_ERR_CUDA, "conv: the CTA-pair kernel does not fit this device");
         max_clusters = n;
-        if (getenv("HCTR_DEBUG")) fprintf(stderr, "hctr_b200: igemm_pair_kernel max active clusters = %d (SMs %d)\n", n, sm_count());
+        if (getenv("HCTR_DEBUG")) fprintf(stderr, "hctr_b200: igemm_pair_kernel<%d> max active clusters = %d (SMs %d)\n", BLOCK_N, n, sm_count());
     }
     const int pairs = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
-    igemm_pair_kernel<<<2 * pairs, kIgemmThreads, PairSmem::kTotal, stream>>>(tmA, tmB, p);
+    kern<<<2 * pairs, kIgemmThreads, L::kTotal, stream>>>(tmA, tmB, p);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }
@@ -226,9 +231,9 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
         CUtensorMap tmA, tmB;
         int rc = make_act_map(&tmA, x, B, H, W, Cin);
         if (rc) return rc;
-        rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, kPairBlockN / 2);
+        rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, block_n / 2);
         if (rc) return rc;
-        return launch_igemm_pair(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+        return launch_igemm_pair<256, 3>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
     }
 
     // thin layers (Cout <= 128) are bound by the L2->SMEM re-reads of the activation tile: fuse the three kw taps

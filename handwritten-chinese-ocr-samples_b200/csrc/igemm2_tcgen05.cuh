@@ -22,17 +22,16 @@
 
 namespace hctr {
 
-constexpr int kPairStages = 3;
 constexpr int kPairKSub = 2;        // 64-element K blocks per pipeline stage (fewer barrier round trips per flop)
-constexpr int kPairBlockN = 256;
 constexpr int kPairAcc = 2;
 
+template <int BLOCK_N, int STAGES>
 struct PairSmem {
     static constexpr int kABytes = kTileM * kBlockK * 2;               // 16 KB: 128 pixels x 64 channels
-    static constexpr int kBBytes = (kPairBlockN / 2) * kBlockK * 2;    // 16 KB: this CTA's 128 weight rows
+    static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;        // this CTA's half of the weight rows
     static constexpr int kStageBytes = kPairKSub * (kABytes + kBBytes);
     static constexpr int kBarBytes = 1024;
-    static constexpr int kTotal = kPairStages * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
+    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -93,11 +92,16 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 
 // EPI_CONV only, no pooling (the rows of a pool pair live in different CTAs). p.h_tiles = H/2 pair rows.
+// BLOCK_N = 256 (Cout % 256 == 0) or 128 (Cout == 128: the single-CTA N=128 tile reads 128 B/clk of operands from
+// shared memory, the limit; a pair reads 96).
+template <int BLOCK_N, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1)
 igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
-    using L = PairSmem;
+    using L = PairSmem<BLOCK_N, STAGES>;
+    constexpr int kPairStages = STAGES;
+    constexpr int kPairBlockN = BLOCK_N;
     constexpr int kAccCols = kPairBlockN;
-    constexpr int kTmemCols = kPairAcc * kAccCols;     // 512
+    constexpr int kTmemCols = kPairAcc * kAccCols;     // 512 or 256
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
