@@ -120,13 +120,15 @@ static bool pair_enabled() {
 static bool use_pair(int H, int Cin, int Cout, int ksize, int pool) {
     // (measured: at Cout = 128 the pair kernel without the kw-fused slab is slower than the single-CTA slab kernel,
     //  763 vs 902 TFLOP/s on 128->128 - the thin layers are bound by L2->SMEM activation traffic, not operand reads)
-    return pair_enabled() && !pool && Cout % 256 == 0 && H % 2 == 0 && (ksize * ksize * (Cin / 64)) % kPairKSub == 0;
+    const bool slab = ksize == 3 && g_kwf_mode != 0;         // one stage per (kh, chunk); otherwise K blocks go in pairs
+    if (Cout == 128) return pair_enabled() && !pool && H % 2 == 0 && slab && getenv("HCTR_PAIR128") != nullptr;
+    return pair_enabled() && !pool && Cout % 256 == 0 && H % 2 == 0 && (slab || (ksize * ksize * (Cin / 64)) % kPairKSub == 0);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int KWF>
 static int launch_igemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
-    using L = PairSmem<BLOCK_N, STAGES>;
-    auto kern = igemm_pair_kernel<BLOCK_N, STAGES>;
+    using L = PairSmem<BLOCK_N, STAGES, KWF>;
+    auto kern = igemm_pair_kernel<BLOCK_N, STAGES, KWF>;
     static int max_clusters = 0;      // per instantiation
     if (max_clusters == 0) {
         HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -228,12 +230,15 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
 
     if (use_pair(H, Cin, Cout, ksize, pool)) {
         // one tile = rows (2*h_tile, 2*h_tile+1) x 128 pixels x 256 channels on a CTA pair
+        const bool slab = ksize == 3 && g_kwf_mode != 0;          // kw-fused activation slab (hctr_debug_set_kwf_mode(0) turns it off)
         CUtensorMap tmA, tmB;
-        int rc = make_act_map(&tmA, x, B, H, W, Cin);
+        int rc = make_act_map(&tmA, x, B, H, W, Cin, 0, slab ? kSlabPix : kTileM);
         if (rc) return rc;
         rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, block_n / 2);
         if (rc) return rc;
-        return launch_igemm_pair<256, 3>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+        if (slab && block_n == 128) return launch_igemm_pair<128, 4, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+        if (slab) return launch_igemm_pair<256, 3, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+        return launch_igemm_pair<256, 3, 0>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
     }
 
     // thin layers (Cout <= 128) are bound by the L2->SMEM re-reads of the activation tile: fuse the three kw taps

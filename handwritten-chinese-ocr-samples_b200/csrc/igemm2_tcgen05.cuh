@@ -25,11 +25,13 @@ namespace hctr {
 constexpr int kPairKSub = 2;        // 64-element K blocks per pipeline stage (fewer barrier round trips per flop)
 constexpr int kPairAcc = 2;
 
-template <int BLOCK_N, int STAGES>
+// KWF (3x3 only, as in igemm_tcgen05.cuh): a stage is one (kh, 64-channel chunk): a 136-pixel activation slab that
+// serves the three kw taps by a whole-row shift of the descriptor start address, plus the three weight half-tiles.
+template <int BLOCK_N, int STAGES, int KWF>
 struct PairSmem {
-    static constexpr int kABytes = kTileM * kBlockK * 2;               // 16 KB: 128 pixels x 64 channels
+    static constexpr int kABytes = (KWF ? kSlabPix : kTileM) * kBlockK * 2;   // 16 KB (17 KB slab)
     static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;        // this CTA's half of the weight rows
-    static constexpr int kStageBytes = kPairKSub * (kABytes + kBBytes);
+    static constexpr int kStageBytes = KWF ? kABytes + 3 * kBBytes : kPairKSub * (kABytes + kBBytes);
     static constexpr int kBarBytes = 1024;
     static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
 };
@@ -94,10 +96,10 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 // EPI_CONV only, no pooling (the rows of a pool pair live in different CTAs). p.h_tiles = H/2 pair rows.
 // BLOCK_N = 256 (Cout % 256 == 0) or 128 (Cout == 128: the single-CTA N=128 tile reads 128 B/clk of operands from
 // shared memory, the limit; a pair reads 96).
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int KWF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1)
 igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
-    using L = PairSmem<BLOCK_N, STAGES>;
+    using L = PairSmem<BLOCK_N, STAGES, KWF>;
     constexpr int kPairStages = STAGES;
     constexpr int kPairBlockN = BLOCK_N;
     constexpr int kAccCols = kPairBlockN;
@@ -130,7 +132,8 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int kblocks = p.ntaps * p.cin_chunks / kPairKSub;      // pipeline steps (host guarantees divisibility)
+    // pipeline steps: KWF one per (kh, chunk); otherwise pairs of 64-wide K blocks (host guarantees divisibility)
+    const int kblocks = KWF ? 3 * p.cin_chunks : p.ntaps * p.cin_chunks / kPairKSub;
     const int pair_id = blockIdx.x >> 1;
     const int num_pairs = gridDim.x >> 1;
 
@@ -151,14 +154,24 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
                     uint8_t* st = smem + stage * L::kStageBytes;
+                    if constexpr (KWF) {
+                        const int kh = kb / p.cin_chunks;
+                        const int ch = kb - kh * p.cin_chunks;
+                        tma_load_4d_pair(st, &tmA, lbar, ch * kBlockK, w0 - 1, h + p.tap_dh[kh * 3], b);
 #pragma unroll
-                    for (int q = 0; q < kPairKSub; ++q) {
-                        const int k64 = kb * kPairKSub + q;
-                        const int tap = k64 / p.cin_chunks;
-                        const int ch = k64 - tap * p.cin_chunks;
-                        tma_load_4d_pair(st + q * (L::kABytes + L::kBBytes), &tmA, lbar, ch * kBlockK, w0 + p.tap_dw[tap], h + p.tap_dh[tap], b);
-                        tma_load_2d_pair(st + q * (L::kABytes + L::kBBytes) + L::kABytes, &tmB, lbar, k64 * kBlockK,
-                                         n_tile * kPairBlockN + (int)rank * (kPairBlockN / 2));
+                        for (int kw = 0; kw < 3; ++kw)
+                            tma_load_2d_pair(st + L::kABytes + kw * L::kBBytes, &tmB, lbar, ((kh * 3 + kw) * p.cin_chunks + ch) * kBlockK,
+                                             n_tile * kPairBlockN + (int)rank * (kPairBlockN / 2));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < kPairKSub; ++q) {
+                            const int k64 = kb * kPairKSub + q;
+                            const int tap = k64 / p.cin_chunks;
+                            const int ch = k64 - tap * p.cin_chunks;
+                            tma_load_4d_pair(st + q * (L::kABytes + L::kBBytes), &tmA, lbar, ch * kBlockK, w0 + p.tap_dw[tap], h + p.tap_dh[tap], b);
+                            tma_load_2d_pair(st + q * (L::kABytes + L::kBBytes) + L::kABytes, &tmB, lbar, k64 * kBlockK,
+                                             n_tile * kPairBlockN + (int)rank * (kPairBlockN / 2));
+                        }
                     }
                     if (++stage == kPairStages) { stage = 0; phase ^= 1; }
                 }
@@ -178,15 +191,31 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (lane == 0) {
-#pragma unroll
-                        for (int q = 0; q < kPairKSub; ++q) {
-                            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes + q * (L::kABytes + L::kBBytes));
+                        if constexpr (KWF) {
+                            const int kh = kb / p.cin_chunks;
+                            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
                             const uint32_t b_addr = a_addr + L::kABytes;
 #pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                                const uint64_t da = make_sw128_kmajor_desc(a_addr + k * kUmmaK * 2);
-                                const uint64_t db = make_sw128_kmajor_desc(b_addr + k * kUmmaK * 2);
-                                umma_bf16_pair(d_base, da, db, idesc, (kb | q | k) != 0 ? 1u : 0u);
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const uint32_t shift = static_cast<uint32_t>(p.tap_dw[kh * 3 + kw] + 1);      // rows into the slab
+#pragma unroll
+                                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                    const uint64_t da = make_sw128_kmajor_desc(a_addr + shift * 128 + k * kUmmaK * 2);
+                                    const uint64_t db = make_sw128_kmajor_desc(b_addr + kw * L::kBBytes + k * kUmmaK * 2);
+                                    umma_bf16_pair(d_base, da, db, idesc, (kb | kw | k) != 0 ? 1u : 0u);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < kPairKSub; ++q) {
+                                const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes + q * (L::kABytes + L::kBBytes));
+                                const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+                                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                    const uint64_t da = make_sw128_kmajor_desc(a_addr + k * kUmmaK * 2);
+                                    const uint64_t db = make_sw128_kmajor_desc(b_addr + k * kUmmaK * 2);
+                                    umma_bf16_pair(d_base, da, db, idesc, (kb | q | k) != 0 ? 1u : 0u);
+                                }
                             }
                         }
                         umma_commit_pair(&empty_bar[stage]);             // stage free in both CTAs once these MMAs retire
