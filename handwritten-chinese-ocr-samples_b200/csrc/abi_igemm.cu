@@ -118,10 +118,10 @@ static bool pair_enabled() {
 }
 // (every layer of the model with Cout % 256 == 0 has Cin % 128 == 0, so the K blocks pair up)
 static bool use_pair(int H, int Cin, int Cout, int ksize, int pool) {
-    // (measured: at Cout = 128 the pair kernel without the kw-fused slab is slower than the single-CTA slab kernel,
-    //  763 vs 902 TFLOP/s on 128->128 - the thin layers are bound by L2->SMEM activation traffic, not operand reads)
+    // (measured: at Cout = 128 the pair kernel is slower than the single-CTA slab kernel, with or without the slab -
+    //  722 / 763 vs 990 TFLOP/s on 128->128: K = 1152 gives 4 us tiles and the cluster-wide accumulator hand-over
+    //  per tile dominates)
     const bool slab = ksize == 3 && g_kwf_mode != 0;         // one stage per (kh, chunk); otherwise K blocks go in pairs
-    if (Cout == 128) return pair_enabled() && !pool && H % 2 == 0 && slab && getenv("HCTR_PAIR128") != nullptr;
     return pair_enabled() && !pool && Cout % 256 == 0 && H % 2 == 0 && (slab || (ksize * ksize * (Cin / 64)) % kPairKSub == 0);
 }
 
@@ -236,7 +236,6 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
         if (rc) return rc;
         rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, block_n / 2);
         if (rc) return rc;
-        if (slab && block_n == 128) return launch_igemm_pair<128, 4, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
         if (slab) return launch_igemm_pair<256, 3, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
         return launch_igemm_pair<256, 3, 0>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
     }
