@@ -50,6 +50,9 @@ CONV_CASES = [
     (1, 4, 100, 128, 256, 1, 0, 0),           # block2.0.downsample
     (1, 4, 129, 256, 512, 1, 0, 0),           # block3.0.downsample
     (3, 2, 1, 64, 64, 3, 1, 1),               # degenerate width
+    (2, 6, 700, 256, 256, 3, 1, 0),           # CTA-pair kernel: several tiles per pair, ragged last span
+    (1, 5, 140, 256, 256, 3, 1, 0),           # odd height: the wide layer stays on the single-CTA kernel
+    (3, 2, 64, 512, 256, 1, 0, 0),            # 1x1 on the pair kernel (K blocks in pairs)
 ]
 
 
@@ -75,6 +78,36 @@ def test_conv_bn_act_kernel(B, H, W, Cin, Cout, k, relu, pool):
     got = y.permute(0, 3, 1, 2).float()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() <= BF16_GATE * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("kwf", [0, 2])
+def test_wide_conv_same_on_every_kernel_variant(kwf):
+    """Cout % 256 == 0, un-pooled: the CTA-pair kernel (tcgen05.mma.cta_group::2), with and without the kw-fused
+    activation slab, against the single-CTA kernel and torch; the variants differ only in fp32 accumulation order."""
+    nat = _nat()
+    lib = nat.lib()
+    B, H, W, Cin, Cout = 2, 4, 333, 256, 512
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).cuda().to(torch.bfloat16)
+    scale = (torch.rand(Cout, generator=g) + 0.5).cuda(); shift = (0.2 * torch.randn(Cout, generator=g)).cuda()
+    xn = x.permute(0, 2, 3, 1).contiguous(); wp = w.permute(0, 2, 3, 1).contiguous()
+    ref = (F.conv2d(x.float(), w.float(), padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).relu()
+    outs = []
+    try:
+        lib.hctr_debug_set_kwf_mode(kwf)
+        for pair in (0, 1):
+            lib.hctr_debug_set_pair_mode(pair)
+            y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            nat.check(lib.hctr_conv_bn_act_fwd(nat.ptr(xn), nat.ptr(wp), nat.ptr(scale), nat.ptr(shift), nat.ptr(y),
+                                               B, H, W, Cin, Cout, 3, 1, 0, nat.stream_ptr()))
+            outs.append(y.permute(0, 3, 1, 2).float())
+    finally:
+        lib.hctr_debug_set_kwf_mode(2); lib.hctr_debug_set_pair_mode(1)
+    for got in outs:
+        assert torch.isfinite(got).all()
+        assert (got - ref).abs().max().item() <= BF16_GATE * ref.abs().max().item()
+    assert (outs[0] - outs[1]).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
 
 
 def test_conv_rejects_bad_shapes():
