@@ -147,7 +147,13 @@ static int launch_igemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         if (getenv("HCTR_DEBUG")) fprintf(stderr, "hctr_b200: igemm_pair_kernel<%d> max active clusters = %d (SMs %d)\n", BLOCK_N, n, sm_count());
     }
     const int pairs = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;
-    kern<<<2 * pairs, kIgemmThreads, L::kTotal, stream>>>(tmA, tmB, p);
+    IgemmParams q = p;
+    // whole columns per pair when they balance (<= 4 % idle tail); HCTR_PAIR_COLS=0 turns it off
+    static const bool cols_off = getenv("HCTR_PAIR_COLS") && getenv("HCTR_PAIR_COLS")[0] == '0';
+    const long long ncols = (long long)p.B * p.w_tiles;
+    const long long padded = (ncols + pairs - 1) / pairs * pairs;
+    q.col_mode = (!cols_off && padded * 100 <= ncols * 104) ? 1 : 0;
+    kern<<<2 * pairs, kIgemmThreads, L::kTotal, stream>>>(tmA, tmB, q);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }

@@ -40,6 +40,7 @@ struct IgemmParams {
     int N;                    // output channels / classes
     // tiling (derived on host)
     int w_tiles, h_tiles, n_tiles, total_tiles;
+    int col_mode;             // CTA-pair kernel: 1 = deal whole (line, span) columns to the pairs (see igemm2_tcgen05.cuh)
     // epilogue
     const float* scale;       // [N] (EPI_CONV) or nullptr
     const float* shift;       // [N] BN shift (EPI_CONV) / bias (EPI_LINEAR)
