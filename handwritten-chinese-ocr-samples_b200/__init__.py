@@ -9,6 +9,7 @@ All arithmetic runs in hand-written CUDA kernels behind the C ABI in include/hct
 from . import native  # noqa: F401
 from . import train_engine  # noqa: F401
 from . import pipeline  # noqa: F401
+from . import ngram_lm  # noqa: F401
 
 __all__ = ["native", "hctr_model", "ctc_codec", "CTCLoss", "TrainStep"]
 

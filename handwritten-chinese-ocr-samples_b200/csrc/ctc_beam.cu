@@ -6,8 +6,10 @@
 //                         np.logaddexp semantics, insertion-ordered stable ranking exactly as the
 //                         reference's dict + sorted(reverse=True).
 #include <cfloat>
+#include <cstring>
 
 #include "common.cuh"
+#include "ngram_lm.cuh"
 #include "../../include/hctr_b200.h"
 
 namespace hctr {
@@ -224,11 +226,28 @@ __device__ bool same_string(const int* parent, const int* chr, int a, int b) {
     return true;
 }
 
+// LM context of the string (trie node `node`) + optional extra character `extra` (class index, -1 = none): the last
+// order-1 words, most recent first, with <s> in front of a short string (kenlm score(..., bos=True))
+__device__ inline void trie_context(const hctr_ngram_lm& lm, const int* __restrict__ n_parent, const int* __restrict__ n_chr,
+                                    int node, int extra, int* ctx, int& m) {
+    const int cap = lm.order - 1;
+    m = 0;
+#pragma unroll
+    for (int i = 0; i < kNgramMaxOrder - 1; ++i) ctx[i] = 0;
+    if (extra >= 0 && m < cap) ctx[m++] = __ldg(lm.vocab + extra);
+    while (m < cap) {
+        const int c = n_chr[node];
+        if (c < 0) { ctx[m++] = lm.bos_id; break; }            // root of the trie: beginning of the sentence
+        ctx[m++] = __ldg(lm.vocab + c);
+        node = n_parent[node];
+    }
+}
+
 __global__ void __launch_bounds__(32)
 ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __restrict__ topk_logp, int Tn, int Bn, int C,
                        int k, int beam_size, double lm_penalty, double len_bonus, const double* __restrict__ lm_table,
-                       int32_t* __restrict__ out_idx, int32_t* __restrict__ out_len, int32_t* __restrict__ status,
-                       unsigned char* __restrict__ workspace, long long ws_per_seq) {
+                       const hctr_ngram_lm ng_lm, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_len,
+                       int32_t* __restrict__ status, unsigned char* __restrict__ workspace, long long ws_per_seq) {
     __shared__ KeptState kept[2];
     __shared__ double Pj[kMaxBeam];
     __shared__ int parentk[kMaxBeam];
@@ -242,6 +261,7 @@ ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __rest
 
     const int b = blockIdx.x, lane = threadIdx.x;
     const int unknown = C - 1;
+    const bool use_ngram = ng_lm.entries != nullptr;
     unsigned char* ws = workspace + (long long)b * ws_per_seq;
     int* g_char = reinterpret_cast<int*>(ws);
     int* g_time = g_char + Tn;
@@ -365,12 +385,31 @@ ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __rest
                 double p = 0.0;
                 for (int q = 0; q < k; ++q) if (cand[q] == idx) p = candp[q];
                 pnb = (idx != K.last[j]) ? __dadd_rn(Pj[j], p) : __dadd_rn(K.pb[j], p);
-                lm = lm_table ? __dadd_rn(K.lmsum[j], lm_table[idx]) : 0.0;
+                if (use_ngram) {
+                    // kenlm: float32 running total; p(idx | last order-1 characters of prefix_j, <s> in front)
+                    int ctx[kNgramMaxOrder - 1]; int m;
+                    trie_context(ng_lm, n_parent, n_chr, K.node[j], -1, ctx, m);
+                    lm = (double)__fadd_rn((float)K.lmsum[j], ngram_word_score(ng_lm, ctx, m, __ldg(ng_lm.vocab + idx)));
+                } else {
+                    lm = lm_table ? __dadd_rn(K.lmsum[j], lm_table[idx]) : 0.0;
+                }
                 plen = (double)(K.len[j] + 1);
             }
             e_lm[e] = lm;                                                       // LM sum over the prefix only
             double lmt = lm;
             if (lm_table) for (int c = 0; c < nsuf; ++c) lmt = __dadd_rn(lmt, lm_table[g_char[gptr + c]]);
+            if (use_ngram && nsuf > 0) {
+                int ctx[kNgramMaxOrder - 1]; int m;
+                if (e_kind[e] >= 0) trie_context(ng_lm, n_parent, n_chr, K.node[e_kind[e]], -1, ctx, m);
+                else trie_context(ng_lm, n_parent, n_chr, K.node[e_src[e]], e_chr[e], ctx, m);
+                float tot = (float)lm;
+                for (int c = 0; c < nsuf; ++c) {
+                    const int w = __ldg(ng_lm.vocab + g_char[gptr + c]);
+                    tot = __fadd_rn(tot, ngram_word_score(ng_lm, ctx, m, w));
+                    ngram_push(ctx, m, ng_lm.order - 1, w);
+                }
+                lmt = (double)tot;
+            }
             const double pt = __dadd_rn(__dmul_rn(lmt, lm_penalty), __dmul_rn(plen, len_bonus));   // :277-281
             e_pb[e] = pb; e_pnb[e] = pnb;
             e_tot[e] = __dadd_rn(logaddexp_np(pb, pnb), pt);                     // Beam.total() :302-303
@@ -460,14 +499,23 @@ long long hctr_ctc_beam_workspace_bytes(int T, int B, int beam_size) {
     return beam_ws_per_seq(T, beam_size) * B;
 }
 
-int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp, int T, int B, int C, int k,
-                                int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
-                                int32_t* out_idx, int32_t* out_len, int32_t* status, void* workspace,
-                                long long workspace_bytes, void* stream) {
+int hctr_ctc_prefix_beam_search_lm(const int32_t* topk_idx, const float* topk_logp, int T, int B, int C, int k,
+                                   int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                   const hctr_ngram_lm* ngram, int32_t* out_idx, int32_t* out_len, int32_t* status,
+                                   void* workspace, long long workspace_bytes, void* stream) {
     HCTR_CHECK(out_idx && out_len && status, HCTR_ERR_INVALID, "beam: null output");
     HCTR_CHECK(k >= 1 && k <= kMaxK, HCTR_ERR_INVALID, "beam: search depth must be in [1,%d] (got %d)", kMaxK, k);
     HCTR_CHECK(beam_size >= 1 && beam_size <= kMaxBeam, HCTR_ERR_INVALID, "beam: beam size must be in [1,%d] (got %d)", kMaxBeam, beam_size);
     HCTR_CHECK(T >= 0 && B >= 0 && C > 1, HCTR_ERR_INVALID, "beam: bad shape");
+    HCTR_CHECK(!(ngram && lm_table), HCTR_ERR_INVALID, "beam: pass either a unigram table or an n-gram model");
+    hctr_ngram_lm lm;
+    memset(&lm, 0, sizeof(lm));
+    if (ngram) {
+        int rc = hctr::check_ngram(ngram, "beam");
+        if (rc) return rc;
+        HCTR_CHECK(ngram->num_ids >= C, HCTR_ERR_INVALID, "beam: the n-gram vocabulary map covers %d ids, the logits have %d classes", ngram->num_ids, C);
+        lm = *ngram;
+    }
     if (B == 0) return HCTR_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (T == 0) {        // no frames: the greedy path is empty for every sequence
@@ -480,11 +528,19 @@ int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp,
     const long long need = hctr_ctc_beam_workspace_bytes(T, B, beam_size);
     HCTR_CHECK(workspace && workspace_bytes >= need, HCTR_ERR_INVALID, "beam: workspace too small (%lld < %lld)", workspace_bytes, need);
     HCTR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, HCTR_ERR_INVALID, "beam: workspace must be 16-byte aligned");
-    ctc_prefix_beam_kernel<<<B, 32, 0, s>>>(topk_idx, topk_logp, T, B, C, k, beam_size, lm_penalty, len_bonus, lm_table,
+    ctc_prefix_beam_kernel<<<B, 32, 0, s>>>(topk_idx, topk_logp, T, B, C, k, beam_size, lm_penalty, len_bonus, lm_table, lm,
                                             out_idx, out_len, status, static_cast<unsigned char*>(workspace),
                                             beam_ws_per_seq(T, beam_size));
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
+}
+
+int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp, int T, int B, int C, int k,
+                                int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                int32_t* out_idx, int32_t* out_len, int32_t* status, void* workspace,
+                                long long workspace_bytes, void* stream) {
+    return hctr_ctc_prefix_beam_search_lm(topk_idx, topk_logp, T, B, C, k, beam_size, lm_penalty, len_bonus, lm_table, nullptr,
+                                          out_idx, out_len, status, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -53,6 +53,7 @@ class ctc_codec(object):
         self.use_beam_search = False
         # device language model for the beam path: per-class unigram log10 scores (None = zero LM)
         self.lm_table = None
+        self.ngram = None               # NgramLM (back-off n-gram on the device) set by set_beam_search(ngram_path='*.arpa')
         self.device = None           # CUDA device used when decode() is handed a NumPy array
 
     # ------------------------------------------------------------------ encode (reference :43-61)
@@ -158,17 +159,21 @@ class ctc_codec(object):
             # this path (out of scope) -> same exception type as a missing dependency
             raise ImportError("hctr_b200: transformer language models (fairseq/OpenVINO) are outside the "
                               "B200 hot path; pass use_tfm_pred=False, use_tfm_score=False")
+        self.lm_table = None            # per-class unigram table (float64 log10 scores), or
+        self.ngram = None               # NgramLM: back-off n-gram model scored inside the kernel; neither = zero LM
         if ngram_path:
-            if not ngram_path.endswith(".npy"):
-                raise NotImplementedError("hctr_b200: KenLM ARPA/binary models are scored on the host in the "
-                                          "reference; the device beam search takes a per-class unigram table "
-                                          "(.npy of %d float64 log10 scores)" % len(self.characters))
-            table = np.load(ngram_path).astype(np.float64)
-            if table.shape != (len(self.characters),):
-                raise ValueError("unigram table must have shape (%d,)" % len(self.characters))
-            self.lm_table = table
-        else:
-            self.lm_table = None        # zero LM
+            if ngram_path.endswith(".npy"):
+                table = np.load(ngram_path).astype(np.float64)
+                if table.shape != (len(self.characters),):
+                    raise ValueError("unigram table must have shape (%d,)" % len(self.characters))
+                self.lm_table = table
+            elif ngram_path.endswith((".arpa", ".arpa.txt", ".lm")):
+                # the reference loads this file with kenlm.Model (utils/ctc_codec.py:120-122); here the ARPA text is
+                # turned into a device hash table and queried inside the beam-search kernel
+                self.ngram = _core().ngram_lm.NgramLM.from_arpa(ngram_path, self)
+            else:
+                raise NotImplementedError("hctr_b200: KenLM binary files are not read; pass the ARPA file lmplz wrote "
+                                          "(*.arpa) or a per-class unigram table (*.npy)")
 
     def skip_search_indices(self, logits):
         """__cbs_skip__ on the device (reference: utils/ctc_codec.py:124-181)."""
@@ -226,10 +231,19 @@ class ctc_codec(object):
                 table = torch.from_numpy(np.ascontiguousarray(self.lm_table, dtype=np.float64)).to(dev)
             ws_bytes = lib.hctr_ctc_beam_workspace_bytes(T, B, beam)
             ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
-            nat.check(lib.hctr_ctc_prefix_beam_search(
-                nat.ptr(tk_idx), nat.ptr(tk_lp), T, B, C, k, beam, float(self.lm_panelty), float(self.len_bonus),
-                nat.ptr(table), nat.ptr(idx), nat.ptr(ln), nat.ptr(status), nat.ptr(ws), ws_bytes, st),
-                "ctc_prefix_beam_search")
+            ngram = getattr(self, "ngram", None)
+            if ngram is not None and hasattr(ngram, "struct"):
+                import ctypes
+                lm = ngram.struct(dev)
+                nat.check(lib.hctr_ctc_prefix_beam_search_lm(
+                    nat.ptr(tk_idx), nat.ptr(tk_lp), T, B, C, k, beam, float(self.lm_panelty), float(self.len_bonus),
+                    None, ctypes.byref(lm), nat.ptr(idx), nat.ptr(ln), nat.ptr(status), nat.ptr(ws), ws_bytes, st),
+                    "ctc_prefix_beam_search_lm")
+            else:
+                nat.check(lib.hctr_ctc_prefix_beam_search(
+                    nat.ptr(tk_idx), nat.ptr(tk_lp), T, B, C, k, beam, float(self.lm_panelty), float(self.len_bonus),
+                    nat.ptr(table), nat.ptr(idx), nat.ptr(ln), nat.ptr(status), nat.ptr(ws), ws_bytes, st),
+                    "ctc_prefix_beam_search")
             if T == 0 or bool((status != 0).any().item()):
                 # reference: top_line[-1] on an empty greedy path raises IndexError (utils/ctc_codec.py:198)
                 raise IndexError("list index out of range")

@@ -134,6 +134,30 @@ int hctr_ctc_prefix_beam_search(const int32_t* topk_idx, const float* topk_logp,
 /* bytes of caller-owned device scratch (greedy look-ahead list + prefix trie) for the call above */
 long long hctr_ctc_beam_workspace_bytes(int T, int B, int beam_size);
 
+/* Back-off n-gram language model for the beam search (reference: kenlm.Model(ngram_path).score(' '.join(prefix +
+ * suffix), eos=False), utils/ctc_codec.py:120-122,276-279; a 5-gram from lmplz, third-party/README.md:28-42). Words are
+ * single characters = class indices; ids: classes 0..C-1, then <s>, </s>, <unk>. One open-addressing hash table over all
+ * orders (linear probing, capacity a power of two): entry i = uint4 {key_lo low, key_lo high, key_hi, float bits of
+ * log10 p}, key_lo = r0 | r1<<16 | r2<<32 | r3<<48 and key_hi = r4 | order<<16 with r0 the most recent word; key_hi == 0
+ * marks an empty slot; slot of a key = splitmix64(key_lo ^ key_hi * 0x9E3779B97F4A7C15) & mask. All device pointers.
+ * hctr_b200/ngram_lm.py builds it from an ARPA file. */
+typedef struct hctr_ngram_lm {
+    const void* entries;          /* uint4 [mask + 1] */
+    const float* backoff;         /* [mask + 1] log10 back-off weight of the n-gram in the same slot */
+    const int32_t* vocab;         /* [num_ids] id -> LM word id: itself, or unk_id for a word without a unigram */
+    unsigned long long mask;      /* capacity - 1 */
+    int order;                    /* 1..5 */
+    int bos_id, unk_id, num_ids;
+} hctr_ngram_lm;
+/* kenlm.Model.score(sentence, bos=True, eos=False) for nseq sequences of class indices ids[offsets[q] .. offsets[q+1]):
+ * float32 accumulation as in KenLM; out: fp32 [nseq]. One thread per sequence. */
+int hctr_ngram_score(const hctr_ngram_lm* lm, const int32_t* ids, const int32_t* offsets, int nseq, float* out, void* stream);
+/* hctr_ctc_prefix_beam_search with the n-gram model above as the language model (lm_table must be NULL then). */
+int hctr_ctc_prefix_beam_search_lm(const int32_t* topk_idx, const float* topk_logp, int T, int B, int C, int k,
+                                   int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                   const hctr_ngram_lm* ngram, int32_t* out_idx, int32_t* out_len, int32_t* status,
+                                   void* workspace, long long workspace_bytes, void* stream);
+
 /* ctc_codec.__cbs_skip__ (utils/ctc_codec.py:124-181): candidates per step are the classes with log-prob > log(0.001)
  * in index order; a single candidate takes the reference's in-place fast path (quirks included), otherwise a
  * duplicate-aware context beam search runs over the candidates. Fused log-softmax/prune pre-pass + one CTA per sequence.

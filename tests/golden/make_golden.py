@@ -92,6 +92,37 @@ def make_beam():
     np.savez_compressed(os.path.join(HERE, "beam.npz"), **out)
 
 
+# ------------------------------------------------------------------ beam search with a back-off n-gram LM
+class ArpaStub(object):
+    """What `kenlm.Model` is to the reference's beam search (utils/ctc_codec.py:120-122,279): .score(sentence, eos=False).
+    kenlm itself is not installed here; the scorer is oracle/ngram.py (KenLM's published query algorithm, float32)."""
+
+    def __init__(self, text):
+        sys.path.insert(0, ROOT)
+        from oracle.ngram import ArpaLM
+        self.lm = ArpaLM(text)
+
+    def score(self, sentence, eos=False):
+        return self.lm.score(sentence, bos=True, eos=eos)
+
+
+def make_beam_ngram():
+    out = {}
+    cases = [("tri", 64, 3, 60, 41, 6, 3, 51), ("five", 80, 2, 120, 42, 7, 5, 52), ("five_wide", 32, 1, 7375, 43, 6, 5, 53)]
+    for name, T, B, C, seed, period, order, lmseed in cases:
+        x = synth.beam_logits(T, B, C, seed, period)
+        chars = synth.charset(C - 2)
+        arpa = synth.arpa_text(chars[:200], order, lmseed, grams_per_order=500)
+        for sname, pen, bonus in (("p2_b58", 2.0, 5.8), ("p1_b2", 1.0, 2.0)):
+            codec = ctc_codec(chars)
+            codec.use_beam_search = True; codec.use_tfm_pred = False; codec.use_tfm_score = False
+            codec.skip_search = False; codec.lm_panelty = pen; codec.len_bonus = bonus
+            codec.ngram = ArpaStub(arpa)
+            out["%s_%s_text" % (name, sname)] = strs(codec.decode(x))
+        out[name + "_shape"] = np.array([T, B, C, seed, period, order, lmseed])
+    np.savez_compressed(os.path.join(HERE, "beam_ngram.npz"), **out)
+
+
 def make_beam_skip():
     """__cbs_skip__ (utils/ctc_codec.py:124-181): pruned candidates + the single-candidate fast path."""
     out = {}
@@ -235,7 +266,7 @@ def make_pad():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["greedy", "beam", "beam_skip", "ctc_loss", "model", "config1", "pad"]
+    which = sys.argv[1:] or ["greedy", "beam", "beam_ngram", "beam_skip", "ctc_loss", "model", "config1", "pad"]
     for w in which:
         print("making", w, flush=True)
         globals()["make_" + w]()

@@ -96,3 +96,40 @@ def peakier(x, boost):
         t, b = np.meshgrid(np.arange(y.shape[0]), np.arange(y.shape[1]), indexing="ij")
         y[t, b, am] += np.float32(boost)
     return y
+
+
+def arpa_text(chars, order, seed, vocab_frac=0.8, grams_per_order=400):
+    """A small, structurally valid ARPA model over single-character words: every n-gram's prefix and suffix exist,
+    random log10 probabilities / back-offs with at most 6 significant digits (what lmplz prints), <unk>, <s>, </s>."""
+    rs = np.random.RandomState(seed)
+    vocab = [c for c in chars if rs.rand() < vocab_frac]
+    words = ["<unk>", "<s>", "</s>"] + vocab
+    levels = [set((w,) for w in words)]
+    for n in range(2, order + 1):
+        prev = sorted(levels[-1])
+        cur = set()
+        tries = 0
+        while len(cur) < grams_per_order and tries < 20 * grams_per_order:
+            tries += 1
+            g = prev[rs.randint(len(prev))]
+            if g[-1] == "</s>":
+                continue
+            w = words[2 + rs.randint(len(words) - 2)]                  # never <unk> or <s> as the predicted word
+            cand = g + (w,)
+            if cand[1:] in levels[-1] and "<unk>" not in cand:         # the suffix must exist too (KenLM requires it)
+                cur.add(cand)
+        levels.append(cur)
+    lines = ["\\data\\"] + ["ngram %d=%d" % (n + 1, len(l)) for n, l in enumerate(levels)] + [""]
+    for n, level in enumerate(levels, start=1):
+        lines.append("\\%d-grams:" % n)
+        for g in sorted(level):
+            p = -round(0.2 + 4.0 * rs.rand(), 5)
+            if g == ("<s>",):
+                p = -99.0
+            if n < order and g[-1] != "</s>":
+                lines.append("%g\t%s\t%g" % (p, " ".join(g), -round(1.5 * rs.rand(), 5)))
+            else:
+                lines.append("%g\t%s" % (p, " ".join(g)))
+        lines.append("")
+    lines.append("\\end\\")
+    return "\n".join(lines) + "\n"

@@ -228,3 +228,53 @@ def test_edit_distance_and_cer_on_device():
     want = [oracle.edit_distance(p, t) for p, t in zip(preds, truths)]
     assert dist.cpu().tolist() == want
     assert nchars == sum(len(t) for t in truths)
+
+
+# ---- back-off n-gram language model inside the beam search (reference: kenlm, utils/ctc_codec.py:120-122,276-279) ------
+def _ngram_codec(C, order, lmseed):
+    from hctr_b200.ngram_lm import NgramLM
+    c = _codec(C)
+    text = synth.arpa_text(synth.charset(C - 2)[:200], order, lmseed, grams_per_order=500)
+    c.set_beam_search(use_tfm_pred=False)
+    c.ngram = NgramLM.from_arpa_text(text, c.dict, C)
+    return c, text
+
+
+def test_ngram_score_on_device_matches_oracle():
+    """hctr_ngram_score == kenlm score(bos=True, eos=False) as restated in oracle/ngram.py, bit for bit (float32)."""
+    from oracle.ngram import ArpaLM
+    C = 300
+    c, text = _ngram_codec(C, 5, 17)
+    o = ArpaLM(text)
+    rs = np.random.RandomState(5)
+    seqs = [rs.randint(1, C - 1, size=rs.randint(0, 30)).tolist() for _ in range(200)]
+    seqs += [rs.randint(1, 201, size=rs.randint(1, 40)).tolist() for _ in range(200)]      # in-vocabulary heavy
+    got = c.ngram.score_ids(seqs)
+    want = np.array([o.score(" ".join(c.characters[i] for i in s)) for s in seqs], np.float32)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("case", ["tri", "five", "five_wide"])
+@pytest.mark.parametrize("setting,pen,bonus", [("p2_b58", 2.0, 5.8), ("p1_b2", 1.0, 2.0)])
+def test_beam_ngram_golden(golden, case, setting, pen, bonus):
+    """The reference's own beam search driven by the ARPA scorer vs the device search with the n-gram table."""
+    g = golden("beam_ngram")
+    T, B, C, seed, period, order, lmseed = [int(v) for v in g[case + "_shape"]]
+    x = synth.beam_logits(T, B, C, seed, period)
+    c, _ = _ngram_codec(C, order, lmseed)
+    c.lm_panelty, c.len_bonus = pen, bonus
+    assert c.decode(torch.from_numpy(x).cuda()) == list(g["%s_%s_text" % (case, setting)])
+
+
+def test_set_beam_search_reads_an_arpa_file(tmp_path):
+    C = 120
+    p = tmp_path / "lm.arpa"
+    p.write_text(synth.arpa_text(synth.charset(C - 2)[:60], 3, 4, grams_per_order=100), encoding="utf-8")
+    c = _codec(C)
+    c.set_beam_search(ngram_path=str(p), use_tfm_pred=False)
+    assert c.ngram is not None and c.ngram.order == 3 and c.lm_table is None
+    x = synth.beam_logits(40, 2, C, 8, 5)
+    out = c.decode(torch.from_numpy(x).cuda())
+    assert len(out) == 2 and all(isinstance(t, str) for t in out)
+    with pytest.raises(NotImplementedError):
+        c.set_beam_search(ngram_path="model.bin", use_tfm_pred=False)

@@ -114,3 +114,79 @@ def test_edit_distance_known_answers():
     assert oracle.edit_distance("", "abc") == 3 and oracle.edit_distance("abc", "") == 3 and oracle.edit_distance("", "") == 0
     assert oracle.edit_distance("intention", "execution") == 5
     assert oracle.edit_distance([1, 2, 3], [1, 2, 3]) == 0
+
+
+# ---- back-off n-gram LM (oracle/ngram.py; kenlm is absent: pinned to hand-computed ARPA values only) -----------------
+_TINY_ARPA = """\\data\\
+ngram 1=6
+ngram 2=4
+ngram 3=2
+
+\\1-grams:
+-1.0\t<unk>
+-99\t<s>\t-0.5
+-1.5\t</s>
+-0.7\ta\t-0.25
+-0.9\tb\t-0.125
+-1.1\tc
+
+\\2-grams:
+-0.3\t<s> a\t-0.0625
+-0.4\ta b\t-0.03125
+-0.6\tb a
+-0.2\tb c
+
+\\3-grams:
+-0.1\t<s> a b
+-0.05\ta b c
+
+\\end\\
+"""
+
+
+def _f32(*terms):
+    t = np.float32(0.0)
+    for v in terms:
+        t = np.float32(t + np.float32(v))
+    return float(t)
+
+
+def test_ngram_oracle_known_answers():
+    """Katz back-off by hand: p(w|ctx) = longest match + back-offs of the longer contexts that exist."""
+    from oracle.ngram import ArpaLM
+    lm = ArpaLM(_TINY_ARPA)
+    assert lm.order == 3
+    # "a b c": p(a|<s>) = -0.3;  p(b|<s> a) = -0.1 (trigram);  p(c|a b) = -0.05 (trigram)
+    assert lm.score("a b c") == _f32(-0.3, -0.1, -0.05)
+    # "b a": p(b|<s>): no "<s> b" -> unigram -0.9 + backoff(<s>) -0.5;  p(a|<s> b): "<s> b a" missing, "b a" = -0.6, and the
+    # longer context "<s> b" does not exist -> no back-off
+    assert lm.score("b a") == _f32(np.float32(np.float32(-0.9) + np.float32(-0.5)), -0.6)
+    # "a c": p(c|<s> a): no "<s> a c", no "a c" -> unigram -1.1 + backoff(a) -0.25 + backoff(<s> a) -0.0625
+    assert lm.score("a c") == _f32(-0.3, np.float32(np.float32(np.float32(-1.1) + np.float32(-0.25)) + np.float32(-0.0625)))
+    # unknown word: <unk> unigram, backed off from the context; then it becomes context itself (no n-gram continues it)
+    assert lm.score("z a") == _f32(np.float32(np.float32(-1.0) + np.float32(-0.5)), -0.7)
+    assert lm.score("") == 0.0
+    assert lm.score("a", eos=True) == _f32(-0.3, np.float32(np.float32(np.float32(-1.5) + np.float32(-0.25)) + np.float32(-0.0625)))
+
+
+def test_ngram_table_builder_matches_oracle():
+    """The product's ARPA reader + hash table (host side of csrc/ngram_lm.cuh) holds exactly the oracle's n-grams."""
+    from oracle.ngram import ArpaLM
+    from hctr_b200.ngram_lm import NgramLM
+    C = 64
+    chars = synth.charset(C - 2)
+    text = synth.arpa_text(chars[:40], 5, 3, grams_per_order=250)
+    o = ArpaLM(text)
+    cd = {ch: i + 1 for i, ch in enumerate(chars)}
+    lm = NgramLM.from_arpa_text(text, cd, C)
+    assert lm.order == 5 and lm.n_grams == len(o.grams)
+    w2i = dict(cd); w2i["<s>"] = C; w2i["</s>"] = C + 1; w2i["<unk>"] = C + 2
+    for g, (p, b) in o.grams.items():
+        assert lm.host_find([w2i[w] for w in g]) == (float(p), float(b)), g
+    assert lm.host_find([w2i[chars[0]], w2i[chars[41]]]) is None
+    # characters without a unigram map to <unk>, the others to themselves
+    have = {g[0] for g in o.grams if len(g) == 1}
+    for ch in chars:
+        assert lm.host["vocab"][cd[ch]] == (cd[ch] if ch in have else C + 2)
+    with pytest.raises(ValueError):
+        NgramLM.from_arpa_text(text.replace("\\5-grams:", "\\6-grams:"), cd, C)
