@@ -9,7 +9,10 @@
 // float64 accumulators, np.logaddexp branch structure, stable ranking by insertion order.
 #include <cfloat>
 
+#include <cstring>
+
 #include "common.cuh"
+#include "ngram_lm.cuh"
 #include "../../include/hctr_b200.h"
 
 namespace hctr {
@@ -157,7 +160,7 @@ struct SkKept {
 __global__ void __launch_bounds__(kSkThreads)
 ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ blank_lp, const int32_t* __restrict__ cand_idx,
                      const float* __restrict__ cand_lp, int Tn, int Bn, int C, int beam_size, double lm_penalty,
-                     double len_bonus, const double* __restrict__ lm_table, int32_t* __restrict__ out_idx,
+                     double len_bonus, const double* __restrict__ lm_table, const hctr_ngram_lm ng_lm, int32_t* __restrict__ out_idx,
                      int32_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned char* __restrict__ workspace,
                      long long ws_per_seq) {
     __shared__ SkKept kept[2];
@@ -243,6 +246,11 @@ ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ bl
                     n_parent[id] = K.node[j]; n_chr[id] = pidx; n_hash[id] = h;
                     K.node[j] = id; K.len[j] += 1; K.last[j] = pidx; K.hash[j] = h;
                     if (lm_table) K.lmsum[j] = __dadd_rn(K.lmsum[j], lm_table[pidx]);
+                    if (ng_lm.entries) {                                              // kenlm: float32 running total
+                        int ctx[kNgramMaxOrder - 1]; int m;
+                        trie_context(ng_lm, n_parent, n_chr, n_parent[id], -1, ctx, m);
+                        K.lmsum[j] = (double)__fadd_rn((float)K.lmsum[j], ngram_word_score(ng_lm, ctx, m, __ldg(ng_lm.vocab + pidx)));
+                    }
                 }
             }
             __threadfence_block();
@@ -335,10 +343,27 @@ ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ bl
                     if (canon[j] == Kc)
                         pnb = sk_logaddexp(pnb, (idx != K.last[j]) ? __dadd_rn(Pj[j], p) : __dadd_rn(K.pb[j], p));
                 lm = lm_table ? __dadd_rn(K.lmsum[Kc], lm_table[idx]) : 0.0;
+                if (ng_lm.entries) {
+                    int ctx[kNgramMaxOrder - 1]; int m;
+                    trie_context(ng_lm, n_parent, n_chr, K.node[Kc], -1, ctx, m);
+                    lm = (double)__fadd_rn((float)K.lmsum[Kc], ngram_word_score(ng_lm, ctx, m, __ldg(ng_lm.vocab + idx)));
+                }
                 plen = (double)(K.len[Kc] + 1);
             }
             double lmt = lm;
             if (lm_table) for (int c = 0; c < nsuf; ++c) lmt = __dadd_rn(lmt, lm_table[g_char[gptr + c]]);
+            if (ng_lm.entries && nsuf > 0) {
+                int ctx[kNgramMaxOrder - 1]; int m;
+                if (e_kind[e] >= 0) trie_context(ng_lm, n_parent, n_chr, K.node[e_kind[e]], -1, ctx, m);
+                else trie_context(ng_lm, n_parent, n_chr, K.node[e_src[e]], e_chr[e], ctx, m);
+                float tot = (float)lm;
+                for (int c = 0; c < nsuf; ++c) {
+                    const int w = __ldg(ng_lm.vocab + g_char[gptr + c]);
+                    tot = __fadd_rn(tot, ngram_word_score(ng_lm, ctx, m, w));
+                    ngram_push(ctx, m, ng_lm.order - 1, w);
+                }
+                lmt = (double)tot;
+            }
             const double pt = __dadd_rn(__dmul_rn(lmt, lm_penalty), __dmul_rn(plen, len_bonus));
             e_pb[e] = pb; e_pnb[e] = pnb;
             e_tot[e] = __dadd_rn(sk_logaddexp(pb, pnb), pt);
@@ -361,7 +386,13 @@ ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ bl
                     const unsigned long long h = sk_mix(K.hash[j], idx);
                     n_parent[id] = K.node[j]; n_chr[id] = idx; n_hash[id] = h;
                     Kn.node[rank] = id; Kn.len[rank] = K.len[j] + 1; Kn.last[rank] = idx; Kn.hash[rank] = h;
-                    Kn.lmsum[rank] = lm_table ? __dadd_rn(K.lmsum[j], lm_table[idx]) : 0.0;
+                    double nl = lm_table ? __dadd_rn(K.lmsum[j], lm_table[idx]) : 0.0;
+                    if (ng_lm.entries) {                  // the same float32 sum the scoring loop formed for this entry
+                        int ctx[kNgramMaxOrder - 1]; int m;
+                        trie_context(ng_lm, n_parent, n_chr, K.node[j], -1, ctx, m);
+                        nl = (double)__fadd_rn((float)K.lmsum[j], ngram_word_score(ng_lm, ctx, m, __ldg(ng_lm.vocab + idx)));
+                    }
+                    Kn.lmsum[rank] = nl;
                 }
             }
         }
@@ -410,6 +441,23 @@ long long hctr_ctc_skip_workspace_bytes(int T, int B) {
 int hctr_ctc_skip_beam_search(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                               int beam_size, double lm_penalty, double len_bonus, const double* lm_table, int32_t* out_idx,
                               int32_t* out_len, int32_t* status, void* workspace, long long workspace_bytes, void* stream) {
+    return hctr_ctc_skip_beam_search_lm(logits, dtype, T, B, C, stride_t, stride_b, beam_size, lm_penalty, len_bonus, lm_table,
+                                        nullptr, out_idx, out_len, status, workspace, workspace_bytes, stream);
+}
+
+int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
+                                 int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                 const hctr_ngram_lm* ngram, int32_t* out_idx, int32_t* out_len, int32_t* status,
+                                 void* workspace, long long workspace_bytes, void* stream) {
+    HCTR_CHECK(!(ngram && lm_table), HCTR_ERR_INVALID, "skip beam: pass either a unigram table or an n-gram model");
+    hctr_ngram_lm lm;
+    memset(&lm, 0, sizeof(lm));
+    if (ngram) {
+        int rc = hctr::check_ngram(ngram, "skip beam");
+        if (rc) return rc;
+        HCTR_CHECK(ngram->num_ids >= C, HCTR_ERR_INVALID, "skip beam: the n-gram vocabulary map covers %d ids, the logits have %d classes", ngram->num_ids, C);
+        lm = *ngram;
+    }
     HCTR_CHECK(out_idx && out_len && status, HCTR_ERR_INVALID, "skip beam: null output");
     HCTR_CHECK(dtype == HCTR_F32 || dtype == HCTR_BF16, HCTR_ERR_INVALID, "skip beam: bad dtype");
     HCTR_CHECK(beam_size >= 1 && beam_size <= kSkMaxBeam, HCTR_ERR_INVALID, "skip beam: beam size must be in [1,%d]", kSkMaxBeam);
@@ -457,7 +505,7 @@ int hctr_ctc_skip_beam_search(const void* logits, int dtype, int T, int B, int C
                                        kSkMaxBeam * (kSkMaxC + 1) * 32));
         configured2 = true;
     }
-    ctc_skip_beam_kernel<<<B, kSkThreads, dyn, s>>>(meta, blank, cidx, clp, T, B, C, beam_size, lm_penalty, len_bonus, lm_table,
+    ctc_skip_beam_kernel<<<B, kSkThreads, dyn, s>>>(meta, blank, cidx, clp, T, B, C, beam_size, lm_penalty, len_bonus, lm_table, lm,
                                                     out_idx, out_len, status, seq_ws, sk_ws_per_seq(T));
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;

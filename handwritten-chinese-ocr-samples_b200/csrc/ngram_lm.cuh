@@ -68,4 +68,21 @@ __device__ __forceinline__ void ngram_push(int* ctx, int& m, int cap, int w) {
     if (m < cap) ++m;
 }
 
+// LM context of the string (trie node `node`) + optional extra character `extra` (class index, -1 = none): the last
+// order-1 words, most recent first, with <s> in front of a short string (kenlm score(..., bos=True))
+__device__ inline void trie_context(const hctr_ngram_lm& lm, const int* __restrict__ n_parent, const int* __restrict__ n_chr,
+                                    int node, int extra, int* ctx, int& m) {
+    const int cap = lm.order - 1;
+    m = 0;
+#pragma unroll
+    for (int i = 0; i < kNgramMaxOrder - 1; ++i) ctx[i] = 0;
+    if (extra >= 0 && m < cap) ctx[m++] = __ldg(lm.vocab + extra);
+    while (m < cap) {
+        const int c = n_chr[node];
+        if (c < 0) { ctx[m++] = lm.bos_id; break; }            // root of the trie: beginning of the sentence
+        ctx[m++] = __ldg(lm.vocab + c);
+        node = n_parent[node];
+    }
+}
+
 }  // namespace hctr

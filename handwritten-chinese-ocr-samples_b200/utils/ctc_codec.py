@@ -193,10 +193,19 @@ class ctc_codec(object):
             nb = lib.hctr_ctc_skip_workspace_bytes(T, B)
             ws = torch.empty((max(nb, 8) + 256,), dtype=torch.uint8, device=dev)
             off = (-ws.data_ptr()) % 256
-            nat.check(lib.hctr_ctc_skip_beam_search(
-                nat.ptr(logits), self._dtype_code(nat, logits), T, B, C, logits.stride(0), logits.stride(1),
-                int(self.beam_size), float(self.lm_panelty), float(self.len_bonus), nat.ptr(table), nat.ptr(idx), nat.ptr(ln),
-                nat.ptr(status), nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()), "ctc_skip_beam_search")
+            ngram = getattr(self, "ngram", None)
+            if ngram is not None and hasattr(ngram, "struct"):
+                import ctypes
+                lm = ngram.struct(dev)
+                nat.check(lib.hctr_ctc_skip_beam_search_lm(
+                    nat.ptr(logits), self._dtype_code(nat, logits), T, B, C, logits.stride(0), logits.stride(1),
+                    int(self.beam_size), float(self.lm_panelty), float(self.len_bonus), None, ctypes.byref(lm), nat.ptr(idx),
+                    nat.ptr(ln), nat.ptr(status), nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()), "ctc_skip_beam_search_lm")
+            else:
+                nat.check(lib.hctr_ctc_skip_beam_search(
+                    nat.ptr(logits), self._dtype_code(nat, logits), T, B, C, logits.stride(0), logits.stride(1),
+                    int(self.beam_size), float(self.lm_panelty), float(self.len_bonus), nat.ptr(table), nat.ptr(idx), nat.ptr(ln),
+                    nat.ptr(status), nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()), "ctc_skip_beam_search")
             st = status.cpu()
             if T == 0 or bool((st == nat.HCTR_ERR_INDEX).any()) or bool((st == -1).any()):
                 raise IndexError("list index out of range")     # reference: utils/ctc_codec.py:139,179

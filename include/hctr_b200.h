@@ -166,6 +166,11 @@ int hctr_ctc_prefix_beam_search_lm(const int32_t* topk_idx, const float* topk_lo
 int hctr_ctc_skip_beam_search(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                               int beam_size, double lm_penalty, double len_bonus, const double* lm_table, int32_t* out_idx,
                               int32_t* out_len, int32_t* status, void* workspace, long long workspace_bytes, void* stream);
+/* the same with the back-off n-gram model as the language model (lm_table must be NULL then) */
+int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
+                                 int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                 const hctr_ngram_lm* ngram, int32_t* out_idx, int32_t* out_len, int32_t* status,
+                                 void* workspace, long long workspace_bytes, void* stream);
 long long hctr_ctc_skip_workspace_bytes(int T, int B);
 int hctr_ctc_skip_max_candidates(void);
 

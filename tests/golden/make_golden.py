@@ -251,6 +251,27 @@ def make_config1():
     np.savez_compressed(os.path.join(HERE, "config1.npz"), **out)
 
 
+def make_beam_skip_ngram():
+    """__cbs_skip__ with the ARPA scorer: fast-path steps keep the LM total only implicitly (the prefix is re-scored)."""
+    out = {}
+    cases = [("small", 48, 3, 40, 21, 4, 2.0, 0.0, 3, 61), ("mid", 96, 2, 300, 22, 8, 2.0, 2.0, 5, 62), ("flat", 60, 2, 60, 25, 3, 0.7, 0.0, 4, 63)]
+    for name, T, B, C, seed, period, noise, boost, order, lmseed in cases:
+        x = synth.beam_logits(T, B, C, seed, period)
+        if noise != 2.0:
+            x = (x * (noise / 2.0)).astype(np.float32)
+        x = synth.peakier(x, boost)
+        chars = synth.charset(C - 2)
+        arpa = synth.arpa_text(chars[:200], order, lmseed, grams_per_order=500)
+        codec = ctc_codec(chars)
+        codec.use_beam_search = True; codec.use_tfm_pred = False; codec.use_tfm_score = False
+        codec.skip_search = True; codec.lm_panelty = 2.0; codec.len_bonus = 5.8
+        codec.ngram = ArpaStub(arpa)
+        out[name + "_shape"] = np.array([T, B, C, seed, period, order, lmseed]); out[name + "_noise"] = np.array(noise)
+        out[name + "_boost"] = np.array(boost)
+        out[name + "_text"] = strs(codec.decode(x))
+    np.savez_compressed(os.path.join(HERE, "beam_skip_ngram.npz"), **out)
+
+
 # ------------------------------------------------------------------ NormalizePAD (utils/dataset.py:78-93)
 def make_pad():
     out = {}
@@ -266,7 +287,7 @@ def make_pad():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["greedy", "beam", "beam_ngram", "beam_skip", "ctc_loss", "model", "config1", "pad"]
+    which = sys.argv[1:] or ["greedy", "beam", "beam_ngram", "beam_skip", "beam_skip_ngram", "ctc_loss", "model", "config1", "pad"]
     for w in which:
         print("making", w, flush=True)
         globals()["make_" + w]()

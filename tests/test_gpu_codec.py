@@ -278,3 +278,19 @@ def test_set_beam_search_reads_an_arpa_file(tmp_path):
     assert len(out) == 2 and all(isinstance(t, str) for t in out)
     with pytest.raises(NotImplementedError):
         c.set_beam_search(ngram_path="model.bin", use_tfm_pred=False)
+
+
+@pytest.mark.parametrize("case", ["small", "mid", "flat"])
+def test_skip_search_ngram_golden(golden, case):
+    """__cbs_skip__ of the reference driven by the ARPA scorer vs the device skip search with the n-gram table."""
+    g = golden("beam_skip_ngram")
+    T, B, C, seed, period, order, lmseed = [int(v) for v in g[case + "_shape"]]
+    noise, boost = float(g[case + "_noise"]), float(g[case + "_boost"])
+    x = synth.beam_logits(T, B, C, seed, period)
+    if noise != 2.0:
+        x = (x * (noise / 2.0)).astype(np.float32)
+    x = synth.peakier(x, boost)
+    c, _ = _ngram_codec(C, order, lmseed)
+    c.skip_search = True
+    c.lm_panelty, c.len_bonus = 2.0, 5.8
+    assert c.decode(torch.from_numpy(x).cuda()) == list(g[case + "_text"])
