@@ -38,6 +38,15 @@ for bonus, tab in ((0.0, None), (5.8, None), (5.8, synth.lm_table(C, 9))):
     codec.set_beam_search(use_tfm_pred=False, lm_panelty=2.0, len_bonus=bonus); codec.lm_table = tab
     ms = timeit(lambda: codec.beam_search_indices(x), n=3, warm=1)
     out["beam_T512_B256_bonus%.1f_%s" % (bonus, "table" if tab is not None else "zero")] = {"ms_total": ms, "sequences_per_s": B / ms * 1e3}
+# the same search with a synthetic 5-gram back-off model (~150k n-grams over 3000 characters) scored inside the kernel
+from hctr_b200.ngram_lm import NgramLM
+t0 = time.time()
+lm5 = NgramLM.from_arpa_text(synth.arpa_text(synth.charset(C - 2)[:3000], 5, 77, grams_per_order=40000), codec.dict, C)
+codec.set_beam_search(use_tfm_pred=False, lm_panelty=2.0, len_bonus=5.8); codec.ngram = lm5
+ms = timeit(lambda: codec.beam_search_indices(x), n=3, warm=1)
+out["beam_T512_B256_bonus5.8_5gram"] = {"ms_total": ms, "sequences_per_s": B / ms * 1e3, "n_grams": lm5.n_grams,
+                                          "table_build_s": time.time() - t0}
+codec.ngram = None
 # spot-check 4 sequences against the oracle (pinned to the reference)
 codec.set_beam_search(use_tfm_pred=False, lm_panelty=2.0, len_bonus=5.8); codec.lm_table = None
 idx, ln = codec.beam_search_indices(x[:, :4].contiguous())
