@@ -291,7 +291,7 @@ def main():
         d[0] += a.elapsed_time(b); d[1] += flops; d[2] += nbytes; d[3] += 1
     total_ms = sum(v[0] for v in by_tag.values())
     # dominant kernel = the 512->512 3x3 conv launches at H=16 (58.6 % of all FLOPs)
-    dom = [(t, v) for t, v in by_tag.items() if t in ("conv3x3_512_512_h16", "conv3x3_512_512_h16_se")]
+    dom = [(t, v) for t, v in by_tag.items() if t.startswith("conv3x3_512_512_h16") and not t.endswith("_pool")]
     dom_ms = sum(v[0] for _, v in dom); dom_fl = sum(v[1] for _, v in dom); dom_n = sum(v[3] for _, v in dom)
     achieved = dom_fl / (dom_ms * 1e-3) / 1e12
     traffic = None

@@ -192,7 +192,7 @@ int hctr_device_supported(int device) {
 
 static int conv_launch(const void* x, const void* w_packed, const float* scale, const float* shift, const void* add,
                        void* y, int B, int H, int W, int Cin, int Cout, int ksize, int relu, int pool, int flip,
-                       void* stream, float* se_partial = nullptr) {
+                       void* stream, float* se_partial = nullptr, int sum_stored = 0, const float* gate = nullptr) {
     HCTR_CHECK(x && w_packed && scale && shift && y, HCTR_ERR_INVALID, "conv: null pointer");
     HCTR_CHECK(ksize == 1 || ksize == 3, HCTR_ERR_INVALID, "conv: ksize must be 1 or 3 (got %d)", ksize);
     HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "conv: empty tensor %dx%dx%d", B, H, W);
@@ -221,6 +221,8 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     p.sub_dh = 1; p.sub_dw = 0;
     p.add = add;
     p.se_partial = se_partial;
+    p.sum_stored = sum_stored;
+    p.gate = gate;
     p.N = Cout;
     p.w_tiles = (W + kTileM - 1) / kTileM;
     p.h_tiles = (H + 1) / 2;
@@ -295,6 +297,25 @@ int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale,
     HCTR_CHECK(se_partial != nullptr, HCTR_ERR_INVALID, "conv_bn_se: null partial buffer");
     HCTR_CHECK(Cin == Cout && ksize == 3, HCTR_ERR_INVALID, "conv_bn_se: BasicBlock conv2 is 3x3 with Cin == Cout (got %d -> %d, k=%d)", Cin, Cout, ksize);
     return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, 0, 0, 0, stream, se_partial);
+}
+
+int hctr_conv_sum_slices(int H, int W, int Cin, int Cout, int ksize) {
+    const int rows = use_pair(H, Cin, Cout, ksize, 0) ? H : (H + 1) / 2;
+    return rows * ((W + kTileM - 1) / kTileM) * 4;
+}
+
+int hctr_conv_bn_act_sum_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
+                             float* partial, int B, int H, int W, int Cin, int Cout, int ksize, int relu, void* stream) {
+    HCTR_CHECK(partial != nullptr, HCTR_ERR_INVALID, "conv_bn_act_sum: null partial buffer");
+    return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, relu, 0, 0, stream, partial, 1);
+}
+
+int hctr_conv_bn_gate_res_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, const float* gate,
+                              const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int relu,
+                              void* stream) {
+    HCTR_CHECK(gate && residual, HCTR_ERR_INVALID, "conv_bn_gate_res: null gate / residual");
+    HCTR_CHECK(aligned16(gate) && aligned16(residual), HCTR_ERR_INVALID, "conv_bn_gate_res: gate and residual must be 16-byte aligned");
+    return conv_launch(x, w_packed, scale, shift, residual, y, B, H, W, Cin, Cout, ksize, relu, 0, 0, stream, nullptr, 0, gate);
 }
 
 int hctr_conv_dgrad(const void* dz, const void* w_packed_t, const float* ones, const float* zeros, const void* add,

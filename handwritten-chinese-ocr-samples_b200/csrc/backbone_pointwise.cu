@@ -160,6 +160,139 @@ se_excite_kernel(const float* __restrict__ partial, int slices, const float* __r
     }
 }
 
+
+// ---------------------------------------------------------------- SE gate computed from the conv's INPUT
+// BasicBlock.forward (models/handwritten_ctr_model.py:47-58): out = relu(se(bn2(conv2(t))) + residual), and the SE gate needs
+// mean_{h,w} of z = bn2(conv2(t)) (:27-28) - a full-tensor dependency that forces z to be written and read again. But the
+// mean of a convolution output is linear in its input:
+//     sum_{h,w} z[co] = scale[co] * sum_{tap,ci} W[co,tap,ci] * S_tap[ci] + H*W*shift[co],
+//     S_tap[ci] = sum of t[.., ci] over the pixels that tap (dh,dw) reads for some output pixel (zero padding excluded)
+//               = total - (first or last row) - (first or last column) + (the corner removed twice).
+// So the gate is known BEFORE conv2 runs, from per-channel sums of t (accumulated in conv1's epilogue), the border rows
+// and columns of t and a [C x 9C] mat-vec with conv2's own bf16 weights; conv2's epilogue then applies gate, residual
+// and ReLU and z never exists in memory. Three small kernels: sums (grid B x kGateSplit), mean of z (grid B x C/64), FCs.
+constexpr int kGateSplit = 16;        // blocks per line in the sums kernel
+constexpr int kGateCo = 64;           // output channels per block in the mean kernel
+
+// psum[b][g][5][C]: partial {total, first row, last row, first column, last column} sums of t over block g's share
+__global__ void __launch_bounds__(256)
+se_gate_sums_kernel(const __nv_bfloat16* __restrict__ t, const float* __restrict__ partial, int slices,
+                    float* __restrict__ psum, int H, int W, int C) {
+    extern __shared__ float part[];                  // [groups][C]
+    const int b = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
+    const int nv = C >> 3;                           // 16-byte vectors per pixel
+    const int groups = blockDim.x / nv;
+    const int vec = tid % nv, grp = tid / nv;
+    const __nv_bfloat16* tb = t + (size_t)b * H * W * C;
+    float* out = psum + ((size_t)b * kGateSplit + g) * 5 * C;
+    // totals: this block adds the producer's slices g, g + kGateSplit, ... (fixed order)
+    {
+        const int ncol4 = C >> 2, g4 = blockDim.x / ncol4;
+        const int col = tid % ncol4, sub = tid / ncol4;
+        if (sub < g4) {
+            const float4* src = reinterpret_cast<const float4*>(partial + (size_t)b * slices * C) + col;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = g + sub * kGateSplit; i < slices; i += g4 * kGateSplit) {
+                const float4 v = __ldg(src + (size_t)i * ncol4);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            reinterpret_cast<float4*>(part + (size_t)sub * C)[col] = a;
+        }
+        __syncthreads();
+        for (int c = tid; c < C; c += blockDim.x) {
+            float s = 0.f;
+            for (int k = 0; k < g4; ++k) s += part[(size_t)k * C + c];
+            out[c] = s;
+        }
+        __syncthreads();
+    }
+    // border rows (first, last) and columns (first, last): this block's share of the pixels
+    for (int which = 0; which < 4; ++which) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        const int n = which < 2 ? W : H;
+        if (grp < groups) {
+            for (int i = g + grp * kGateSplit; i < n; i += groups * kGateSplit) {
+                const size_t pix = which == 0 ? (size_t)i : which == 1 ? (size_t)(H - 1) * W + i
+                                 : which == 2 ? (size_t)i * W : (size_t)i * W + (W - 1);
+                const uint4 q = ld_nc_v4(tb + pix * C + vec * 8);
+                acc[0] += bf16_lo(q.x); acc[1] += bf16_hi(q.x); acc[2] += bf16_lo(q.y); acc[3] += bf16_hi(q.y);
+                acc[4] += bf16_lo(q.z); acc[5] += bf16_hi(q.z); acc[6] += bf16_lo(q.w); acc[7] += bf16_hi(q.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[(size_t)grp * C + vec * 8 + j] = acc[j];
+        }
+        __syncthreads();
+        for (int c = tid; c < C; c += blockDim.x) {
+            float s = 0.f;
+            for (int k = 0; k < groups; ++k) s += part[(size_t)k * C + c];
+            out[(1 + which) * C + c] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// mean_z[b][co] for this block's kGateCo output channels
+__global__ void __launch_bounds__(512)
+se_gate_mean_kernel(const __nv_bfloat16* __restrict__ t, const float* __restrict__ psum, const __nv_bfloat16* __restrict__ wp,
+                    const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ mean_z,
+                    int H, int W, int C) {
+    extern __shared__ float sm[];
+    float* S = sm;                                   // [9][C] window sums
+    float* bord = S + 9 * C;                         // [8][C]: R0, RL, C0, CL, corners 00, 0L, L0, LL
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const __nv_bfloat16* tb = t + (size_t)b * H * W * C;
+    const float* ps = psum + (size_t)b * kGateSplit * 5 * C;
+    for (int i = tid; i < 5 * C; i += blockDim.x) {
+        float s = 0.f;
+        for (int g = 0; g < kGateSplit; ++g) s += ps[(size_t)g * 5 * C + i];     // fixed order
+        if (i < C) S[4 * C + i] = s;                 // centre tap (dh = dw = 0) reads every pixel
+        else bord[i - C] = s;
+    }
+    for (int c = tid; c < C; c += blockDim.x) {
+        bord[4 * C + c] = __bfloat162float(tb[c]);
+        bord[5 * C + c] = __bfloat162float(tb[(size_t)(W - 1) * C + c]);
+        bord[6 * C + c] = __bfloat162float(tb[(size_t)(H - 1) * W * C + c]);
+        bord[7 * C + c] = __bfloat162float(tb[((size_t)(H - 1) * W + (W - 1)) * C + c]);
+    }
+    __syncthreads();
+    // window sums per tap: tap = kh*3 + kw reads input (h + kh - 1, w + kw - 1)
+    for (int i = tid; i < 9 * C; i += blockDim.x) {
+        const int tap = i / C, c = i - tap * C;
+        if (tap == 4) continue;
+        const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+        float s = S[4 * C + c];
+        if (dh == -1) s -= bord[1 * C + c];          // the last row is never read
+        if (dh == 1) s -= bord[0 * C + c];           // the first row is never read
+        if (dw == -1) s -= bord[3 * C + c];
+        if (dw == 1) s -= bord[2 * C + c];
+        if (dh != 0 && dw != 0)                      // the corner removed with its row and again with its column
+            s += bord[(4 + (dh == -1 ? 2 : 0) + (dw == -1 ? 1 : 0)) * C + c];
+        S[tap * C + c] = s;
+    }
+    __syncthreads();
+    // one warp per output channel: 9*C-long dot product with conv2's packed bf16 weights [co][tap][ci]
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int K = 9 * C;
+    const float inv_hw = 1.0f / ((float)H * (float)W);
+    const int co_end = min(C, (int)(blockIdx.y + 1) * kGateCo);
+    for (int co = blockIdx.y * kGateCo + warp; co < co_end; co += nwarps) {
+        const __nv_bfloat16* wr = wp + (size_t)co * K;
+        float s = 0.f;
+        for (int k = lane * 8; k < K; k += 256) {
+            const uint4 q = ld_nc_v4(wr + k);
+            s = fmaf(bf16_lo(q.x), S[k + 0], s); s = fmaf(bf16_hi(q.x), S[k + 1], s);
+            s = fmaf(bf16_lo(q.y), S[k + 2], s); s = fmaf(bf16_hi(q.y), S[k + 3], s);
+            s = fmaf(bf16_lo(q.z), S[k + 4], s); s = fmaf(bf16_hi(q.z), S[k + 5], s);
+            s = fmaf(bf16_lo(q.w), S[k + 6], s); s = fmaf(bf16_hi(q.w), S[k + 7], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) mean_z[(size_t)b * C + co] = fmaf(s * inv_hw, scale[co], shift[co]);
+    }
+}
+
 // ---------------------------------------------------------------- SE scale + residual + ReLU
 // reference: BasicBlock.forward tail (models/handwritten_ctr_model.py:30,54-58); dropout is identity in eval().
 __global__ void __launch_bounds__(256)
@@ -236,6 +369,40 @@ int hctr_se_excite(const float* partial, int slices, const float* w1, const floa
                                                                            1.0f / (float)HW);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
+}
+
+long long hctr_se_gate_workspace_bytes(int B, int C) {
+    if (B <= 0 || C <= 0) return 0;
+    return ((long long)B * kGateSplit * 5 * C + (long long)B * C) * (long long)sizeof(float);
+}
+
+int hctr_se_gate_from_input(const void* t, const float* partial, int slices, const void* conv_w_packed, const float* scale,
+                            const float* shift, const float* w1, const float* w2, float* gate, int B, int H, int W, int C,
+                            int Cr, void* workspace, long long workspace_bytes, void* stream) {
+    HCTR_CHECK(t && partial && conv_w_packed && scale && shift && w1 && w2 && gate, HCTR_ERR_INVALID, "se_gate_from_input: null pointer");
+    HCTR_CHECK(B > 0 && H > 0 && W > 0 && slices > 0 && Cr > 0, HCTR_ERR_INVALID, "se_gate_from_input: bad shape");
+    HCTR_CHECK(C % 32 == 0 && C >= 32 && 256 % (C / 8) == 0, HCTR_ERR_INVALID, "se_gate_from_input: C/8 must divide 256 (C=%d)", C);
+    HCTR_CHECK(al16(t) && al16(partial) && al16(conv_w_packed), HCTR_ERR_INVALID, "se_gate_from_input: 16-byte alignment");
+    HCTR_CHECK(workspace && al16(workspace) && workspace_bytes >= hctr_se_gate_workspace_bytes(B, C), HCTR_ERR_INVALID,
+               "se_gate_from_input: workspace too small or misaligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* psum = static_cast<float*>(workspace);
+    float* mean_z = psum + (size_t)B * kGateSplit * 5 * C;
+    const int groups = 256 / (C / 8), g4 = 256 / (C / 4);
+    const size_t sm1 = (size_t)(groups > g4 ? groups : g4) * C * sizeof(float);
+    se_gate_sums_kernel<<<dim3(B, kGateSplit), 256, sm1, s>>>(static_cast<const __nv_bfloat16*>(t), partial, slices, psum, H, W, C);
+    HCTR_CUDA(cudaGetLastError());
+    const size_t sm2 = (size_t)17 * C * sizeof(float);
+    static size_t configured = 0;
+    if (sm2 > configured) {
+        HCTR_CUDA(cudaFuncSetAttribute(se_gate_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        configured = sm2;
+    }
+    se_gate_mean_kernel<<<dim3(B, (C + kGateCo - 1) / kGateCo), 512, sm2, s>>>(
+        static_cast<const __nv_bfloat16*>(t), psum, static_cast<const __nv_bfloat16*>(conv_w_packed), scale, shift, mean_z, H, W, C);
+    HCTR_CUDA(cudaGetLastError());
+    // SELayer.fc on the means (the squeeze stage of se_excite degenerates to one slice with weight 1)
+    return hctr_se_excite(mean_z, 1, w1, w2, gate, B, C, Cr, 1, stream);
 }
 
 int hctr_se_scale_residual_relu(const void* x, const float* gate, const void* residual, void* y, int B, int H, int W,

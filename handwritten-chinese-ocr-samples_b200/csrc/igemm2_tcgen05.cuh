@@ -271,6 +271,17 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int h = tl.h_tile * 2 + (int)rank;
             const int w = w_tile * kTileM + pix;
 
+            if (p.add && w < p.W && h < p.H) {
+                // the residual of this tile is needed only after the accumulator is complete: pull it into L2 now, while
+                // the main loop of this tile is still running
+                const size_t row_off = p.out_line_pitch
+                    ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N
+                    : ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.N;
+                const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(p.add) + row_off + n_tile * kPairBlockN + half * (kPairBlockN / 2);
+#pragma unroll
+                for (int q = 0; q < kPairBlockN / 2; q += 64)      // 128-byte lines of this thread's half row
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(r + q));
+            }
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
@@ -290,13 +301,51 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
                 }
                 const bool ok = (w < p.W) && (h < p.H);
+                if (p.gate) {
+                    // SE gate folded into the producing conv: out = relu(bn(conv) * gate[b, c] + residual)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 gt = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(b) * p.N + n0 + j));
+                        v[j] *= gt.x; v[j + 1] *= gt.y; v[j + 2] *= gt.z; v[j + 3] *= gt.w;
+                    }
+                }
+                const size_t off = p.out_line_pitch
+                    ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N + n0
+                    : ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.N + n0;
+                float pre[32];                                       // fp32 BN output (the SE squeeze of conv2 sums these)
+                if (p.se_partial && !p.sum_stored) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pre[j] = v[j];
+                }
+                if (ok && p.add) {
+                    const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.add) + off);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 a = ld_nc_v4(src + q);
+                        v[8 * q + 0] += bf16_lo(a.x); v[8 * q + 1] += bf16_hi(a.x);
+                        v[8 * q + 2] += bf16_lo(a.y); v[8 * q + 3] += bf16_hi(a.y);
+                        v[8 * q + 4] += bf16_lo(a.z); v[8 * q + 5] += bf16_hi(a.z);
+                        v[8 * q + 6] += bf16_lo(a.w); v[8 * q + 7] += bf16_hi(a.w);
+                    }
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float a0 = v[j], a1 = v[j + 1];
+                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                    pk[j >> 1] = pack_bf16x2(a0, a1);
+                }
                 if (p.se_partial) {
-                    // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum over this warp's 32
-                    // pixels by a transpose-reduce butterfly; afterwards lane L holds column n0+L. One slot per
-                    // (line, row, 128-px span, warp): fixed-order final sum in se_excite.
+                    // per-channel sum over this warp's 32 pixels by a transpose-reduce butterfly; afterwards lane L holds
+                    // column n0+L. One slot per (line, row, 128-px span, warp): fixed-order final sum in the consumer.
+                    // Either the fp32 BN output (SELayer squeeze of this conv, models/handwritten_ctr_model.py:27-28) or the
+                    // values as stored (bf16) when the NEXT conv's squeeze is derived from this tensor (se_gate_from_input).
                     float tsum[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) tsum[j] = ok ? v[j] : 0.f;
+                    for (int j = 0; j < 32; j += 2) {
+                        tsum[j] = !ok ? 0.f : (p.sum_stored ? bf16_lo(pk[j >> 1]) : pre[j]);
+                        tsum[j + 1] = !ok ? 0.f : (p.sum_stored ? bf16_hi(pk[j >> 1]) : pre[j + 1]);
+                    }
 #define HCTR_BFLY(O)                                                                      \
                     {                                                                     \
                         const bool upper = (lane & (O)) != 0;                             \
@@ -312,29 +361,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     if (h < p.H) p.se_partial[slot * p.N + n0 + lane] = tsum[0];
                 }
                 if (ok) {
-                    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
-                    const size_t off = p.out_line_pitch
-                        ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N + n0
-                        : ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.N + n0;
-                    if (p.add) {
-                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.add) + off);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 a = ld_nc_v4(src + q);
-                            v[8 * q + 0] += bf16_lo(a.x); v[8 * q + 1] += bf16_hi(a.x);
-                            v[8 * q + 2] += bf16_lo(a.y); v[8 * q + 3] += bf16_hi(a.y);
-                            v[8 * q + 4] += bf16_lo(a.z); v[8 * q + 5] += bf16_hi(a.z);
-                            v[8 * q + 6] += bf16_lo(a.w); v[8 * q + 7] += bf16_hi(a.w);
-                        }
-                    }
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        float a0 = v[j], a1 = v[j + 1];
-                        if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                        pk[j >> 1] = pack_bf16x2(a0, a1);
-                    }
-                    uint4* dst = reinterpret_cast<uint4*>(out + off);
+                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off);
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);

@@ -51,6 +51,10 @@ struct IgemmParams {
     long long out_line_pitch; // EPI_CONV: elements between consecutive lines b of the output (0 = out_H*W*N)
     float* se_partial;        // EPI_CONV: optional [B][h_tiles*w_tiles][4][N] per-(tile, warp) channel sums of the fp32
                               // epilogue output (the SE squeeze folded into the producing conv; deterministic)
+    int sum_stored;           // 1: the sums are taken over the values as STORED (after gate/add/ReLU, rounded to bf16) -
+                              // what the next convolution will read - instead of the fp32 BN output
+    const float* gate;        // EPI_CONV: optional [B][N] per-(line, channel) factor applied after BN, before `add`
+                              // (the SE gate folded into the producing conv: out = relu(bn(conv)*gate + add))
     int out_dtype;            // EPI_LINEAR: HCTR_F32 | HCTR_BF16
     long long out_pitch;      // EPI_LINEAR: elements between consecutive (b,w) rows
     float2* lse_partial;      // EPI_LINEAR: optional [B*W][n_tiles*2] (max, sum exp(x-max)) per (row, column half-tile) of the
@@ -222,6 +226,24 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             const int h0 = h_tile * sub_rows;
             const int w0 = w_tile * sub_cols * kTileM;
 
+            if constexpr (EPI == EPI_CONV) {
+                if (p.add && !p.pool) {
+                    // pull this tile's residual rows into L2 while its main loop is still running
+#pragma unroll
+                    for (int s = 0; s < NUM_SUB; ++s) {
+                        const int w = w0 + s * p.sub_dw * kTileM + pix;
+                        const int h = h0 + s * p.sub_dh;
+                        if (w < p.W && h < p.out_H) {
+                            const size_t off = p.out_line_pitch
+                                ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N
+                                : ((static_cast<size_t>(b) * p.out_H + h) * p.W + w) * p.N;
+                            const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(p.add) + off + n_tile * BLOCK_N + half * (BLOCK_N / 2);
+#pragma unroll
+                            for (int q = 0; q < BLOCK_N / 2; q += 64) asm volatile("prefetch.global.L2 [%0];" :: "l"(r + q));
+                        }
+                    }
+                }
+            }
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
@@ -251,6 +273,14 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             v[s][j + 3] = fmaf(v[s][j + 3], sc.w, sh.w);
                         }
                     }
+                    if (p.gate) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 gt = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(b) * p.N + n0 + j));
+#pragma unroll
+                            for (int s = 0; s < NUM_SUB; ++s) { v[s][j] *= gt.x; v[s][j + 1] *= gt.y; v[s][j + 2] *= gt.z; v[s][j + 3] *= gt.w; }
+                        }
+                    }
                     if (p.se_partial) {
                         // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum over this
                         // warp's 32 pixels x NUM_SUB rows by a transpose-reduce butterfly (31 shuffles per 32 columns);
@@ -262,7 +292,12 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
                             for (int s = 0; s < NUM_SUB; ++s) {
                                 const bool ok = (w0 + s * p.sub_dw * kTileM + pix < p.W) && (h0 + s * p.sub_dh < p.out_H);
-                                a += ok ? v[s][j] : 0.f;
+                                float x = v[s][j];
+                                if (p.sum_stored) {                  // un-pooled, no `add`: the value as it will be stored
+                                    if (p.relu) x = fmaxf(x, 0.f);
+                                    x = __bfloat162float(__float2bfloat16_rn(x));
+                                }
+                                a += ok ? x : 0.f;
                             }
                             tsum[j] = a;
                         }

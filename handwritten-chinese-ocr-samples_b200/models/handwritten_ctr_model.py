@@ -263,31 +263,59 @@ class hctr_model(nn.Module):
         H //= 2
         for units, tail in plan.stages:
             for u in units:
-                t = self._conv(nat, a, u["conv1"], B, H, W, relu=True, pool=False)
-                # conv2 + bn2 with the SE squeeze folded into its epilogue (per-tile channel sums)
-                spec = u["conv2"]
-                C = spec.cout
-                slices = lib.hctr_conv_se_slices(H, W, C)
-                partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
-                v = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
-                self._launch(nat, "conv3x3_%d_%d_h%d_se" % (spec.cin, spec.cout, H), 2.0 * B * H * W * C * spec.cin * 9,
-                             2.0 * (t.numel() + v.numel() + spec.w.numel()), lib.hctr_conv_bn_se_fwd,
-                             nat.ptr(t), nat.ptr(spec.w), nat.ptr(spec.scale), nat.ptr(spec.shift), nat.ptr(v), nat.ptr(partial),
-                             B, H, W, spec.cin, spec.cout, spec.ksize, st)
-                del t
-                gate = torch.empty((B, C), dtype=torch.float32, device=dev)
-                self._launch(nat, "se_excite", 0.0, 4.0 * partial.numel(), lib.hctr_se_excite,
-                             nat.ptr(partial), slices, nat.ptr(u["se_w1"]), nat.ptr(u["se_w2"]), nat.ptr(gate),
-                             B, C, u["se_w1"].shape[0], H * W, st)
-                res = a if u["shortcut"] is None else self._conv(nat, a, u["shortcut"], B, H, W, relu=False, pool=False)
-                out = torch.empty_like(v)
-                self._launch(nat, "se_scale_residual_relu", 0.0, 6.0 * v.numel(), lib.hctr_se_scale_residual_relu,
-                             nat.ptr(v), nat.ptr(gate), nat.ptr(res), nat.ptr(out), B, H, W, C, st)
-                a = out
-                del v, res
+                a = self._residual_unit(nat, lib, a, u, B, H, W, st, dev)
             a = self._conv(nat, a, tail, B, H, W, relu=True, pool=True)
             H //= 2
         return self._classify(nat, a, plan, B, H, W)
+
+    def _residual_unit(self, nat, lib, a, u, B, H, W, st, dev):
+        """BasicBlock.forward (reference :47-58). Default: the SE gate is derived from conv1's output (its mean over the
+        line is linear in it), so conv2's epilogue applies gate, residual and ReLU and bn2's output never exists in memory.
+        `self.se_from_input = False` runs the literal sequence conv2 -> squeeze -> excite -> scale/residual/ReLU pass."""
+        c1, c2 = u["conv1"], u["conv2"]
+        C = c2.cout
+        if not getattr(self, "se_from_input", True):
+            t = self._conv(nat, a, c1, B, H, W, relu=True, pool=False)
+            slices = lib.hctr_conv_se_slices(H, W, C)
+            partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
+            v = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
+            self._launch(nat, "conv3x3_%d_%d_h%d_se" % (c2.cin, c2.cout, H), 2.0 * B * H * W * C * c2.cin * 9,
+                         2.0 * (t.numel() + v.numel() + c2.w.numel()), lib.hctr_conv_bn_se_fwd,
+                         nat.ptr(t), nat.ptr(c2.w), nat.ptr(c2.scale), nat.ptr(c2.shift), nat.ptr(v), nat.ptr(partial),
+                         B, H, W, c2.cin, c2.cout, c2.ksize, st)
+            del t
+            gate = torch.empty((B, C), dtype=torch.float32, device=dev)
+            self._launch(nat, "se_excite", 0.0, 4.0 * partial.numel(), lib.hctr_se_excite,
+                         nat.ptr(partial), slices, nat.ptr(u["se_w1"]), nat.ptr(u["se_w2"]), nat.ptr(gate),
+                         B, C, u["se_w1"].shape[0], H * W, st)
+            res = a if u["shortcut"] is None else self._conv(nat, a, u["shortcut"], B, H, W, relu=False, pool=False)
+            out = torch.empty_like(v)
+            self._launch(nat, "se_scale_residual_relu", 0.0, 6.0 * v.numel(), lib.hctr_se_scale_residual_relu,
+                         nat.ptr(v), nat.ptr(gate), nat.ptr(res), nat.ptr(out), B, H, W, C, st)
+            return out
+        # conv1 + bn1 + relu, with the per-channel sums of the stored tensor t
+        slices = lib.hctr_conv_sum_slices(H, W, c1.cin, c1.cout, c1.ksize)
+        partial = torch.empty((B, slices, C), dtype=torch.float32, device=dev)
+        t = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
+        self._launch(nat, "conv3x3_%d_%d_h%d_sum" % (c1.cin, c1.cout, H), 2.0 * B * H * W * c1.cout * c1.cin * 9,
+                     2.0 * (a.numel() + t.numel() + c1.w.numel()), lib.hctr_conv_bn_act_sum_fwd,
+                     nat.ptr(a), nat.ptr(c1.w), nat.ptr(c1.scale), nat.ptr(c1.shift), nat.ptr(t), nat.ptr(partial),
+                     B, H, W, c1.cin, c1.cout, c1.ksize, 1, st)
+        gate = torch.empty((B, C), dtype=torch.float32, device=dev)
+        ws_bytes = lib.hctr_se_gate_workspace_bytes(B, C)
+        ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=dev)
+        self._launch(nat, "se_gate_from_input", 2.0 * B * C * 9 * C, 4.0 * partial.numel() + 2.0 * B * c2.w.numel(),
+                     lib.hctr_se_gate_from_input, nat.ptr(t), nat.ptr(partial), slices, nat.ptr(c2.w), nat.ptr(c2.scale),
+                     nat.ptr(c2.shift), nat.ptr(u["se_w1"]), nat.ptr(u["se_w2"]), nat.ptr(gate), B, H, W, C,
+                     u["se_w1"].shape[0], nat.ptr(ws), ws_bytes, st)
+        self.launch_count += 2                      # sums, mean and FC kernels behind one entry point
+        res = a if u["shortcut"] is None else self._conv(nat, a, u["shortcut"], B, H, W, relu=False, pool=False)
+        out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=dev)
+        self._launch(nat, "conv3x3_%d_%d_h%d_gate_res" % (c2.cin, c2.cout, H), 2.0 * B * H * W * C * c2.cin * 9,
+                     2.0 * (t.numel() + res.numel() + out.numel() + c2.w.numel()), lib.hctr_conv_bn_gate_res_fwd,
+                     nat.ptr(t), nat.ptr(c2.w), nat.ptr(c2.scale), nat.ptr(c2.shift), nat.ptr(gate), nat.ptr(res), nat.ptr(out),
+                     B, H, W, c2.cin, c2.cout, c2.ksize, 1, st)
+        return out
 
     def _classify(self, nat, feat, plan, B, Hf, W):
         n = self.noutput

@@ -68,6 +68,25 @@ int hctr_conv_se_slices(int H, int W, int Cout);
 int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
                         float* se_partial, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 
+/* The residual block without the intermediate tensor (BasicBlock.forward, models/handwritten_ctr_model.py:47-58):
+ * the SE gate needs mean_hw(bn2(conv2(t))), which is linear in t - sum_hw z[co] = scale[co] * sum_{tap,ci} W[co,tap,ci] *
+ * S_tap[ci] + HW*shift[co] with S_tap = the sum of t over the pixels tap (dh,dw) reads - so it is computed BEFORE conv2:
+ *   hctr_conv_bn_act_sum_fwd   conv1 + bn1 + relu, plus per-(tile, warp) channel sums of the STORED bf16 output t:
+ *                              partial fp32 [B][hctr_conv_sum_slices(H,W,Cin,Cout,ksize)][Cout]
+ *   hctr_se_gate_from_input    totals + border rows/columns of t + a [C x 9C] mat-vec with conv2's packed weights ->
+ *                              mean z -> SELayer.fc (:19-24) -> gate fp32 [B][C]
+ *   hctr_conv_bn_gate_res_fwd  conv2 + bn2, times gate[b,c], plus the residual, ReLU - one write, no re-read. */
+int hctr_conv_sum_slices(int H, int W, int Cin, int Cout, int ksize);
+int hctr_conv_bn_act_sum_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
+                             float* partial, int B, int H, int W, int Cin, int Cout, int ksize, int relu, void* stream);
+long long hctr_se_gate_workspace_bytes(int B, int C);
+int hctr_se_gate_from_input(const void* t, const float* partial, int slices, const void* conv_w_packed, const float* scale,
+                            const float* shift, const float* w1, const float* w2, float* gate, int B, int H, int W, int C,
+                            int Cr, void* workspace, long long workspace_bytes, void* stream);
+int hctr_conv_bn_gate_res_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, const float* gate,
+                              const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int relu,
+                              void* stream);
+
 /* Tuning/debug switch for the thin (Cout <= 128) 3x3 layers: 0 = one TMA box per tap; 2 (default) = kw-fused: one
  * 136-pixel activation slab per (kh, 64-channel chunk) serves the three kw taps by shifting the UMMA descriptor start
  * address by whole 128-byte rows (3x fewer L2->SMEM activation bytes, +15 % on those layers); 1 = the same plus the

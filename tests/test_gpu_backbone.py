@@ -312,3 +312,61 @@ def test_classifier_fused_log_softmax(dtype):
                                       nat.HCTR_F32 if dtype == torch.float32 else nat.HCTR_BF16, pitch, B, 4, W, 512, N,
                                       nat.stream_ptr()))
     assert torch.equal(plain, out)                      # the fused epilogue stores the same logits
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 8, 200, 128), (2, 4, 300, 256), (1, 6, 129, 512)])
+def test_se_gate_from_conv_input(B, H, W, C):
+    """The SE gate computed BEFORE conv2 from sums of conv2's input (mean of a conv output is linear in the input) equals
+    sigmoid(fc2(relu(fc1(mean_hw(bn2(conv2(t))))))) of the reference (models/handwritten_ctr_model.py:26-30,52-54)."""
+    nat = _nat(); lib = nat.lib()
+    g = torch.Generator().manual_seed(C + W)
+    Cr = C // 16
+    a = torch.randn(B, C, H, W, generator=g).cuda().to(torch.bfloat16)
+    w1c = (torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5).cuda().to(torch.bfloat16)
+    w2c = (torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5).cuda().to(torch.bfloat16)
+    s1 = (torch.rand(C, generator=g) + 0.5).cuda(); h1 = (0.2 * torch.randn(C, generator=g)).cuda()
+    s2 = (torch.rand(C, generator=g) + 0.5).cuda(); h2 = (0.5 * torch.randn(C, generator=g)).cuda()
+    f1 = (torch.randn(Cr, C, generator=g) / C ** 0.5).cuda(); f2 = (torch.randn(C, Cr, generator=g) / Cr ** 0.5).cuda()
+    an = a.permute(0, 2, 3, 1).contiguous()
+    wp1 = w1c.permute(0, 2, 3, 1).contiguous(); wp2 = w2c.permute(0, 2, 3, 1).contiguous()
+    slices = lib.hctr_conv_sum_slices(H, W, C, C, 3)
+    partial = torch.full((B, slices, C), float("nan"), device="cuda")
+    t = torch.empty((B, H, W, C), dtype=torch.bfloat16, device="cuda")
+    nat.check(lib.hctr_conv_bn_act_sum_fwd(nat.ptr(an), nat.ptr(wp1), nat.ptr(s1), nat.ptr(h1), nat.ptr(t), nat.ptr(partial),
+                                           B, H, W, C, C, 3, 1, nat.stream_ptr()))
+    # the partial sums are exactly the sums of the stored bf16 tensor
+    assert (partial.sum(1) - t.float().sum((1, 2))).abs().max().item() <= 1e-3 * max(1.0, t.float().sum((1, 2)).abs().max().item())
+    gate = torch.empty((B, C), device="cuda")
+    nb = lib.hctr_se_gate_workspace_bytes(B, C)
+    ws = torch.empty((nb // 4,), device="cuda")
+    nat.check(lib.hctr_se_gate_from_input(nat.ptr(t), nat.ptr(partial), slices, nat.ptr(wp2), nat.ptr(s2), nat.ptr(h2),
+                                          nat.ptr(f1), nat.ptr(f2), nat.ptr(gate), B, H, W, C, Cr, nat.ptr(ws), nb,
+                                          nat.stream_ptr()))
+    tt = t.permute(0, 3, 1, 2).float()
+    z = F.conv2d(tt, w2c.float(), padding=1) * s2.view(1, -1, 1, 1) + h2.view(1, -1, 1, 1)
+    ref_gate = torch.sigmoid(F.linear(F.relu(F.linear(z.mean((2, 3)), f1)), f2))
+    assert (gate - ref_gate).abs().max().item() <= 2e-5
+    # conv2 with the gate, the residual and ReLU in its epilogue
+    res = torch.randn(B, H, W, C, generator=g).cuda().to(torch.bfloat16)
+    out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device="cuda")
+    nat.check(lib.hctr_conv_bn_gate_res_fwd(nat.ptr(t), nat.ptr(wp2), nat.ptr(s2), nat.ptr(h2), nat.ptr(gate), nat.ptr(res),
+                                            nat.ptr(out), B, H, W, C, C, 3, 1, nat.stream_ptr()))
+    ref = (z * ref_gate.view(B, C, 1, 1) + res.permute(0, 3, 1, 2).float()).relu()
+    got = out.permute(0, 3, 1, 2).float()
+    assert (got - ref).abs().max().item() <= BF16_GATE * ref.abs().max().item()
+
+
+def test_model_same_with_and_without_the_fused_se_path():
+    from hctr_b200.models.handwritten_ctr_model import hctr_model
+    torch.manual_seed(3)
+    m = hctr_model(7375).cuda().eval()
+    with torch.no_grad():
+        for mod in m.modules():                       # non-trivial BN statistics and SE gates
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5); mod.weight.uniform_(0.8, 1.2); mod.bias.normal_(0, 0.1)
+    x = torch.from_numpy(synth.text_lines(2, 320, 5)).cuda()
+    with torch.no_grad():
+        m.se_from_input = True; a = m(x).float()
+        m.se_from_input = False; b = m(x).float()
+    scale = b.abs().max().item()
+    assert (a - b).abs().max().item() <= 0.06 * scale and (a - b).abs().mean().item() <= 0.01 * scale
