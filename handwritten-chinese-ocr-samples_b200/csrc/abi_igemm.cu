@@ -125,10 +125,10 @@ static bool use_pair(int H, int Cin, int Cout, int ksize, int pool) {
     return pair_enabled() && !pool && Cout % 256 == 0 && H % 2 == 0 && (slab || (ksize * ksize * (Cin / 64)) % kPairKSub == 0);
 }
 
-template <int BLOCK_N, int STAGES, int KWF>
+template <int BLOCK_N, int STAGES, int KWF, int ADD>
 static int launch_igemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
     using L = PairSmem<BLOCK_N, STAGES, KWF>;
-    auto kern = igemm_pair_kernel<BLOCK_N, STAGES, KWF>;
+    auto kern = igemm_pair_kernel<BLOCK_N, STAGES, KWF, ADD>;
     static int max_clusters = 0;      // per instantiation
     if (max_clusters == 0) {
         HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -244,8 +244,12 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
         if (rc) return rc;
         rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, block_n / 2);
         if (rc) return rc;
-        if (slab) return launch_igemm_pair<256, 3, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
-        return launch_igemm_pair<256, 3, 0>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+        cudaStream_t cs = static_cast<cudaStream_t>(stream);
+        if (add) {
+            HCTR_CHECK(se_partial == nullptr, HCTR_ERR_INVALID, "conv: channel sums and a residual cannot be combined");
+            return slab ? launch_igemm_pair<256, 3, 1, 1>(tmA, tmB, p, cs) : launch_igemm_pair<256, 3, 0, 1>(tmA, tmB, p, cs);
+        }
+        return slab ? launch_igemm_pair<256, 3, 1, 0>(tmA, tmB, p, cs) : launch_igemm_pair<256, 3, 0, 0>(tmA, tmB, p, cs);
     }
 
     // thin layers (Cout <= 128) are bound by the L2->SMEM re-reads of the activation tile: fuse the three kw taps

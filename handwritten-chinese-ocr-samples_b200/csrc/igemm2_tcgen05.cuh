@@ -33,7 +33,12 @@ struct PairSmem {
     static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;        // this CTA's half of the weight rows
     static constexpr int kStageBytes = KWF ? kABytes + 3 * kBBytes : kPairKSub * (kABytes + kBBytes);
     static constexpr int kBarBytes = 1024;
-    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
+    // epilogue staging: per epilogue warp 32 pixel rows of one 32-channel chunk (64 B, pitch 80 B = conflict-free for
+    // both the per-pixel and the transposed access), used to turn per-thread 16-byte global accesses at a 2*N-byte stride
+    // (128 L2 requests per warp and chunk) into 64-byte runs (32 requests)
+    static constexpr int kEpiPitch = 80;
+    static constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch;
+    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + 1024 /*alignment slack*/;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -129,7 +134,11 @@ __device__ __forceinline__ PairTile pair_tile(const IgemmParams& p, int pair_id,
 // EPI_CONV only, no pooling (the rows of a pool pair live in different CTAs). p.h_tiles = H/2 pair rows.
 // BLOCK_N = 256 (Cout % 256 == 0) or 128 (Cout == 128: the single-CTA N=128 tile reads 128 B/clk of operands from
 // shared memory, the limit; a pair reads 96).
-template <int BLOCK_N, int STAGES, int KWF>
+// ADD = 1: the epilogue adds a residual tensor (p.add; dgrad, and conv2 of a residual block with p.gate): the residual of
+// the whole tile row is fetched into registers BEFORE the wait for the accumulator, so that its latency hides behind the
+// main loop (fetched per 32-column chunk right before use it made the epilogue longer than the main loop of the
+// K = 2304 layers: 1200 instead of 1590 TFLOP/s). That variant has no room for the channel-sum butterfly (se_partial).
+template <int BLOCK_N, int STAGES, int KWF, int ADD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1)
 igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
     using L = PairSmem<BLOCK_N, STAGES, KWF>;
@@ -146,6 +155,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* acc_full = empty_bar + kPairStages;                          // [kPairAcc]
     uint64_t* acc_empty = acc_full + kPairAcc;                             // [kPairAcc]      (leader's are used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kPairAcc);
+    uint8_t* epi_base = bar_base + L::kBarBytes;                           // [kEpiWarps][32][kEpiPitch]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -271,101 +281,126 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int h = tl.h_tile * 2 + (int)rank;
             const int w = w_tile * kTileM + pix;
 
-            if (p.add && w < p.W && h < p.H) {
-                // the residual of this tile is needed only after the accumulator is complete: pull it into L2 now, while
-                // the main loop of this tile is still running
-                const size_t row_off = p.out_line_pitch
-                    ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N
-                    : ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.N;
-                const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(p.add) + row_off + n_tile * kPairBlockN + half * (kPairBlockN / 2);
+            constexpr int kChunks = kPairBlockN / 2 / 32;
+            const bool ok = (w < p.W) && (h < p.H);
+            // element offset of (this warp's pixel 0, first column of this warp's half); pixel r of the warp is r*N further
+            const int wq = w_tile * kTileM + quad * 32;
+            const size_t warp_off = (p.out_line_pitch
+                ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + wq) * p.N
+                : ((static_cast<size_t>(b) * p.H + h) * p.W + wq) * p.N) + n_tile * kPairBlockN + half * (kPairBlockN / 2);
+            // transposed role of this lane: 16-byte piece tq of pixel rows tr, tr+8, tr+16, tr+24
+            const int tr = lane >> 2, tq = lane & 3;
+            uint8_t* ebuf = epi_base + (warp - 2) * (32 * L::kEpiPitch);
+            uint4 rb[ADD ? kChunks * 4 : 1];
+            if constexpr (ADD) {
+                // the residual of the whole tile row, fetched as 64-byte runs before the accumulator is awaited
+                if (h < p.H) {
 #pragma unroll
-                for (int q = 0; q < kPairBlockN / 2; q += 64)      // 128-byte lines of this thread's half row
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(r + q));
+                    for (int ck = 0; ck < kChunks; ++ck)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = tr + 8 * i;
+                            rb[ck * 4 + i] = make_uint4(0u, 0u, 0u, 0u);
+                            if (wq + r < p.W)
+                                rb[ck * 4 + i] = ld_nc_v4(static_cast<const __nv_bfloat16*>(p.add) + warp_off + static_cast<size_t>(r) * p.N + ck * 32 + tq * 8);
+                        }
+                }
+            }
+            // per-channel epilogue factors of this tile, one column per lane, fetched before the accumulator is awaited and
+            // broadcast by shuffle below: y = acc*scale + shift (conv bias and eval-mode BN folded, fp32), times the SE gate
+            // when it is folded into the producing conv (out = relu(bn(conv) * gate[b, c] + residual))
+            float scl[kChunks], shl[kChunks];
+#pragma unroll
+            for (int ck = 0; ck < kChunks; ++ck) {
+                const int n = n_tile * kPairBlockN + half * (kPairBlockN / 2) + ck * 32 + lane;
+                scl[ck] = __ldg(p.scale + n); shl[ck] = __ldg(p.shift + n);
+                if (p.gate) {
+                    const float gt = __ldg(p.gate + static_cast<size_t>(b) * p.N + n);
+                    scl[ck] *= gt; shl[ck] *= gt;
+                }
             }
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
-#pragma unroll 1
-            for (int c0 = half * (kPairBlockN / 2); c0 < (half + 1) * (kPairBlockN / 2); c0 += 32) {
+#pragma unroll
+            for (int ck = 0; ck < kChunks; ++ck) {
+                const int c0 = half * (kPairBlockN / 2) + ck * 32;
                 const int n0 = n_tile * kPairBlockN + c0;
                 float v[32];
                 tmem_ld_32x32(t_base + c0, v);
-                // y = acc*scale + shift  (conv bias and eval-mode BN folded, fp32)
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
-                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + j));
-                    v[j + 0] = fmaf(v[j + 0], sc.x, sh.x);
-                    v[j + 1] = fmaf(v[j + 1], sc.y, sh.y);
-                    v[j + 2] = fmaf(v[j + 2], sc.z, sh.z);
-                    v[j + 3] = fmaf(v[j + 3], sc.w, sh.w);
-                }
-                const bool ok = (w < p.W) && (h < p.H);
-                if (p.gate) {
-                    // SE gate folded into the producing conv: out = relu(bn(conv) * gate[b, c] + residual)
+                for (int j = 0; j < 32; ++j)
+                    v[j] = fmaf(v[j], __shfl_sync(0xffffffffu, scl[ck], j), __shfl_sync(0xffffffffu, shl[ck], j));
+                if constexpr (ADD) {
+                    // residual: transposed registers -> staging rows -> this lane's own pixel
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 gt = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(b) * p.N + n0 + j));
-                        v[j] *= gt.x; v[j + 1] *= gt.y; v[j + 2] *= gt.z; v[j + 3] *= gt.w;
-                    }
-                }
-                const size_t off = p.out_line_pitch
-                    ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N + n0
-                    : ((static_cast<size_t>(b) * p.H + h) * p.W + w) * p.N + n0;
-                float pre[32];                                       // fp32 BN output (the SE squeeze of conv2 sums these)
-                if (p.se_partial && !p.sum_stored) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) pre[j] = v[j];
-                }
-                if (ok && p.add) {
-                    const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.add) + off);
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(ebuf + (tr + 8 * i) * L::kEpiPitch + tq * 16) = rb[ck * 4 + i];
+                    __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const uint4 a = ld_nc_v4(src + q);
+                        const uint4 a = *reinterpret_cast<const uint4*>(ebuf + lane * L::kEpiPitch + q * 16);
                         v[8 * q + 0] += bf16_lo(a.x); v[8 * q + 1] += bf16_hi(a.x);
                         v[8 * q + 2] += bf16_lo(a.y); v[8 * q + 3] += bf16_hi(a.y);
                         v[8 * q + 4] += bf16_lo(a.z); v[8 * q + 5] += bf16_hi(a.z);
                         v[8 * q + 6] += bf16_lo(a.w); v[8 * q + 7] += bf16_hi(a.w);
                     }
+                    __syncwarp();
                 }
-                uint32_t pk[16];
+                if constexpr (!ADD) {
+                    if (p.se_partial) {
+                        // per-channel sum over this warp's 32 pixels by a transpose-reduce butterfly; afterwards lane L holds
+                        // column n0+L. One slot per (line, row, 128-px span, warp): fixed-order final sum in the consumer.
+                        // Either the fp32 BN output (SELayer squeeze of this conv, models/handwritten_ctr_model.py:27-28) or
+                        // the values as stored (ReLU, bf16) when the NEXT conv's squeeze is derived from this tensor.
+                        float tsum[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float a0 = v[j], a1 = v[j + 1];
-                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                    pk[j >> 1] = pack_bf16x2(a0, a1);
-                }
-                if (p.se_partial) {
-                    // per-channel sum over this warp's 32 pixels by a transpose-reduce butterfly; afterwards lane L holds
-                    // column n0+L. One slot per (line, row, 128-px span, warp): fixed-order final sum in the consumer.
-                    // Either the fp32 BN output (SELayer squeeze of this conv, models/handwritten_ctr_model.py:27-28) or the
-                    // values as stored (bf16) when the NEXT conv's squeeze is derived from this tensor (se_gate_from_input).
-                    float tsum[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        tsum[j] = !ok ? 0.f : (p.sum_stored ? bf16_lo(pk[j >> 1]) : pre[j]);
-                        tsum[j + 1] = !ok ? 0.f : (p.sum_stored ? bf16_hi(pk[j >> 1]) : pre[j + 1]);
-                    }
-#define HCTR_BFLY(O)                                                                      \
-                    {                                                                     \
-                        const bool upper = (lane & (O)) != 0;                             \
-                        _Pragma("unroll") for (int i = 0; i < (O); ++i) {                 \
-                            const float send = upper ? tsum[i] : tsum[i + (O)];           \
-                            const float keep = upper ? tsum[i + (O)] : tsum[i];           \
-                            tsum[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));     \
-                        }                                                                 \
-                    }
-                    HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
+                        for (int j = 0; j < 32; ++j) {
+                            float x = v[j];
+                            if (p.sum_stored) {
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                x = __bfloat162float(__float2bfloat16_rn(x));
+                            }
+                            tsum[j] = ok ? x : 0.f;
+                        }
+#define HCTR_BFLY(O)                                                                          \
+                        {                                                                     \
+                            const bool upper = (lane & (O)) != 0;                             \
+                            _Pragma("unroll") for (int i = 0; i < (O); ++i) {                 \
+                                const float send = upper ? tsum[i] : tsum[i + (O)];           \
+                                const float keep = upper ? tsum[i + (O)] : tsum[i];           \
+                                tsum[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));     \
+                            }                                                                 \
+                        }
+                        HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
 #undef HCTR_BFLY
-                    const size_t slot = ((static_cast<size_t>(b) * p.H + h) * p.w_tiles + w_tile) * 4 + quad;
-                    if (h < p.H) p.se_partial[slot * p.N + n0 + lane] = tsum[0];
+                        const size_t slot = ((static_cast<size_t>(b) * p.H + h) * p.w_tiles + w_tile) * 4 + quad;
+                        if (h < p.H) p.se_partial[slot * p.N + n0 + lane] = tsum[0];
+                    }
                 }
-                if (ok) {
-                    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + off);
+                // pack to bf16, stage this lane's pixel row, write the chunk out as 64-byte runs
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a0 = v[8 * q + 2 * j], a1 = v[8 * q + 2 * j + 1];
+                        if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                        pk[j] = pack_bf16x2(a0, a1);
+                    }
+                    *reinterpret_cast<uint4*>(ebuf + lane * L::kEpiPitch + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
+                __syncwarp();
+                if (h < p.H) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = tr + 8 * i;
+                        if (wq + r < p.W)
+                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + warp_off + static_cast<size_t>(r) * p.N + ck * 32 + tq * 8) =
+                                *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                    }
+                }
+                __syncwarp();
             }
             // release this accumulator stage back to the leader's MMA warp
             tc_fence_before();
