@@ -10,6 +10,7 @@ from . import native  # noqa: F401
 from . import train_engine  # noqa: F401
 from . import pipeline  # noqa: F401
 from . import ngram_lm  # noqa: F401
+from . import checkpoint  # noqa: F401
 
 __all__ = ["native", "hctr_model", "ctc_codec", "CTCLoss", "TrainStep"]
 

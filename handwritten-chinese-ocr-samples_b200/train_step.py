@@ -46,10 +46,62 @@ def allreduce_bucket(flat, start, end, group=None, async_op=False):
     return dist.all_reduce(flat[start:end], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+def sgd_state_dict(names, offsets, shapes, momentum_flat, group, have_momentum):
+    """Host logic: the flat momentum buffer as a `torch.optim.SGD.state_dict()` (the 'optimizer' entry of the reference's
+    checkpoints, main.py:348 / :262): parameters are numbered in registration order, each with a `momentum_buffer` of the
+    parameter's shape (absent before the first step, as in torch)."""
+    state = {}
+    if have_momentum:
+        for i, k in enumerate(names):
+            s, n = offsets[k]
+            state[i] = {"momentum_buffer": momentum_flat[s:s + n].detach().clone().view(shapes[k])}
+    pg = {k: v for k, v in group.items() if k != "params"}
+    pg["params"] = list(range(len(names)))
+    return {"state": state, "param_groups": [pg]}
+
+
+def load_sgd_state_dict(sd, names, offsets, shapes, momentum_flat, group):
+    """Inverse of sgd_state_dict: accepts the state_dict of a torch.optim.SGD over the same parameters (same order).
+    Returns True when momentum buffers were present (the next step is then not a 'first step')."""
+    groups = sd["param_groups"]
+    if len(groups) != 1 or len(groups[0]["params"]) != len(names):
+        raise ValueError("loaded state dict has a different number of parameter groups / parameters "
+                         "(expected 1 group of %d)" % len(names))
+    if groups[0].get("nesterov") or groups[0].get("dampening", 0) not in (0, 0.0):
+        raise ValueError("hctr_b200 TrainStep: nesterov / dampening are not implemented (the reference uses neither)")
+    for k in ("lr", "momentum", "weight_decay"):
+        if k in groups[0]:
+            group[k] = groups[0][k]
+    ids = groups[0]["params"]
+    state = sd.get("state", {})
+    have = False
+    momentum_flat.zero_()
+    for i, k in enumerate(names):
+        st = state.get(ids[i], state.get(str(ids[i])))
+        if st is None or st.get("momentum_buffer") is None:
+            continue
+        buf = st["momentum_buffer"]
+        if tuple(buf.shape) != tuple(shapes[k]):
+            raise ValueError("momentum_buffer of parameter %d (%s) has shape %s, expected %s"
+                             % (i, k, tuple(buf.shape), tuple(shapes[k])))
+        s, n = offsets[k]
+        momentum_flat[s:s + n].copy_(buf.reshape(-1).to(momentum_flat.dtype))
+        have = True
+    return have
+
+
+def adjust_learning_rate(optimizer, epoch, args):
+    """The reference's schedule (main.py:579-584): initial LR decayed by 10 every 30 epochs. Works on a TrainStep or
+    any torch optimizer (both expose `param_groups`)."""
+    lr = args.lr * (0.1 ** (epoch // 30))
+    for param_group in optimizer.param_groups:
+        param_group['lr'] = lr
+
+
 class TrainStep(object):
     def __init__(self, model, lr=1e-3, momentum=0.9, weight_decay=1e-4, max_norm=5.0, process_group=None):
         self.model = model
-        self.lr, self.momentum, self.weight_decay, self.max_norm = lr, momentum, weight_decay, max_norm
+        self.max_norm = max_norm
         self.group = process_group
         self.engine = TrainEngine(model)
         named = [(k, p) for k, p in model.named_parameters()]
@@ -57,6 +109,12 @@ class TrainStep(object):
         if dev.type != "cuda":
             raise RuntimeError("hctr_b200 TrainStep: parameters must live on a CUDA device (no CPU fallback)")
         self.offsets, total, self.buckets = plan_buckets([(k, p.numel()) for k, p in named])
+        self.names = [k for k, _ in named]
+        self.shapes = {k: tuple(p.shape) for k, p in named}
+        # one parameter group, laid out like torch.optim.SGD's so that `for g in optimizer.param_groups: g['lr'] = ...`
+        # (main.py:582-583) steers the fused update
+        self.param_groups = [{"lr": lr, "momentum": momentum, "dampening": 0, "weight_decay": weight_decay,
+                              "nesterov": False, "params": [p for _, p in named]}]
         self.flat_params = torch.zeros((total,), dtype=torch.float32, device=dev)
         self.flat_grads = torch.zeros((total,), dtype=torch.float32, device=dev)
         self.momentum_buf = torch.zeros((total,), dtype=torch.float32, device=dev)
@@ -69,6 +127,7 @@ class TrainStep(object):
         self.norm = torch.zeros((2,), dtype=torch.float32, device=dev)        # {total_norm, clip coefficient}
         self._ws = torch.empty((nat.lib().hctr_sgd_workspace_bytes(),), dtype=torch.uint8, device=dev)
         self.steps = 0
+        self._have_momentum = False
         self._pin = None
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
 
@@ -124,7 +183,30 @@ class TrainStep(object):
                 w.wait()
             nat.check(lib.hctr_sgd_clip_step(nat.ptr(self.flat_params), nat.ptr(self.flat_grads), nat.ptr(self.momentum_buf),
                                              self.flat_params.numel(), 1.0 / self.world, self.max_norm, self.lr, self.momentum,
-                                             self.weight_decay, int(self.steps == 0), nat.ptr(self.norm), nat.ptr(self._ws), st),
+                                             self.weight_decay, int(not self._have_momentum), nat.ptr(self.norm), nat.ptr(self._ws), st),
                       "sgd_clip_step")
             self.steps += 1
+            self._have_momentum = True
         return loss.reshape(())
+
+    # hyper-parameters live in param_groups[0] (torch.optim convention)
+    lr = property(lambda self: float(self.param_groups[0]["lr"]),
+                  lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    momentum = property(lambda self: float(self.param_groups[0]["momentum"]),
+                        lambda self, v: self.param_groups[0].__setitem__("momentum", v))
+    weight_decay = property(lambda self: float(self.param_groups[0]["weight_decay"]),
+                            lambda self, v: self.param_groups[0].__setitem__("weight_decay", v))
+
+    def state_dict(self):
+        """Same layout as `torch.optim.SGD(model.parameters(), ...).state_dict()`, i.e. what the reference stores under
+        checkpoint['optimizer'] (main.py:348) and restores at :262."""
+        return sgd_state_dict(self.names, self.offsets, self.shapes, self.momentum_buf, self.param_groups[0],
+                              self._have_momentum)
+
+    def load_state_dict(self, sd):
+        self._have_momentum = load_sgd_state_dict(sd, self.names, self.offsets, self.shapes, self.momentum_buf,
+                                                  self.param_groups[0])
+
+    def zero_grad(self, set_to_none=False):
+        """Kept for call-site compatibility (main.py:425): the kernels overwrite the flat gradient buffer every step."""
+        return None

@@ -158,3 +158,50 @@ def test_fused_train_step_matches_reference_loop():
     for k in keys:
         if "running" in k:
             assert torch.allclose(ma.state_dict()[k], mb.state_dict()[k], rtol=2e-2, atol=2e-3), k
+
+
+def test_train_step_resumes_from_a_reference_format_checkpoint(tmp_path):
+    """Save after two steps (main.py:343-349 layout), load into a fresh model + TrainStep AND into torch.optim.SGD
+    (what the reference's resume path constructs, main.py:251-265); a third step from the restored state is
+    bit-identical to the third step of the uninterrupted run."""
+    from hctr_b200 import checkpoint as ck
+    from hctr_b200.train_step import TrainStep, adjust_learning_rate
+    NC, B, W = 41, 2, 128
+    x = torch.from_numpy(synth.text_lines(B, W, 91)).cuda()
+    tg, tl = synth.ctc_targets(B, NC, 3, 6, 92)
+    ma = _model(NC, 7).cuda().train(); ma.dropout_enabled = False
+    ts = TrainStep(ma, lr=0.01, momentum=0.9, weight_decay=1e-4, max_norm=5.0)
+    assert ts.state_dict()["state"] == {}                            # like torch before the first step
+    for _ in range(2):
+        ts.step(x, tg, tl, seed=1)
+
+    class Args(object):
+        model_type = "hctr"; multiprocessing_distributed = False; rank = 0; lr = 0.01
+    paths = ck.save_checkpoint(ck.make_state(0, ma, 0.5, ts), Args, is_best=False, directory=str(tmp_path))
+    mb = _model(NC, 8).cuda().train(); mb.dropout_enabled = False
+    tb = TrainStep(mb, lr=1.0, momentum=0.0, weight_decay=0.0, max_norm=5.0)
+    assert ck.load_checkpoint(paths[0], mb, tb, map_location="cuda") == (1, 0.5)
+    assert (tb.lr, tb.momentum, tb.weight_decay) == (0.01, 0.9, 1e-4)
+    # the same file restores a stock torch optimizer over the same parameters
+    mc = _model(NC, 9).cuda()
+    opt = torch.optim.SGD(mc.parameters(), lr=1.0)
+    ck.load_checkpoint(paths[0], mc, opt, map_location="cuda")
+    sd_t, sd_o = opt.state_dict(), ts.state_dict()
+    assert sd_t["param_groups"][0]["momentum"] == 0.9 and len(sd_t["state"]) == len(list(mc.parameters()))
+    for i in sd_o["state"]:
+        assert torch.equal(sd_t["state"][i]["momentum_buffer"], sd_o["state"][i]["momentum_buffer"])
+    la = ts.step(x, tg, tl, seed=2)
+    lb = tb.step(x, tg, tl, seed=2)
+    assert la.item() == lb.item()
+    for (ka, pa), (kb, pb) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        assert ka == kb and torch.equal(pa, pb), ka
+    assert torch.equal(ts.momentum_buf, tb.momentum_buf)
+    # LR schedule of main.py:579-584 drives the fused update through param_groups
+    adjust_learning_rate(tb, 30, Args)
+    assert tb.lr == pytest.approx(0.001)
+    before = tb.flat_params.clone()
+    tb.step(x, tg, tl, seed=3)
+    ts.step(x, tg, tl, seed=3)
+    step_b = (tb.flat_params - before).abs().max().item()
+    step_a = (ts.flat_params - before).abs().max().item()
+    assert 0 < step_b < step_a
