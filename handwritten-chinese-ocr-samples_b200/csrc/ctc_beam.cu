@@ -2,9 +2,10 @@
 // __cbs_full__ :183-210, __context_beam_search__ :212-285, Beam :288-307).
 //   kernel 1 (HBM-bound): per (t,b) row, one warp: online log-sum-exp + per-lane sorted top-k in registers,
 //                         merged across the warp; emits candidates in descending log-prob order.
-//   kernel 2 (latency-bound): one warp per sequence walks the time steps; float64 accumulators,
-//                         np.logaddexp semantics, insertion-ordered stable ranking exactly as the
-//                         reference's dict + sorted(reverse=True).
+//   kernel 2 (latency-bound): one 128-thread CTA per sequence walks the time steps, every step fully
+//                         parallel over (beam, candidate) pairs; float64 accumulators, np.logaddexp
+//                         semantics, insertion-ordered stable ranking exactly as the reference's dict +
+//                         sorted(reverse=True).
 #include <cfloat>
 #include <cstring>
 
@@ -194,20 +195,30 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, 
 
 // ---------------------------------------------------------------------------------------------- beam search
 __device__ __forceinline__ double logaddexp_np(double x, double y) {
-    // numpy npy_logaddexp for doubles
+    // numpy npy_logaddexp for doubles:  x == y -> x + ln 2;  d = x - y;  d > 0 -> x + log1p(exp(-d));  d <= 0 -> y + log1p(exp(d));
+    // NaN -> d.  Written with selects so that all lanes of a warp run ONE exp and ONE log1p (the branchy form serialised
+    // the lanes that took different sides); the operations and their operands are the same, so are the bits.
+    const double d = __dsub_rn(x, y);
+    const bool pos = d > 0;
+    const double hi = pos ? x : y;
+    const double arg = pos ? -d : d;
+    const double r = __dadd_rn(hi, log1p(exp(arg)));
     if (x == y) return __dadd_rn(x, 0.693147180559945309417232121458176568);
-    const double tmp = __dsub_rn(x, y);
-    if (tmp > 0) return __dadd_rn(x, log1p(exp(-tmp)));
-    if (tmp <= 0) return __dadd_rn(y, log1p(exp(tmp)));
-    return tmp;
+    if (d != d) return d;
+    return r;
 }
 
+constexpr int kBeamThreads = 128;
+constexpr int kNoKey = 0x7fffffff;
+
 struct KeptState {
-    int node[kMaxBeam];
+    int node[kMaxBeam];                    // trie node of the prefix
+    int par[kMaxBeam];                     // trie node of the prefix minus its last character
     int len[kMaxBeam];
     int last[kMaxBeam];
     unsigned long long hash[kMaxBeam];
-    double pb[kMaxBeam], pnb[kMaxBeam], lmsum[kMaxBeam];
+    unsigned long long phash[kMaxBeam];    // hash of the prefix minus its last character
+    double pb[kMaxBeam], pnb[kMaxBeam], P[kMaxBeam], lmsum[kMaxBeam];     // P = Beam.prob() = logaddexp(pb, pnb)
 };
 
 __device__ __forceinline__ unsigned long long mix_hash(unsigned long long h, int c) {
@@ -226,23 +237,33 @@ __device__ bool same_string(const int* parent, const int* chr, int a, int b) {
     return true;
 }
 
-__global__ void __launch_bounds__(32)
+// One CTA of 128 threads per sequence. A time step of the reference (:212-285) is five block-wide phases, none of them
+// serial in the number of beams x candidates:
+//   A  per kept beam: which kept beam is its prefix minus the last character (hash + exact check); prefetch of the
+//      next step's candidates
+//   B  per (beam j, candidate q) pair: does prefix_j + c already exist among the kept beams? -> "new entry" bit mask;
+//      per kept beam: the position in the reference's double loop at which its dict entry is created (its own first
+//      valid candidate, or the earlier pair that extends its parent to it)
+//   C  dict insertion order = rank of the creation positions: popcount of the new-entry mask + count of earlier kept keys
+//   D  per entry: <= 2 contributions per accumulator, two convergent float64 logaddexp calls, LM score
+//   E  stable descending rank by counting, the best beam_size become the next kept beams
+__global__ void __launch_bounds__(kBeamThreads)
 ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __restrict__ topk_logp, int Tn, int Bn, int C,
                        int k, int beam_size, double lm_penalty, double len_bonus, const double* __restrict__ lm_table,
                        const hctr_ngram_lm ng_lm, int32_t* __restrict__ out_idx, int32_t* __restrict__ out_len,
                        int32_t* __restrict__ status, unsigned char* __restrict__ workspace, long long ws_per_seq) {
     __shared__ KeptState kept[2];
-    __shared__ double Pj[kMaxBeam];
     __shared__ int parentk[kMaxBeam];
-    __shared__ int cand[kMaxK];
-    __shared__ double candp[kMaxK];
-    __shared__ int ent_of_kept[kMaxBeam];
+    __shared__ int key[kMaxBeam];                   // creation position of a kept beam's entry (kNoKey: not created)
+    __shared__ int cand[2][kMaxK];
+    __shared__ double candp[2][kMaxK];
+    __shared__ unsigned newmask[kMaxBeam * kMaxK / 32];
     __shared__ int e_kind[kMaxGen];                 // >=0: kept index j''; <0: NEW
     __shared__ int e_src[kMaxGen], e_chr[kMaxGen];
-    __shared__ double e_pb[kMaxGen], e_pnb[kMaxGen], e_tot[kMaxGen], e_lm[kMaxGen];
-    __shared__ int s_ngen;
+    __shared__ double e_pb[kMaxGen], e_pnb[kMaxGen], e_P[kMaxGen], e_tot[kMaxGen], e_lm[kMaxGen];
+    __shared__ int s_ngen, s_ng, s_qblank;
 
-    const int b = blockIdx.x, lane = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int unknown = C - 1;
     const bool use_ngram = ng_lm.entries != nullptr;
     unsigned char* ws = workspace + (long long)b * ws_per_seq;
@@ -251,123 +272,175 @@ ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __rest
     const int cap = Tn * beam_size + 1;
     int* n_parent = g_time + Tn;
     int* n_chr = n_parent + cap;
-    unsigned long long* n_hash = reinterpret_cast<unsigned long long*>(
-        (reinterpret_cast<uintptr_t>(n_chr + cap) + 7) & ~uintptr_t(7));
 
-    // ---- top_line: greedy (char, t) list from the top-1 candidates (:188-195), warp compaction
-    int ng = 0;
-    for (int base = 0; base < Tn; base += 32) {
-        const int t = base + lane;
-        int cur = 0, keep = 0;
-        if (t < Tn) {
-            cur = topk_idx[((long long)t * Bn + b) * k];
-            const int prev = t > 0 ? topk_idx[((long long)(t - 1) * Bn + b) * k] : -1;
-            keep = (cur != 0) && (cur != unknown) && !(t > 0 && prev == cur);
+    // ---- top_line: greedy (char, t) list from the top-1 candidates (:188-195), compaction by warp 0
+    if (warp == 0) {
+        int ng = 0;
+        for (int base = 0; base < Tn; base += 32) {
+            const int t = base + lane;
+            int cur = 0, keep = 0;
+            if (t < Tn) {
+                cur = topk_idx[((long long)t * Bn + b) * k];
+                const int prev = t > 0 ? topk_idx[((long long)(t - 1) * Bn + b) * k] : -1;
+                keep = (cur != 0) && (cur != unknown) && !(t > 0 && prev == cur);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int pos = ng + __popc(bal & ((1u << lane) - 1));
+                g_char[pos] = cur; g_time[pos] = t;
+            }
+            ng += __popc(bal);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int pos = ng + __popc(bal & ((1u << lane) - 1));
-            g_char[pos] = cur; g_time[pos] = t;
+        if (lane == 0) {
+            s_ng = ng;
+            n_parent[0] = 0; n_chr[0] = -1;
+            kept[0].node[0] = 0; kept[0].par[0] = 0; kept[0].len[0] = 0; kept[0].last[0] = -1;
+            kept[0].hash[0] = 0x243F6A8885A308D3ull; kept[0].phash[0] = 0;
+            kept[0].pb[0] = 0.0; kept[0].pnb[0] = -INFINITY; kept[0].P[0] = 0.0; kept[0].lmsum[0] = 0.0;   // Beam() :289-297
         }
-        ng += __popc(bal);
     }
-    __syncwarp();
+    if (tid >= 32 && tid < 32 + k) {                 // candidates of step 0
+        const long long o = (long long)b * k + (tid - 32);
+        cand[0][tid - 32] = topk_idx[o];
+        candp[0][tid - 32] = (double)topk_logp[o];
+    }
+    __syncthreads();
+    const int ng = s_ng;
     if (ng == 0) {                                   // reference: top_line[-1] -> IndexError (:198)
-        if (lane == 0) { status[b] = HCTR_ERR_INDEX; out_len[b] = 0; }
+        if (tid == 0) { status[b] = HCTR_ERR_INDEX; out_len[b] = 0; }
         return;
     }
     int end_step = g_time[ng - 1] + 4;               // :198-199
     if (end_step >= Tn) end_step = Tn;
 
-    if (lane == 0) {
-        n_parent[0] = 0; n_chr[0] = -1; n_hash[0] = 0x243F6A8885A308D3ull;
-        kept[0].node[0] = 0; kept[0].len[0] = 0; kept[0].last[0] = -1; kept[0].hash[0] = n_hash[0];
-        kept[0].pb[0] = 0.0; kept[0].pnb[0] = -INFINITY; kept[0].lmsum[0] = 0.0;       // Beam() :289-297
-    }
     int nkept = 1, cur_buf = 0, gptr = 0;
-    __syncwarp();
+    int next_time = g_time[0];
 
     for (int t = 0; t < end_step; ++t) {
         KeptState& K = kept[cur_buf];
         KeptState& Kn = kept[cur_buf ^ 1];
-        while (gptr < ng && g_time[gptr] <= t) ++gptr;                 // suffix = next <=4 greedy chars after t (:202-203)
+        const int* cd = cand[t & 1];
+        const double* cp = candp[t & 1];               // fp32 log-probs, promoted on addition
+        while (gptr < ng && next_time <= t) {          // suffix = next <=4 greedy chars after t (:202-203)
+            ++gptr;
+            next_time = gptr < ng ? g_time[gptr] : kNoKey;
+        }
         int nsuf = ng - gptr; if (nsuf > 4) nsuf = 4;
 
-        if (lane < k) {
-            const long long o = ((long long)t * Bn + b) * k + lane;
-            cand[lane] = topk_idx[o];
-            candp[lane] = (double)topk_logp[o];                        // fp32 log-prob promoted on addition
-        }
-        if (lane < nkept) {
-            Pj[lane] = logaddexp_np(K.pb[lane], K.pnb[lane]);          // Beam.prob() of the INPUT beam (:299-300)
+        // ---- A
+        if (tid < nkept) {
             // which kept beam (if any) is this beam's prefix minus its last character?
             int pk = -1;
-            if (K.len[lane] > 0) {
-                const int par = n_parent[K.node[lane]];
+            if (K.len[tid] > 0) {
+                const int par = K.par[tid];
+                const unsigned long long ph = K.phash[tid];
                 for (int j = 0; j < nkept; ++j) {
-                    if (K.len[j] != K.len[lane] - 1) continue;
-                    if (K.node[j] == par || (K.hash[j] == n_hash[par] && same_string(n_parent, n_chr, K.node[j], par))) {
+                    if (K.len[j] != K.len[tid] - 1) continue;
+                    if (K.node[j] == par || (K.hash[j] == ph && same_string(n_parent, n_chr, K.node[j], par))) {
                         pk = j; break;
                     }
                 }
             }
-            parentk[lane] = pk;
-            ent_of_kept[lane] = -1;
+            parentk[tid] = pk;
+        } else if (tid >= 32 && tid < 32 + k) {
+            if (t + 1 < end_step) {
+                const long long o = ((long long)(t + 1) * Bn + b) * k + (tid - 32);
+                cand[(t + 1) & 1][tid - 32] = topk_idx[o];
+                candp[(t + 1) & 1][tid - 32] = (double)topk_logp[o];
+            }
+        } else if (tid == 64) {
+            int qb = -1;
+            for (int q = 0; q < k; ++q) if (cd[q] == 0) qb = q;
+            s_qblank = qb;
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ---- insertion order of the reference's gen_beams dict (:235-255), simulated sequentially
-        if (lane == 0) {
-            int ngen = 0;
-            for (int j = 0; j < nkept; ++j) {
-                for (int q = 0; q < k; ++q) {
-                    const int idx = cand[q];
-                    if (idx >= unknown) continue;                                  // :238-239
-                    if (ent_of_kept[j] < 0) { ent_of_kept[j] = ngen; e_kind[ngen] = j; ++ngen; }   // :243-244
-                    if (idx == 0) continue;
-                    int tgt = -1;                                                  // prefix_j + idx equals a kept prefix?
+        // ---- B
+        const int npairs = nkept * k;
+        for (int base = 0; base < npairs; base += kBeamThreads) {
+            const int p = base + tid;
+            bool isnew = false;
+            if (p < npairs) {
+                const int j = p / k, q = p - j * k;
+                const int idx = cd[q];
+                if (idx < unknown && idx != 0) {                                  // :238-239; blank extends nothing
+                    isnew = true;                                                 // unless prefix_j + idx is a kept prefix
                     for (int j2 = 0; j2 < nkept; ++j2)
-                        if (parentk[j2] == j && K.last[j2] == idx) { tgt = j2; break; }
-                    if (tgt >= 0) {
-                        if (ent_of_kept[tgt] < 0) { ent_of_kept[tgt] = ngen; e_kind[ngen] = tgt; ++ngen; }
-                    } else {
-                        e_kind[ngen] = -1; e_src[ngen] = j; e_chr[ngen] = idx;    // :253-255
-                        ++ngen;
-                    }
+                        if (parentk[j2] == j && K.last[j2] == idx) { isnew = false; break; }
                 }
             }
-            s_ngen = ngen;
+            const unsigned bal = __ballot_sync(0xffffffffu, isnew);
+            if (lane == 0) newmask[(base >> 5) + warp] = bal;
         }
-        __syncwarp();
-        const int ngen = s_ngen;
+        if (tid < nkept) {
+            // the dict entry of kept beam `tid` is created by its own first valid candidate (:243-244) or, earlier, by the
+            // pair (parent beam, candidate == its last character) that extends the parent to it (:250-252)
+            int own = kNoKey, ref = kNoKey;
+            for (int q = k - 1; q >= 0; --q) if (cd[q] < unknown) own = 2 * (tid * k + q);
+            const int pj = parentk[tid];
+            if (pj >= 0)
+                for (int q = 0; q < k; ++q) if (cd[q] == K.last[tid]) ref = 2 * (pj * k + q) + 1;
+            key[tid] = own < ref ? own : ref;
+        }
+        __syncthreads();
 
-        // ---- scores: every entry gathers its (at most two) contributions; np.logaddexp is symmetric and
-        //      logaddexp(-inf, a) == a, so the result is bit-identical to the reference's accumulation order.
-        for (int e = lane; e < ngen; e += 32) {
-            double pb = -INFINITY, pnb = -INFINITY, lm, plen;
-            if (e_kind[e] >= 0) {
-                const int j2 = e_kind[e];
-                for (int q = 0; q < k; ++q) {
-                    const int idx = cand[q];
-                    if (idx >= unknown) continue;
-                    if (idx == 0) pb = logaddexp_np(pb, __dadd_rn(Pj[j2], candp[q]));                  // :246-249
-                    else if (idx == K.last[j2]) pnb = logaddexp_np(pnb, __dadd_rn(K.pnb[j2], candp[q])); // :264-265
-                }
-                const int j = parentk[j2];
-                if (j >= 0) {
-                    for (int q = 0; q < k; ++q) {
-                        if (cand[q] != K.last[j2] || cand[q] >= unknown || cand[q] == 0) continue;
-                        const double add = (cand[q] != K.last[j]) ? __dadd_rn(Pj[j], candp[q])        // :256-258
-                                                                   : __dadd_rn(K.pb[j], candp[q]);    // :261-262
-                        pnb = logaddexp_np(pnb, add);
-                    }
+        // ---- C: entry index = number of entries created at earlier positions
+        const int nwords = (npairs + 31) >> 5;
+        for (int base = 0; base < npairs; base += kBeamThreads) {
+            const int p = base + tid;
+            if (p < npairs && ((newmask[p >> 5] >> (p & 31)) & 1u)) {
+                int e = __popc(newmask[p >> 5] & ((1u << (p & 31)) - 1u));
+                for (int w = 0; w < (p >> 5); ++w) e += __popc(newmask[w]);
+                for (int j2 = 0; j2 < nkept; ++j2) e += (key[j2] < 2 * p + 1) ? 1 : 0;
+                const int j = p / k;
+                e_kind[e] = -1; e_src[e] = j; e_chr[e] = cd[p - j * k];            // :253-255
+            }
+        }
+        if (tid < nkept && key[tid] != kNoKey) {
+            const int lim = key[tid] >> 1;                       // new entries of pairs p < lim come first
+            int e = 0;
+            for (int w = 0; w < nwords; ++w) {
+                const int lo = w << 5;
+                unsigned m = newmask[w];
+                if (lim < lo + 32) m = (lim <= lo) ? 0u : (m & ((1u << (lim - lo)) - 1u));
+                e += __popc(m);
+            }
+            for (int j2 = 0; j2 < nkept; ++j2) e += (key[j2] < key[tid]) ? 1 : 0;
+            e_kind[e] = tid;
+        }
+        if (tid == kBeamThreads - 1) {
+            int n = 0;
+            for (int w = 0; w < nwords; ++w) n += __popc(newmask[w]);
+            for (int j2 = 0; j2 < nkept; ++j2) n += (key[j2] != kNoKey) ? 1 : 0;
+            s_ngen = n;
+        }
+        __syncthreads();
+        const int ngen = s_ngen;
+        const int qblank = s_qblank;
+
+        // ---- D: scores. Every accumulator receives at most two contributions (the candidates of a step are distinct
+        //      classes); np.logaddexp is symmetric and logaddexp(-inf, a) == a + 0, so one unconditional call per
+        //      accumulator is bit-identical to the reference's accumulation in loop order.
+        for (int e = tid; e < ngen; e += kBeamThreads) {
+            double pb = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, lm, plen;
+            const int kind = e_kind[e];
+            if (kind >= 0) {
+                const int j2 = kind;
+                if (qblank >= 0) pb = __dadd_rn(__dadd_rn(K.P[j2], cp[qblank]), 0.0);                    // :246-249
+                int qrep = -1;
+                for (int q = 0; q < k; ++q) if (cd[q] == K.last[j2]) qrep = q;
+                if (qrep >= 0) {
+                    c1 = __dadd_rn(K.pnb[j2], cp[qrep]);                                                 // :264-265
+                    const int j = parentk[j2];
+                    if (j >= 0) c2 = (cd[qrep] != K.last[j]) ? __dadd_rn(K.P[j], cp[qrep])               // :256-258
+                                                             : __dadd_rn(K.pb[j], cp[qrep]);             // :261-262
                 }
                 lm = K.lmsum[j2]; plen = (double)K.len[j2];
             } else {
                 const int j = e_src[e], idx = e_chr[e];
                 double p = 0.0;
-                for (int q = 0; q < k; ++q) if (cand[q] == idx) p = candp[q];
-                pnb = (idx != K.last[j]) ? __dadd_rn(Pj[j], p) : __dadd_rn(K.pb[j], p);
+                for (int q = 0; q < k; ++q) if (cd[q] == idx) p = cp[q];
+                c1 = (idx != K.last[j]) ? __dadd_rn(K.P[j], p) : __dadd_rn(K.pb[j], p);
                 if (use_ngram) {
                     // kenlm: float32 running total; p(idx | last order-1 characters of prefix_j, <s> in front)
                     int ctx[kNgramMaxOrder - 1]; int m;
@@ -378,12 +451,13 @@ ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __rest
                 }
                 plen = (double)(K.len[j] + 1);
             }
+            const double pnb = logaddexp_np(c1, c2);
             e_lm[e] = lm;                                                       // LM sum over the prefix only
             double lmt = lm;
             if (lm_table) for (int c = 0; c < nsuf; ++c) lmt = __dadd_rn(lmt, lm_table[g_char[gptr + c]]);
             if (use_ngram && nsuf > 0) {
                 int ctx[kNgramMaxOrder - 1]; int m;
-                if (e_kind[e] >= 0) trie_context(ng_lm, n_parent, n_chr, K.node[e_kind[e]], -1, ctx, m);
+                if (kind >= 0) trie_context(ng_lm, n_parent, n_chr, K.node[kind], -1, ctx, m);
                 else trie_context(ng_lm, n_parent, n_chr, K.node[e_src[e]], e_chr[e], ctx, m);
                 float tot = (float)lm;
                 for (int c = 0; c < nsuf; ++c) {
@@ -394,39 +468,40 @@ ctc_prefix_beam_kernel(const int32_t* __restrict__ topk_idx, const float* __rest
                 lmt = (double)tot;
             }
             const double pt = __dadd_rn(__dmul_rn(lmt, lm_penalty), __dmul_rn(plen, len_bonus));   // :277-281
-            e_pb[e] = pb; e_pnb[e] = pnb;
-            e_tot[e] = __dadd_rn(logaddexp_np(pb, pnb), pt);                     // Beam.total() :302-303
+            const double P = logaddexp_np(pb, pnb);                              // Beam.prob() :299-300
+            e_pb[e] = pb; e_pnb[e] = pnb; e_P[e] = P;
+            e_tot[e] = __dadd_rn(P, pt);                                         // Beam.total() :302-303
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ---- sorted(..., key=total, reverse=True)[:beam_size]: stable, ties keep insertion order (:283-285)
+        // ---- E: sorted(..., key=total, reverse=True)[:beam_size]: stable, ties keep insertion order (:283-285)
         const int keep_n = ngen < beam_size ? ngen : beam_size;
-        for (int e = lane; e < ngen; e += 32) {
+        for (int e = tid; e < ngen; e += kBeamThreads) {
             const double te = e_tot[e];
             int rank = 0;
             for (int f = 0; f < ngen; ++f) rank += (e_tot[f] > te) || (e_tot[f] == te && f < e);
             if (rank < keep_n) {
-                Kn.pb[rank] = e_pb[e]; Kn.pnb[rank] = e_pnb[e]; Kn.lmsum[rank] = e_lm[e];
+                Kn.pb[rank] = e_pb[e]; Kn.pnb[rank] = e_pnb[e]; Kn.P[rank] = e_P[e]; Kn.lmsum[rank] = e_lm[e];
                 if (e_kind[e] >= 0) {
                     const int j2 = e_kind[e];
-                    Kn.node[rank] = K.node[j2]; Kn.len[rank] = K.len[j2]; Kn.last[rank] = K.last[j2]; Kn.hash[rank] = K.hash[j2];
+                    Kn.node[rank] = K.node[j2]; Kn.par[rank] = K.par[j2]; Kn.len[rank] = K.len[j2]; Kn.last[rank] = K.last[j2];
+                    Kn.hash[rank] = K.hash[j2]; Kn.phash[rank] = K.phash[j2];
                 } else {
                     const int j = e_src[e], idx = e_chr[e];
                     const int id = 1 + t * beam_size + rank;
-                    const unsigned long long h = mix_hash(K.hash[j], idx);
-                    n_parent[id] = K.node[j]; n_chr[id] = idx; n_hash[id] = h;
-                    Kn.node[rank] = id; Kn.len[rank] = K.len[j] + 1; Kn.last[rank] = idx; Kn.hash[rank] = h;
+                    n_parent[id] = K.node[j]; n_chr[id] = idx;
+                    Kn.node[rank] = id; Kn.par[rank] = K.node[j]; Kn.len[rank] = K.len[j] + 1; Kn.last[rank] = idx;
+                    Kn.hash[rank] = mix_hash(K.hash[j], idx); Kn.phash[rank] = K.hash[j];
                 }
             }
         }
-        __threadfence_block();
-        __syncwarp();
+        __syncthreads();                                 // also orders the trie writes in global memory for the block
         nkept = keep_n;
         cur_buf ^= 1;
     }
 
     // ---- texts.append(kept_beams[0].prefix) (:208)
-    if (lane == 0) {
+    if (tid == 0) {
         const KeptState& K = kept[cur_buf];
         const int L = K.len[0];
         int node = K.node[0];
@@ -511,7 +586,7 @@ int hctr_ctc_prefix_beam_search_lm(const int32_t* topk_idx, const float* topk_lo
     const long long need = hctr_ctc_beam_workspace_bytes(T, B, beam_size);
     HCTR_CHECK(workspace && workspace_bytes >= need, HCTR_ERR_INVALID, "beam: workspace too small (%lld < %lld)", workspace_bytes, need);
     HCTR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, HCTR_ERR_INVALID, "beam: workspace must be 16-byte aligned");
-    ctc_prefix_beam_kernel<<<B, 32, 0, s>>>(topk_idx, topk_logp, T, B, C, k, beam_size, lm_penalty, len_bonus, lm_table, lm,
+    ctc_prefix_beam_kernel<<<B, kBeamThreads, 0, s>>>(topk_idx, topk_logp, T, B, C, k, beam_size, lm_penalty, len_bonus, lm_table, lm,
                                             out_idx, out_len, status, static_cast<unsigned char*>(workspace),
                                             beam_ws_per_seq(T, beam_size));
     HCTR_CUDA(cudaGetLastError());
