@@ -294,18 +294,24 @@ def main():
     dom = [(t, v) for t, v in by_tag.items() if t.startswith("conv3x3_512_512_h16") and not t.endswith("_pool")]
     dom_ms = sum(v[0] for _, v in dom); dom_fl = sum(v[1] for _, v in dom); dom_n = sum(v[3] for _, v in dom)
     achieved = dom_fl / (dom_ms * 1e-3) / 1e12
+    # DRAM bytes per launch from the ncu --set full captures (profiles/ncu_traffic.json), launch-weighted over the two
+    # variants of this layer: conv1 (+channel sums; reads x, writes t) and conv2 (+gate+residual+ReLU; reads t and the residual)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and dom_n:
         with open(tpath) as fh:
-            traffic = json.load(fh)["igemm_conv3x3_512_512_B64_H16_W2048"]["dram_bytes_per_launch"]
+            tj = json.load(fh)
+        n_res = sum(v[3] for t, v in dom if t.endswith("_gate_res"))
+        traffic = (tj["igemm_conv3x3_512_512_B64_H16_W2048_gate_res"]["dram_bytes_per_launch"] * n_res
+                   + tj["igemm_conv3x3_512_512_B64_H16_W2048"]["dram_bytes_per_launch"] * (dom_n - n_res)) / dom_n
+    dom_bytes = sum(v[2] for _, v in dom)
     roofline = {
         "kernel": "igemm_pair_kernel (tcgen05.mma.cta_group::2, M=256 x N=256 per CTA pair, 3 stages x 128 K, 2 TMEM accumulator stages) on the 512->512 3x3 convs (B=64,H=16,W=2048)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops_sustained"], "peak_kind": "bf16_tflops_sustained (%s)" % peaks["source"],
         "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
         "flops_per_launch": dom_fl / max(dom_n, 1), "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, profiles/ncu_traffic.json)",
-        "algorithmic_bytes_per_launch": 2.0 * B_PER_GPU * 16 * WIDTH * 512 * 2 + 2.0 * 512 * 4608,
+        "algorithmic_bytes_per_launch": dom_bytes / max(dom_n, 1),
         "launches_per_step": dom_n // trace_steps, "avg_launch_ms": dom_ms / max(dom_n, 1),
         "share_of_forward": dom_ms / total_ms,
     }

@@ -32,6 +32,11 @@ template <> struct LoadVec<float> {
         o[0] = __uint_as_float(q.x); o[1] = __uint_as_float(q.y); o[2] = __uint_as_float(q.z); o[3] = __uint_as_float(q.w);
     }
     static __device__ __forceinline__ float one(const float* p) { return __ldg(p); }
+    static __device__ __forceinline__ float one_smem(const float* p) { return *p; }
+    static __device__ __forceinline__ void load_smem(const unsigned char* p, float (&o)[4]) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+    }
 };
 template <> struct LoadVec<__nv_bfloat16> {
     static constexpr int N = 8;
@@ -43,153 +48,251 @@ template <> struct LoadVec<__nv_bfloat16> {
     static __device__ __forceinline__ float one(const __nv_bfloat16* p) {
         return __uint_as_float(static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(p)) << 16);
     }
+    static __device__ __forceinline__ float one_smem(const __nv_bfloat16* p) { return one(p); }
+    static __device__ __forceinline__ void load_smem(const unsigned char* p, float (&o)[8]) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        o[0] = bf16_lo(q.x); o[1] = bf16_hi(q.x); o[2] = bf16_lo(q.y); o[3] = bf16_hi(q.y);
+        o[4] = bf16_lo(q.z); o[5] = bf16_hi(q.z); o[6] = bf16_lo(q.w); o[7] = bf16_hi(q.w);
+    }
 };
 
-// One CTA (256 threads) per (t,b) row; the row is staged once in shared memory as fp32:
-//   pass 1  global -> smem (16-byte loads), per-thread maximum
-//   bound   every warp sorts its 32 lane maxima (bitonic, shuffles); the k-th largest of one warp's lane maxima is a
-//           valid lower bound for the k-th largest of the row (k distinct elements are >= it); tau = best warp's bound
-//   pass 2  smem: sum exp(x - max) and collect the few elements >= tau into a candidate list
+// Persistent CTAs of 256 threads; a CTA walks rows (t,b) = blockIdx.x, +gridDim.x, ... and keeps TWO row buffers in
+// shared memory: while row i is reduced, the bulk-copy engine (cp.async.bulk global -> shared, mbarrier complete_tx)
+// already streams row i+1, so HBM latency is never on a row's critical path and the SM needs no spare occupancy to hide it.
+// A row is staged in its own dtype (bf16 rows cost half the shared memory and bandwidth). Rows need not be 16-byte
+// aligned (C = 7375 floats): the bulk copy moves the 16-byte-aligned interior [lo, hi) of the row to offset 16 of the
+// buffer, the < 16-byte head and tail land next to it through registers, fetched one row ahead as well.
+// The kernel is bound by instruction issue, not by latency (first persistent version: 38 instructions per element, 56 %
+// issue-active with 24 warps/SM, slower than HBM allows), so the two passes work on 16-byte shared-memory vectors and
+// everything per row is kept short:
+//   pass 1  per-thread maximum (ld.shared.v4 + a max tree); maxima of the 16 half-warps -> shared memory
+//   bound   the k-th largest of the 16 half-warp maxima is a valid lower bound tau for the k-th largest element of the
+//           row (k distinct elements are >= it; ~15 elements of a random row reach it); every warp ranks the 16 values
+//           itself (16 broadcast reads), no extra barrier; the row maximum falls out of the same 16 values
+//   pass 2  sum exp(x - max) and collect the few elements >= tau (one compare per vector on its maximum)
 //   rank    candidates ranked by counting (value desc, index asc) -> the top k in order; exact for any input.
 // If more than kMaxCand elements reach tau (e.g. constant rows) an exact k-round arg-max fallback runs instead.
+// Three block barriers per row, no single-thread sections, one 32-bit division per row.
 constexpr int kTopkThreads = 256;
 constexpr int kMaxCand = 512;
+constexpr int kTopkEdge = 16;          // head + tail elements of a row that do not belong to the aligned interior (< 16 B each)
 
-__device__ __forceinline__ float warp_kth_largest(float v, int k, int lane) {
-    // bitonic sort of 32 lane values, descending; returns the value that ends up in lane k-1
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const float o = __shfl_xor_sync(0xffffffffu, v, stride);
-            const bool up = ((lane & size) == 0);                 // this block sorts descending if 'up'
-            const bool lower = ((lane & stride) == 0);
-            const float hi = fmaxf(v, o), lo = fminf(v, o);
-            v = (lower == up) ? hi : lo;
-        }
-    }
-    return __shfl_sync(0xffffffffu, v, k - 1);
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// geometry of one row in global memory / in its shared-memory buffer (element 0 lives at byte 16 - head_bytes)
+struct TopkRow {
+    const unsigned char* a0;           // first byte of the row
+    int head_bytes;                    // [a0, lo): bytes in front of the 16-byte-aligned interior
+    int body_bytes;                    // [lo, hi): multiple of 16 (0 for tiny rows: everything travels through registers)
+};
+template <typename T>
+__device__ __forceinline__ TopkRow topk_row(const T* logits, unsigned row, unsigned Bn, long long stride_t, long long stride_b,
+                                            int row_bytes) {
+    const unsigned t = row / Bn, b = row - t * Bn;
+    TopkRow r;
+    r.a0 = reinterpret_cast<const unsigned char*>(logits + (long long)t * stride_t + (long long)b * stride_b);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(r.a0);
+    const uintptr_t lo = (a + 15) & ~uintptr_t(15), hi = (a + row_bytes) & ~uintptr_t(15);
+    if (hi > lo) { r.head_bytes = (int)(lo - a); r.body_bytes = (int)(hi - lo); }
+    else { r.head_bytes = 0; r.body_bytes = 0; }
+    return r;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kTopkThreads)
-ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
-                           int k, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp,
+ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn, int C, long long stride_t, long long stride_b,
+                           int k, int nbuf, int buf_bytes, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp,
                            float* __restrict__ lse_out) {
     constexpr int V = LoadVec<T>::N;
-    extern __shared__ float rowbuf[];                              // [C] the row as fp32
-    __shared__ float red[8];
-    __shared__ float s_max, s_tau, s_logs;
-    __shared__ int s_ncand;
+    extern __shared__ __align__(128) unsigned char rowbufs[];      // [nbuf][buf_bytes]
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ float gmax[16], red_sum[8];
+    __shared__ int s_ncand[2];
     __shared__ float cand_v[kMaxCand];
     __shared__ int cand_i[kMaxCand];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long row = blockIdx.x;                              // row = t*B + b
-    const int t = (int)(row / Bn), b = (int)(row - (long long)t * Bn);
-    const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+    const int row_bytes = C * (int)sizeof(T);
+    const int kk = k < 16 ? k : 16;
 
-    // ---- pass 1: stage the row, per-thread max
-    float tmax = -INFINITY;
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
-    int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
-    if (head > C) head = C;
-    if (tid < head) { const float x = LoadVec<T>::one(p + tid); rowbuf[tid] = x; tmax = fmaxf(tmax, x); }
-    const int nvec = (C - head) / V;
-    const T* pv = p + head;
-    for (int vi = tid; vi < nvec; vi += kTopkThreads) {
-        float x[V];
-        LoadVec<T>::load(pv + (long long)vi * V, x);
-#pragma unroll
-        for (int j = 0; j < V; ++j) { rowbuf[head + vi * V + j] = x[j]; tmax = fmaxf(tmax, x[j]); }
-    }
-    const int tail0 = head + nvec * V;
-    if (tail0 + tid < C) { const float x = LoadVec<T>::one(p + tail0 + tid); rowbuf[tail0 + tid] = x; tmax = fmaxf(tmax, x); }
-    if (tid == 0) s_ncand = 0;
-    // ---- bound: k-th largest lane maximum of each warp, block max
-    const float kth = warp_kth_largest(tmax, k < 32 ? k : 32, lane);
-    float wmax = tmax;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    __shared__ float red_kth[8];
-    if (lane == 0) { red[warp] = wmax; red_kth[warp] = kth; }
-    __syncthreads();
-    if (tid == 0) {
-        float m = red[0], tau = red_kth[0];
-        for (int i = 1; i < kTopkThreads / 32; ++i) { m = fmaxf(m, red[i]); tau = fmaxf(tau, red_kth[i]); }
-        s_max = m; s_tau = tau;
-    }
-    __syncthreads();
-    const float m = s_max, tau = s_tau;
-    // ---- pass 2: sum of exp and candidate collection
-    float sum = 0.f;
-    for (int c = tid; c < C; c += kTopkThreads) {
-        const float x = rowbuf[c];
-        sum += __expf(x - m);
-        if (x >= tau) {
-            const int slot = atomicAdd(&s_ncand, 1);
-            if (slot < kMaxCand) { cand_v[slot] = x; cand_i[slot] = c; }
+    // thread 0: bulk copy of the interior of row r into buffer s
+    auto issue = [&](const TopkRow& r, int s) {
+        if (r.body_bytes > 0) {
+            mbar_arrive_expect_tx(&full_bar[s], (uint32_t)r.body_bytes);
+            bulk_g2s(rowbufs + (size_t)s * buf_bytes + 16, r.a0 + r.head_bytes, (uint32_t)r.body_bytes, &full_bar[s]);
+        } else {
+            mbar_arrive(&full_bar[s]);
         }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncthreads();                                               // red[] reuse + candidates visible
-    if (lane == 0) red[warp] = sum;
-    __syncthreads();
+    };
+    // threads < kTopkEdge: byte offset inside the row of the head/tail element this thread carries (-1: none)
+    auto edge_offset = [&](const TopkRow& r) -> int {
+        const int nhead = r.head_bytes / (int)sizeof(T);
+        const int off = tid < nhead ? tid * (int)sizeof(T) : r.head_bytes + r.body_bytes + (tid - nhead) * (int)sizeof(T);
+        return (tid < kTopkEdge && off < row_bytes) ? off : -1;
+    };
+
     if (tid == 0) {
-        float sacc = 0.f;
-        for (int i = 0; i < kTopkThreads / 32; ++i) sacc += red[i];   // fixed order
-        const float logs = logf(sacc);
-        s_logs = logs;
-        lse_out[row] = m + logs;
+        mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+        fence_barrier_init();
+        s_ncand[0] = 0; s_ncand[1] = 0;
     }
     __syncthreads();
-    const float logs = s_logs;
-    const int ncand = s_ncand;
-    if (ncand <= kMaxCand) {
-        // ---- rank by counting: exact order (value desc, index asc), independent of the collection order
-        for (int e = tid; e < ncand; e += kTopkThreads) {
-            const float v = cand_v[e]; const int ci = cand_i[e];
-            int rank = 0;
-            for (int f = 0; f < ncand; ++f) rank += cand_better(cand_v[f], cand_i[f], v, ci) ? 1 : 0;
-            if (rank < k) {
-                topk_idx[row * k + rank] = ci;
-                topk_logp[row * k + rank] = (v - m) - logs;         // scipy: (x - max) - log(sum(exp(x - max)))
+    long long row = blockIdx.x;
+    TopkRow cur = topk_row(logits, (unsigned)(row < rows ? row : 0), (unsigned)Bn, stride_t, stride_b, row_bytes);
+    if (row < rows) {
+        if (tid == 0) issue(cur, 0);
+        const int off = edge_offset(cur);
+        if (off >= 0) *reinterpret_cast<T*>(rowbufs + 16 - cur.head_bytes + off) = *reinterpret_cast<const T*>(cur.a0 + off);
+    }
+    __syncthreads();
+
+    for (int it = 0; row < rows; row += gridDim.x, ++it) {
+        const int s = nbuf == 2 ? (it & 1) : 0;
+        const long long next = row + gridDim.x;
+        // ---- row i+1: bulk copy into the other buffer (its last reader finished before the barrier that ended row i-1)
+        TopkRow nxt = cur;
+        T edge_val = T();
+        int edge_off = -1;
+        if (next < rows) {
+            nxt = topk_row(logits, (unsigned)next, (unsigned)Bn, stride_t, stride_b, row_bytes);
+            if (nbuf == 2) {
+                if (tid == 0) issue(nxt, s ^ 1);
+                edge_off = edge_offset(nxt);
+                if (edge_off >= 0) edge_val = *reinterpret_cast<const T*>(nxt.a0 + edge_off);
             }
         }
-    } else {
-        // ---- exact fallback: k rounds of block arg-best with exclusion of what was already emitted
-        __shared__ float bv_s[8];
-        __shared__ int bi_s[8];
-        __shared__ float last_v;
-        __shared__ int last_i;
-        if (tid == 0) { last_v = INFINITY; last_i = -1; }
+        unsigned char* buf = rowbufs + (size_t)s * buf_bytes;
+        const T* rb = reinterpret_cast<const T*>(buf + 16 - cur.head_bytes);          // element 0 of the row
+        const int nhead = cur.head_bytes / (int)sizeof(T);
+        const int nvec = cur.body_bytes >> 4;
+        const int tail0 = nhead + nvec * V;
+        // the scalar (head/tail) element of this thread, if any
+        const int sc = tid < nhead ? tid : tail0 + (tid - nhead);
+        const bool has_sc = tid < kTopkEdge && sc < C;
+        mbar_wait(&full_bar[s], (nbuf == 2 ? (it >> 1) : it) & 1);
+
+        // ---- pass 1: per-thread max
+        float tmax = has_sc ? LoadVec<T>::one_smem(rb + sc) : -INFINITY;
+#pragma unroll 2
+        for (int vi = tid; vi < nvec; vi += kTopkThreads) {
+            float x[V];
+            LoadVec<T>::load_smem(buf + 16 + (vi << 4), x);
+#pragma unroll
+            for (int j = 0; j < V; j += 2) tmax = fmaxf(tmax, fmaxf(x[j], x[j + 1]));
+        }
+        float hmax = tmax;                                           // maximum of this half-warp
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+        if ((lane & 15) == 0) gmax[tid >> 4] = hmax;
+        if (tid == 0) s_ncand[(it + 1) & 1] = 0;
         __syncthreads();
-        for (int r = 0; r < k; ++r) {
-            const float lv = last_v; const int li = last_i;
-            float bv = -INFINITY; int bi = 0x7fffffff;
-            for (int c = tid; c < C; c += kTopkThreads) {
-                const float x = rowbuf[c];
-                // eligible: strictly after (lv, li) in the (value desc, index asc) order
-                const bool elig = (x < lv) || (x == lv && c > li);
-                if (elig && cand_better(x, c, bv, bi)) { bv = x; bi = c; }
-            }
+        // every warp: rank the 16 half-warp maxima (value desc, index asc); tau = the kk-th largest, m = the largest
+        const float gv = gmax[lane & 15];
+        int grank = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+        for (int j = 0; j < 16; ++j) {
+            const float o = gmax[j];
+            grank += (o > gv || (o == gv && j < (lane & 15))) ? 1 : 0;
+        }
+        const unsigned at_tau = __ballot_sync(0xffffffffu, grank == kk - 1) & 0xffffu;
+        const unsigned at_max = __ballot_sync(0xffffffffu, grank == 0) & 0xffffu;
+        // NaN maxima cannot be ranked (every compare is false): fall back to "everything is a candidate"
+        const float tau = at_tau ? __shfl_sync(0xffffffffu, gv, __ffs(at_tau) - 1) : -INFINITY;
+        const float m = at_max ? __shfl_sync(0xffffffffu, gv, __ffs(at_max) - 1) : gv;
+
+        // ---- pass 2: sum of exp and candidate collection
+        float sum = 0.f;
+        if (has_sc) {
+            const float x = LoadVec<T>::one_smem(rb + sc);
+            sum += __expf(x - m);
+            if (x >= tau) {
+                const int slot = atomicAdd(&s_ncand[it & 1], 1);
+                if (slot < kMaxCand) { cand_v[slot] = x; cand_i[slot] = sc; }
             }
-            if (lane == 0) { bv_s[warp] = bv; bi_s[warp] = bi; }
-            __syncthreads();
-            if (tid == 0) {
+        }
+#pragma unroll 2
+        for (int vi = tid; vi < nvec; vi += kTopkThreads) {
+            float x[V];
+            LoadVec<T>::load_smem(buf + 16 + (vi << 4), x);
+            float vmax = fmaxf(x[0], x[1]);
+#pragma unroll
+            for (int j = 2; j < V; j += 2) vmax = fmaxf(vmax, fmaxf(x[j], x[j + 1]));
+#pragma unroll
+            for (int j = 0; j < V; ++j) sum += __expf(x[j] - m);
+            if (!(vmax < tau)) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if (x[j] >= tau) {
+                        const int slot = atomicAdd(&s_ncand[it & 1], 1);
+                        if (slot < kMaxCand) { cand_v[slot] = x[j]; cand_i[slot] = nhead + vi * V + j; }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) red_sum[warp] = sum;
+        __syncthreads();
+        float sacc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kTopkThreads / 32; ++i) sacc += red_sum[i];          // fixed order
+        const float logs = logf(sacc);
+        if (tid == 0) lse_out[row] = m + logs;
+        const int ncand = s_ncand[it & 1];
+        if (ncand <= kMaxCand) {
+            // ---- rank by counting: exact order (value desc, index asc), independent of the collection order
+            for (int e = tid; e < ncand; e += kTopkThreads) {
+                const float v = cand_v[e]; const int ci = cand_i[e];
+                int rank = 0;
+                for (int f = 0; f < ncand; ++f) rank += cand_better(cand_v[f], cand_i[f], v, ci) ? 1 : 0;
+                if (rank < k) {
+                    topk_idx[row * k + rank] = ci;
+                    topk_logp[row * k + rank] = (v - m) - logs;         // scipy: (x - max) - log(sum(exp(x - max)))
+                }
+            }
+        } else {
+            // ---- exact fallback: k rounds of block arg-best with exclusion of what was already emitted
+            __shared__ float bv_s[8];
+            __shared__ int bi_s[8];
+            float lv = INFINITY; int li = -1;
+            for (int r = 0; r < k; ++r) {
+                float bv = -INFINITY; int bi = 0x7fffffff;
+                for (int c = tid; c < C; c += kTopkThreads) {
+                    const float x = LoadVec<T>::one_smem(rb + c);
+                    // eligible: strictly after (lv, li) in the (value desc, index asc) order
+                    const bool elig = (x < lv) || (x == lv && c > li);
+                    if (elig && cand_better(x, c, bv, bi)) { bv = x; bi = c; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+                }
+                __syncthreads();                                    // previous round's readers are done
+                if (lane == 0) { bv_s[warp] = bv; bi_s[warp] = bi; }
+                __syncthreads();
                 float v = bv_s[0]; int i2 = bi_s[0];
                 for (int q = 1; q < kTopkThreads / 32; ++q) if (cand_better(bv_s[q], bi_s[q], v, i2)) { v = bv_s[q]; i2 = bi_s[q]; }
-                last_v = v; last_i = i2;
-                topk_idx[row * k + r] = i2;
-                topk_logp[row * k + r] = (v - m) - logs;
+                lv = v; li = i2;
+                if (tid == 0) {
+                    topk_idx[row * k + r] = i2;
+                    topk_logp[row * k + r] = (v - m) - logs;
+                }
             }
+        }
+        // ---- end of row: the edge elements of row i+1 go next to its bulk-copied interior
+        if (edge_off >= 0) *reinterpret_cast<T*>(rowbufs + (size_t)(s ^ 1) * buf_bytes + 16 - nxt.head_bytes + edge_off) = edge_val;
+        __syncthreads();
+        if (nbuf == 1 && next < rows) {                              // single-buffer mode (rows too large for two buffers)
+            if (tid == 0) issue(nxt, 0);
+            const int off = edge_offset(nxt);
+            if (off >= 0) *reinterpret_cast<T*>(rowbufs + 16 - nxt.head_bytes + off) = *reinterpret_cast<const T*>(nxt.a0 + off);
             __syncthreads();
         }
+        cur = nxt;
     }
 }
 
@@ -527,21 +630,31 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     HCTR_CHECK(logits != nullptr, HCTR_ERR_INVALID, "topk: null logits");
     const long long rows = (long long)T * B;
     HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "topk: too many rows");
-    const size_t smem = (size_t)C * sizeof(float);
-    HCTR_CHECK(smem <= 160 * 1024, HCTR_ERR_INVALID, "topk: %d classes do not fit the shared-memory row buffer", C);
+    const size_t esz = dtype == HCTR_F32 ? 4 : 2;
+    const int buf_bytes = (int)(((size_t)C * esz + 32 + 127) & ~size_t(127));        // row + 16 bytes of misalignment either side
+    HCTR_CHECK((size_t)C * 4 <= 160 * 1024, HCTR_ERR_INVALID, "topk: %d classes do not fit the shared-memory row buffer", C);
+    const int nbuf = 2 * (size_t)buf_bytes <= 200 * 1024 ? 2 : 1;
+    const size_t smem = (size_t)nbuf * buf_bytes;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    static bool configured = false;
-    if (!configured) {
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int dev = 0;
+        HCTR_CUDA(cudaGetDevice(&dev));
+        HCTR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    // persistent grid: as many CTAs as fit (shared memory: two row buffers + ~5 KB static each), at most 8 per SM
+    long long per_sm = (220 * 1024) / (long long)(smem + 6 * 1024);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const long long grid = rows < per_sm * num_sms ? rows : per_sm * num_sms;
     if (dtype == HCTR_F32)
-        ctc_topk_logsoftmax_kernel<float><<<(int)rows, kTopkThreads, smem, s>>>(
-            static_cast<const float*>(logits), T, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
+        ctc_topk_logsoftmax_kernel<float><<<(int)grid, kTopkThreads, smem, s>>>(
+            static_cast<const float*>(logits), rows, B, C, stride_t, stride_b, k, nbuf, buf_bytes, topk_idx, topk_logp, lse);
     else
-        ctc_topk_logsoftmax_kernel<__nv_bfloat16><<<(int)rows, kTopkThreads, smem, s>>>(
-            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
+        ctc_topk_logsoftmax_kernel<__nv_bfloat16><<<(int)grid, kTopkThreads, smem, s>>>(
+            static_cast<const __nv_bfloat16*>(logits), rows, B, C, stride_t, stride_b, k, nbuf, buf_bytes, topk_idx, topk_logp, lse);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }

@@ -106,6 +106,61 @@ def test_topk_logsoftmax_vs_oracle():
             assert np.array_equal(np.take_along_axis(xf, got, 2), np.take_along_axis(xf, oracle.topk(lpb, k), 2))
 
 
+def _run_topk(xt, k):
+    from hctr_b200 import native as nat
+    T, B, C = xt.shape
+    ti = torch.empty((T, B, k), dtype=torch.int32, device="cuda")
+    tp = torch.empty((T, B, k), dtype=torch.float32, device="cuda")
+    lse = torch.empty((T, B), dtype=torch.float32, device="cuda")
+    nat.check(nat.lib().hctr_ctc_topk_logsoftmax(nat.ptr(xt), nat.HCTR_F32 if xt.dtype == torch.float32 else nat.HCTR_BF16,
+                                                 T, B, C, xt.stride(0), xt.stride(1), k, nat.ptr(ti), nat.ptr(tp),
+                                                 nat.ptr(lse), nat.stream_ptr()))
+    torch.cuda.synchronize()
+    return ti.cpu().numpy(), tp.cpu().numpy(), lse.cpu().numpy()
+
+
+@pytest.mark.parametrize("T,B,C,k", [(700, 5, 301, 10), (97, 11, 7375, 10), (33, 2, 5, 3), (64, 3, 40001, 16), (300, 4, 17, 1)])
+def test_topk_logsoftmax_many_rows_per_cta_and_odd_shapes(T, B, C, k):
+    """More rows than resident CTAs (every CTA walks several rows through both shared-memory buffers), rows that are
+    not 16-byte aligned (odd C), tiny rows (all elements through registers), rows too large for two buffers."""
+    rng = np.random.default_rng(C * 7 + T)
+    x = (3.0 * rng.standard_normal((T, B, C))).astype(np.float32)
+    lp = oracle.log_softmax(x)
+    tk = oracle.topk(x, k)              # ranked on the raw values (log_softmax rounding can merge neighbours)
+    ti, tp, lse = _run_topk(torch.from_numpy(x).cuda(), k)
+    assert np.array_equal(ti, tk)
+    ref = np.take_along_axis(lp, tk, axis=2)
+    assert np.abs(tp - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    m = x.max(axis=2)
+    ref_lse = m + np.log(np.exp(x - m[..., None]).sum(axis=2, dtype=np.float64))
+    assert np.abs(lse - ref_lse).max() <= 1e-5 * max(1.0, np.abs(ref_lse).max())
+    # bf16 rows (2-byte aligned starts): compare the selected VALUES (rounding creates ties)
+    xb = torch.from_numpy(x).cuda().to(torch.bfloat16)
+    tib, _, _ = _run_topk(xb, k)
+    xf = xb.float().cpu().numpy()
+    assert np.array_equal(np.take_along_axis(xf, tib, 2), np.take_along_axis(xf, oracle.topk(oracle.log_softmax(xf), k), 2))
+
+
+def test_topk_logsoftmax_strided_views_and_constant_rows():
+    """The model's logits are a permuted, pitched view ([B,W,pitch] -> [W,B,C]); constant rows overflow the candidate
+    list and take the exact arg-max fallback (ties -> lowest index, numpy argsort of the reversed stable order aside)."""
+    T, B, C, k = 50, 6, 1001, 10
+    rng = np.random.default_rng(5)
+    base = torch.from_numpy((2.0 * rng.standard_normal((B, T, C + 3))).astype(np.float32)).cuda()
+    view = base[:, :, :C].permute(1, 0, 2)                       # [T,B,C], strides (C+3, T*(C+3), 1)
+    ti, tp, _ = _run_topk(view, k)
+    x = view.cpu().numpy()
+    lp = oracle.log_softmax(np.ascontiguousarray(x))
+    tk = oracle.topk(x, k)
+    assert np.array_equal(ti, tk)
+    assert np.abs(tp - np.take_along_axis(lp, tk, 2)).max() <= 2e-6 * np.abs(lp).max()
+    const = torch.zeros((3, 2, 777), dtype=torch.float32, device="cuda")
+    const[1, 1, 5] = 1.0
+    ti, tp, _ = _run_topk(const, 4)
+    assert ti[0, 0].tolist() == [0, 1, 2, 3] and ti[1, 1].tolist() == [5, 0, 1, 2]
+    assert np.allclose(tp[0, 0], -np.log(777.0), rtol=1e-6)
+
+
 BEAM_CASES = [(c, s) for c in ("small", "mid", "wide") for s in ("zero_b0", "zero_b58", "tab_p2", "tab_p08")]
 
 
