@@ -117,12 +117,24 @@ static bool pair_enabled() {
     return g_pair_mode != 0;
 }
 // (every layer of the model with Cout % 256 == 0 has Cin % 128 == 0, so the K blocks pair up)
-static bool use_pair(int H, int Cin, int Cout, int ksize, int pool) {
+// Pooled layers on the pair kernel: the two rows of a (2,1) window live in the two CTAs of a pair, which combine them
+// with red.global.max.v4.bf16x2 into a zero-filled output (needs ReLU: all operands >= 0). HCTR_IGEMM_PAIR_POOL=0 keeps
+// them on the single-CTA kernel (A/B measurements).
+static bool pair_pool_enabled() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HCTR_IGEMM_PAIR_POOL");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode == 1;
+}
+static bool use_pair(int H, int Cin, int Cout, int ksize, int pool, int relu = 0, bool plain = false) {
     // (measured: at Cout = 128 the pair kernel is slower than the single-CTA slab kernel, with or without the slab -
     //  722 / 763 vs 990 TFLOP/s on 128->128: K = 1152 gives 4 us tiles and the cluster-wide accumulator hand-over
     //  per tile dominates)
     const bool slab = ksize == 3 && g_kwf_mode != 0;         // one stage per (kh, chunk); otherwise K blocks go in pairs
-    return pair_enabled() && !pool && Cout % 256 == 0 && H % 2 == 0 && (slab || (ksize * ksize * (Cin / 64)) % kPairKSub == 0);
+    if (pool && !(relu && plain && pair_pool_enabled())) return false;
+    return pair_enabled() && Cout % 256 == 0 && H % 2 == 0 && (slab || (ksize * ksize * (Cin / 64)) % kPairKSub == 0);
 }
 
 template <int BLOCK_N, int STAGES, int KWF, int ADD>
@@ -236,7 +248,7 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "conv: too many tiles");
     p.total_tiles = (int)total;
 
-    if (use_pair(H, Cin, Cout, ksize, pool)) {
+    if (use_pair(H, Cin, Cout, ksize, pool, relu, !add && !se_partial && !gate)) {
         // one tile = rows (2*h_tile, 2*h_tile+1) x 128 pixels x 256 channels on a CTA pair
         const bool slab = ksize == 3 && g_kwf_mode != 0;          // kw-fused activation slab (hctr_debug_set_kwf_mode(0) turns it off)
         CUtensorMap tmA, tmB;
@@ -245,6 +257,8 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
         rc = make_weight_map(&tmB, w_packed, Cout, p.ntaps * Cin, block_n / 2);
         if (rc) return rc;
         cudaStream_t cs = static_cast<cudaStream_t>(stream);
+        if (pool)        // identity of the max reduction over ReLU outputs
+            HCTR_CUDA(cudaMemsetAsync(y, 0, (size_t)B * (H / 2) * W * Cout * sizeof(__nv_bfloat16), cs));
         if (add) {
             HCTR_CHECK(se_partial == nullptr, HCTR_ERR_INVALID, "conv: channel sums and a residual cannot be combined");
             return slab ? launch_igemm_pair<256, 3, 1, 1>(tmA, tmB, p, cs) : launch_igemm_pair<256, 3, 0, 1>(tmA, tmB, p, cs);

@@ -24,6 +24,14 @@ __device__ __forceinline__ bool cand_better(float v, int i, float w, int j) {
     return v > w || (v == w && i < j);
 }
 
+// exp(x) for x <= 0 as one multiply and one MUFU: ex2.approx.ftz flushes results below 2^-126 to zero, which is what a
+// sum of exponentials wants (__expf adds a range check and two scalings per element for the denormal range)
+__device__ __forceinline__ float exp_neg_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 template <typename T> struct LoadVec;
 template <> struct LoadVec<float> {
     static constexpr int N = 4;
@@ -67,12 +75,16 @@ template <> struct LoadVec<__nv_bfloat16> {
 // everything per row is kept short:
 //   pass 1  per-thread maximum (ld.shared.v4 + a max tree); maxima of the 16 half-warps -> shared memory
 //   bound   the k-th largest of the 16 half-warp maxima is a valid lower bound tau for the k-th largest element of the
-//           row (k distinct elements are >= it; ~15 elements of a random row reach it); every warp ranks the 16 values
-//           itself (16 broadcast reads), no extra barrier; the row maximum falls out of the same 16 values
+//           row (k distinct elements are >= it; ~15 elements of a random row reach it); each warp ranks two of the 16 values
+//           (one compare per lane + a ballot); the row maximum falls out of the same ranking
 //   pass 2  sum exp(x - max) and collect the few elements >= tau (one compare per vector on its maximum)
 //   rank    candidates ranked by counting (value desc, index asc) -> the top k in order; exact for any input.
 // If more than kMaxCand elements reach tau (e.g. constant rows) an exact k-round arg-max fallback runs instead.
-// Three block barriers per row, no single-thread sections, one 32-bit division per row.
+// Four block barriers per row, no single-thread sections, no division per row.
+// Measured and dropped: a register-resident variant (two warps per row, 29 independent 16-byte loads per lane, both passes
+// on registers, no staging) executes a third fewer instructions but needs 221 registers - 8 warps per SM - and a fully
+// unrolled 2000-instruction body per row: 27 % issue-active (fixed-latency and instruction-fetch stalls), 1.9 ms against
+// 1.2 ms for this kernel on the config-5 tensor.
 constexpr int kTopkThreads = 256;
 constexpr int kMaxCand = 512;
 constexpr int kTopkEdge = 16;          // head + tail elements of a row that do not belong to the aligned interior (< 16 B each)
@@ -89,9 +101,8 @@ struct TopkRow {
     int body_bytes;                    // [lo, hi): multiple of 16 (0 for tiny rows: everything travels through registers)
 };
 template <typename T>
-__device__ __forceinline__ TopkRow topk_row(const T* logits, unsigned row, unsigned Bn, long long stride_t, long long stride_b,
+__device__ __forceinline__ TopkRow topk_row(const T* logits, unsigned t, unsigned b, long long stride_t, long long stride_b,
                                             int row_bytes) {
-    const unsigned t = row / Bn, b = row - t * Bn;
     TopkRow r;
     r.a0 = reinterpret_cast<const unsigned char*>(logits + (long long)t * stride_t + (long long)b * stride_b);
     const uintptr_t a = reinterpret_cast<uintptr_t>(r.a0);
@@ -110,6 +121,7 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
     extern __shared__ __align__(128) unsigned char rowbufs[];      // [nbuf][buf_bytes]
     __shared__ __align__(8) uint64_t full_bar[2];
     __shared__ float gmax[16], red_sum[8];
+    __shared__ float s_tau, s_m;
     __shared__ int s_ncand[2];
     __shared__ float cand_v[kMaxCand];
     __shared__ int cand_i[kMaxCand];
@@ -140,7 +152,10 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
     }
     __syncthreads();
     long long row = blockIdx.x;
-    TopkRow cur = topk_row(logits, (unsigned)(row < rows ? row : 0), (unsigned)Bn, stride_t, stride_b, row_bytes);
+    // (t, b) of the rows this CTA walks, advanced without a division: row += gridDim.x
+    const unsigned step_t = gridDim.x / (unsigned)Bn, step_b = gridDim.x % (unsigned)Bn;
+    unsigned row_t = blockIdx.x / (unsigned)Bn, row_b = blockIdx.x % (unsigned)Bn;
+    TopkRow cur = topk_row(logits, row < rows ? row_t : 0u, row < rows ? row_b : 0u, stride_t, stride_b, row_bytes);
     if (row < rows) {
         if (tid == 0) issue(cur, 0);
         const int off = edge_offset(cur);
@@ -156,7 +171,9 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
         T edge_val = T();
         int edge_off = -1;
         if (next < rows) {
-            nxt = topk_row(logits, (unsigned)next, (unsigned)Bn, stride_t, stride_b, row_bytes);
+            row_t += step_t; row_b += step_b;
+            if (row_b >= (unsigned)Bn) { row_b -= (unsigned)Bn; ++row_t; }
+            nxt = topk_row(logits, row_t, row_b, stride_t, stride_b, row_bytes);
             if (nbuf == 2) {
                 if (tid == 0) issue(nxt, s ^ 1);
                 edge_off = edge_offset(nxt);
@@ -188,25 +205,27 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
         if ((lane & 15) == 0) gmax[tid >> 4] = hmax;
         if (tid == 0) s_ncand[(it + 1) & 1] = 0;
         __syncthreads();
-        // every warp: rank the 16 half-warp maxima (value desc, index asc); tau = the kk-th largest, m = the largest
-        const float gv = gmax[lane & 15];
-        int grank = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float o = gmax[j];
-            grank += (o > gv || (o == gv && j < (lane & 15))) ? 1 : 0;
+        // rank the 16 half-warp maxima (value desc, index asc; a permutation of 0..15): warp w ranks values 2w and 2w+1,
+        // lane l compares value 2w + (l >> 4) with value l & 15, a ballot counts; tau = the kk-th largest, m = the largest
+        {
+            const int vi = 2 * warp + (lane >> 4);
+            const float gv = gmax[vi], o = gmax[lane & 15];
+            const bool ahead = o > gv || (o == gv && (lane & 15) < vi);
+            const unsigned bal = __ballot_sync(0xffffffffu, ahead);
+            const int grank = __popc(lane < 16 ? (bal & 0xffffu) : (bal >> 16));
+            if ((lane & 15) == 0) {
+                if (grank == kk - 1) s_tau = gv;
+                if (grank == 0) s_m = gv;
+            }
         }
-        const unsigned at_tau = __ballot_sync(0xffffffffu, grank == kk - 1) & 0xffffu;
-        const unsigned at_max = __ballot_sync(0xffffffffu, grank == 0) & 0xffffu;
-        // NaN maxima cannot be ranked (every compare is false): fall back to "everything is a candidate"
-        const float tau = at_tau ? __shfl_sync(0xffffffffu, gv, __ffs(at_tau) - 1) : -INFINITY;
-        const float m = at_max ? __shfl_sync(0xffffffffu, gv, __ffs(at_max) - 1) : gv;
+        __syncthreads();
+        const float tau = s_tau, m = s_m;
 
         // ---- pass 2: sum of exp and candidate collection
         float sum = 0.f;
         if (has_sc) {
             const float x = LoadVec<T>::one_smem(rb + sc);
-            sum += __expf(x - m);
+            sum += exp_neg_fast(x - m);
             if (x >= tau) {
                 const int slot = atomicAdd(&s_ncand[it & 1], 1);
                 if (slot < kMaxCand) { cand_v[slot] = x; cand_i[slot] = sc; }
@@ -220,7 +239,7 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
 #pragma unroll
             for (int j = 2; j < V; j += 2) vmax = fmaxf(vmax, fmaxf(x[j], x[j + 1]));
 #pragma unroll
-            for (int j = 0; j < V; ++j) sum += __expf(x[j] - m);
+            for (int j = 0; j < V; ++j) sum += exp_neg_fast(x[j] - m);
             if (!(vmax < tau)) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -631,10 +650,7 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     const long long rows = (long long)T * B;
     HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "topk: too many rows");
     const size_t esz = dtype == HCTR_F32 ? 4 : 2;
-    const int buf_bytes = (int)(((size_t)C * esz + 32 + 127) & ~size_t(127));        // row + 16 bytes of misalignment either side
     HCTR_CHECK((size_t)C * 4 <= 160 * 1024, HCTR_ERR_INVALID, "topk: %d classes do not fit the shared-memory row buffer", C);
-    const int nbuf = 2 * (size_t)buf_bytes <= 200 * 1024 ? 2 : 1;
-    const size_t smem = (size_t)nbuf * buf_bytes;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -644,6 +660,9 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
         HCTR_CUDA(cudaGetDevice(&dev));
         HCTR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    const int buf_bytes = (int)(((size_t)C * esz + 32 + 127) & ~size_t(127));        // row + 16 bytes of misalignment either side
+    const int nbuf = 2 * (size_t)buf_bytes <= 200 * 1024 ? 2 : 1;
+    const size_t smem = (size_t)nbuf * buf_bytes;
     // persistent grid: as many CTAs as fit (shared memory: two row buffers + ~5 KB static each), at most 8 per SM
     long long per_sm = (220 * 1024) / (long long)(smem + 6 * 1024);
     if (per_sm < 1) per_sm = 1;

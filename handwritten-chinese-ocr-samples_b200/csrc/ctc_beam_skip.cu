@@ -131,11 +131,15 @@ ctc_prune_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C,
 
 // ------------------------------------------------------------------------------------------------ search
 __device__ __forceinline__ double sk_logaddexp(double x, double y) {
+    // numpy npy_logaddexp, written with selects (one exp + one log1p for all lanes; same operations, same bits)
+    const double d = __dsub_rn(x, y);
+    const bool pos = d > 0;
+    const double hi = pos ? x : y;
+    const double arg = pos ? -d : d;
+    const double r = __dadd_rn(hi, log1p(exp(arg)));
     if (x == y) return __dadd_rn(x, 0.693147180559945309417232121458176568);
-    const double tmp = __dsub_rn(x, y);
-    if (tmp > 0) return __dadd_rn(x, log1p(exp(-tmp)));
-    if (tmp <= 0) return __dadd_rn(y, log1p(exp(tmp)));
-    return tmp;
+    if (d != d) return d;
+    return r;
 }
 __device__ __forceinline__ unsigned long long sk_mix(unsigned long long h, int c) {
     h ^= (unsigned long long)(c + 1) * 0x9E3779B97F4A7C15ull;

@@ -285,9 +285,12 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const bool ok = (w < p.W) && (h < p.H);
             // element offset of (this warp's pixel 0, first column of this warp's half); pixel r of the warp is r*N further
             const int wq = w_tile * kTileM + quad * 32;
+            // pooled layers (p.pool): both CTAs of the pair own one of the two rows of a (2,1) max-pool window and combine
+            // them in the pooled row h_tile of the [B][H/2][W][N] output with a vector bf16 max reduction in L2 (below)
+            const int ho = p.pool ? tl.h_tile : h;
             const size_t warp_off = (p.out_line_pitch
-                ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + wq) * p.N
-                : ((static_cast<size_t>(b) * p.H + h) * p.W + wq) * p.N) + n_tile * kPairBlockN + half * (kPairBlockN / 2);
+                ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(ho) * p.W + wq) * p.N
+                : ((static_cast<size_t>(b) * p.out_H + ho) * p.W + wq) * p.N) + n_tile * kPairBlockN + half * (kPairBlockN / 2);
             // transposed role of this lane: 16-byte piece tq of pixel rows tr, tr+8, tr+16, tr+24
             const int tr = lane >> 2, tq = lane & 3;
             uint8_t* ebuf = epi_base + (warp - 2) * (32 * L::kEpiPitch);
@@ -395,9 +398,18 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = tr + 8 * i;
-                        if (wq + r < p.W)
-                            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + warp_off + static_cast<size_t>(r) * p.N + ck * 32 + tq * 8) =
-                                *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                        if (wq + r < p.W) {
+                            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + warp_off + static_cast<size_t>(r) * p.N + ck * 32 + tq * 8;
+                            const uint4 val = *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                            if (p.pool) {
+                                // max(relu(a), relu(b)) with the output zero-filled by the host: every operand is >= 0, so
+                                // the order of the two CTAs' reductions does not matter and bf16 max is exact
+                                asm volatile("red.relaxed.gpu.global.max.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+                                             :: "l"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+                            } else {
+                                *reinterpret_cast<uint4*>(dst) = val;
+                            }
+                        }
                     }
                 }
                 __syncwarp();

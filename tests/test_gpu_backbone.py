@@ -53,6 +53,8 @@ CONV_CASES = [
     (2, 6, 700, 256, 256, 3, 1, 0),           # CTA-pair kernel: several tiles per pair, ragged last span
     (1, 5, 140, 256, 256, 3, 1, 0),           # odd height: the wide layer stays on the single-CTA kernel
     (3, 2, 64, 512, 256, 1, 0, 0),            # 1x1 on the pair kernel (K blocks in pairs)
+    (2, 6, 700, 256, 256, 3, 1, 1),           # pooled layer on the pair kernel (max reduction across the two CTAs), ragged
+    (5, 16, 1100, 512, 512, 3, 1, 1),         # the same with more column tiles than CTA pairs
 ]
 
 
