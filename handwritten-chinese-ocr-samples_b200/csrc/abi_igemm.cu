@@ -89,10 +89,10 @@ static int sm_count() {
     return n;
 }
 
-template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0, int ADDREG = 0>
+template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
     using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES, KWF>;
-    auto kern = igemm_tcgen05_kernel<BLOCK_N, NUM_SUB, STAGES, ACC_STAGES, EPI, KWF, ADDREG>;
+    auto kern = igemm_tcgen05_kernel<BLOCK_N, NUM_SUB, STAGES, ACC_STAGES, EPI, KWF>;
     static bool configured = false;   // per instantiation
     if (!configured) {
         HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -277,7 +277,6 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (kwf) {
         if (block_n == 64) return launch_igemm<64, 2, 3, 2, EPI_CONV, 1>(tmA, tmB, p, s);
-        if (add && !pool) return launch_igemm<128, 2, 2, 2, EPI_CONV, 1, 1>(tmA, tmB, p, s);      // residual through registers
         return launch_igemm<128, 2, 2, 2, EPI_CONV, 1>(tmA, tmB, p, s);
     }
     switch (block_n) {

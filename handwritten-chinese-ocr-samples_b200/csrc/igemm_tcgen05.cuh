@@ -77,9 +77,7 @@ struct IgemmSmem {
     static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
 };
 
-// ADDREG = 1 (BLOCK_N <= 128, un-pooled, p.add set): the residual of the tile is fetched into registers before the wait
-// on the accumulator (see the epilogue); a separate instantiation so that the other variants keep their register budget.
-template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0, int ADDREG = 0>
+template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmB,
@@ -228,35 +226,20 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             const int h0 = h_tile * sub_rows;
             const int w0 = w_tile * sub_cols * kTileM;
 
-            // Residual (p.add): fetched BEFORE the wait on the accumulator so that its latency hides behind the main loop of
-            // this tile - into registers for the thin tiles (BLOCK_N <= 128: 2 sub-tiles x 2 chunks x 64 B per thread; fetched
-            // per chunk after the wait the residual variant of 128->128 ran at 800 instead of 950 TFLOP/s), as an L2
-            // prefetch for BLOCK_N = 256 (128 registers would not fit).
-            constexpr bool kRegResidual = (EPI == EPI_CONV) && (BLOCK_N <= 128) && (ADDREG != 0);
-            constexpr int kWarpChunks = BLOCK_N / 2 / 32;
-            uint4 rres[kRegResidual ? NUM_SUB * kWarpChunks * 4 : 1];
             if constexpr (EPI == EPI_CONV) {
                 if (p.add && !p.pool) {
+                    // pull this tile's residual rows into L2 while its main loop is still running
 #pragma unroll
                     for (int s = 0; s < NUM_SUB; ++s) {
                         const int w = w0 + s * p.sub_dw * kTileM + pix;
                         const int h = h0 + s * p.sub_dh;
-                        const bool inb = w < p.W && h < p.out_H;
-                        const size_t off = p.out_line_pitch
-                            ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N
-                            : ((static_cast<size_t>(b) * p.out_H + h) * p.W + w) * p.N;
-                        const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(p.add) + off + n_tile * BLOCK_N + half * (BLOCK_N / 2);
-                        if constexpr (kRegResidual) {
+                        if (w < p.W && h < p.out_H) {
+                            const size_t off = p.out_line_pitch
+                                ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + w) * p.N
+                                : ((static_cast<size_t>(b) * p.out_H + h) * p.W + w) * p.N;
+                            const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(p.add) + off + n_tile * BLOCK_N + half * (BLOCK_N / 2);
 #pragma unroll
-                            for (int q = 0; q < kWarpChunks * 4; ++q) {
-                                rres[s * kWarpChunks * 4 + q] = make_uint4(0u, 0u, 0u, 0u);
-                                if (inb) rres[s * kWarpChunks * 4 + q] = ld_nc_v4(r + q * 8);
-                            }
-                        } else {
-                            if (inb) {
-#pragma unroll
-                                for (int q = 0; q < BLOCK_N / 2; q += 64) asm volatile("prefetch.global.L2 [%0];" :: "l"(r + q));
-                            }
+                            for (int q = 0; q < BLOCK_N / 2; q += 64) asm volatile("prefetch.global.L2 [%0];" :: "l"(r + q));
                         }
                     }
                 }
@@ -268,9 +251,8 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             float run_m[NUM_SUB], run_s[NUM_SUB];
 #pragma unroll
             for (int s = 0; s < NUM_SUB; ++s) { run_m[s] = -3.0e38f; run_s[s] = 0.f; }
-#pragma unroll (kRegResidual ? kWarpChunks : 1)
-            for (int ci = 0; ci < kWarpChunks; ++ci) {
-                const int c0 = half * (BLOCK_N / 2) + ci * 32;
+#pragma unroll 1
+            for (int c0 = half * (BLOCK_N / 2); c0 < (half + 1) * (BLOCK_N / 2); c0 += 32) {
                 const int n0 = n_tile * BLOCK_N + c0;
                 if (n0 >= p.N) break;                    // warp-uniform
                 float v[NUM_SUB][32];
@@ -365,9 +347,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                     const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.add) + off);
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
-                                        uint4 a;
-                                        if constexpr (kRegResidual) a = rres[(s * kWarpChunks + ci) * 4 + q];
-                                        else a = ld_nc_v4(src + q);
+                                        const uint4 a = ld_nc_v4(src + q);
                                         v[s][8 * q + 0] += bf16_lo(a.x); v[s][8 * q + 1] += bf16_hi(a.x);
                                         v[s][8 * q + 2] += bf16_lo(a.y); v[s][8 * q + 3] += bf16_hi(a.y);
                                         v[s][8 * q + 4] += bf16_lo(a.z); v[s][8 * q + 5] += bf16_hi(a.z);
