@@ -183,7 +183,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const PairTile tl = pair_tile(p, pair_id, num_pairs, it);
@@ -231,7 +231,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         if constexpr (KWF) {
                             const int kh = kb / p.cin_chunks;
                             const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);

@@ -120,7 +120,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.n_tiles;
@@ -173,7 +173,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t b_addr = a_addr + NUM_SUB * L::kABytes;
                     if constexpr (KWF) {

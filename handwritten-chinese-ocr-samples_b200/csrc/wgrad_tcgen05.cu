@@ -92,7 +92,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 int split, tap, mt, nt; decode(item, split, tap, mt, nt);
@@ -128,7 +128,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
                     const uint32_t b_addr = a_addr + L::kABytes;
 #pragma unroll
