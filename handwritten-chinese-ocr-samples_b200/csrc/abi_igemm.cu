@@ -79,24 +79,27 @@ static int make_weight_map(CUtensorMap* m, const void* w, int N, int K, int bloc
 }
 
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
+        int n = 0;
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        once.mark(dev, n);
+        return n;
     }
-    return n;
+    return once.get(dev);
 }
 
 template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
     using L = IgemmSmem<BLOCK_N, NUM_SUB, STAGES, KWF>;
     auto kern = igemm_tcgen05_kernel<BLOCK_N, NUM_SUB, STAGES, ACC_STAGES, EPI, KWF>;
-    static bool configured = false;   // per instantiation
-    if (!configured) {
+    static PerDeviceOnce once;        // per instantiation
+    int dev;
+    if (once.need(dev)) {
         HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        configured = true;
+        once.mark(dev);
     }
     int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
     kern<<<grid, kIgemmThreads, L::kTotal, stream>>>(tmA, tmB, p);
@@ -141,8 +144,12 @@ template <int BLOCK_N, int STAGES, int KWF, int ADD>
 static int launch_igemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmParams& p, cudaStream_t stream) {
     using L = PairSmem<BLOCK_N, STAGES, KWF>;
     auto kern = igemm_pair_kernel<BLOCK_N, STAGES, KWF, ADD>;
-    static int max_clusters = 0;      // per instantiation
-    if (max_clusters == 0) {
+    static PerDeviceOnce once;        // per instantiation; value = max active clusters on that device
+    int dev;
+    int max_clusters = 0;
+    if (!once.need(dev)) {
+        max_clusters = once.get(dev);
+    } else {
         HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * sm_count());
@@ -156,6 +163,7 @@ static int launch_igemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         HCTR_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
         HCTR_CHECK(n > 0, HCTR_ERR_CUDA, "conv: the CTA-pair kernel does not fit this device");
         max_clusters = n;
+        once.mark(dev, n);
         if (getenv("HCTR_DEBUG")) fprintf(stderr, "hctr_b200: igemm_pair_kernel<%d> max active clusters = %d (SMs %d)\n", BLOCK_N, n, sm_count());
     }
     const int pairs = p.total_tiles < max_clusters ? p.total_tiles : max_clusters;

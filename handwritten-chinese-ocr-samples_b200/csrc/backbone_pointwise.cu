@@ -393,10 +393,12 @@ int hctr_se_gate_from_input(const void* t, const float* partial, int slices, con
     se_gate_sums_kernel<<<dim3(B, kGateSplit), 256, sm1, s>>>(static_cast<const __nv_bfloat16*>(t), partial, slices, psum, H, W, C);
     HCTR_CUDA(cudaGetLastError());
     const size_t sm2 = (size_t)17 * C * sizeof(float);
-    static size_t configured = 0;
-    if (sm2 > configured) {
-        HCTR_CUDA(cudaFuncSetAttribute(se_gate_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-        configured = sm2;
+    HCTR_CHECK(sm2 <= 200 * 1024, HCTR_ERR_INVALID, "se_gate: %d channels do not fit shared memory", C);
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
+        HCTR_CUDA(cudaFuncSetAttribute(se_gate_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        once.mark(dev);
     }
     se_gate_mean_kernel<<<dim3(B, (C + kGateCo - 1) / kGateCo), 512, sm2, s>>>(
         static_cast<const __nv_bfloat16*>(t), psum, static_cast<const __nv_bfloat16*>(conv_w_packed), scale, shift, mean_z, H, W, C);

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 
@@ -40,6 +41,27 @@ enum : int {
 };
 
 enum : int { HCTR_F32 = 0, HCTR_BF16 = 1 };
+
+// ---------------------------------------------------------------- per-device one-time setup (host)
+// cudaFuncSetAttribute and occupancy numbers belong to a device; a process may drive several (the ABI promises
+// re-entrancy across devices). Each launcher keeps one of these per kernel: `int dev; if (once.need(dev)) {...; once.mark(dev);}`.
+// Racing threads at worst configure twice (idempotent).
+struct PerDeviceOnce {
+    static constexpr int kMaxDev = 64;
+    std::atomic<unsigned long long> done{0};
+    int value[kMaxDev] = {};                     // optional per-device result (occupancy, SM count)
+    bool need(int& dev) {
+        dev = 0;
+        cudaGetDevice(&dev);
+        return dev < 0 || dev >= kMaxDev || !((done.load(std::memory_order_acquire) >> dev) & 1ull);
+    }
+    void mark(int dev, int v = 0) {
+        if (dev < 0 || dev >= kMaxDev) return;
+        value[dev] = v;
+        done.fetch_or(1ull << dev, std::memory_order_release);
+    }
+    int get(int dev) const { return (dev >= 0 && dev < kMaxDev) ? value[dev] : 0; }
+};
 
 // ---------------------------------------------------------------- small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -652,13 +652,15 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     const size_t esz = dtype == HCTR_F32 ? 4 : 2;
     HCTR_CHECK((size_t)C * 4 <= 160 * 1024, HCTR_ERR_INVALID, "topk: %d classes do not fit the shared-memory row buffer", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    static int num_sms = 0;
-    if (num_sms == 0) {
+    static PerDeviceOnce once;                     // value = SM count of the device
+    int dev, num_sms;
+    if (once.need(dev)) {
         HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        int dev = 0;
-        HCTR_CUDA(cudaGetDevice(&dev));
         HCTR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        once.mark(dev, num_sms);
+    } else {
+        num_sms = once.get(dev);
     }
     const int buf_bytes = (int)(((size_t)C * esz + 32 + 127) & ~size_t(127));        // row + 16 bytes of misalignment either side
     const int nbuf = 2 * (size_t)buf_bytes <= 200 * 1024 ? 2 : 1;

@@ -489,11 +489,14 @@ int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, in
     long long tables = rows * (8 + 4 + kSkMaxC * 8);
     tables = (tables + 255) & ~255ll;
     unsigned char* seq_ws = reinterpret_cast<unsigned char*>(base + tables);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
         HCTR_CUDA(cudaFuncSetAttribute(ctc_prune_logsoftmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         HCTR_CUDA(cudaFuncSetAttribute(ctc_prune_logsoftmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_skip_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSkMaxBeam * (kSkMaxC + 1) * 32));
+        once.mark(dev);
     }
     if (dtype == HCTR_F32)
         ctc_prune_logsoftmax_kernel<float><<<(int)rows, kPruneThreads, smem, s>>>(static_cast<const float*>(logits), T, B, C, stride_t,
@@ -503,12 +506,6 @@ int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, in
             static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, meta, blank, cidx, clp);
     HCTR_CUDA(cudaGetLastError());
     const size_t dyn = (size_t)beam_size * (kSkMaxC + 1) * (3 * sizeof(double) + sizeof(int) + 2 * sizeof(short));
-    static bool configured2 = false;
-    if (!configured2) {
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_skip_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSkMaxBeam * (kSkMaxC + 1) * 32));
-        configured2 = true;
-    }
     ctc_skip_beam_kernel<<<B, kSkThreads, dyn, s>>>(meta, blank, cidx, clp, T, B, C, beam_size, lm_penalty, len_bonus, lm_table, lm,
                                                     out_idx, out_len, status, seq_ws, sk_ws_per_seq(T));
     HCTR_CUDA(cudaGetLastError());

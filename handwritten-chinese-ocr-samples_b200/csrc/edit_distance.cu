@@ -76,10 +76,11 @@ extern "C" int hctr_edit_distance(const int32_t* pred_idx, const int32_t* pred_l
     if (B == 0) return HCTR_OK;
     const size_t smem = 2 * (size_t)(max_pred_len + 1) * sizeof(int);
     HCTR_CHECK(smem <= 200 * 1024, HCTR_ERR_INVALID, "edit_distance: prediction too long (%d)", max_pred_len);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
         HCTR_CUDA(cudaFuncSetAttribute(edit_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+        once.mark(dev);
     }
     edit_distance_kernel<<<B, kEdThreads, smem, static_cast<cudaStream_t>(stream)>>>(pred_idx, pred_len, pred_pitch, targets,
                                                                                   target_lengths, dist);

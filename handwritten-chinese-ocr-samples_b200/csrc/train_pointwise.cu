@@ -634,10 +634,11 @@ int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int 
     p.dw1 = dw1; p.dw2 = dw2; p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.P = P; p.Q = Q; p.R = R;
     const size_t smem = ((size_t)4 * B * C + (size_t)B * (gate ? Cr : 0)) * sizeof(float);
     HCTR_CHECK(smem <= 200 * 1024, HCTR_ERR_INVALID, "train_bwd_finalize: B*C too large for one block (%zu bytes)", smem);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
         HCTR_CUDA(cudaFuncSetAttribute(train_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+        once.mark(dev);
     }
     bwd_slice_reduce_kernel<<<(B * C + 63) / 64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         const_cast<float*>(pA2), const_cast<float*>(pA3), slices, B, C);

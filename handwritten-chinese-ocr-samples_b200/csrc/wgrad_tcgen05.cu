@@ -234,10 +234,11 @@ template <int BLOCK_N, int NUM_SUB, int STAGES>
 static int launch_wgrad(const CUtensorMap& g, const CUtensorMap& x, const WgradParams& p, cudaStream_t s) {
     using L = WgSmem<BLOCK_N, NUM_SUB, STAGES>;
     auto kern = wgrad_tcgen05_kernel<BLOCK_N, NUM_SUB, STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;        // per instantiation
+    int cfg_dev;
+    if (once.need(cfg_dev)) {
         HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-        configured = true;
+        once.mark(cfg_dev);
     }
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
