@@ -372,3 +372,26 @@ def test_model_same_with_and_without_the_fused_se_path():
         m.se_from_input = False; b = m(x).float()
     scale = b.abs().max().item()
     assert (a - b).abs().max().item() <= 0.06 * scale and (a - b).abs().mean().item() <= 0.01 * scale
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_one_process_drives_two_devices():
+    """The library keeps its one-time setup (function attributes, occupancy) per device: the same process runs the model,
+    the codec and the beam search on cuda:0 and cuda:1 (the current device stays 0) with bit-identical results."""
+    from hctr_b200.utils.ctc_codec import ctc_codec
+    x = torch.from_numpy(synth.text_lines(2, 300, 71))
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        m = _model(101, 9).to(dev).eval()
+        logits = m(x.to(dev))
+        codec = ctc_codec(synth.charset(99))
+        idx, ln = codec.greedy_indices(logits)
+        codec.set_beam_search(use_tfm_pred=False, len_bonus=0.0)
+        peaky = torch.from_numpy(synth.beam_logits(40, 2, 101, 5, 4)).to(dev)
+        bidx, bln = codec.beam_search_indices(peaky)
+        torch.cuda.synchronize(dev)
+        outs.append((logits.cpu(), idx.cpu(), ln.cpu(), bidx.cpu(), bln.cpu()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    assert torch.cuda.current_device() == 0
