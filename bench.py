@@ -330,9 +330,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        cval, cdt = run_cpu_sample(WIDTH, 1, repeats=2)
+        # bounded sample: one untimed warm-up line (thread pool, oneDNN primitives), then ~10-15 s of CPU work
+        run_cpu_sample(WIDTH, 1, repeats=1)
+        cval, cdt = run_cpu_sample(WIDTH, 1, repeats=8)
         cpu_baseline = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "2 steps of 1 line 128x2048 (fp32 torch forward + C greedy decode, %.1f s/step)" % cdt}
+                        "sample": "8 steps of 1 line 128x2048 after 1 warm-up (fp32 torch forward + C greedy decode, %.1f s/step)" % cdt}
 
     if rank == 0:
         out = {
