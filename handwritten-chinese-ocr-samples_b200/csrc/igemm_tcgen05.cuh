@@ -74,7 +74,11 @@ struct IgemmSmem {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = NUM_SUB * kABytes + (KWF ? 3 : 1) * kBBytes;
     static constexpr int kBarBytes = 1024;
-    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024 /*alignment slack*/;
+    // epilogue staging: per epilogue warp 32 pixel rows of one 32-channel chunk (64 B, pitch 80 B = conflict-free for the
+    // per-pixel and the transposed access): per-thread 16-byte global stores at a 2*N-byte stride become 64-byte runs
+    static constexpr int kEpiPitch = 80;
+    static constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch;
+    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + 1024 /*alignment slack*/;
 };
 
 template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0>
@@ -97,6 +101,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     uint64_t* acc_full = empty_bar + STAGES;                               // [ACC_STAGES]
     uint64_t* acc_empty = acc_full + ACC_STAGES;                           // [ACC_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+    uint8_t* epi_base = bar_base + L::kBarBytes;                           // [kEpiWarps][32][kEpiPitch]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -244,6 +249,24 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     }
                 }
             }
+            // per-channel epilogue factors of this warp's columns, one column per lane and chunk, fetched before the wait on the
+            // accumulator and broadcast by shuffle below (vector __ldg's per chunk sat on the epilogue's critical path, which
+            // bounds the 1x1 and 64-channel layers): y = acc*scale + shift, times the SE gate when it is folded in
+            constexpr int kWarpChunks = BLOCK_N / 2 / 32;
+            float scl[kWarpChunks], shl[kWarpChunks];
+            if constexpr (EPI == EPI_CONV) {
+#pragma unroll
+                for (int ck = 0; ck < kWarpChunks; ++ck) {
+                    const int n = n_tile * BLOCK_N + half * (BLOCK_N / 2) + ck * 32 + lane;
+                    scl[ck] = __ldg(p.scale + n); shl[ck] = __ldg(p.shift + n);
+                    if (p.gate) {
+                        const float gt = __ldg(p.gate + static_cast<size_t>(b) * p.N + n);
+                        scl[ck] *= gt; shl[ck] *= gt;
+                    }
+                }
+            }
+            uint8_t* ebuf = epi_base + (warp - 2) * (32 * L::kEpiPitch);
+            const int tr = lane >> 2, tq = lane & 3;     // transposed role: 16-byte piece tq of pixel rows tr, tr+8, tr+16, tr+24
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
@@ -252,7 +275,8 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
             for (int s = 0; s < NUM_SUB; ++s) { run_m[s] = -3.0e38f; run_s[s] = 0.f; }
 #pragma unroll 1
-            for (int c0 = half * (BLOCK_N / 2); c0 < (half + 1) * (BLOCK_N / 2); c0 += 32) {
+            for (int ck = 0; ck < kWarpChunks; ++ck) {
+                const int c0 = half * (BLOCK_N / 2) + ck * 32;
                 const int n0 = n_tile * BLOCK_N + c0;
                 if (n0 >= p.N) break;                    // warp-uniform
                 float v[NUM_SUB][32];
@@ -260,26 +284,15 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                 for (int s = 0; s < NUM_SUB; ++s) tmem_ld_32x32(t_base + s * BLOCK_N + c0, v[s]);
 
                 if constexpr (EPI == EPI_CONV) {
-                    // y = acc*scale + shift  (conv bias and eval-mode BN folded, fp32), ReLU, H-pair max
+                    // y = acc*scale + shift  (conv bias and eval-mode BN folded, fp32; SE gate folded into both), ReLU, H-pair max
+                    float sc_l = scl[0], sh_l = shl[0];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
-                        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + j));
+                    for (int q = 1; q < kWarpChunks; ++q) { if (ck == q) { sc_l = scl[q]; sh_l = shl[q]; } }
 #pragma unroll
-                        for (int s = 0; s < NUM_SUB; ++s) {
-                            v[s][j + 0] = fmaf(v[s][j + 0], sc.x, sh.x);
-                            v[s][j + 1] = fmaf(v[s][j + 1], sc.y, sh.y);
-                            v[s][j + 2] = fmaf(v[s][j + 2], sc.z, sh.z);
-                            v[s][j + 3] = fmaf(v[s][j + 3], sc.w, sh.w);
-                        }
-                    }
-                    if (p.gate) {
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __shfl_sync(0xffffffffu, sc_l, j), sh = __shfl_sync(0xffffffffu, sh_l, j);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 gt = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(b) * p.N + n0 + j));
-#pragma unroll
-                            for (int s = 0; s < NUM_SUB; ++s) { v[s][j] *= gt.x; v[s][j + 1] *= gt.y; v[s][j + 2] *= gt.z; v[s][j + 3] *= gt.w; }
-                        }
+                        for (int s = 0; s < NUM_SUB; ++s) v[s][j] = fmaf(v[s][j], sc, sh);
                     }
                     if (p.se_partial) {
                         // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum over this
@@ -317,23 +330,32 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     }
                     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
                     if (p.pool) {
-                        const int w = w0 + pix;
                         const int ho = h_tile;
-                        if (w < p.W && ho < p.out_H) {
-                            uint32_t pk[16];
+                        const int wq = w0 + quad * 32;                   // this warp's first pixel
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) {
-                                float a0 = fmaxf(v[0][j], v[NUM_SUB - 1][j]);
-                                float a1 = fmaxf(v[0][j + 1], v[NUM_SUB - 1][j + 1]);
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float a0 = fmaxf(v[0][8 * q + 2 * j], v[NUM_SUB - 1][8 * q + 2 * j]);
+                                float a1 = fmaxf(v[0][8 * q + 2 * j + 1], v[NUM_SUB - 1][8 * q + 2 * j + 1]);
                                 if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                                pk[j >> 1] = pack_bf16x2(a0, a1);
+                                pk[j] = pack_bf16x2(a0, a1);
                             }
-                            uint4* dst = reinterpret_cast<uint4*>(
-                                out + ((static_cast<size_t>(b) * p.out_H + ho) * p.W + w) * p.N + n0);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            *reinterpret_cast<uint4*>(ebuf + lane * L::kEpiPitch + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
+                        __syncwarp();
+                        if (ho < p.out_H) {
+                            __nv_bfloat16* obase = out + ((static_cast<size_t>(b) * p.out_H + ho) * p.W + wq) * p.N + n0;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int r = tr + 8 * i;
+                                if (wq + r < p.W)
+                                    *reinterpret_cast<uint4*>(obase + static_cast<size_t>(r) * p.N + tq * 8) =
+                                        *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                            }
+                        }
+                        __syncwarp();
                     } else {
 #pragma unroll
                         for (int s = 0; s < NUM_SUB; ++s) {
@@ -354,18 +376,34 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                         v[s][8 * q + 6] += bf16_lo(a.w); v[s][8 * q + 7] += bf16_hi(a.w);
                                     }
                                 }
-                                uint32_t pk[16];
-#pragma unroll
-                                for (int j = 0; j < 32; j += 2) {
-                                    float a0 = v[s][j], a1 = v[s][j + 1];
-                                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                                    pk[j >> 1] = pack_bf16x2(a0, a1);
-                                }
-                                uint4* dst = reinterpret_cast<uint4*>(out + off);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    dst[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                             }
+                            // pack, stage this lane's pixel row, write the chunk out as 64-byte runs
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float a0 = v[s][8 * q + 2 * j], a1 = v[s][8 * q + 2 * j + 1];
+                                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+                                    pk[j] = pack_bf16x2(a0, a1);
+                                }
+                                *reinterpret_cast<uint4*>(ebuf + lane * L::kEpiPitch + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            }
+                            __syncwarp();
+                            if (h < p.out_H) {
+                                const int wq = w0 + s * p.sub_dw * kTileM + quad * 32;       // this warp's first pixel
+                                const size_t woff = p.out_line_pitch
+                                    ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + wq) * p.N + n0
+                                    : ((static_cast<size_t>(b) * p.out_H + h) * p.W + wq) * p.N + n0;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int r = tr + 8 * i;
+                                    if (wq + r < p.W)
+                                        *reinterpret_cast<uint4*>(out + woff + static_cast<size_t>(r) * p.N + tq * 8) =
+                                            *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                                }
+                            }
+                            __syncwarp();
                         }
                     }
                 } else {
