@@ -81,6 +81,7 @@ SIGNATURES = {
     "hctr_sgd_workspace_bytes": (_L, []),
     "hctr_edit_distance": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "hctr_normalize_pad": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "hctr_resize_area_u8": (_I, [_P, _I, _I, _L, _P, _I, _I, _L, _P]),
 }
 
 _lib = None

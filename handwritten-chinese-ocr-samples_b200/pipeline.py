@@ -47,6 +47,37 @@ def shard_batches(batches, world):
     return out
 
 
+def resized_width(src_h, src_w, height=128, rule="dataset"):
+    """Width of a line after the reference's resize to `height`: utils/dataset.py:54-55 (`int(width * (img_h / height))`,
+    rule "dataset") or test.py:210-212 (`int(height * (float(w) / float(h)))`, rule "test")."""
+    if rule == "dataset":
+        return int(src_w * (height / src_h))
+    if rule == "test":
+        return int(height * (float(src_w) / float(src_h)))
+    raise ValueError("rule must be 'dataset' or 'test'")
+
+
+def resize_line(image, height=128, rule="dataset", device=None):
+    """cv2.resize(image, (new_width, height), interpolation=cv2.INTER_AREA) on the GPU, bit-identical to OpenCV
+    (reference: utils/dataset.py:53-57, test.py:206-214). image: uint8 [h,w] numpy array or CUDA tensor (any row stride).
+    Returns a uint8 CUDA tensor [height, new_width]."""
+    if isinstance(image, np.ndarray):
+        if device is None:
+            raise ValueError("resize_line: a device is needed for a host image")
+        image = torch.from_numpy(np.ascontiguousarray(image, dtype=np.uint8)).to(device, non_blocking=True)
+    if image.dtype != torch.uint8 or image.dim() != 2 or not image.is_cuda or image.stride(1) != 1:
+        raise ValueError("resize_line: expected a uint8 [h,w] CUDA tensor with unit column stride")
+    h, w = image.shape
+    new_w = resized_width(h, w, height, rule)
+    if new_w <= 0:
+        raise ValueError("resize_line: the line collapses to zero width")
+    with torch.cuda.device(image.device):
+        out = torch.empty((height, new_w), dtype=torch.uint8, device=image.device)
+        nat.check(nat.lib().hctr_resize_area_u8(nat.ptr(image), h, w, image.stride(0), nat.ptr(out), height, new_w, new_w,
+                                                nat.stream_ptr()), "resize_area")
+    return out
+
+
 def make_batch(images, indices, width, device):
     """uint8 [128,w] numpy lines -> device fp32 [B,1,128,width], normalised and border-padded on the GPU."""
     H = images[indices[0]].shape[0]

@@ -288,6 +288,14 @@ long long hctr_sgd_workspace_bytes(void);
 int hctr_normalize_pad(const void* pixels, const long long* offsets, const int32_t* widths, float* out, int B, int H,
                        int Wb, void* stream);
 
+/* cv2.resize(line, (dst_w, dst_h), interpolation=cv2.INTER_AREA) for one uint8 grayscale line (device pointers, row pitches in
+ * bytes): the reference's resize to height 128 in front of NormalizePAD (utils/dataset.py:53-57, test.py:206-214; the caller
+ * computes dst_w = int(src_w * dst_h / src_h) as the reference does). Bit-identical to OpenCV's C++ paths: area-weighted
+ * mean (float32, table order) when both scale factors are >= 1, integer-sum fast path for integer factors, otherwise the
+ * bilinear fixed-point path with INTER_AREA's coefficient rule. */
+int hctr_resize_area_u8(const void* src, int src_h, int src_w, long long src_pitch, void* dst, int dst_h, int dst_w,
+                        long long dst_pitch, void* stream);
+
 /* ---- evaluation (the step after decode: main.py:497-517, test.py:266-286) -------------------------------------- */
 
 /* Levenshtein distance of each decoded label sequence to its ground truth (editdistance.eval(pre, tru)); CER =

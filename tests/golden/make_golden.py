@@ -286,8 +286,30 @@ def make_pad():
     np.savez_compressed(os.path.join(HERE, "pad.npz"), **out)
 
 
+def make_resize():
+    """cv2.resize(..., INTER_AREA) to height 128 exactly as the reference calls it (utils/dataset.py:53-57, test.py:206-214):
+    random lines of the listed sizes plus the five bundled images (sources stored: the GPU box has no /root/reference)."""
+    import cv2
+    out = {"cv2_version": np.array(cv2.__version__)}
+    for i, (sh, sw, seed) in enumerate(synth.RESIZE_CASES):
+        src = synth.resize_source(sh, sw, seed)
+        ratio = 128 / sh
+        new_w = int(sw * ratio)                                            # utils/dataset.py:54-55
+        out["dst%d" % i] = cv2.resize(src, (new_w, 128), interpolation=cv2.INTER_AREA)
+    names = sorted(f for f in os.listdir("/root/reference/images") if f.startswith("0000") and f.endswith(".jpg"))
+    for i, f in enumerate(names):
+        src = cv2.imread(os.path.join("/root/reference/images", f))
+        src = cv2.cvtColor(src, cv2.COLOR_BGR2GRAY)                        # test.py:207-208
+        ratio = float(src.shape[1]) / float(src.shape[0])
+        tw = int(128 * ratio)                                              # test.py:210-212
+        out["img_src%d" % i] = src
+        out["img_dst%d" % i] = cv2.resize(src, (tw, 128), fx=0, fy=0, interpolation=cv2.INTER_AREA)
+    np.savez_compressed(os.path.join(HERE, "resize.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["greedy", "beam", "beam_ngram", "beam_skip", "beam_skip_ngram", "ctc_loss", "model", "config1", "pad"]
+    which = sys.argv[1:] or ["greedy", "beam", "beam_ngram", "beam_skip", "beam_skip_ngram", "ctc_loss", "model", "config1", "pad",
+                             "resize"]
     for w in which:
         print("making", w, flush=True)
         globals()["make_" + w]()

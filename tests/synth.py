@@ -133,3 +133,18 @@ def arpa_text(chars, order, seed, vocab_frac=0.8, grams_per_order=400):
         lines.append("")
     lines.append("\\end\\")
     return "\n".join(lines) + "\n"
+
+
+# cv2.resize(INTER_AREA) parity cases (tests/golden/resize.npz): (source height, source width, seed) - shrinking (area-weighted
+# mean), enlarging (bilinear with INTER_AREA coefficients), integer factors (fast path), mixed factors, tiny sources
+RESIZE_CASES = [
+    (359, 500, 1), (250, 371, 2), (183, 378, 3), (130, 696, 4), (347, 179, 5),
+    (110, 272, 6), (57, 427, 7), (30, 634, 8), (99, 635, 9),
+    (384, 300, 10), (512, 512, 11), (640, 333, 12), (128, 300, 13), (256, 512, 14),
+    (127, 100, 15), (129, 100, 16), (300, 50, 17), (9, 40, 18),
+]
+
+
+def resize_source(sh, sw, seed):
+    """Random uint8 line of the given size (legacy RandomState, as the fixture generator uses)."""
+    return np.random.RandomState(1000 + seed).randint(0, 256, size=(sh, sw)).astype(np.uint8)
