@@ -79,16 +79,22 @@ def resize_line(image, height=128, rule="dataset", device=None):
 
 
 def make_batch(images, indices, width, device):
-    """uint8 [128,w] numpy lines -> device fp32 [B,1,128,width], normalised and border-padded on the GPU."""
+    """uint8 [128,w] lines (numpy arrays, or CUDA tensors as `resize_line` returns them) -> device fp32 [B,1,128,width],
+    normalised and border-padded on the GPU."""
     H = images[indices[0]].shape[0]
     ws = np.array([images[i].shape[1] for i in indices], dtype=np.int32)
     if int(ws.max()) > width:
         raise ValueError("a line is wider than its bucket")
     offs = np.zeros(len(indices), dtype=np.int64)
     offs[1:] = np.cumsum(ws[:-1].astype(np.int64) * H)
-    flat = np.concatenate([np.ascontiguousarray(images[i], dtype=np.uint8).reshape(-1) for i in indices])
+    on_device = isinstance(images[indices[0]], torch.Tensor)
+    if not on_device:
+        flat = np.concatenate([np.ascontiguousarray(images[i], dtype=np.uint8).reshape(-1) for i in indices])
     with torch.cuda.device(device):
-        pix = torch.from_numpy(flat).to(device, non_blocking=True)
+        if on_device:
+            pix = torch.cat([images[i].to(device).contiguous().reshape(-1) for i in indices])
+        else:
+            pix = torch.from_numpy(flat).to(device, non_blocking=True)
         d_off = torch.from_numpy(offs).to(device, non_blocking=True)
         d_w = torch.from_numpy(ws).to(device, non_blocking=True)
         out = torch.empty((len(indices), 1, H, width), dtype=torch.float32, device=device)
@@ -97,16 +103,28 @@ def make_batch(images, indices, width, device):
     return out
 
 
-def recognize_lines(model, codec, images, rank=0, world=1, multiple=256, column_budget=131072, device=None):
-    """Decode this rank's share of `images` (list of uint8 [128,w] arrays). Returns {line index: text}."""
+def recognize_lines(model, codec, images, rank=0, world=1, multiple=256, column_budget=131072, device=None,
+                    resize_height=None, resize_rule="test"):
+    """Decode this rank's share of `images` (list of uint8 [128,w] arrays). Returns {line index: text}.
+    With `resize_height` (128 for the reference model) the images are raw grayscale lines of any height: widths are
+    planned with the reference's rule (`resized_width`), and each of this rank's lines is resized on the device
+    (`resize_line`, cv2.INTER_AREA bit-exact) right before its batch is padded - test.py:204-227 without the host resize."""
     device = device if device is not None else next(model.parameters()).device
-    batches = bucket_lines([im.shape[1] for im in images], multiple, column_budget)
+    if resize_height is None:
+        widths = [im.shape[1] for im in images]
+    else:
+        widths = [resized_width(im.shape[0], im.shape[1], resize_height, resize_rule) for im in images]
+    batches = bucket_lines(widths, multiple, column_budget)
     mine = shard_batches(batches, world)[rank]
     result = {}
     with torch.no_grad():
         for bi in mine:
             wb, idx = batches[bi]
-            x = make_batch(images, idx, wb, device)
+            if resize_height is None:
+                x = make_batch(images, idx, wb, device)
+            else:
+                lines = {i: resize_line(images[i], resize_height, resize_rule, device=device) for i in idx}
+                x = make_batch(lines, idx, wb, device)
             texts = codec.decode(model(x))
             for i, t in zip(idx, texts):
                 result[i] = t

@@ -80,3 +80,21 @@ def test_sharded_recognition_matches_per_batch_reference_padding():
         x = torch.stack(batch).unsqueeze(1).cuda()
         texts = codec.decode(m(x))
         assert [got[i] for i in idx] == texts
+
+
+@pytest.mark.gpu
+def test_recognition_from_raw_lines_resizes_on_the_device(golden):
+    """Raw grayscale lines of arbitrary height (the five bundled images, 48..77 px high): device resize + pad + model + decode
+    gives the texts obtained from cv2-resized lines (fixture outputs of cv2 itself)."""
+    from hctr_b200.models.handwritten_ctr_model import hctr_model
+    from hctr_b200.utils.ctc_codec import ctc_codec
+    from hctr_b200.pipeline import recognize_lines
+    g = golden("resize")
+    raw = [g["img_src%d" % i] for i in range(5)]
+    resized = [g["img_dst%d" % i] for i in range(5)]
+    torch.manual_seed(23)
+    m = hctr_model(101).cuda().eval()
+    codec = ctc_codec(synth.charset(99))
+    a = recognize_lines(m, codec, raw, multiple=256, column_budget=8192, resize_height=128, resize_rule="test")
+    b = recognize_lines(m, codec, resized, multiple=256, column_budget=8192)
+    assert a == b and sorted(a) == list(range(5))
