@@ -57,3 +57,16 @@ def test_device_resize_bit_exact_vs_cv2_and_oracle(golden):
     assert np.array_equal(got, oresize.resize_area(view.cpu().numpy(), resized_width(160, 667, 64), 64))
     with pytest.raises(ValueError):
         resize_line(big.float(), 128)
+
+
+def test_oracle_matches_cv2_live_where_cv2_is_installed():
+    """Beyond the committed fixtures: wherever opencv-python is importable (the build container and the GPU image have it),
+    the restatement is compared with cv2.resize itself on fresh random shapes, including exact integer factors."""
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(2024)
+    shapes = [(int(rs.randint(6, 420)), int(rs.randint(6, 900))) for _ in range(30)] + [(384, 301), (512, 260), (128, 77), (64, 640)]
+    for sh, sw in shapes:
+        src = rs.randint(0, 256, size=(sh, sw)).astype(np.uint8)
+        dw = max(1, int(sw * (128 / sh)))
+        want = cv2.resize(src, (dw, 128), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(oresize.resize_area(src, dw, 128), want), (sh, sw, dw)
