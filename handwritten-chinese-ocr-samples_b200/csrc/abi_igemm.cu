@@ -1,5 +1,6 @@
 // C-ABI entry points for the tensor-core path: conv3x3 / conv1x1 (+BN+ReLU+pool) and the
 // column classifier. Declared in include/hctr_b200.h.
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -8,6 +9,7 @@
 
 #include "igemm2_tcgen05.cuh"
 #include "../../include/hctr_b200.h"
+#include "../../include/hctr_b200_testing.h"
 
 namespace hctr {
 
@@ -107,17 +109,36 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     return HCTR_OK;
 }
 
-static int g_kwf_mode = 2;     // measured on B200: the plain 128-byte start-address shift is what the hardware expects
+// kw-fused activation slab (one 136-pixel box per (kh, 64-channel chunk) serves the three kw taps; the UMMA descriptor
+// start address is shifted by whole 128-byte rows, the swizzle XOR comes from the absolute shared-memory address).
+// 1 = on (default), 0 = one TMA box per tap. Process-wide switches for A/B measurements and the variant tests only:
+// HCTR_IGEMM_KWF / HCTR_IGEMM_PAIR in the environment, or the test hooks of include/hctr_b200_testing.h.
+static std::atomic<int> g_kwf_mode{-1};
+static int kwf_mode() {
+    int m = g_kwf_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char* e = getenv("HCTR_IGEMM_KWF");
+        m = (e && e[0] == '0') ? 0 : 1;
+        g_kwf_mode.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
 
 // CTA-pair kernel (cta_group::2): used for the wide (Cout % 256 == 0), un-pooled convolutions. HCTR_IGEMM_PAIR=0 falls
 // back to the single-CTA kernel (A/B measurements).
-static int g_pair_mode = -1;
+static std::atomic<int> g_pair_mode{-1};
 static bool pair_enabled() {
-    if (g_pair_mode < 0) {
+    int m = g_pair_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
         const char* e = getenv("HCTR_IGEMM_PAIR");
-        g_pair_mode = (e && e[0] == '0') ? 0 : 1;
+        m = (e && e[0] == '0') ? 0 : 1;
+        g_pair_mode.store(m, std::memory_order_relaxed);
     }
-    return g_pair_mode != 0;
+    return m != 0;
+}
+static bool test_hooks_enabled() {
+    const char* e = getenv("HCTR_TEST_HOOKS");
+    return e && e[0] == '1';
 }
 // (every layer of the model with Cout % 256 == 0 has Cin % 128 == 0, so the K blocks pair up)
 // Pooled layers on the pair kernel: the two rows of a (2,1) window live in the two CTAs of a pair, which combine them
@@ -135,7 +156,7 @@ static bool use_pair(int H, int Cin, int Cout, int ksize, int pool, int relu = 0
     // (measured: at Cout = 128 the pair kernel is slower than the single-CTA slab kernel, with or without the slab -
     //  722 / 763 vs 990 TFLOP/s on 128->128: K = 1152 gives 4 us tiles and the cluster-wide accumulator hand-over
     //  per tile dominates)
-    const bool slab = ksize == 3 && g_kwf_mode != 0;         // one stage per (kh, chunk); otherwise K blocks go in pairs
+    const bool slab = ksize == 3 && kwf_mode() != 0;         // one stage per (kh, chunk); otherwise K blocks go in pairs
     if (pool && !(relu && plain && pair_pool_enabled())) return false;
     return pair_enabled() && Cout % 256 == 0 && H % 2 == 0 && (slab || (ksize * ksize * (Cin / 64)) % kPairKSub == 0);
 }
@@ -258,7 +279,7 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
 
     if (use_pair(H, Cin, Cout, ksize, pool, relu, !add && !se_partial && !gate)) {
         // one tile = rows (2*h_tile, 2*h_tile+1) x 128 pixels x 256 channels on a CTA pair
-        const bool slab = ksize == 3 && g_kwf_mode != 0;          // kw-fused activation slab (hctr_debug_set_kwf_mode(0) turns it off)
+        const bool slab = ksize == 3 && kwf_mode() != 0;          // kw-fused activation slab (HCTR_IGEMM_KWF=0 turns it off)
         CUtensorMap tmA, tmB;
         int rc = make_act_map(&tmA, x, B, H, W, Cin, 0, slab ? kSlabPix : kTileM);
         if (rc) return rc;
@@ -275,8 +296,7 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     }
 
     // thin layers (Cout <= 128) are bound by the L2->SMEM re-reads of the activation tile: fuse the three kw taps
-    const int kwf = (ksize == 3 && block_n <= 128) ? g_kwf_mode : 0;
-    p.kwf_base_offset = (kwf == 1);
+    const int kwf = (ksize == 3 && block_n <= 128) ? kwf_mode() : 0;
     CUtensorMap tmA, tmB;
     int rc = make_act_map(&tmA, x, B, H, W, Cin, 0, kwf ? kSlabPix : kTileM);
     if (rc) return rc;
@@ -294,22 +314,18 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     }
 }
 
-// 0 = one TMA box per tap, 2 = kw-fused slab addressed by shifting the descriptor start address by whole 128-byte rows
-// (default; the swizzle XOR is taken from the absolute shared-memory address, so no base_offset is needed), 1 = the same
-// with the row phase also written to the descriptor's base_offset field (measured WRONG on B200 - kept for the record)
-int hctr_debug_set_kwf_mode(int mode) {
-    g_kwf_mode = mode;
+// Test hook (include/hctr_b200_testing.h): selects the kernel variant of the NEXT conv launches of this process.
+// Refused unless HCTR_TEST_HOOKS=1 is in the environment, so a product process cannot change variants by accident.
+int hctr_testing_set_conv_variant(int kw_fused_slab, int cta_pairs) {
+    HCTR_CHECK(test_hooks_enabled(), HCTR_ERR_UNSUPPORTED, "test hooks are disabled (set HCTR_TEST_HOOKS=1)");
+    g_kwf_mode.store(kw_fused_slab ? 1 : 0, std::memory_order_relaxed);
+    g_pair_mode.store(cta_pairs ? 1 : 0, std::memory_order_relaxed);
     return HCTR_OK;
 }
 
 int hctr_conv_bn_act_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, int B,
                          int H, int W, int Cin, int Cout, int ksize, int relu, int pool, void* stream) {
     return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, relu, pool, 0, stream);
-}
-
-int hctr_debug_set_pair_mode(int mode) {
-    g_pair_mode = mode ? 1 : 0;
-    return HCTR_OK;
 }
 
 int hctr_conv_se_slices(int H, int W, int Cout) {

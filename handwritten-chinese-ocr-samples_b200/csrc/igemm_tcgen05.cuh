@@ -35,7 +35,6 @@ struct IgemmParams {
     int ntaps;
     int8_t tap_dh[kMaxTaps];
     int8_t tap_dw[kMaxTaps];
-    int kwf_base_offset;      // KWF: 1 = put the slab row phase into the descriptor's base_offset field
     int sub_dh, sub_dw;       // offset of sub-tile s relative to sub-tile 0: (s*sub_dh rows, s*sub_dw*128 px)
     int N;                    // output channels / classes
     // tiling (derived on host)
@@ -191,7 +190,6 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
                                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                                     uint64_t da = make_sw128_kmajor_desc(a_addr + s * L::kABytes + shift * 128 + k * kUmmaK * 2);
-                                    if (p.kwf_base_offset) da |= static_cast<uint64_t>(shift & 7u) << 49;         // swizzle phase of row 0
                                     const uint64_t db = make_sw128_kmajor_desc(b_addr + kw * L::kBBytes + k * kUmmaK * 2);
                                     umma_bf16(d_base + s * BLOCK_N, da, db, idesc, (kb | kw | k) != 0 ? 1u : 0u);
                                 }

@@ -84,15 +84,21 @@ sqnorm_partial_kernel(const float* __restrict__ g, long long n, float* __restric
     }
 }
 // stage 2: total norm (fixed order) -> clip coefficient (torch.nn.utils.clip_grad_norm_: max_norm / (norm + 1e-6), <= 1)
+// A non-finite norm (NaN/Inf gradient) publishes out[2] = 1 and coef = 0: the update is then skipped entirely, as the
+// reference does twice over (main.py:413 skips a batch whose loss is not finite; GradScaler.step skips optimizer.step()
+// when it found an Inf) - clipping alone would write NaN into every parameter (inf * 0).
 __global__ void clip_coef_kernel(const float* __restrict__ partial, int n, float grad_scale, float max_norm,
-                                 float* __restrict__ out /* [0]=total_norm, [1]=coef */) {
+                                 float* __restrict__ out /* [0]=total_norm, [1]=coef, [2]=1 if the step is skipped */) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s = 0.0;
         for (int i = 0; i < n; ++i) s += (double)partial[i];
         const float norm = sqrtf((float)s) * grad_scale;
+        const bool finite = isfinite(norm);
         float coef = max_norm / (norm + 1e-6f);
         if (coef > 1.f) coef = 1.f;
-        out[0] = norm; out[1] = max_norm > 0.f ? coef : 1.f;
+        out[0] = norm;
+        out[1] = !finite ? 0.f : (max_norm > 0.f ? coef : 1.f);
+        out[2] = finite ? 0.f : 1.f;
     }
 }
 // stage 3: SGD(momentum, weight_decay) exactly as torch.optim.SGD (dampening 0, no nesterov):
@@ -100,6 +106,13 @@ __global__ void clip_coef_kernel(const float* __restrict__ partial, int n, float
 __global__ void __launch_bounds__(256)
 sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
                 const float* __restrict__ coef, float grad_scale, float lr, float momentum, float wd, int first) {
+    if (coef[2] != 0.f) {
+        // skipped step: parameters and momentum stay as they are; a skipped FIRST step leaves a zero momentum buffer, so the
+        // next step (momentum*0 + g) is the first step torch would have taken
+        if (first)
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) buf[i] = 0.f;
+        return;
+    }
     const float c = coef[1] * grad_scale;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float w = p[i];

@@ -167,7 +167,10 @@ class hctr_model(nn.Module):
 
     # -------------------------------------------------------------------------------- plan cache
     def _current_key(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        # torch-side changes show up as (data_ptr, _version); kernels that update parameters or running statistics through
+        # raw pointers (hctr_sgd_clip_step, hctr_bn_finalize_train) bump `_param_generation` instead
+        return (self.__dict__.get("_param_generation", 0),) + tuple(
+            (t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _get_plan(self):
         key = self._current_key()

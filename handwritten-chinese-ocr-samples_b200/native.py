@@ -29,9 +29,7 @@ SIGNATURES = {
     "hctr_device_supported": (_I, [_I]),
     "hctr_stem_conv_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "hctr_conv_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
-    "hctr_debug_set_kwf_mode": (_I, [_I]),
     "hctr_conv_se_slices": (_I, [_I, _I, _I]),
-    "hctr_debug_set_pair_mode": (_I, [_I]),
     "hctr_conv_bn_se_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hctr_conv_sum_slices": (_I, [_I, _I, _I, _I, _I]),
     "hctr_conv_bn_act_sum_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -84,6 +82,11 @@ SIGNATURES = {
     "hctr_resize_area_u8": (_I, [_P, _I, _I, _L, _P, _I, _I, _L, _P]),
 }
 
+# include/hctr_b200_testing.h: hooks for tests/, refused by the library unless HCTR_TEST_HOOKS=1
+TESTING_SIGNATURES = {
+    "hctr_testing_set_conv_variant": (_I, [_I, _I]),
+}
+
 _lib = None
 
 
@@ -100,7 +103,7 @@ def lib():
                 "hctr_b200: %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU/PyTorch fallback for this path)" % LIB_PATH)
         handle = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(TESTING_SIGNATURES.items()):
             fn = getattr(handle, name)          # AttributeError here = header/library mismatch
             fn.restype = res
             fn.argtypes = args

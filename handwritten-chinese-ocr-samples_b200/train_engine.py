@@ -13,8 +13,6 @@ import torch
 
 from . import native as nat
 
-_BN_EPS = 1e-5
-
 
 def _mix_seed(base, k):
     x = (base + 0x9E3779B97F4A7C15 * (k + 1)) & 0xFFFFFFFFFFFFFFFF
@@ -38,6 +36,14 @@ class TrainEngine(object):
         self.need_backward = True
         self._ones = {}
         self._zeros = {}
+        self._tracked = {}            # id(bn) -> host copy of num_batches_tracked (only for momentum=None modules)
+
+    def _batches_tracked(self, bn):
+        n = self._tracked.get(id(bn))
+        if n is None:
+            n = int(bn.num_batches_tracked.item()) if bn.num_batches_tracked is not None else 0
+            self._tracked[id(bn)] = n
+        return n
 
     # ------------------------------------------------------------------ small helpers
     def _const(self, cache, n, val, dev):
@@ -78,12 +84,24 @@ class TrainEngine(object):
         nat.check(lib.hctr_chan_stats(nat.ptr(z), nat.ptr(psum), nat.ptr(psq), B, H, W, cout, st), "chan_stats")
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)         # mean, invstd, scale, shift
         line_sum = torch.empty((B, cout), dtype=torch.float32, device=dev)
-        momentum = bn.momentum if bn.momentum is not None else 0.1
+        track = bn.track_running_stats and bn.running_mean is not None
+        if bn.momentum is None:
+            # torch: momentum=None is the cumulative moving average, factor 1/num_batches_tracked (counted from this batch);
+            # the counter is a host-side integer here so that no device read sits on the launch path
+            momentum = 1.0 / float(self._batches_tracked(bn) + 1)
+        else:
+            momentum = float(bn.momentum)
         nat.check(lib.hctr_bn_finalize_train(nat.ptr(psum), nat.ptr(psq), B, slices, cout, H * W, nat.ptr(bn.weight.detach()),
-                                             nat.ptr(bn.bias.detach()), _BN_EPS, momentum, nat.ptr(bn.running_mean),
-                                             nat.ptr(bn.running_var), nat.ptr(stats[0]), nat.ptr(stats[1]), nat.ptr(stats[2]),
-                                             nat.ptr(stats[3]), nat.ptr(line_sum), st), "bn_finalize")
-        bn.num_batches_tracked += 1
+                                             nat.ptr(bn.bias.detach()), float(bn.eps), momentum,
+                                             nat.ptr(bn.running_mean) if track else None,
+                                             nat.ptr(bn.running_var) if track else None, nat.ptr(stats[0]), nat.ptr(stats[1]),
+                                             nat.ptr(stats[2]), nat.ptr(stats[3]), nat.ptr(line_sum), st), "bn_finalize")
+        if track:
+            bn.num_batches_tracked += 1
+            if id(bn) in self._tracked:
+                self._tracked[id(bn)] += 1
+        m = self.model
+        m.__dict__["_param_generation"] = m.__dict__.get("_param_generation", 0) + 1    # running stats changed by a kernel
         s = _Saved()
         s.name, s.x, s.z, s.res = name, x, z, res
         s.mean, s.invstd, s.scale, s.shift, s.line_sum = stats[0], stats[1], stats[2], stats[3], line_sum

@@ -46,6 +46,18 @@ def allreduce_bucket(flat, start, end, group=None, async_op=False):
     return dist.all_reduce(flat[start:end], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+def broadcast_state(tensors, src=0, group=None):
+    """Host logic of DDP's construction-time sync (main.py:237: DistributedDataParallel broadcasts rank 0's parameters
+    and buffers): every tensor in `tensors` is overwritten in place with rank `src`'s. No-op without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    n = 0
+    for t in tensors:
+        dist.broadcast(t, src=src, group=group)
+        n += 1
+    return n
+
+
 def sgd_state_dict(names, offsets, shapes, momentum_flat, group, have_momentum):
     """Host logic: the flat momentum buffer as a `torch.optim.SGD.state_dict()` (the 'optimizer' entry of the reference's
     checkpoints, main.py:348 / :262): parameters are numbered in registration order, each with a `momentum_buffer` of the
@@ -98,6 +110,15 @@ def adjust_learning_rate(optimizer, epoch, args):
         param_group['lr'] = lr
 
 
+_PIN_RING = 3
+
+
+def _bump_generation(model):
+    """Tell the model that parameters or buffers were updated through raw pointers (no torch `_version` bump): the
+    eval-mode plan (folded BN, packed weights) must be rebuilt on the next eval forward."""
+    model.__dict__["_param_generation"] = model.__dict__.get("_param_generation", 0) + 1
+
+
 class TrainStep(object):
     def __init__(self, model, lr=1e-3, momentum=0.9, weight_decay=1e-4, max_norm=5.0, process_group=None):
         self.model = model
@@ -124,12 +145,50 @@ class TrainStep(object):
             self.flat_params[s:s + n].copy_(p.detach().reshape(-1))
             p.data = self.flat_params[s:s + n].view(p.shape)                  # same Parameter object, new storage
             self.grad_views[k] = self.flat_grads[s:s + n].view(p.shape)
-        self.norm = torch.zeros((2,), dtype=torch.float32, device=dev)        # {total_norm, clip coefficient}
+        self.norm = torch.zeros((4,), dtype=torch.float32, device=dev)        # {total_norm, clip coefficient, skipped, -}
         self._ws = torch.empty((nat.lib().hctr_sgd_workspace_bytes(),), dtype=torch.uint8, device=dev)
         self.steps = 0
         self._have_momentum = False
-        self._pin = None
+        # label staging: a ring of pinned buffers, each guarded by the event of the H2D copy that last read it (the host
+        # runs ahead of the GPU; rewriting a single buffer would hand step N the labels of step N+1)
+        self._pins = [None] * _PIN_RING
+        self._pin_events = [None] * _PIN_RING
+        self._pin_next = 0
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1:
+            self.sync_replicas()
+
+    def sync_replicas(self, src=0):
+        """What DistributedDataParallel does at construction (main.py:237): every replica starts from rank `src`'s
+        parameters and buffers (the reference's --seed defaults to None, so unseeded ranks would otherwise average
+        gradients into diverging weights). Also called after load_state_dict so that momentum is replicated too."""
+        if self.world <= 1:
+            return
+        broadcast_state([self.flat_params, self.momentum_buf] + list(self.model.buffers()), src, self.group)
+        _bump_generation(self.model)
+
+    @property
+    def skipped(self):
+        """Device flag (0-d fp32 tensor): 1 when the last step met a non-finite gradient norm and left parameters and
+        momentum untouched - the reference's `if not torch.isfinite(loss): continue` / GradScaler skip (main.py:413,433)."""
+        return self.norm[2]
+
+    def _stage_labels(self, tg_host, tl_host, dev):
+        n_t, B = tg_host.numel(), tl_host.numel()
+        i = self._pin_next
+        self._pin_next = (i + 1) % _PIN_RING
+        if self._pin_events[i] is not None:
+            self._pin_events[i].synchronize()          # the copy that last read this buffer has run
+        if self._pins[i] is None or self._pins[i].numel() < n_t + B:
+            self._pins[i] = torch.empty((max(4096, 2 * (n_t + B)),), dtype=torch.int32).pin_memory()
+        pin = self._pins[i]
+        pin[:n_t].copy_(tg_host.reshape(-1))
+        pin[n_t:n_t + B].copy_(tl_host.to(torch.int32).reshape(-1))
+        staged = pin[:n_t + B].to(dev, non_blocking=True)
+        ev = self._pin_events[i] or torch.cuda.Event()
+        ev.record()
+        self._pin_events[i] = ev
+        return staged[:n_t], staged[n_t:n_t + B]
 
     def step(self, x, targets, target_lengths, seed=None):
         """x: fp32 [B,1,128,W] CUDA; targets: int32 concatenated labels; target_lengths: int32 [B] (host or device).
@@ -150,13 +209,14 @@ class TrainStep(object):
             # labels travel through pinned staging buffers with async copies: a pageable H2D would block the host until
             # every kernel of the previous step has finished and serialise CPU enqueue with GPU execution
             tg_host = torch.as_tensor(targets).to(torch.int32)
-            n_t = tg_host.numel()
-            if self._pin is None or self._pin.numel() < n_t + B:
-                self._pin = torch.empty((max(4096, 2 * (n_t + B)),), dtype=torch.int32).pin_memory()
-            self._pin[:n_t].copy_(tg_host.reshape(-1))
-            self._pin[n_t:n_t + B].copy_(tl_host.to(torch.int32).reshape(-1))
-            staged = self._pin[:n_t + B].to(dev, non_blocking=True)
-            tg, tl = staged[:n_t], staged[n_t:n_t + B]
+            if tg_host.is_cuda:
+                tg_host = tg_host.cpu()
+            if tl_host.numel() != B:
+                raise ValueError("target_lengths has %d entries for a batch of %d" % (tl_host.numel(), B))
+            if int(tl_host.sum().item()) != tg_host.numel() or int(tl_host.min().item()) < 0:
+                raise ValueError("targets holds %d labels but target_lengths sums to %d"
+                                 % (tg_host.numel(), int(tl_host.sum().item())))
+            tg, tl = self._stage_labels(tg_host, tl_host, dev)
             il = torch.full((B,), W, dtype=torch.int32, device=dev)            # preds_sizes = [T]*B (main.py:388)
             nll = torch.empty((B,), dtype=torch.float32, device=dev)
             loss = torch.empty((1,), dtype=torch.float32, device=dev)
@@ -187,6 +247,7 @@ class TrainStep(object):
                       "sgd_clip_step")
             self.steps += 1
             self._have_momentum = True
+            _bump_generation(m)              # parameters / running stats changed behind torch's back (raw pointers)
         return loss.reshape(())
 
     # hyper-parameters live in param_groups[0] (torch.optim convention)
@@ -206,6 +267,7 @@ class TrainStep(object):
     def load_state_dict(self, sd):
         self._have_momentum = load_sgd_state_dict(sd, self.names, self.offsets, self.shapes, self.momentum_buf,
                                                   self.param_groups[0])
+        broadcast_state([self.momentum_buf], 0, self.group)
 
     def zero_grad(self, set_to_none=False):
         """Kept for call-site compatibility (main.py:425): the kernels overwrite the flat gradient buffer every step."""

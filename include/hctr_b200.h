@@ -87,14 +87,6 @@ int hctr_conv_bn_gate_res_fwd(const void* x, const void* w_packed, const float* 
                               const void* residual, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int relu,
                               void* stream);
 
-/* Tuning/debug switch for the thin (Cout <= 128) 3x3 layers: 0 = one TMA box per tap; 2 (default) = kw-fused: one
- * 136-pixel activation slab per (kh, 64-channel chunk) serves the three kw taps by shifting the UMMA descriptor start
- * address by whole 128-byte rows (3x fewer L2->SMEM activation bytes, +15 % on those layers); 1 = the same plus the
- * descriptor base_offset field (measured wrong on B200; kept to document the experiment). */
-int hctr_debug_set_kwf_mode(int mode);
-/* 0 = keep the wide convolutions on the single-CTA kernel instead of the CTA-pair (cta_group::2) kernel (measurements) */
-int hctr_debug_set_pair_mode(int mode);
-
 /* SELayer squeeze (:27-28): deterministic two-stage mean over (H,W) incl. padded columns.
  * x: bf16 NHWC; partial: fp32 workspace [B][slices][C]; the second stage runs inside hctr_se_excite.
  * `slices` must equal hctr_se_slices(H, W). */
@@ -274,7 +266,9 @@ int hctr_stem_wgrad(const void* dz, const float* x, float* dw, int B, int H, int
 long long hctr_stem_wgrad_workspace_bytes(int B, int H, int W);
 /* Optimizer tail over flat fp32 buffers (main.py:210-213,430-438): total_norm = ||grad*grad_scale||_2,
  * coef = min(1, max_norm/(total_norm+1e-6)) (clip_grad_norm_), then SGD with momentum and weight decay as
- * torch.optim.SGD. norm_out: fp32 [2] = {total_norm, coef}; workspace: hctr_sgd_workspace_bytes(). */
+ * torch.optim.SGD. norm_out: fp32 [4] = {total_norm, coef, skipped, unused}: a non-finite total_norm sets skipped = 1 and
+ * leaves parameters and momentum untouched (main.py:413 `if not torch.isfinite(loss): continue`, GradScaler.step);
+ * workspace: hctr_sgd_workspace_bytes(). */
 int hctr_sgd_clip_step(float* params, const float* grads, float* momentum_buf, long long n, float grad_scale,
                        float max_norm, float lr, float momentum, float weight_decay, int first_step, float* norm_out,
                        float* workspace, void* stream);

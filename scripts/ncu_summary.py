@@ -21,6 +21,14 @@ WANT = [
 ]
 
 
+_BYTE_UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def to_bytes(value, unit):
+    """ncu scales every column on its own (a read in Gbyte next to a write in Mbyte): convert before adding."""
+    return float(value.replace(",", "")) * _BYTE_UNITS[unit]
+
+
 def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -32,9 +40,9 @@ def main(path):
             if w in hdr:
                 i = hdr.index(w)
                 print("  %-100s %16s %s" % (w, r[i], units[i]))
-        rd = float(r[hdr.index("dram__bytes_read.sum")]); wr = float(r[hdr.index("dram__bytes_write.sum")])
-        u = units[hdr.index("dram__bytes_read.sum")]
-        print("  traffic (dram read+write)  %.4f %s" % (rd + wr, u))
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        total = to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw])
+        print("  traffic (dram read+write)  %.4f GB" % (total / 1e9))
         print()
 
 

@@ -14,8 +14,8 @@ from hctr_b200 import native
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "hctr_b200.h")).read()
+def _declared_symbols(header="hctr_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(hctr_[a-z0-9_]+)\s*\(", text)))
 
@@ -31,6 +31,11 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), "libhctr_b200.so does not export %s" % s
     # and the Python binding table covers the header one to one
     assert sorted(native.SIGNATURES) == syms
+    assert not [s for s in syms if "debug" in s or "testing" in s]          # no diagnostic switches in the product ABI
+    hooks = _declared_symbols("hctr_b200_testing.h")
+    assert sorted(native.TESTING_SIGNATURES) == hooks and all(hasattr(lib, s) for s in hooks)
+    os.environ.pop("HCTR_TEST_HOOKS", None)
+    assert native.lib().hctr_testing_set_conv_variant(1, 1) == native.HCTR_ERR_UNSUPPORTED
     assert native.lib().hctr_abi_version() == 1
 
 

@@ -205,3 +205,146 @@ def test_train_step_resumes_from_a_reference_format_checkpoint(tmp_path):
     step_b = (tb.flat_params - before).abs().max().item()
     step_a = (ts.flat_params - before).abs().max().item()
     assert 0 < step_b < step_a
+
+
+def test_back_to_back_steps_with_different_labels():
+    """The host runs ahead of the GPU (step() returns a device loss, no sync): the label staging buffers must not be
+    rewritten before the previous step's async H2D copy has executed. Three steps with three different label sets and no
+    synchronisation in between must give the losses of the same steps run with a full sync after each one."""
+    from hctr_b200.train_step import TrainStep
+    NC, B, W = 41, 2, 512
+    x = torch.from_numpy(synth.text_lines(B, W, 101)).cuda()
+    label_sets = [synth.ctc_targets(B, NC, lo, hi, seed) for lo, hi, seed in ((3, 6, 1), (20, 30, 2), (1, 2, 3), (9, 14, 4))]
+
+    def run(sync):
+        m = _model(NC, 13).cuda().train(); m.dropout_enabled = False
+        ts = TrainStep(m, lr=0.01, momentum=0.9, weight_decay=1e-4, max_norm=5.0)
+        out = []
+        for tg, tl in label_sets:
+            out.append(ts.step(x, tg, tl, seed=5))
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return [v.item() for v in out], ts.flat_params.clone()
+
+    la, pa = run(sync=False)
+    lb, pb = run(sync=True)
+    assert la == lb, (la, lb)
+    assert torch.equal(pa, pb)
+    assert len(set(la)) == len(la)                       # the label sets really differ
+
+
+def test_train_step_rejects_inconsistent_labels_and_skips_non_finite_steps():
+    from hctr_b200.train_step import TrainStep
+    NC, B, W = 41, 2, 64
+    x = torch.from_numpy(synth.text_lines(B, W, 111)).cuda()
+    tg, tl = synth.ctc_targets(B, NC, 3, 6, 5)
+    m = _model(NC, 14).cuda().train(); m.dropout_enabled = False
+    ts = TrainStep(m, lr=0.01)
+    with pytest.raises(ValueError):
+        ts.step(x, tg[:-1], tl)                          # lengths do not add up to the label count
+    ts.step(x, tg, tl, seed=1)
+    assert ts.skipped.item() == 0.0
+    before, mom = ts.flat_params.clone(), ts.momentum_buf.clone()
+    bad = x.clone(); bad[0, 0, 5, 7] = float("nan")     # NaN input -> NaN gradients -> the update is skipped (main.py:413)
+    ts.step(bad, tg, tl, seed=2)
+    assert ts.skipped.item() == 1.0
+    assert torch.equal(ts.flat_params, before) and torch.equal(ts.momentum_buf, mom)
+    ts.step(x, tg, tl, seed=3)
+    assert ts.skipped.item() == 0.0 and not torch.equal(ts.flat_params, before)
+
+
+def test_eval_plan_follows_raw_pointer_updates():
+    """Parameters and BN running statistics are updated by kernels through raw pointers (no torch _version bump): the
+    eval-mode plan must still be rebuilt - eval logits after a training step equal those of a fresh model that loaded
+    the updated state_dict."""
+    from hctr_b200.train_step import TrainStep
+    NC, B, W = 41, 2, 64
+    x = torch.from_numpy(synth.text_lines(B, W, 121)).cuda()
+    tg, tl = synth.ctc_targets(B, NC, 3, 6, 6)
+    m = _model(NC, 15).cuda()
+    with torch.no_grad():
+        m.eval(); y0 = m(x).clone()                      # builds the plan
+    m.train(); m.dropout_enabled = False
+    ts = TrainStep(m, lr=0.05)
+    ts.step(x, tg, tl, seed=1)
+    with torch.no_grad():
+        m.eval(); y1 = m(x).clone()
+    fresh = _model(NC, 16).cuda()
+    fresh.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    with torch.no_grad():
+        fresh.eval(); y2 = fresh(x)
+    assert torch.equal(y1, y2) and not torch.equal(y0, y1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the one collective of the path: the data-parallel gradient exchange (main.py:222-237) over NCCL on two GPUs
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    from hctr_b200.train_step import TrainStep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    solo = [dist.new_group(ranks=[r]) for r in range(world)]        # singleton groups: a TrainStep without an exchange
+    NC, Bl, W = 41, 2, 128
+    xs = [torch.from_numpy(synth.text_lines(Bl, W, 300 + r)).to(dev) for r in range(world)]
+    labels = [synth.ctc_targets(Bl, NC, 3, 6, 400 + r) for r in range(world)]
+
+    def fresh(seed):
+        m = _model(NC, seed).to(dev).train(); m.dropout_enabled = False
+        return m
+    # every rank computes every shard's local gradient on its own (kernels are deterministic: same bits on both GPUs)
+    local = []
+    for r in range(world):
+        ts_l = TrainStep(fresh(21), lr=0.01, momentum=0.9, weight_decay=1e-4, max_norm=5.0, process_group=solo[rank])
+        assert ts_l.world == 1
+        ts_l.step(xs[r], labels[r][0], labels[r][1], seed=9)
+        local.append(ts_l.flat_grads.clone())
+    # replicas are built from DIFFERENT seeds: the construction-time broadcast must make them rank 0's (seed 21)
+    m = fresh(21 + rank)
+    ts = TrainStep(m, lr=0.01, momentum=0.9, weight_decay=1e-4, max_norm=5.0)
+    assert ts.world == world
+    p0 = ts.flat_params.clone()
+    ref_p0 = TrainStep(fresh(21), process_group=solo[rank]).flat_params
+    same_start = bool(torch.equal(p0, ref_p0))
+    loss = ts.step(xs[rank], labels[rank][0], labels[rank][1], seed=9)
+    torch.cuda.synchronize()
+    total = local[0] + local[1]                                      # NCCL sum of two fp32 buffers: commutative, exact
+    exch_exact = bool(torch.equal(ts.flat_grads, total))
+    g = total / world
+    norm = g.double().norm().float()
+    coef = torch.clamp(5.0 / (norm + 1e-6), max=1.0)
+    want = p0 - 0.01 * (g * coef + 1e-4 * p0)
+    upd_err = (ts.flat_params - want).abs().max().item()
+    gathered = [torch.empty_like(ts.flat_params) for _ in range(world)]
+    dist.all_gather(gathered, ts.flat_params)
+    replicas_equal = bool(torch.equal(gathered[0], gathered[1]))
+    q.put((rank, same_start, exch_exact, upd_err, replicas_equal, float(ts.norm[0].item()), float(norm.item()), float(loss.item())))
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_over_nccl_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import os
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, same_start, exch_exact, upd_err, replicas_equal, norm_dev, norm_ref, loss in res:
+        assert same_start, "rank %d did not start from rank 0's parameters" % rank
+        assert exch_exact, "rank %d: all-reduced flat gradient != sum of the per-shard gradients" % rank
+        assert upd_err <= 1e-6, (rank, upd_err)
+        assert replicas_equal
+        assert abs(norm_dev - norm_ref) <= 1e-5 * norm_ref
+    assert res[0][7] != res[1][7]                        # per-rank losses (the reference does not reduce the loss)

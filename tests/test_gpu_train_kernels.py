@@ -204,7 +204,7 @@ def test_stem_wgrad_and_fused_sgd():
     n = 1000003
     p0 = torch.randn(n, device="cuda"); g0 = torch.randn(n, device="cuda") * 0.02
     pr = p0.clone().requires_grad_(True); opt = torch.optim.SGD([pr], lr=1e-3, momentum=0.9, weight_decay=1e-4)
-    pm = p0.clone(); buf = torch.zeros(n, device="cuda"); normo = torch.zeros(2, device="cuda"); ws = _ws(lib.hctr_sgd_workspace_bytes())
+    pm = p0.clone(); buf = torch.zeros(n, device="cuda"); normo = torch.zeros(4, device="cuda"); ws = _ws(lib.hctr_sgd_workspace_bytes())
     for step in range(4):
         gs = g0 * (step + 1)
         pr.grad = gs.clone(); tn = torch.nn.utils.clip_grad_norm_([pr], 5.0); opt.step()
@@ -212,3 +212,17 @@ def test_stem_wgrad_and_fused_sgd():
                                          nat.ptr(normo), nat.ptr(ws), S()))
         assert abs(normo[0].item() - tn.item()) <= 1e-5 * tn.item()
         assert (pm - pr.detach()).abs().max().item() <= 1e-6
+        assert normo[2].item() == 0.0
+    # a non-finite gradient skips the update (main.py:413, GradScaler.step): parameters and momentum stay bit-identical
+    for bad in (float("nan"), float("inf")):
+        gs = g0.clone(); gs[12345] = bad
+        p_before, b_before = pm.clone(), buf.clone()
+        nat.check(lib.hctr_sgd_clip_step(nat.ptr(pm), nat.ptr(gs), nat.ptr(buf), n, 1.0, 5.0, 1e-3, 0.9, 1e-4, 0,
+                                         nat.ptr(normo), nat.ptr(ws), S()))
+        assert normo[2].item() == 1.0 and normo[1].item() == 0.0
+        assert torch.equal(pm, p_before) and torch.equal(buf, b_before)
+    # ... and a skipped FIRST step leaves a zero momentum buffer
+    buf2 = torch.full((n,), 7.0, device="cuda"); gs = g0.clone(); gs[0] = float("nan"); p_before = pm.clone()
+    nat.check(lib.hctr_sgd_clip_step(nat.ptr(pm), nat.ptr(gs), nat.ptr(buf2), n, 1.0, 5.0, 1e-3, 0.9, 1e-4, 1,
+                                     nat.ptr(normo), nat.ptr(ws), S()))
+    assert torch.equal(pm, p_before) and buf2.abs().max().item() == 0.0

@@ -190,3 +190,71 @@ def test_ngram_table_builder_matches_oracle():
         assert lm.host["vocab"][cd[ch]] == (cd[ch] if ch in have else C + 2)
     with pytest.raises(ValueError):
         NgramLM.from_arpa_text(text.replace("\\5-grams:", "\\6-grams:"), cd, C)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# model forward: oracle/hctr_forward.py pinned on the CPU to logits the REFERENCE module produced (make_golden.make_model)
+
+def _seeded_state_dict(num_classes, seed):
+    """Seed-identical parameters of the reference constructor (hash-checked against the reference's in test_abi_cpu /
+    below); only the parameter HOLDER of the product is used here - the arithmetic under test is the oracle's."""
+    import torch
+    from hctr_b200.models.handwritten_ctr_model import hctr_model
+    torch.manual_seed(seed)
+    return {k: v.detach().clone() for k, v in hctr_model(num_classes).state_dict().items()}
+
+
+def _sd_hash(sd):
+    import hashlib
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode()); h.update(v.numpy().tobytes())
+    return h.hexdigest()
+
+
+def test_forward_oracle_matches_reference_logits_small_model(golden):
+    import torch
+    from oracle import hctr_forward
+    g = golden("model")
+    sd = _seeded_state_dict(37, 4321)
+    assert _sd_hash(sd) == str(g["small_sd_hash"][0])
+    x = torch.from_numpy(synth.text_lines(2, 72, 51))
+    with torch.no_grad():
+        y = hctr_forward.forward(x, sd)
+    ref = torch.from_numpy(g["small_default_logits"])
+    assert tuple(y.shape) == tuple(ref.shape) == (72, 2, 37)
+    assert (y - ref).abs().max().item() <= 1e-5
+    # BN-calibrated regime (logits O(1), the only regime where they are not ~ linear.bias): running statistics from the
+    # reference's own train-mode pass
+    cal = dict(sd)
+    for k in sd:
+        if "small_cal." + k in g:
+            cal[k] = torch.from_numpy(g["small_cal." + k])
+    with torch.no_grad():
+        yc = hctr_forward.forward(x, cal)
+    refc = torch.from_numpy(g["small_cal_logits"])
+    assert refc.abs().max().item() > 1.0
+    assert (yc - refc).abs().max().item() <= 1e-3 * refc.abs().max().item()
+    assert (yc.argmax(2) == refc.argmax(2)).float().mean().item() >= 0.99
+    # and the oracle's own calibration pass reproduces the reference's running statistics
+    own = hctr_forward.calibrate_bn(sd, torch.from_numpy(synth.text_lines(3, 96, 52)))
+    for k in sd:
+        if "small_cal." + k in g:
+            want = torch.from_numpy(g["small_cal." + k])
+            assert torch.allclose(own[k], want, rtol=1e-3, atol=1e-6), k
+
+
+def test_forward_oracle_matches_reference_full_charset(golden):
+    import torch
+    from oracle import hctr_forward
+    from oracle.codec import CodecTables
+    g = golden("model")
+    sd = _seeded_state_dict(7375, 1234)
+    assert _sd_hash(sd) == str(g["sd_hash_7375_seed1234"][0])
+    x = torch.from_numpy(synth.text_lines(1, 136, 53))
+    with torch.no_grad():
+        y = hctr_forward.forward(x, sd)
+    assert (y[0, 0] - torch.from_numpy(g["full_default_logits_t0"])).abs().max().item() <= 1e-5
+    assert abs(y.abs().max().item() - float(g["full_default_absmax"])) <= 1e-5
+    _, idx, ln = oracle.greedy_decode(y.contiguous().numpy())
+    assert CodecTables(synth.charset(7373)).to_text(idx, ln) == list(g["full_default_text"])

@@ -54,6 +54,21 @@ def _worker(rank, world, port, q):
     ok = True
     for i, (name, (s, n)) in enumerate(offsets.items()):
         ok &= bool(torch.allclose(avg[s:s + n], torch.full((n,), (i + 1) * (1 + 2) / 2.0)))
+    # DDP's construction-time sync (main.py:237): unseeded replicas start from rank 0's parameters and buffers
+    from hctr_b200.train_step import broadcast_state
+    from hctr_b200.models.handwritten_ctr_model import hctr_model
+    torch.manual_seed(100 + rank)                       # the reference's --seed defaults to None: ranks differ
+    m = hctr_model(11)
+    for b in m.buffers():
+        if b.dtype.is_floating_point:
+            b.add_(float(rank))
+    params = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    n = broadcast_state([params] + list(m.buffers()), src=0)
+    torch.manual_seed(100)
+    m0 = hctr_model(11)
+    want = torch.cat([p.detach().reshape(-1) for p in m0.parameters()])
+    ok &= n == 1 + len(list(m.buffers())) and bool(torch.equal(params, want))
+    ok &= all(bool(torch.equal(a, b)) for a, b in zip(m.buffers(), m0.buffers()))
     q.put((rank, ok, [b[0] for b in buckets]))
     dist.destroy_process_group()
 
