@@ -20,10 +20,26 @@
 //   C (HBM-bound): one CTA per row: grad = (softmax - occupancy) * scale written in one pass, where
 //                  occupancy_c = sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - ll - lp[t, l'_s]).
 // Logits are read twice and the gradient written once: (2*s_in + s_out) * T*B*C bytes.
+//
+// Round 2 - the OVERLAPPED path (default when a gradient is asked for and a row fits a per-warp buffer):
+//   rows  (HBM-bound, ctc_rows_kernel): ONE pass per logits row on a warp-private shared-memory copy (bulk copy): max,
+//         exp and sum, the label gather for the recursion, AND the dense part of the gradient softmax*scale - which needs
+//         no alpha/beta. The logits are read once and the gradient written once: (s_in + s_out) * T*B*C bytes of DRAM
+//         traffic instead of (2*s_in + s_out). Rows are dealt to the warps from BOTH ends of the time axis and every
+//         finished row bumps a per-(sequence, 8-row granule) counter with release semantics.
+//   scan  (latency-bound, ctc_scan_kernel<K, true>): launched on a helper stream at the same time; before it stages the
+//         label probabilities of a granule it acquires that counter. alpha consumes rows from t = 0 upwards, beta from
+//         t = T-1 downwards, so the 2*T dependent recursion steps - a third of the old call at B = 16, with the whole
+//         GPU idle around 2*B warps - run underneath the memory-bound pass instead of after it.
+//   fix   (ctc_fix_kernel): after both, one warp per row subtracts the occupancy at the <= L+1 distinct label classes
+//         (a few dozen 2-byte read-modify-writes per row).
+// HCTR_CTC_OVERLAP=0 keeps the three sequential passes (needed under ncu, which serialises kernels).
 #include <cfloat>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
+#include "row_stage.cuh"
 #include "../../include/hctr_b200.h"
 
 namespace hctr {
@@ -32,6 +48,7 @@ struct CtcWs {
     float* lse;        // [B][T]
     float* lpg;        // [B][T][Sp]     log-prob of l'_s at (t,b) (log-space fallback)
     double* pg;        // [B][T][Sp]     probability of l'_s at (t,b), zero beyond S (scaled linear recursion)
+    double* pgr;       // [B][T][Sp]     the same row mirrored: pgr[q] = pg[S-1-q] (what the beta scan reads front to back)
     double* alpha;     // [B][T][Sa]     linear mode: alpha_t(s) / 2^ea[t][s/K];  log mode: log alpha_t(s)
     double* beta;      // [B][T][Sa]     linear mode: MIRRORED, beta[s'] = beta_t(S-1-s') / 2^eb[t][s'/K];  log mode: log beta_t(s)
     int* ea;           // [B][T][32]     per lane of the scan: (binary exponent << 1) | (a state was dropped at this step)
@@ -42,7 +59,13 @@ struct CtcWs {
     int* flag;         // [B]            1 = this sequence takes the log-space recursion
     int* canon;        // [B][Sp]        first s' with the same class as s
     int* toff;         // [B]            offset of sequence b in the concatenated targets
+    int* len;          // [B]            target length clamped to [0, max_target_len] (never trust device lengths)
+    int* lab;          // [B][Lp]        labels clamped to [0, C-1]
+    int* prog;         // [B][NG]        rows of granule g (8 time steps) whose label probabilities are in place
+    int* err;          // [4]            bit 0: a length / label was out of range; bit 1: the scan timed out waiting for rows
+    int Lp, NG;
 };
+constexpr int kGranule = 8;          // time steps per progress counter
 
 __host__ __device__ inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
@@ -58,6 +81,7 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     const long long o_lse = take(4ll * B * T);
     const long long o_lpg = take(4ll * B * T * Sp);
     const long long o_pg = take(8ll * B * T * Sp);
+    const long long o_pgr = take(8ll * B * T * Sp + 64);
     const long long o_alpha = take(8ll * B * T * Sa);
     const long long o_beta = take(8ll * B * T * Sa);
     const long long o_ea = take(4ll * B * T * 32);
@@ -68,12 +92,19 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     const long long o_flag = take(4ll * B);
     const long long o_canon = take(4ll * B * Sp);
     const long long o_toff = take(4ll * B);
+    const int Lp = (Sp - 1) / 2 > 0 ? (Sp - 1) / 2 : 1;          // >= max_target_len (Sp >= 2L+1)
+    const int NG = (T + kGranule - 1) / kGranule;
+    const long long o_len = take(4ll * B);
+    const long long o_lab = take(4ll * B * Lp);
+    const long long o_prog = take(4ll * B * NG);
+    const long long o_err = take(16);
     if (total) *total = off;
     CtcWs w;
     char* p = static_cast<char*>(base);
     w.lse = reinterpret_cast<float*>(p + o_lse);
     w.lpg = reinterpret_cast<float*>(p + o_lpg);
     w.pg = reinterpret_cast<double*>(p + o_pg);
+    w.pgr = reinterpret_cast<double*>(p + o_pgr);
     w.alpha = reinterpret_cast<double*>(p + o_alpha);
     w.beta = reinterpret_cast<double*>(p + o_beta);
     w.ea = reinterpret_cast<int*>(p + o_ea);
@@ -84,6 +115,11 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     w.flag = reinterpret_cast<int*>(p + o_flag);
     w.canon = reinterpret_cast<int*>(p + o_canon);
     w.toff = reinterpret_cast<int*>(p + o_toff);
+    w.len = reinterpret_cast<int*>(p + o_len);
+    w.lab = reinterpret_cast<int*>(p + o_lab);
+    w.prog = reinterpret_cast<int*>(p + o_prog);
+    w.err = reinterpret_cast<int*>(p + o_err);
+    w.Lp = Lp; w.NG = NG;
     return w;
 }
 
@@ -117,25 +153,45 @@ template <> struct Ld<__nv_bfloat16> {
     static __device__ __forceinline__ void st_one(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
-// ---------------------------------------------------------------- prep: target offsets + canonical states
-__global__ void ctc_prep_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen, int B, int Sp,
-                                int force_log, CtcWs w) {
-    __shared__ int s_off;
+// ---------------------------------------------------------------- prep: sanitised labels, canonical states, counters
+// Lengths and labels live in device memory and are NOT trusted: every later kernel reads the clamped copies made here
+// (length in [0, max_target_len], label in [0, C-1]), so a wrong length can no longer index outside the workspace or
+// the logits row. Out-of-range input sets err bit 0 and the loss becomes NaN.
+__global__ void ctc_prep_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen, int B, int C, int Sp,
+                                int max_target_len, int force_log, CtcWs w) {
+    __shared__ int s_off, s_len, s_bad;
     const int b = blockIdx.x;
     if (threadIdx.x == 0) {
-        int off = 0;
-        for (int i = 0; i < b; ++i) off += tlen[i];
-        s_off = off; w.toff[b] = off;
+        int off = 0, bad = 0;
+        for (int i = 0; i < b; ++i) {
+            const int li = tlen[i];
+            bad |= (li < 0 || li > max_target_len);
+            off += min(max(li, 0), max_target_len);
+        }
+        const int lb = tlen[b];
+        bad |= (lb < 0 || lb > max_target_len);
+        s_off = off; s_len = min(max(lb, 0), max_target_len); s_bad = bad;
+        w.toff[b] = off; w.len[b] = s_len;
         w.flag[b] = force_log;              // 1: more states than the one-warp scan holds
     }
     __syncthreads();
-    const int L = tlen[b], S = 2 * L + 1;
+    const int L = s_len, S = 2 * L + 1;
     const int32_t* tg = targets + s_off;
+    int* lab = w.lab + (long long)b * w.Lp;
+    int bad = 0;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const int c = tg[i];
+        bad |= (c < 0 || c >= C);
+        lab[i] = min(max(c, 0), C - 1);
+    }
+    if (bad || (threadIdx.x == 0 && s_bad)) atomicOr(&w.err[0], 1);
+    for (int g = threadIdx.x; g < w.NG; g += blockDim.x) w.prog[(long long)b * w.NG + g] = 0;
+    __syncthreads();
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
-        const int c = (s & 1) ? tg[s >> 1] : 0;
+        const int c = (s & 1) ? lab[s >> 1] : 0;
         int first = s;
         for (int q = (s & 1) ? 1 : 0; q < s; q += ((c == 0) ? 2 : 1)) {
-            const int cq = (q & 1) ? tg[q >> 1] : 0;
+            const int cq = (q & 1) ? lab[q >> 1] : 0;
             if (cq == c) { first = q; break; }
         }
         w.canon[(long long)b * Sp + s] = first;
@@ -207,10 +263,11 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
         lse = mm + logf(ss);
     }
     if (lane == 0) w.lse[row] = lse;
-    const int L = tlen[b], S = 2 * L + 1;
-    const int32_t* tg = targets + w.toff[b];
+    const int L = w.len[b], S = 2 * L + 1;
+    const int* tg = w.lab + (long long)b * w.Lp;
     float* dst = w.lpg + row * Sp;
     double* dpr = w.pg + row * Sp;
+    double* dpm = w.pgr + row * Sp;
     bool small = false;
     for (int q = lane; q < Sp; q += 32) {
         float lp = 0.f;
@@ -221,6 +278,9 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
             pr = (double)expf(lp);
             small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);       // exp(-inf) = 0 is exact in linear space
             small |= !(lp == lp);                                        // NaN: let the log-space path propagate it
+            dpm[S - 1 - q] = pr;
+        } else {
+            dpm[q] = 0.0;
         }
         dst[q] = lp;
         dpr[q] = pr;
@@ -240,10 +300,17 @@ constexpr int kRebaseDiff = 900;                     // adopt the left neighbour
 constexpr int kScanChunkStates = 32;                 // steps per staged chunk x states per lane
 constexpr int kScanStageDoubles = 3 * kScanChunkStates * 32;     // 3 chunks in flight = 24 KB
 
-__device__ __forceinline__ void cp_async_f64(void* smem_dst, const double* src, bool valid) {
-    const int bytes = valid ? 8 : 0;                                      // 0 source bytes = zero fill
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(smem_dst)), "l"(src), "r"(bytes) : "memory");
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kScanWaitLimitNs = 4000000000ull;    // a protocol bug must end the kernel, not hang the GPU
 
 __device__ __forceinline__ double pow2_clamped(int x) {          // 2^x, exact, x clamped to the normal range
     x = max(-1022, min(1023, x));
@@ -256,20 +323,23 @@ __device__ __forceinline__ double pow2_clamped(int x) {          // 2^x, exact, 
 // factor of each other, states far apart do not, so the dynamic range across lanes is unlimited like in log space.
 // Steps come in pairs: the first of a pair handles exponents (adopt / compare with the left neighbour, rescale by a
 // power of two, look for dropped states), the second is the bare recursion.
-template <int K>
+// POLL (overlapped path): the label probabilities are being produced by ctc_rows_kernel while this kernel runs; before
+// the rows of a granule are staged, lane 0 acquires the granule's progress counter (prefetched one granule ahead so the
+// L2 round trip is off the recursion's critical path) and the warp synchronises on the answer.
+template <int K, bool POLL>
 __global__ void __launch_bounds__(32)
-ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__ tlen, const int32_t* __restrict__ ilen,
-                int Tn, int Sp, float* __restrict__ nll_out, CtcWs w) {
+ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restrict__ nll_out, CtcWs w) {
     constexpr int CH = kScanChunkStates / K;          // steps per staged chunk (even)
     constexpr int SA = 32 * K;                        // alpha/beta row pitch: every lane's states exist in memory
-    static_assert(CH % 2 == 0 && K % 2 == 0, "pairs of steps, pairs of states");
+    constexpr int KP = K / 2;                         // 16-byte pairs of states per lane
+    static_assert(CH % 2 == 0 && K % 4 == 0, "pairs of steps, 32-byte aligned runs of states");
     __shared__ __align__(16) double stage[kScanStageDoubles];
     __shared__ double fin_v[2];
     __shared__ int fin_e[2];
     const int b = blockIdx.x, lane = threadIdx.x;
     const bool rev = blockIdx.y == 1;
-    if (w.flag[b]) return;                            // already sent to the log-space recursion
-    const int L = tlen[b], S = 2 * L + 1;
+    if (!POLL && w.flag[b]) return;                   // already sent to the log-space recursion
+    const int L = w.len[b], S = 2 * L + 1;
     const int Tb = min(ilen[b], Tn);
     if (Tb <= 0) {
         if (!rev && lane == 0) {
@@ -279,7 +349,7 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
         }
         return;
     }
-    const int32_t* tg = targets + w.toff[b];
+    const int* tg = w.lab + (long long)b * w.Lp;
     const int s0 = lane * K;
     // transition s'-2 -> s' is allowed iff l''_{s'} is a label different from l''_{s'-2} (same test in either direction);
     // kept as 0/1 multipliers so that the recursion is fused multiply-adds without selects
@@ -294,7 +364,8 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
             if ((s & 1) && tg[s >> 1] != tg[s2 >> 1]) skd[j] = 1.0;
         }
     }
-    const double* P = w.pg + (long long)b * Tn * Sp;
+    // alpha reads pg, beta reads the mirrored copy pgr: either way state s' of this scan is element s' of the row
+    const double* P = (rev ? w.pgr : w.pg) + (long long)b * Tn * Sp;
     const long long tstep = rev ? -1 : 1;             // rows advance forwards for alpha, backwards for beta
     const int t_first = rev ? Tb - 1 : 0;
     double* orow = (rev ? w.beta : w.alpha) + ((long long)b * Tn + t_first) * SA + s0;
@@ -302,28 +373,65 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
 
     const int nsteps = Tb - 1;                        // steps i = 1 .. Tb-1; step i reads row t_first + i*tstep
     const int nchunks = (nsteps + CH - 1) / CH;
-    // source of this lane's state j in a row (mirrored for beta). States beyond S are zero-filled (0 source bytes; the
-    // address still lies inside the workspace). Rows past the last step are clamped to the last row (copied, unused).
-    const int src_off = rev ? S - 1 - s0 : s0;
-    const double* isrc = P + (long long)t_first * Sp + src_off;          // row of the next step to be staged
+
+    // ---- progress protocol (POLL): steps i < ready have their rows in place
+    const int* prog = w.prog + (long long)b * w.NG;
+    int ready = POLL ? 0 : 0x7fffffff;
+    int gnext = rev ? (Tb - 1) / kGranule : 0;        // next granule to acquire: upwards for alpha, downwards for beta
+    int pend = 0;                                     // lane 0: prefetched counter of granule gnext
+    bool timed_out = false;
+    if (POLL && lane == 0) pend = ld_acquire_gpu(prog + gnext);
+    auto ensure = [&](int i_hi) {                     // warp-uniform: rows of steps 0..i_hi are complete on return
+        while (ready <= i_hi && !timed_out) {
+            int ok = 1;
+            if (lane == 0) {
+                const int target = min(kGranule, Tn - gnext * kGranule);
+                int cnt = pend;
+                if (cnt < target) {
+                    const unsigned long long t0 = global_timer_ns();
+                    do {
+                        __nanosleep(100);
+                        cnt = ld_acquire_gpu(prog + gnext);
+                        if (cnt < target && global_timer_ns() - t0 > kScanWaitLimitNs) { ok = 0; break; }
+                    } while (cnt < target);
+                }
+            }
+            ok = __shfl_sync(0xffffffffu, ok, 0);     // the other lanes' reads are ordered after lane 0's acquire
+            if (!ok) { timed_out = true; break; }
+            ready = rev ? Tb - gnext * kGranule : (gnext + 1) * kGranule;
+            gnext += rev ? -1 : 1;
+            if (lane == 0 && gnext >= 0 && gnext < w.NG) pend = ld_acquire_gpu(prog + gnext);
+        }
+    };
+
+    // States beyond Sp are zero-filled (0 source bytes; the address still lies inside the workspace); states in [S, Sp) are
+    // zeros in memory. Rows past the last step are clamped to the last row (copied, unused).
+    const double* isrc = P + (long long)t_first * Sp + s0;                // row of the next step to be staged
     const long long istride = tstep * Sp;
     int ileft = nsteps;                                                    // steps not yet staged
-    int nbytes[K];
+    int istaged = 0;                                                       // last step whose row has been requested
+    int nbytes[KP];
 #pragma unroll
-    for (int j = 0; j < K; ++j) nbytes[j] = (s0 + j < S) ? 8 : 0;
-    const uint32_t stage_u32 = smem_u32(stage) + lane * 8;
+    for (int jp = 0; jp < KP; ++jp) nbytes[jp] = (s0 + 2 * jp < Sp) ? 16 : 0;
+    const uint32_t stage_u32 = smem_u32(stage) + lane * 16;
     auto issue = [&](int slot) {
+        if (POLL) {
+            const int hi = min(istaged + CH, nsteps);
+            ensure(hi);
+            istaged = hi;
+        }
         const uint32_t dst = stage_u32 + slot * (kScanChunkStates * 32 * 8);
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             if (ileft > 0) { isrc += istride; --ileft; }
 #pragma unroll
-            for (int j = 0; j < K; ++j)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
-                             :: "r"(dst + (u * K + j) * 256), "l"(rev ? isrc - j : isrc + j), "r"(nbytes[j]) : "memory");
+            for (int jp = 0; jp < KP; ++jp)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                             :: "r"(dst + (u * KP + jp) * 512), "l"(isrc + 2 * jp), "r"(nbytes[jp]) : "memory");
         }
         cp_async_commit();
     };
+    if (POLL) ensure(0);
     issue(0);
     issue(1);
 
@@ -331,11 +439,11 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
     double v[K];
     bool empty = true;                                // all of this lane's states are exactly zero
     {
-        const double* src = P + (long long)t_first * Sp + src_off;
+        const double* src = P + (long long)t_first * Sp + s0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int sp = s0 + j;
-            v[j] = (sp < 2 && sp < S) ? (rev ? src[-j] : src[j]) : 0.0;
+            v[j] = (sp < 2 && sp < S) ? __ldcg(src + j) : 0.0;
             empty &= (v[j] == 0.0);
         }
 #pragma unroll
@@ -347,8 +455,9 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
     int slot = 0;
     for (int c = 0; c < nchunks; ++c) {
         issue(slot == 0 ? 2 : slot - 1);
+        if (POLL && timed_out) break;                 // warp-uniform
         cp_async_wait<2>();                           // chunk c has landed (each lane reads only what it copied itself)
-        const double* buf = stage + slot * (kScanChunkStates * 32) + lane;
+        const double2* buf = reinterpret_cast<const double2*>(stage) + slot * (kScanChunkStates * 16) + lane;
         slot = slot == 2 ? 0 : slot + 1;
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
@@ -383,9 +492,12 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
                 const double sc = pow2_clamped(-d);
                 e += d;
                 int mh = 0;
+                double2 pp[KP];
+#pragma unroll
+                for (int jp = 0; jp < KP; ++jp) pp[jp] = buf[(u * KP + jp) * 32];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    const double ps = buf[(u * K + j) * 32] * sc;
+                    const double ps = ((j & 1) ? pp[j >> 1].y : pp[j >> 1].x) * sc;
                     double a;
                     if (j == 0)      a = fma(fma(n2, skd[0], n1), r, v[0]);
                     else if (j == 1) a = fma(n1 * skd[1], r, v[1] + v[0]);
@@ -405,9 +517,12 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
             } else {
                 // ---- bare step: this lane keeps its units
                 const double r = nempty ? 0.0 : pow2_clamped(ne - e);
+                double2 pp[KP];
+#pragma unroll
+                for (int jp = 0; jp < KP; ++jp) pp[jp] = buf[(u * KP + jp) * 32];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    const double ps = buf[(u * K + j) * 32];
+                    const double ps = (j & 1) ? pp[j >> 1].y : pp[j >> 1].x;
                     double a;
                     if (j == 0)      a = fma(fma(n2, skd[0], n1), r, v[0]);
                     else if (j == 1) a = fma(n1 * skd[1], r, v[1] + v[0]);
@@ -424,6 +539,14 @@ ctc_scan_kernel(const int32_t* __restrict__ targets, const int32_t* __restrict__
         }
     }
     cp_async_wait<0>();
+    if (POLL && timed_out) {
+        // the rows never arrived (protocol bug, or the two kernels could not run concurrently): report, do not hang
+        if (lane == 0) {
+            atomicOr(&w.err[0], 2);
+            if (!rev) { w.ll[b] = NAN; w.pfin[b] = 1.0; w.efin[b] = 0; nll_out[b] = NAN; }
+        }
+        return;
+    }
     if (!rev) {
         // likelihood = alpha(S-1) + alpha(S-2) at the last step, each in its lane's units
 #pragma unroll
@@ -477,7 +600,7 @@ ctc_scan_verify_kernel(const int32_t* __restrict__ tlen, const int32_t* __restri
     const int eb_l = have_beta ? w.eb[row * 32 + lane] : 0;
     if (!__any_sync(0xffffffffu, ((ea_l | eb_l) & 1) != 0)) return;
     if (!have_beta) { if (lane == 0) w.flag[b] = 1; return; }
-    const int S = 2 * tlen[b] + 1;
+    const int S = 2 * w.len[b] + 1;
     const double* al = w.alpha + row * SA;
     const double* be = w.beta + row * SA;
     const double* pr = w.pg + row * Sp;
@@ -515,8 +638,8 @@ ctc_alpha_beta_log_kernel(const int32_t* __restrict__ targets, const int32_t* __
     const int b = blockIdx.x, s = threadIdx.x;
     if (!w.flag[b]) return;
     const bool is_beta = blockIdx.y == 1;
-    const int L = tlen[b], S = 2 * L + 1, Tb = min(ilen[b], Tn);
-    const int32_t* tg = targets + w.toff[b];
+    const int L = w.len[b], S = 2 * L + 1, Tb = min(ilen[b], Tn);
+    const int* tg = w.lab + (long long)b * w.Lp;
     const int W = Sp + 4;
     double* bufA = smd;
     double* bufB = smd + W;
@@ -609,12 +732,13 @@ ctc_alpha_beta_log_kernel(const int32_t* __restrict__ targets, const int32_t* __
 }
 
 // ---------------------------------------------------------------- loss = mean_b(nll_b / max(L_b, 1))
-__global__ void ctc_mean_loss_kernel(const float* __restrict__ nll, const int32_t* __restrict__ tlen, int B,
-                                     float* __restrict__ loss) {
+__global__ void ctc_mean_loss_kernel(const float* __restrict__ nll, const int* __restrict__ len, const int* __restrict__ err,
+                                     int B, float* __restrict__ loss) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += nll[b] / (float)max(tlen[b], 1);
-        loss[0] = acc / (float)B;
+        for (int b = 0; b < B; ++b) acc += nll[b] / (float)max(len[b], 1);
+        // out-of-range lengths / labels, or a scan that never received its rows: the result is not a loss
+        loss[0] = err[0] ? NAN : acc / (float)B;
     }
 }
 
@@ -630,6 +754,38 @@ __device__ __forceinline__ bool split_pow2(double v, double& m, int& x) {
     return hi > 0 && ex != 0 && ex != 0x7ff;
 }
 
+// state occupancy alpha_t(s) beta_t(s) / (p_t(l'_s) * likelihood) of one row into occ[0..S) (shared memory), by `nthr`
+// cooperating threads. Linear mode: mantissa / exponent arithmetic on the block-floating-point scan results.
+__device__ __forceinline__ void ctc_occupancy(long long row, int b, int S, int Sp, int Sa, int kscan, double ll, const CtcWs& w,
+                                              float* occ, int tid, int nthr) {
+    const double* al = w.alpha + row * Sa;
+    const double* be = w.beta + row * Sa;
+    if (w.flag[b]) {
+        const float* lpr = w.lpg + row * Sp;
+        for (int s = tid; s < S; s += nthr) {
+            const double e = al[s] + be[s] - (double)lpr[s] - ll;        // -inf if either side is unreachable
+            occ[s] = (e == e) ? expf((float)e) : 0.f;
+        }
+    } else {
+        const double* pr = w.pg + row * Sp;
+        const int* ea = w.ea + row * 32;
+        const int* eb = w.eb + row * 32;
+        const int efin = w.efin[b];
+        double mf; int xf;
+        split_pow2(w.pfin[b], mf, xf);
+        for (int s = tid; s < S; s += nthr) {
+            double ma, mb, mp; int xa, xb, xp;
+            const bool ok = split_pow2(al[s], ma, xa) & split_pow2(be[S - 1 - s], mb, xb) & split_pow2(pr[s], mp, xp);
+            float o = 0.f;
+            if (ok) {
+                const int x = xa + xb - xp - xf + (ea[s / kscan] >> 1) + (eb[(S - 1 - s) / kscan] >> 1) - efin;
+                o = (x < -140) ? 0.f : ldexpf((float)(ma * mb / (mp * mf)), min(x, 8));
+            }
+            occ[s] = o;
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kGradThreads)
 ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t,
@@ -641,40 +797,13 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     const int b = (int)(row / Tn), t = (int)(row - (long long)b * Tn);
     const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
     T* g = grad + (long long)t * stride_t + (long long)b * stride_b;
-    const int L = tlen[b], S = 2 * L + 1;
+    const int L = w.len[b], S = 2 * L + 1;
     const double ll = w.ll[b];
     const bool dead = (t >= ilen[b]) || (ll == -INFINITY);          // beyond the input length / zero_infinity
     const float scale = dead ? 0.f : grad_scale / ((float)max(L, 1) * (float)Bn);
     const float lse = dead ? 0.f : w.lse[row];
 
-    if (!dead) {
-        const double* al = w.alpha + row * Sa;
-        const double* be = w.beta + row * Sa;
-        if (w.flag[b]) {
-            const float* lpr = w.lpg + row * Sp;
-            for (int s = threadIdx.x; s < S; s += blockDim.x) {
-                const double e = al[s] + be[s] - (double)lpr[s] - ll;        // -inf if either side is unreachable
-                occ[s] = (e == e) ? expf((float)e) : 0.f;
-            }
-        } else {
-            const double* pr = w.pg + row * Sp;
-            const int* ea = w.ea + row * 32;
-            const int* eb = w.eb + row * 32;
-            const int efin = w.efin[b];
-            double mf; int xf;
-            split_pow2(w.pfin[b], mf, xf);
-            for (int s = threadIdx.x; s < S; s += blockDim.x) {
-                double ma, mb, mp; int xa, xb, xp;
-                const bool ok = split_pow2(al[s], ma, xa) & split_pow2(be[S - 1 - s], mb, xb) & split_pow2(pr[s], mp, xp);
-                float o = 0.f;
-                if (ok) {
-                    const int x = xa + xb - xp - xf + (ea[s / kscan] >> 1) + (eb[(S - 1 - s) / kscan] >> 1) - efin;
-                    o = (x < -140) ? 0.f : ldexpf((float)(ma * mb / (mp * mf)), min(x, 8));
-                }
-                occ[s] = o;
-            }
-        }
-    }
+    if (!dead) ctc_occupancy(row, b, S, Sp, Sa, kscan, ll, w, occ, threadIdx.x, blockDim.x);
     // dense part: softmax * scale
     const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
     int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
@@ -706,7 +835,7 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     __syncthreads();
     // label classes: subtract the occupancy, summed over the states that share a class in a fixed order
     const int* canon = w.canon + (long long)b * Sp;
-    const int32_t* tg = targets + w.toff[b];
+    const int* tg = w.lab + (long long)b * w.Lp;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         if (canon[s] != s) continue;
         float acc = 0.f;
@@ -715,6 +844,383 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
         const int c = (s & 1) ? tg[s >> 1] : 0;
         Ld<T>::st_one(g + c, (__expf(Ld<T>::one(p + c) - lse) - acc) * scale);
     }
+}
+
+
+// ================================================================ overlapped path: rows / fix kernels
+constexpr int kRowsMaxWarps = 8;
+
+// per-warp shared-memory buffer of the rows kernel (bytes) and where the row is staged inside it.
+//   fp32 rows: staged at offset 0 (element 0 at byte 16 - head), exp() values overwrite the row in place.
+//   bf16 rows: exp() values are fp32 - the body element i goes to byte 32 + 4 i - and the bf16 row is staged in the upper
+//   part of the same buffer (body element i at stage_off + 16 + 2 i) so that the expansion runs in place: an iteration of
+//   the warp converts 128 elements (reads 256 B, writes 512 B), and stage_off >= 2C + 288 keeps every write below the bytes
+//   later iterations still have to read (a __syncwarp between an iteration's loads and its stores covers the last ones).
+__host__ __device__ inline int rows_stage_off(int C, int elem_size) {
+    return elem_size == 4 ? 0 : ((2 * C + 15) / 16 * 16 + 576);
+}
+__host__ __device__ inline int rows_buf_bytes(int C, int elem_size) {
+    const int body = (C * elem_size + 15) / 16 * 16;
+    return rows_stage_off(C, elem_size) + 16 + body + 16 + (elem_size == 4 ? 0 : 64);
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short h) { return __uint_as_float(static_cast<uint32_t>(h) << 16); }
+
+// One warp per logits row (see the header of this file). Grid: persistent CTAs of `nw` warps, rows dealt in the order
+// (t = 0, all b), (t = T-1, all b), (t = 1, all b), (t = T-2, all b), ... so that both recursions are fed from their starts.
+template <typename T, bool GRAD>
+__global__ void __launch_bounds__(kRowsMaxWarps * 32)
+ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t,
+                long long stride_b, const int32_t* __restrict__ ilen, int Sp, const float* __restrict__ lse_in,
+                float grad_scale, int buf_bytes, int stage_off, CtcWs w) {
+    constexpr int ES = (int)sizeof(T);
+    constexpr bool BF = ES == 2;
+    extern __shared__ __align__(128) unsigned char rows_smem[];        // [nw][buf_bytes], then [nw][Sp] floats
+    __shared__ __align__(8) uint64_t bars[kRowsMaxWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned char* buf = rows_smem + (size_t)warp * buf_bytes;
+    float* xg = reinterpret_cast<float*>(rows_smem + (size_t)nw * buf_bytes) + (size_t)warp * Sp;
+    unsigned char* stage = buf + stage_off;
+    uint64_t* bar = &bars[warp];
+    if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncwarp();
+    const int row_bytes = C * ES;
+    const int nk = (Tn + 1) / 2;
+    const long long total = (long long)nk * 2 * Bn;
+    const long long tw = (long long)gridDim.x * nw;
+    uint32_t phase = 0;
+    for (long long v = (long long)blockIdx.x * nw + warp; v < total; v += tw) {
+        const int k = (int)(v / (2 * Bn));
+        const int r = (int)(v - (long long)k * 2 * Bn);
+        int t, b;
+        if (r < Bn) { t = k; b = r; }
+        else { t = Tn - 1 - k; b = r - Bn; if (t == k) continue; }     // odd T: the middle row belongs to the first half
+        const long long row = (long long)b * Tn + t;
+        const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+        T* g = GRAD ? grad + (long long)t * stride_t + (long long)b * stride_b : nullptr;
+        const bool live = t < ilen[b];
+        if (live) {
+            const RowGeom rg = row_geom(p, row_bytes);
+            warp_stage_row<ES>(stage, rg, row_bytes, bar, lane);
+            const int L = w.len[b], S = 2 * L + 1;
+            const int* tg = w.lab + (long long)b * w.Lp;
+            const int nhead = rg.head_bytes / ES;
+            const int nvec = rg.body_bytes >> 4;                         // 16-byte vectors of the aligned interior
+            const int tail0 = nhead + nvec * (16 / ES);
+            const int sc = lane < nhead ? lane : tail0 + (lane - nhead); // the head / tail element this lane carries
+            const bool has_sc = lane < 16 && sc < C;
+            const unsigned char* e0 = stage + 16 - rg.head_bytes;        // element 0 of the staged row
+            const unsigned char* body = stage + 16;
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            __syncwarp();                                                // head / tail elements stored by the first lanes
+            // ---- raw logits of the blank-interleaved labels (before anything is overwritten)
+            for (int q = lane; q < S; q += 32) {
+                const int c = (q & 1) ? tg[q >> 1] : 0;
+                xg[q] = BF ? bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(e0 + 2 * c))
+                           : *reinterpret_cast<const float*>(e0 + 4 * c);
+            }
+            float x_sc = 0.f;
+            if (has_sc) x_sc = BF ? bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(e0 + 2 * sc))
+                                  : *reinterpret_cast<const float*>(e0 + 4 * sc);
+            float lse, mul;                                               // gradient = value * mul
+            const float scale = grad_scale / ((float)max(L, 1) * (float)Bn);
+            const bool given = lse_in != nullptr;
+            float m = 0.f;
+            if (!given) {
+                // ---- pass 1: maximum
+                m = has_sc ? x_sc : -INFINITY;
+                if (BF) {
+                    __nv_bfloat162 mm = __float2bfloat162_rn(-INFINITY);
+#pragma unroll 4
+                    for (int vi = lane; vi < nvec; vi += 32) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(body + (vi << 4));
+                        const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.x), *reinterpret_cast<const __nv_bfloat162*>(&q.y));
+                        const __nv_bfloat162 c2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.z), *reinterpret_cast<const __nv_bfloat162*>(&q.w));
+                        mm = __hmax2(mm, __hmax2(a, c2));
+                    }
+                    m = fmaxf(m, fmaxf(__low2float(mm), __high2float(mm)));
+                } else {
+#pragma unroll 4
+                    for (int vi = lane; vi < nvec; vi += 32) {
+                        const float4 q = *reinterpret_cast<const float4*>(body + (vi << 4));
+                        m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+                    }
+                }
+                m = warp_max(m);
+                __syncwarp();                                             // all gather / edge reads precede the overwrites
+                // ---- pass 2: e = exp(x - m) kept in shared memory (fp32), sum
+                float sum = 0.f;
+                float e_sc = 0.f;
+                if (has_sc) {
+                    e_sc = ex2_fast((x_sc - m) * kLog2e); sum = e_sc;
+                    if (!BF) *reinterpret_cast<float*>(stage + 16 - rg.head_bytes + 4 * sc) = e_sc;
+                }
+                if (BF) {
+                    const int nunit = nvec * 2;                           // 4-element units: 8 B in, 16 B out, conflict-free
+                    const int niter = (nunit + 31) >> 5;
+                    for (int it = 0; it < niter; ++it) {
+                        const int u = (it << 5) + lane;
+                        uint2 q = make_uint2(0u, 0u);
+                        if (u < nunit) q = *reinterpret_cast<const uint2*>(body + (u << 3));
+                        __syncwarp();                                    // every lane has its input before anybody overwrites
+                        if (u < nunit) {
+                            float4 e;
+                            e.x = ex2_fast((bf16_lo(q.x) - m) * kLog2e); e.y = ex2_fast((bf16_hi(q.x) - m) * kLog2e);
+                            e.z = ex2_fast((bf16_lo(q.y) - m) * kLog2e); e.w = ex2_fast((bf16_hi(q.y) - m) * kLog2e);
+                            sum += (e.x + e.y) + (e.z + e.w);
+                            *reinterpret_cast<float4*>(buf + 32 + (u << 4)) = e;
+                        }
+                    }
+                    __syncwarp();
+                    if (has_sc) {                                         // head: float index 8 - nhead + j; tail: 8 + 8 nvec + i
+                        const int fi = lane < nhead ? 8 - nhead + lane : 8 + nvec * 8 + (lane - nhead);
+                        *reinterpret_cast<float*>(buf + 4 * fi) = e_sc;
+                    }
+                } else {
+#pragma unroll 2
+                    for (int vi = lane; vi < nvec; vi += 32) {
+                        float4 q = *reinterpret_cast<const float4*>(body + (vi << 4));
+                        q.x = ex2_fast((q.x - m) * kLog2e); q.y = ex2_fast((q.y - m) * kLog2e);
+                        q.z = ex2_fast((q.z - m) * kLog2e); q.w = ex2_fast((q.w - m) * kLog2e);
+                        sum += (q.x + q.y) + (q.z + q.w);
+                        *reinterpret_cast<float4*>(buf + 16 + (vi << 4)) = q;
+                    }
+                }
+                sum = warp_sum(sum);
+                lse = m + logf(sum);
+                mul = scale / sum;
+                x_sc = e_sc;                                              // what the gradient pass multiplies
+            } else {
+                lse = lse_in[row];
+                mul = scale;
+            }
+            if (lane == 0) w.lse[row] = lse;
+            // ---- label probabilities for the recursion (plain and mirrored), log-probs for the log-space fallback
+            {
+                float* dst = w.lpg + row * Sp;
+                double* dpr = w.pg + row * Sp;
+                double* dpm = w.pgr + row * Sp;
+                bool small = false;
+                for (int q = lane; q < Sp; q += 32) {
+                    float lp = 0.f;
+                    double pr = 0.0;
+                    if (q < S) {
+                        lp = xg[q] - lse;
+                        pr = (double)expf(lp);
+                        small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);
+                        small |= !(lp == lp);
+                        dpm[S - 1 - q] = pr;
+                    } else {
+                        dpm[q] = 0.0;
+                    }
+                    dst[q] = lp;
+                    dpr[q] = pr;
+                }
+                if (__any_sync(0xffffffffu, small) && lane == 0) w.flag[b] = 1;
+            }
+            // ---- pass 3: dense part of the gradient, softmax * scale (the label classes are corrected by ctc_fix_kernel)
+            if (GRAD) {
+                const bool same_align = ((reinterpret_cast<uintptr_t>(g) & 15) == (reinterpret_cast<uintptr_t>(p) & 15));
+                unsigned char* gb = reinterpret_cast<unsigned char*>(g);
+                if (same_align) {
+                    if (BF) {
+                        const int nunit = nvec * 2;
+                        unsigned char* gbody = gb + rg.head_bytes;
+                        if (!given) {
+#pragma unroll 4
+                            for (int u = lane; u < nunit; u += 32) {
+                                const float4 e = *reinterpret_cast<const float4*>(buf + 32 + (u << 4));
+                                *reinterpret_cast<uint2*>(gbody + (u << 3)) = make_uint2(pack_bf16x2(e.x * mul, e.y * mul), pack_bf16x2(e.z * mul, e.w * mul));
+                            }
+                        } else {
+#pragma unroll 4
+                            for (int u = lane; u < nunit; u += 32) {
+                                const uint2 q = *reinterpret_cast<const uint2*>(body + (u << 3));
+                                const float a0 = ex2_fast((bf16_lo(q.x) - lse) * kLog2e) * mul, a1 = ex2_fast((bf16_hi(q.x) - lse) * kLog2e) * mul;
+                                const float a2 = ex2_fast((bf16_lo(q.y) - lse) * kLog2e) * mul, a3 = ex2_fast((bf16_hi(q.y) - lse) * kLog2e) * mul;
+                                *reinterpret_cast<uint2*>(gbody + (u << 3)) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
+                            }
+                        }
+                    } else {
+                        unsigned char* gbody = gb + rg.head_bytes;
+#pragma unroll 4
+                        for (int vi = lane; vi < nvec; vi += 32) {
+                            float4 q = *reinterpret_cast<const float4*>(body + (vi << 4));     // e (in place) or the raw logits
+                            if (given) {
+                                q.x = ex2_fast((q.x - lse) * kLog2e); q.y = ex2_fast((q.y - lse) * kLog2e);
+                                q.z = ex2_fast((q.z - lse) * kLog2e); q.w = ex2_fast((q.w - lse) * kLog2e);
+                            }
+                            q.x *= mul; q.y *= mul; q.z *= mul; q.w *= mul;
+                            *reinterpret_cast<float4*>(gbody + (vi << 4)) = q;
+                        }
+                    }
+                    if (has_sc) {
+                        const float val = (given ? ex2_fast((x_sc - lse) * kLog2e) : x_sc) * mul;
+                        Ld<T>::st_one(g + sc, val);
+                    }
+                } else {
+                    // gradient row aligned differently from the logits row: element-wise stores
+                    for (int j = lane; j < C; j += 32) {
+                        float val;
+                        if (given) {
+                            const float x = BF ? bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(e0 + 2 * j))
+                                               : *reinterpret_cast<const float*>(e0 + 4 * j);
+                            val = ex2_fast((x - lse) * kLog2e);
+                        } else if (BF) {
+                            val = *reinterpret_cast<const float*>(buf + 4 * (8 - nhead + j));
+                        } else {
+                            val = *reinterpret_cast<const float*>(e0 + 4 * j);
+                        }
+                        Ld<T>::st_one(g + j, val * mul);
+                    }
+                }
+            }
+        } else if (GRAD) {
+            // beyond the input length of this sequence: zero gradient
+            const RowGeom gg = row_geom(g, row_bytes);
+            unsigned char* gb = reinterpret_cast<unsigned char*>(g);
+            const int nvec = gg.body_bytes >> 4;
+            for (int vi = lane; vi < nvec; vi += 32) *reinterpret_cast<uint4*>(gb + gg.head_bytes + (vi << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            const int nhead = gg.head_bytes / ES;
+            const int tail0 = nhead + nvec * (16 / ES);
+            const int sc = lane < nhead ? lane : tail0 + (lane - nhead);
+            if (lane < 16 && sc < C) Ld<T>::st_one(g + sc, 0.f);
+        }
+        // ---- this row's probabilities are in place: publish (release) for the scans
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            atomicAdd(&w.prog[(long long)b * w.NG + t / kGranule], 1);
+        }
+        fence_proxy_async();                  // the next bulk copy (async proxy) overwrites what this warp just read / wrote
+        __syncwarp();
+    }
+}
+
+// After the scans: one warp per row subtracts the state occupancy at the label classes,
+//   grad[c] = (softmax_c - sum_{s: l'_s = c} occ(s)) * scale
+// duplicates of a class summed in a fixed order (deterministic), and zeroes the rows of sequences with an infinite loss
+// (zero_infinity). Same arithmetic as the tail of ctc_grad_kernel.
+constexpr int kFixWarps = 8;
+template <typename T>
+__global__ void __launch_bounds__(kFixWarps * 32)
+ctc_fix_kernel(T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t, long long stride_b,
+               const int32_t* __restrict__ ilen, int Sp, int Sa, int kscan, float grad_scale, CtcWs w) {
+    extern __shared__ float fix_occ[];                                  // [kFixWarps][Sp]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * kFixWarps + warp;     // row = b*T + t
+    if (row >= (long long)Tn * Bn) return;
+    const int b = (int)(row / Tn), t = (int)(row - (long long)b * Tn);
+    if (t >= ilen[b]) return;                                            // zeroed by the rows kernel
+    T* g = grad + (long long)t * stride_t + (long long)b * stride_b;
+    const double ll = w.ll[b];
+    if (ll == -INFINITY) {
+        // zero_infinity: the whole row (the rows kernel wrote softmax * scale before the likelihood was known)
+        const RowGeom gg = row_geom(g, C * (int)sizeof(T));
+        unsigned char* gb = reinterpret_cast<unsigned char*>(g);
+        const int nvec = gg.body_bytes >> 4;
+        for (int vi = lane; vi < nvec; vi += 32) *reinterpret_cast<uint4*>(gb + gg.head_bytes + (vi << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        const int nhead = gg.head_bytes / (int)sizeof(T);
+        const int tail0 = nhead + nvec * (16 / (int)sizeof(T));
+        const int sc = lane < nhead ? lane : tail0 + (lane - nhead);
+        if (lane < 16 && sc < C) Ld<T>::st_one(g + sc, 0.f);
+        return;
+    }
+    const int L = w.len[b], S = 2 * L + 1;
+    const float scale = grad_scale / ((float)max(L, 1) * (float)Bn);
+    float* occ = fix_occ + (size_t)warp * Sp;
+    ctc_occupancy(row, b, S, Sp, Sa, kscan, ll, w, occ, lane, 32);
+    __syncwarp();
+    const int* canon = w.canon + (long long)b * Sp;
+    const int* tg = w.lab + (long long)b * w.Lp;
+    const float* lpr = w.lpg + row * Sp;                                 // log-softmax at the label classes
+    for (int s = lane; s < S; s += 32) {
+        if (canon[s] != s) continue;
+        float acc = 0.f;
+        for (int q = s; q < S; q += ((s & 1) ? 1 : 2))
+            if (canon[q] == s) acc += occ[q];
+        const int c = (s & 1) ? tg[s >> 1] : 0;
+        Ld<T>::st_one(g + c, (__expf(lpr[s]) - acc) * scale);
+    }
+}
+
+
+// ---------------------------------------------------------------- host side of the overlapped path
+// helper stream + fork/join events, one set per device, created on first use (the only persistent state of this file)
+struct CtcSide {
+    std::mutex mu;
+    cudaStream_t helper = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int ctc_side(CtcSide** out) {
+    static CtcSide sides[PerDeviceOnce::kMaxDev];
+    static std::mutex create_mu;
+    int dev = 0;
+    HCTR_CUDA(cudaGetDevice(&dev));
+    HCTR_CHECK(dev >= 0 && dev < PerDeviceOnce::kMaxDev, HCTR_ERR_INVALID, "ctc_loss: device index %d out of range", dev);
+    CtcSide& sd = sides[dev];
+    {
+        std::lock_guard<std::mutex> guard(create_mu);
+        if (sd.helper == nullptr) {
+            HCTR_CUDA(cudaStreamCreateWithFlags(&sd.helper, cudaStreamNonBlocking));
+            HCTR_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
+            HCTR_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
+        }
+    }
+    *out = &sd;
+    return HCTR_OK;
+}
+
+struct RowsPlan { int warps, buf_bytes, stage_off, grid; size_t smem; };
+// warps per CTA: as many per-warp row buffers as fit beside one scan CTA (24.6 KB of static shared memory) on the SM
+static int rows_plan(int C, int esz, int Sp, long long rows, RowsPlan* p) {
+    int dev = 0, smem_sm = 0, smem_optin = 0, sms = 0;
+    HCTR_CUDA(cudaGetDevice(&dev));
+    HCTR_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    HCTR_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    HCTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    p->buf_bytes = rows_buf_bytes(C, esz);
+    p->stage_off = rows_stage_off(C, esz);
+    const int per_warp = p->buf_bytes + Sp * 4;
+    const int scan_cta = kScanStageDoubles * 8 + 1024 + 1024;         // its static shared memory + the per-CTA reservation
+    int budget = smem_sm - scan_cta - 1024 - 256;                      // our own reservation and static barriers
+    if (budget > smem_optin - 256) budget = smem_optin - 256;
+    int warps = budget / per_warp;
+    if (warps > kRowsMaxWarps) warps = kRowsMaxWarps;
+    p->warps = warps;
+    p->smem = (size_t)(warps > 0 ? warps : 0) * per_warp;
+    long long ctas = warps > 0 ? (rows + warps - 1) / warps : 0;
+    p->grid = (int)(ctas < sms ? ctas : sms);
+    return HCTR_OK;
+}
+
+template <typename T, bool GRAD>
+static int launch_rows_t(const RowsPlan& p, const void* logits, void* grad, int T_, int B, int C, long long stride_t,
+                         long long stride_b, const int32_t* ilen, int Sp, const float* row_lse, float grad_scale,
+                         const CtcWs& w, cudaStream_t s) {
+    auto kern = ctc_rows_kernel<T, GRAD>;
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
+        int optin = 0;
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 256));
+        once.mark(dev);
+    }
+    kern<<<p.grid, p.warps * 32, p.smem, s>>>(static_cast<const T*>(logits), static_cast<T*>(grad), T_, B, C, stride_t, stride_b,
+                                              ilen, Sp, row_lse, grad_scale, p.buf_bytes, p.stage_off, w);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+static int launch_rows(const RowsPlan& p, const void* logits, void* grad, int dtype, int T_, int B, int C, long long stride_t,
+                       long long stride_b, const int32_t* ilen, int Sp, const float* row_lse, float grad_scale,
+                       const CtcWs& w, cudaStream_t s) {
+    if (dtype == HCTR_F32)
+        return grad ? launch_rows_t<float, true>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s)
+                    : launch_rows_t<float, false>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
+    return grad ? launch_rows_t<__nv_bfloat16, true>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s)
+                : launch_rows_t<__nv_bfloat16, false>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
 }
 
 }  // namespace hctr
@@ -756,57 +1262,103 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     HCTR_CHECK(workspace && workspace_bytes >= need, HCTR_ERR_INVALID, "ctc_loss: workspace too small (%lld < %lld)", workspace_bytes, need);
     HCTR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, HCTR_ERR_INVALID, "ctc_loss: workspace must be 256-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long rows = (long long)T * B;
+    HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "ctc_loss: too many rows");
 
     static const bool debug_force_log = getenv("HCTR_CTC_DEBUG_FORCE_LOG") != nullptr;           // diagnostics only
-    ctc_prep_kernel<<<B, 128, 0, s>>>(targets, target_lengths, B, Sp, (kscan == 0 || debug_force_log) ? 1 : 0, w);
-    HCTR_CUDA(cudaGetLastError());
-    const long long rows = (long long)T * B;
-    const long long blocksA = (rows + kLseWarps - 1) / kLseWarps;
-    HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "ctc_loss: too many rows");
-    if (dtype == HCTR_F32)
-        ctc_lse_gather_kernel<float><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
-            static_cast<const float*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Sp, row_lse, w);
-    else
-        ctc_lse_gather_kernel<__nv_bfloat16><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Sp, row_lse, w);
+    static const bool debug_no_fallback = getenv("HCTR_CTC_DEBUG_NO_FALLBACK") != nullptr;     // diagnostics only
+    const char* ov = getenv("HCTR_CTC_OVERLAP");                      // read per call: tests and profiling runs flip it
+    const bool overlap_off = ov && ov[0] == '0';
+    HCTR_CUDA(cudaMemsetAsync(w.err, 0, 16, s));
+    ctc_prep_kernel<<<B, 128, 0, s>>>(targets, target_lengths, B, C, Sp, max_target_len, (kscan == 0 || debug_force_log) ? 1 : 0, w);
     HCTR_CUDA(cudaGetLastError());
 
-    // fast path: one warp per (sequence, direction); the beta recursion is only needed for the gradient
-    const dim3 gridB(B, grad != nullptr ? 2 : 1);
     const int have_beta = grad != nullptr;
+    const dim3 gridB(B, have_beta ? 2 : 1);
     const int blocksV = (int)((rows + 7) / 8);
-#define HCTR_SCAN(K)                                                                                              \
-    ctc_scan_kernel<K><<<gridB, 32, 0, s>>>(targets, target_lengths, input_lengths, T, Sp, nll, w);               \
-    HCTR_CUDA(cudaGetLastError());                                                                                \
-    ctc_scan_verify_kernel<K><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, Sp, have_beta, w);     \
-    HCTR_CUDA(cudaGetLastError());
+    const int esz = dtype == HCTR_F32 ? 4 : 2;
+
+    // ---- overlapped path: does a row fit a per-warp buffer, with room left on the SM for a scan CTA?
+    RowsPlan plan;
+    bool overlap = !overlap_off && kscan != 0 && !debug_force_log && 2ll * B <= 4096;
+    if (overlap) {
+        int rc = rows_plan(C, esz, Sp, rows, &plan);
+        if (rc) return rc;
+        overlap = plan.warps >= 2;
+    }
+    if (overlap) {
+        CtcSide* side = nullptr;
+        int rc = ctc_side(&side);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> guard(side->mu);                 // one enqueue at a time per device (shared helper stream)
+        // fork: the scans only need the prep kernel
+        HCTR_CUDA(cudaEventRecord(side->fork, s));
+        HCTR_CUDA(cudaStreamWaitEvent(side->helper, side->fork, 0));
+        switch (kscan) {
+            case 4:  ctc_scan_kernel<4, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
+            case 8:  ctc_scan_kernel<8, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
+            default: ctc_scan_kernel<16, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
+        }
+        HCTR_CUDA(cudaGetLastError());
+        HCTR_CUDA(cudaEventRecord(side->join, side->helper));
+        rc = launch_rows(plan, logits, grad, dtype, T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse, grad_scale, w, s);
+        if (rc) return rc;
+        HCTR_CUDA(cudaStreamWaitEvent(s, side->join, 0));           // join
+    } else {
+        const long long blocksA = (rows + kLseWarps - 1) / kLseWarps;
+        if (dtype == HCTR_F32)
+            ctc_lse_gather_kernel<float><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
+                static_cast<const float*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Sp, row_lse, w);
+        else
+            ctc_lse_gather_kernel<__nv_bfloat16><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
+                static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Sp, row_lse, w);
+        HCTR_CUDA(cudaGetLastError());
+        // one warp per (sequence, direction); the beta recursion is only needed for the gradient
+        switch (kscan) {
+            case 4:  ctc_scan_kernel<4, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
+            case 8:  ctc_scan_kernel<8, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
+            case 16: ctc_scan_kernel<16, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
+            default: break;
+        }
+        HCTR_CUDA(cudaGetLastError());
+    }
     switch (kscan) {
-        case 4:  { HCTR_SCAN(4) } break;
-        case 8:  { HCTR_SCAN(8) } break;
-        case 16: { HCTR_SCAN(16) } break;
+        case 4:  ctc_scan_verify_kernel<4><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, Sp, have_beta, w); break;
+        case 8:  ctc_scan_verify_kernel<8><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, Sp, have_beta, w); break;
+        case 16: ctc_scan_verify_kernel<16><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, Sp, have_beta, w); break;
         default: break;
     }
-#undef HCTR_SCAN
+    HCTR_CUDA(cudaGetLastError());
     // log-space recursion for the flagged sequences (exits at once for the others)
     const int threads = (2 * max_target_len + 1 + 31) / 32 * 32;
     const size_t smB = (size_t)(2 * (Sp + 4) + 2) * sizeof(double);
-    static const bool debug_no_fallback = getenv("HCTR_CTC_DEBUG_NO_FALLBACK") != nullptr;     // diagnostics only
     if (!debug_no_fallback) {
         ctc_alpha_beta_log_kernel<<<gridB, threads, smB, s>>>(targets, target_lengths, input_lengths, T, Sp, Sa, nll, w);
         HCTR_CUDA(cudaGetLastError());
     }
-    ctc_mean_loss_kernel<<<1, 32, 0, s>>>(nll, target_lengths, B, loss);
+    ctc_mean_loss_kernel<<<1, 32, 0, s>>>(nll, w.len, w.err, B, loss);
     HCTR_CUDA(cudaGetLastError());
     if (grad != nullptr) {
-        const size_t smC = (size_t)Sp * sizeof(float);
-        if (dtype == HCTR_F32)
-            ctc_grad_kernel<float><<<(int)rows, kGradThreads, smC, s>>>(
-                static_cast<const float*>(logits), static_cast<float*>(grad), T, B, C, stride_t, stride_b, targets,
-                target_lengths, input_lengths, Sp, Sa, kscan, grad_scale, w);
-        else
-            ctc_grad_kernel<__nv_bfloat16><<<(int)rows, kGradThreads, smC, s>>>(
-                static_cast<const __nv_bfloat16*>(logits), static_cast<__nv_bfloat16*>(grad), T, B, C, stride_t, stride_b,
-                targets, target_lengths, input_lengths, Sp, Sa, kscan, grad_scale, w);
+        if (overlap) {
+            const size_t smF = (size_t)kFixWarps * Sp * sizeof(float);
+            const int blocksF = (int)((rows + kFixWarps - 1) / kFixWarps);
+            if (dtype == HCTR_F32)
+                ctc_fix_kernel<float><<<blocksF, kFixWarps * 32, smF, s>>>(static_cast<float*>(grad), T, B, C, stride_t, stride_b,
+                                                                         input_lengths, Sp, Sa, kscan, grad_scale, w);
+            else
+                ctc_fix_kernel<__nv_bfloat16><<<blocksF, kFixWarps * 32, smF, s>>>(static_cast<__nv_bfloat16*>(grad), T, B, C, stride_t,
+                                                                                 stride_b, input_lengths, Sp, Sa, kscan, grad_scale, w);
+        } else {
+            const size_t smC = (size_t)Sp * sizeof(float);
+            if (dtype == HCTR_F32)
+                ctc_grad_kernel<float><<<(int)rows, kGradThreads, smC, s>>>(
+                    static_cast<const float*>(logits), static_cast<float*>(grad), T, B, C, stride_t, stride_b, targets,
+                    target_lengths, input_lengths, Sp, Sa, kscan, grad_scale, w);
+            else
+                ctc_grad_kernel<__nv_bfloat16><<<(int)rows, kGradThreads, smC, s>>>(
+                    static_cast<const __nv_bfloat16*>(logits), static_cast<__nv_bfloat16*>(grad), T, B, C, stride_t, stride_b,
+                    targets, target_lengths, input_lengths, Sp, Sa, kscan, grad_scale, w);
+        }
         HCTR_CUDA(cudaGetLastError());
     }
     return HCTR_OK;

@@ -192,3 +192,72 @@ def test_ctc_loss_only_no_gradient():
     assert abs(loss - oloss) <= 1e-4 * abs(oloss)
     loss2, grad, _ = _run_flags(x, tg, tl, [T] * B)
     assert abs(loss2 - loss) <= 1e-6 * abs(loss)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("T,B,C,lo,hi", [(2048, 4, 7375, 20, 60), (257, 3, 101, 1, 9), (64, 2, 37, 0, 3), (1, 2, 11, 0, 1)])
+def test_ctc_loss_overlapped_and_sequential_paths_agree(monkeypatch, dtype, T, B, C, lo, hi):
+    """Round 2: the default path reads every logits row once (lse + label gather + dense gradient from a warp-private
+    shared-memory copy) while the alpha/beta scans run underneath on a helper stream, fed through progress counters;
+    HCTR_CTC_OVERLAP=0 runs the three sequential passes. Same loss, same gradient (the dense part differs only by
+    exp(x-m)*(scale/sum) vs exp(x-lse)*scale), for contiguous and model-layout (pitched, permuted) logits, with ragged
+    input lengths, odd T, and T = 1."""
+    from hctr_b200.ctc_loss import CTCLoss
+    x = synth.ctc_like_logits(T, B, C, 7 + T)
+    tg, tl = synth.ctc_targets(B, C, lo, hi, 9 + T)
+    il = [T] * B
+    if T > 8:
+        il[-1] = T - 5
+    results = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("HCTR_CTC_OVERLAP", mode)
+        for layout in ("contiguous", "model"):
+            if layout == "contiguous":
+                xt = torch.from_numpy(x).cuda().to(dtype).requires_grad_(True)
+                view = xt
+            else:
+                pitch = (C + 7) // 8 * 8
+                buf = torch.zeros(B, T, pitch, device="cuda", dtype=dtype)
+                buf[:, :, :C] = torch.from_numpy(x).cuda().to(dtype).permute(1, 0, 2)
+                xt = buf.requires_grad_(True)
+                view = xt[:, :, :C].permute(1, 0, 2)
+            loss = CTCLoss.from_logits(view, torch.from_numpy(tg), torch.IntTensor(il), torch.from_numpy(tl))
+            loss.backward()
+            g = xt.grad.float()
+            if layout == "model":
+                assert g[:, :, C:].abs().max().item() == 0.0 if pitch > C else True
+                g = g[:, :, :C].permute(1, 0, 2)
+            results.append((loss.item(), g.contiguous().cpu()))
+    xo = torch.from_numpy(x).to(dtype).float().numpy()
+    oloss, _, ograd = oracle.ctc_loss(xo, tg, il, tl)
+    gate = 1e-5 if dtype == torch.float32 else 2.0 ** -8 * float(np.abs(ograd).max()) + 1e-7
+    for loss, g in results:
+        assert abs(loss - oloss) <= 1e-4 * abs(oloss) + 1e-6, (loss, oloss)
+        assert np.abs(g.numpy() - ograd).max() <= gate
+    assert abs(results[0][0] - results[2][0]) <= 1e-6 * abs(oloss) + 1e-7
+
+
+def test_ctc_loss_bad_lengths_and_labels_do_not_touch_memory_out_of_bounds():
+    """Device-side lengths / labels are not trusted: out-of-range values are clamped for addressing and the loss is NaN."""
+    from hctr_b200 import native as nat
+    T, B, C, max_l = 32, 2, 17, 4
+    lib = nat.lib()
+    x = torch.randn(T, B, C, device="cuda")
+    tg = torch.tensor([1, 2, 3, 99, 5, 6, 7, 8], dtype=torch.int32, device="cuda")          # label 99 >= C
+    tl = torch.tensor([4, 4], dtype=torch.int32, device="cuda")
+    il = torch.full((B,), T, dtype=torch.int32, device="cuda")
+    nb = lib.hctr_ctc_loss_workspace_bytes(T, B, max_l)
+    ws = torch.empty(nb + 256, dtype=torch.uint8, device="cuda"); off = (-ws.data_ptr()) % 256
+    nll = torch.empty(B, device="cuda"); loss = torch.empty(1, device="cuda"); grad = torch.empty_like(x)
+
+    def run(tlen):
+        nat.check(lib.hctr_ctc_loss_fwd_bwd(nat.ptr(x), nat.HCTR_F32, T, B, C, x.stride(0), x.stride(1), nat.ptr(tg), nat.ptr(tlen),
+                                            nat.ptr(il), max_l, None, nat.ptr(nll), nat.ptr(loss), nat.ptr(grad), 1.0,
+                                            nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()))
+        torch.cuda.synchronize()
+        return loss.item()
+    assert run(tl) != run(tl)                                                  # NaN: a label is out of range
+    tg[3] = 4
+    assert run(tl) == run(tl)                                                  # finite and reproducible once repaired
+    bad = run(torch.tensor([4, 4000], dtype=torch.int32, device="cuda"))       # length beyond max_target_len
+    assert bad != bad
