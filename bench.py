@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the bounded extra legs (configs 3/4/5, CTC / top-k rooflines, ...)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":
@@ -326,6 +327,46 @@ def main():
                      "gbs": v[2] / (v[0] * 1e-3) / 1e9}
                  for t, v in sorted(by_tag.items(), key=lambda kv: -kv[1][0])}
 
+    # ---------------- bounded extra legs: the other BASELINE configs and north-star rooflines (bench_extras.py)
+    extras = {}
+    if not args.no_extras:
+        import bench_extras as bx
+        t_extras = time.time()
+        if rank == 0:
+            bx._guard(extras, "codec", lambda: bx.codec_legs(native, codec, dev, peaks))
+            if isinstance(extras.get("codec"), dict) and "error" not in extras["codec"]:
+                extras.update(extras.pop("codec"))
+            bx._guard(extras, "roofline_ctc_loss", lambda: bx.ctc_loss_legs(native, dev, peaks))
+            bx._guard(extras, "value_bn_calibrated_uniform_input", lambda: bx.bn_calibrated_leg(hctr_model, codec, dev, B_PER_GPU, WIDTH))
+            bx._guard(extras, "gpu_library_baseline", lambda: bx.gpu_library_leg(dev, WIDTH))
+            bx._guard(extras, "b1_latency_ms", lambda: bx.b1_latency_leg(model, codec, dev))
+        # config 3: every rank decodes its share of the ragged lines (no collective on the data path)
+        c3 = {}
+        bx._guard(c3, "leg", lambda: bx.c3_bucketed_leg(model, codec, dev, rank, world))
+        barrier()
+        if "error" in c3["leg"]:
+            extras["c3_bucketed"] = c3["leg"]
+        else:
+            secs = max_over_ranks(c3["leg"]["seconds"])
+            n_lines = c3["leg"]["lines_this_rank"]
+            if world > 1:
+                t = torch.tensor([n_lines], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                n_lines = int(t.item())
+            extras["c3_bucketed"] = bx.c3_finish(c3["leg"], secs, n_lines, world)
+        # config 4: the training step; the one collective of the path runs here when N > 1
+        logits = None
+        torch.cuda.empty_cache()
+        if world > 1:
+            per_gpu = max(1, 16 // world)
+            bx._guard(extras, "c4_train_step", lambda: bx.c4_train_leg(dev, rank, world, per_gpu))
+        else:
+            c4 = {}
+            bx._guard(c4, "lines_2", lambda: bx.c4_train_leg(dev, rank, world, 2))
+            bx._guard(c4, "lines_16", lambda: bx.c4_train_leg(dev, rank, world, 16, steps=3, warmup=2))
+            extras["c4_train_step"] = c4
+        extras["extras_seconds"] = time.time() - t_extras
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -353,6 +394,7 @@ def main():
             "roofline": roofline, "roofline_decode": roofline_decode, "cpu_baseline": cpu_baseline,
             "clocks": clocks, "kernel_breakdown": breakdown,
         }
+        out.update(extras)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
