@@ -313,20 +313,29 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
 }
 
 // ---------------------------------------------------------------------------------------------- top-k, one warp per row
-// Round 2. The CTA-per-row kernel above spends 28 warp-instructions per element: a 7375-class row gives each of 256 threads
-// 29 elements, and four block barriers, shared-memory hand-overs and per-row pointer arithmetic of every thread weigh more
-// than the element loops (ncu: issue-bound at 62 %, DRAM 39 %). Here ONE WARP owns a row: it stages the row in its own
-// shared-memory buffer(s) (bulk copy, per-warp mbarrier), makes both passes alone - 230 elements per lane, so the
-// per-row bookkeeping is amortised eight times better - and nothing in a row's life needs a block barrier:
-//   pass 1  per-lane maximum (16-byte shared-memory vectors)
+// Round 2. The CTA-per-row kernel above spends 28 warp-instructions per element (ncu: issue-bound at 62 %, DRAM 39 %): a
+// 7375-class row gives each of 256 threads 29 elements, and four block barriers, the shared-memory staging protocol and
+// per-row pointer arithmetic weigh more than the element loops. Here ONE WARP owns a row - 230 elements per lane, the
+// per-row bookkeeping amortised eight times better, no block barrier - and reads it twice straight from global memory:
+//   pass 1  per-lane maximum, 16-byte loads, four independent chains (the only pass that goes to DRAM)
 //   bound   the k-th largest of the 32 lane maxima is a lower bound tau for the k-th largest element (k distinct elements
 //           reach it); found by k rounds of redux.sync max over order-preserving integer keys; round 1 gives the row max
-//   pass 2  sum exp(x - max); the few elements >= tau go to a per-warp candidate list
+//   pass 2  the same warp re-reads its row (an L2 hit: it touched it microseconds ago): sum exp(x - max); the few elements
+//           >= tau go to a per-warp candidate list
 //   rank    candidates ranked by counting (value desc, index asc) -> the top k in order; exact for any input; a row with
 //           more than kWarpMaxCand candidates (constant rows) takes an exact k-round arg-max instead.
-// Rows too large for at least four per-warp buffers stay on the CTA-per-row kernel.
+// 32-40 warps per SM hide the latency; every byte crosses the L2 twice, and the L2 (about 8 TB/s) becomes the bound:
+// bf16 rows 0.475 ms on the config-5 tensor = 0.62 of the HBM peak (CTA-per-row: 0.85 ms, 0.35); fp32 rows 1.08 ms, no
+// better than the CTA-per-row kernel's 1.00 ms - so fp32 rows stay there (unless they do not fit its shared memory).
+// Measured and dropped on the way (fp32 / bf16 on that tensor), each meant to read the row only once:
+//   the row staged in a warp-private shared-memory buffer by bulk copy: 7 warps per SM cannot hide their own latencies,
+//     1.29 / 0.95 ms;
+//   one pass with a per-lane top-4 in registers + online log-sum-exp: a lane's rare insertions are not rare per warp
+//     (32 lanes): 26 instructions per element, 1.53 / 1.22 ms;
+//   four warps per row with the row in registers (all loads in flight at once): 155 / 113 registers, 12-16 warps per SM,
+//     20 instructions per element once the candidate pushes and the ranking are counted: 1.46 / 1.23 ms.
 constexpr int kWarpMaxCand = 128;
-constexpr int kTopkMaxWarps = 8;
+constexpr int kTopkWarps = 8;
 
 __device__ __forceinline__ int float_order_key(float x) {            // monotonic float -> int (NaN sorts above +inf)
     const int i = __float_as_int(x);
@@ -334,154 +343,151 @@ __device__ __forceinline__ int float_order_key(float x) {            // monotoni
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kTopkMaxWarps * 32)
+__global__ void __launch_bounds__(kTopkWarps * 32)
 ctc_topk_warp_kernel(const T* __restrict__ logits, long long rows, int Bn, int C, long long stride_t, long long stride_b,
-                     int k, int nbuf, int buf_bytes, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp,
-                     float* __restrict__ lse_out) {
-    constexpr int ES = (int)sizeof(T);
-    constexpr int V = 16 / ES;
-    extern __shared__ __align__(128) unsigned char wbufs[];             // [nw][nbuf][buf_bytes]
-    __shared__ __align__(8) uint64_t bars[kTopkMaxWarps][2];
-    __shared__ float cand_v[kTopkMaxWarps][kWarpMaxCand];
-    __shared__ int cand_i[kTopkMaxWarps][kWarpMaxCand];
-    __shared__ int ncand_s[kTopkMaxWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    unsigned char* mybuf = wbufs + (size_t)warp * nbuf * buf_bytes;
-    if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); fence_barrier_init(); ncand_s[warp] = 0; }
+                     int k, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp, float* __restrict__ lse_out) {
+    constexpr int V = LoadVec<T>::N;
+    __shared__ float cand_v[kTopkWarps][kWarpMaxCand];
+    __shared__ int cand_i[kTopkWarps][kWarpMaxCand];
+    __shared__ int ncand_s[kTopkWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * kTopkWarps + warp;
+    if (lane == 0) ncand_s[warp] = 0;
     __syncwarp();
-    const int row_bytes = C * ES;
+    if (row >= rows) return;
+    const long long t = row / Bn, b = row - t * Bn;
+    const T* p = logits + t * stride_t + b * stride_b;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > C) head = C;
+    const int nvec = (C - head) / V;
+    const int tail0 = head + nvec * V;
+    const T* pv = p + head;
     const int kk = k < 32 ? k : 32;
-    const long long tw = (long long)gridDim.x * nw;
-    long long row = (long long)blockIdx.x * nw + warp;
-    auto row_ptr = [&](long long r) -> const T* {
-        const long long t = r / Bn, b = r - t * Bn;
-        return logits + t * stride_t + b * stride_b;
-    };
-    RowGeom cur = row_geom(logits, row_bytes);
-    if (row < rows) {
-        cur = row_geom(row_ptr(row), row_bytes);
-        warp_stage_row<ES>(mybuf, cur, row_bytes, &bars[warp][0], lane);
-    }
-    for (int it = 0; row < rows; row += tw, ++it) {
-        const int s = nbuf == 2 ? (it & 1) : 0;
-        const long long next = row + tw;
-        RowGeom nxt = cur;
-        if (next < rows) {
-            nxt = row_geom(row_ptr(next), row_bytes);
-            // two buffers: row i+1 streams in while row i is reduced (the buffer's last reads ended with row i-1)
-            if (nbuf == 2) warp_stage_row<ES>(mybuf + (size_t)(s ^ 1) * buf_bytes, nxt, row_bytes, &bars[warp][s ^ 1], lane);
-        }
-        unsigned char* buf = mybuf + (size_t)s * buf_bytes;
-        const unsigned char* e0 = buf + 16 - cur.head_bytes;              // element 0
-        const unsigned char* body = buf + 16;
-        const int nhead = cur.head_bytes / ES;
-        const int nvec = cur.body_bytes >> 4;
-        const int tail0 = nhead + nvec * V;
-        const int sc = lane < nhead ? lane : tail0 + (lane - nhead);
-        const bool has_sc = lane < 16 && sc < C;
-        mbar_wait(&bars[warp][s], (nbuf == 2 ? (it >> 1) : it) & 1);
-        __syncwarp();
-        float x_sc = -INFINITY;
-        if (has_sc) x_sc = LoadVec<T>::one_smem(reinterpret_cast<const T*>(e0) + sc);
+    // the scalar elements in front of / behind the aligned interior (< V each)
+    float x_h = -INFINITY, x_t = -INFINITY;
+    if (lane < head) x_h = LoadVec<T>::one(p + lane);
+    if (tail0 + lane < C) x_t = LoadVec<T>::one(p + tail0 + lane);
 
-        // ---- pass 1: per-lane maximum
-        float lm = x_sc;
-#pragma unroll 4
-        for (int vi = lane; vi < nvec; vi += 32) {
+    // ---- pass 1: per-lane maximum
+    float lm = fmaxf(x_h, x_t);
+    {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int vi = lane;
+        for (; vi + 96 < nvec; vi += 128) {
+            float x[4][V];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) LoadVec<T>::load(pv + (long long)(vi + 32 * u) * V, x[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int j = 0; j < V; j += 2) m4[u] = fmaxf(m4[u], fmaxf(x[u][j], x[u][j + 1]));
+            }
+        }
+        for (; vi < nvec; vi += 32) {
             float x[V];
-            LoadVec<T>::load_smem(body + (vi << 4), x);
+            LoadVec<T>::load(pv + (long long)vi * V, x);
 #pragma unroll
-            for (int j = 0; j < V; j += 2) lm = fmaxf(lm, fmaxf(x[j], x[j + 1]));
+            for (int j = 0; j < V; j += 2) m4[0] = fmaxf(m4[0], fmaxf(x[j], x[j + 1]));
         }
-        // ---- tau = kk-th largest lane maximum, m = the largest
-        float m, tau;
-        {
-            int key = float_order_key(lm);
-            const int dead = (int)0x80000000;
-            int mx = __reduce_max_sync(0xffffffffu, key);
-            m = __shfl_sync(0xffffffffu, lm, __ffs(__ballot_sync(0xffffffffu, key == mx)) - 1);
-            tau = m;
-            for (int r = 1; r < kk; ++r) {
-                const unsigned hit = __ballot_sync(0xffffffffu, key == mx);
-                const int first = __ffs(hit) - 1;
-                if (lane == first) key = dead;                          // one lane leaves per round
-                mx = __reduce_max_sync(0xffffffffu, key);
+        lm = fmaxf(lm, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+    }
+    // ---- tau = kk-th largest lane maximum, m = the largest
+    float m, tau;
+    {
+        int key = float_order_key(lm);
+        const int dead = (int)0x80000000;
+        int mx = __reduce_max_sync(0xffffffffu, key);
+        m = __shfl_sync(0xffffffffu, lm, __ffs(__ballot_sync(0xffffffffu, key == mx)) - 1);
+        tau = m;
+        for (int r = 1; r < kk; ++r) {
+            const unsigned hit = __ballot_sync(0xffffffffu, key == mx);
+            const int first = __ffs(hit) - 1;
+            if (lane == first) key = dead;                              // one lane leaves per round
+            mx = __reduce_max_sync(0xffffffffu, key);
+        }
+        if (kk > 1) tau = __shfl_sync(0xffffffffu, lm, __ffs(__ballot_sync(0xffffffffu, key == mx)) - 1);
+    }
+    // ---- pass 2: sum of exp and candidate collection
+    auto push = [&](float x, int idx) {
+        const int slot = atomicAdd(&ncand_s[warp], 1);
+        if (slot < kWarpMaxCand) { cand_v[warp][slot] = x; cand_i[warp][slot] = idx; }
+    };
+    float sum = 0.f;
+    if (lane < head) { sum += exp_neg_fast(x_h - m); if (x_h >= tau) push(x_h, lane); }
+    if (tail0 + lane < C) { sum += exp_neg_fast(x_t - m); if (x_t >= tau) push(x_t, tail0 + lane); }
+    {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        int vi = lane;
+        for (; vi + 96 < nvec; vi += 128) {
+            float x[4][V];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) LoadVec<T>::load(pv + (long long)(vi + 32 * u) * V, x[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float vmax = fmaxf(x[u][0], x[u][1]);
+                float acc = exp_neg_fast(x[u][0] - m) + exp_neg_fast(x[u][1] - m);
+#pragma unroll
+                for (int j = 2; j < V; j += 2) {
+                    vmax = fmaxf(vmax, fmaxf(x[u][j], x[u][j + 1]));
+                    acc += exp_neg_fast(x[u][j] - m) + exp_neg_fast(x[u][j + 1] - m);
+                }
+                s4[u] += acc;
+                if (!(vmax < tau)) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+                        if (x[u][j] >= tau) push(x[u][j], head + (vi + 32 * u) * V + j);
+                }
             }
-            if (kk > 1) tau = __shfl_sync(0xffffffffu, lm, __ffs(__ballot_sync(0xffffffffu, key == mx)) - 1);
         }
-        // ---- pass 2: sum of exp and candidate collection
-        float sum = 0.f;
-        if (has_sc) {
-            sum += exp_neg_fast(x_sc - m);
-            if (x_sc >= tau) {
-                const int slot = atomicAdd(&ncand_s[warp], 1);
-                if (slot < kWarpMaxCand) { cand_v[warp][slot] = x_sc; cand_i[warp][slot] = sc; }
-            }
-        }
-#pragma unroll 2
-        for (int vi = lane; vi < nvec; vi += 32) {
+        for (; vi < nvec; vi += 32) {
             float x[V];
-            LoadVec<T>::load_smem(body + (vi << 4), x);
-            float vmax = fmaxf(x[0], x[1]);
+            LoadVec<T>::load(pv + (long long)vi * V, x);
 #pragma unroll
-            for (int j = 2; j < V; j += 2) vmax = fmaxf(vmax, fmaxf(x[j], x[j + 1]));
-#pragma unroll
-            for (int j = 0; j < V; ++j) sum += exp_neg_fast(x[j] - m);
-            if (!(vmax < tau)) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    if (x[j] >= tau) {
-                        const int slot = atomicAdd(&ncand_s[warp], 1);
-                        if (slot < kWarpMaxCand) { cand_v[warp][slot] = x[j]; cand_i[warp][slot] = nhead + vi * V + j; }
-                    }
-                }
+            for (int j = 0; j < V; ++j) {
+                s4[0] += exp_neg_fast(x[j] - m);
+                if (x[j] >= tau) push(x[j], head + vi * V + j);
             }
         }
-        sum = warp_sum(sum);
-        const float logs = logf(sum);
-        if (lane == 0) lse_out[row] = m + logs;
-        __syncwarp();                                                   // candidate list complete
-        const int ncand = ncand_s[warp];
-        int32_t* oi = topk_idx + row * k;
-        float* op = topk_logp + row * k;
-        if (ncand <= kWarpMaxCand) {
-            // ---- rank by counting: exact order (value desc, index asc), independent of the collection order
-            for (int e = lane; e < ncand; e += 32) {
-                const float v = cand_v[warp][e]; const int ci = cand_i[warp][e];
-                int rank = 0;
-                for (int f = 0; f < ncand; ++f) rank += cand_better(cand_v[warp][f], cand_i[warp][f], v, ci) ? 1 : 0;
-                if (rank < k) {
-                    oi[rank] = ci;
-                    op[rank] = (v - m) - logs;                           // scipy: (x - max) - log(sum(exp(x - max)))
-                }
-            }
-        } else {
-            // ---- exact fallback: k rounds of warp arg-best with exclusion of what was already emitted
-            const T* rb = reinterpret_cast<const T*>(e0);
-            float lv = INFINITY; int li = -1;
-            for (int r = 0; r < k; ++r) {
-                float bv = -INFINITY; int bi = 0x7fffffff;
-                for (int c = lane; c < C; c += 32) {
-                    const float x = LoadVec<T>::one_smem(rb + c);
-                    const bool elig = (x < lv) || (x == lv && c > li);
-                    if (elig && cand_better(x, c, bv, bi)) { bv = x; bi = c; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                    const int ov_i = __shfl_xor_sync(0xffffffffu, bi, o);
-                    if (cand_better(ov, ov_i, bv, bi)) { bv = ov; bi = ov_i; }
-                }
-                lv = bv; li = bi;
-                if (lane == 0) { oi[r] = bi; op[r] = (bv - m) - logs; }
+        sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    }
+    sum = warp_sum(sum);
+    const float logs = logf(sum);
+    if (lane == 0) lse_out[row] = m + logs;
+    __syncwarp();                                                       // candidate list complete
+    const int ncand = ncand_s[warp];
+    int32_t* oi = topk_idx + row * k;
+    float* op = topk_logp + row * k;
+    if (ncand <= kWarpMaxCand) {
+        // ---- rank by counting: exact order (value desc, index asc), independent of the collection order
+        for (int e = lane; e < ncand; e += 32) {
+            const float v = cand_v[warp][e]; const int ci = cand_i[warp][e];
+            int rank = 0;
+            for (int f = 0; f < ncand; ++f) rank += cand_better(cand_v[warp][f], cand_i[warp][f], v, ci) ? 1 : 0;
+            if (rank < k) {
+                oi[rank] = ci;
+                op[rank] = (v - m) - logs;                               // scipy: (x - max) - log(sum(exp(x - max)))
             }
         }
-        __syncwarp();
-        if (lane == 0) ncand_s[warp] = 0;
-        fence_proxy_async();                    // this buffer's next writer is the bulk-copy engine
-        __syncwarp();
-        if (nbuf == 1 && next < rows) warp_stage_row<ES>(mybuf, nxt, row_bytes, &bars[warp][0], lane);
-        cur = nxt;
+    } else {
+        // ---- exact fallback: k rounds of warp arg-best with exclusion of what was already emitted
+        float lv = INFINITY; int li = -1;
+        for (int r = 0; r < k; ++r) {
+            float bv = -INFINITY; int bi = 0x7fffffff;
+            for (int c = lane; c < C; c += 32) {
+                const float x = LoadVec<T>::one(p + c);
+                const bool elig = (x < lv) || (x == lv && c > li);
+                if (elig && cand_better(x, c, bv, bi)) { bv = x; bi = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int ov_i = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (cand_better(ov, ov_i, bv, bi)) { bv = ov; bi = ov_i; }
+            }
+            lv = bv; li = bi;
+            if (lane == 0) { oi[r] = bi; op[r] = (bv - m) - logs; }
+        }
     }
 }
 
@@ -820,7 +826,6 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     const long long rows = (long long)T * B;
     HCTR_CHECK(rows < (1ll << 31), HCTR_ERR_INVALID, "topk: too many rows");
     const size_t esz = dtype == HCTR_F32 ? 4 : 2;
-    HCTR_CHECK((size_t)C * 4 <= 160 * 1024, HCTR_ERR_INVALID, "topk: %d classes do not fit the shared-memory row buffer", C);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     static PerDeviceOnce once;                     // value = SM count of the device
     int dev, num_sms;
@@ -832,38 +837,36 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     } else {
         num_sms = once.get(dev);
     }
-    // ---- one warp per row when at least four per-warp row buffers fit the SM
+    // ---- one warp per row (two passes, the second from L2): bf16 rows, and rows too large for the shared-memory kernel
     {
-        static PerDeviceOnce once_w;                // value = opt-in shared memory per block
-        int dev_w, optin = 0;
-        if (once_w.need(dev_w)) {
-            HCTR_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev_w));
-            HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 10 * 1024));
-            HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_warp_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 10 * 1024));
-            once_w.mark(dev_w, optin);
-        } else {
-            optin = once_w.get(dev_w);
-        }
-        static const bool warp_off = getenv("HCTR_TOPK_WARP") && getenv("HCTR_TOPK_WARP")[0] == '0';      // A/B measurements
-        const int wbuf = (int)(((size_t)C * esz + 32 + 15) & ~size_t(15));
-        const long long budget = optin - 10 * 1024;                       // static: candidate lists + barriers ~ 8.3 KB
-        int wnbuf = (2ll * wbuf * 6 <= budget) ? 2 : 1;
-        long long warps = budget / ((long long)wnbuf * wbuf);
-        if (warps > kTopkMaxWarps) warps = kTopkMaxWarps;
-        if (!warp_off && warps >= 4) {
-            const size_t wsmem = (size_t)warps * wnbuf * wbuf;
-            // small rows: several CTAs per SM keep enough rows in flight
-            long long per_sm_w = (long long)(optin) / (long long)(wsmem + 10 * 1024);
-            if (per_sm_w < 1) per_sm_w = 1;
-            if (per_sm_w > 4) per_sm_w = 4;
-            const long long ctas = (rows + warps - 1) / warps;
-            const long long grid_w = ctas < per_sm_w * num_sms ? ctas : per_sm_w * num_sms;
+        const char* wv = getenv("HCTR_TOPK_WARP");                        // "0" / "1": force the CTA-per-row / warp-per-row kernel
+        const bool fits_smem = (size_t)C * 4 <= 160 * 1024;
+        bool use_warp = dtype == HCTR_BF16 || !fits_smem;
+        if (wv && wv[0] == '0' && fits_smem) use_warp = false;
+        if (wv && wv[0] == '1') use_warp = true;
+        if (use_warp) {
+            const long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
+            // four CTAs (32 warps) per SM, enforced by an unused dynamic shared-memory request: measured 0.476 ms against
+            // 0.546 ms with the 40 warps per SM the register count alone allows (bf16, config-5 tensor)
+            static PerDeviceOnce once_w;                                 // value = shared memory per SM
+            int dev_w, smem_sm = 0;
+            if (once_w.need(dev_w)) {
+                int optin = 0;
+                HCTR_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev_w));
+                HCTR_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev_w));
+                HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_warp_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 10 * 1024));
+                HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_warp_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 10 * 1024));
+                once_w.mark(dev_w, smem_sm);
+            } else {
+                smem_sm = once_w.get(dev_w);
+            }
+            const size_t pad = (size_t)(smem_sm / 5) - 9 * 1024;          // static 8.3 KB + 1 KB reserved per CTA: 4 fit, 5 do not
             if (dtype == HCTR_F32)
-                ctc_topk_warp_kernel<float><<<(int)grid_w, (int)warps * 32, wsmem, s>>>(
-                    static_cast<const float*>(logits), rows, B, C, stride_t, stride_b, k, wnbuf, wbuf, topk_idx, topk_logp, lse);
+                ctc_topk_warp_kernel<float><<<(int)blocks, kTopkWarps * 32, pad, s>>>(
+                    static_cast<const float*>(logits), rows, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
             else
-                ctc_topk_warp_kernel<__nv_bfloat16><<<(int)grid_w, (int)warps * 32, wsmem, s>>>(
-                    static_cast<const __nv_bfloat16*>(logits), rows, B, C, stride_t, stride_b, k, wnbuf, wbuf, topk_idx, topk_logp, lse);
+                ctc_topk_warp_kernel<__nv_bfloat16><<<(int)blocks, kTopkWarps * 32, pad, s>>>(
+                    static_cast<const __nv_bfloat16*>(logits), rows, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
             HCTR_CUDA(cudaGetLastError());
             return HCTR_OK;
         }

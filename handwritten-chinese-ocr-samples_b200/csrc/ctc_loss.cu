@@ -21,19 +21,19 @@
 //                  occupancy_c = sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - ll - lp[t, l'_s]).
 // Logits are read twice and the gradient written once: (2*s_in + s_out) * T*B*C bytes.
 //
-// Round 2 - the OVERLAPPED path (default when a gradient is asked for and a row fits a per-warp buffer):
-//   rows  (HBM-bound, ctc_rows_kernel): ONE pass per logits row on a warp-private shared-memory copy (bulk copy): max,
-//         exp and sum, the label gather for the recursion, AND the dense part of the gradient softmax*scale - which needs
-//         no alpha/beta. The logits are read once and the gradient written once: (s_in + s_out) * T*B*C bytes of DRAM
-//         traffic instead of (2*s_in + s_out). Rows are dealt to the warps from BOTH ends of the time axis and every
-//         finished row bumps a per-(sequence, 8-row granule) counter with release semantics.
-//   scan  (latency-bound, ctc_scan_kernel<K, true>): launched on a helper stream at the same time; before it stages the
-//         label probabilities of a granule it acquires that counter. alpha consumes rows from t = 0 upwards, beta from
-//         t = T-1 downwards, so the 2*T dependent recursion steps - a third of the old call at B = 16, with the whole
-//         GPU idle around 2*B warps - run underneath the memory-bound pass instead of after it.
-//   fix   (ctc_fix_kernel): after both, one warp per row subtracts the occupancy at the <= L+1 distinct label classes
-//         (a few dozen 2-byte read-modify-writes per row).
-// HCTR_CTC_OVERLAP=0 keeps the three sequential passes (needed under ncu, which serialises kernels).
+// Round 2 - the ONE-PASS ROWS path (default whenever a logits row fits the registers of four warps, C <= 8192 fp32 / 16384
+// bf16); its kernels run back to back on the caller's stream, or - opt-in, HCTR_CTC_OVERLAP=1, measured slower - overlapped:
+//   rows  (HBM-bound, ctc_rows_kernel): ONE pass per logits row, the row held in the registers of four warps: max, exp
+//         and sum, the label gather for the recursion, AND the dense part of the gradient softmax*scale - which needs no
+//         alpha/beta. The logits are read once and the gradient written once: (s_in + s_out) * T*B*C bytes of DRAM
+//         traffic instead of (2*s_in + s_out). Rows are dealt to the CTAs from BOTH ends of the time axis and every
+//         finished row bumps a per-(sequence, 8-row granule) counter (release).
+//   scan  (latency-bound, ctc_scan_kernel<K, POLL>): unchanged recursion; 16-byte cp.async.cg staging from the plain
+//         (alpha) / mirrored (beta) probability rows. POLL = the overlapped schedule: launched on a helper stream at the
+//         same time as the rows kernel, it waits on a granule's counter before staging its rows.
+//   fix   (ctc_fix_kernel): one warp per row subtracts the occupancy at the <= L+1 distinct label classes (a few dozen
+//         2-byte read-modify-writes per row; blank = a fixed warp tree, repeated labels = a precomputed chain).
+// HCTR_CTC_OVERLAP=0 keeps the round-1 sequential passes A/B/C (also the fallback for rows that do not fit).
 #include <cfloat>
 #include <cstdlib>
 #include <mutex>
@@ -58,6 +58,7 @@ struct CtcWs {
     int* efin;         // [B]
     int* flag;         // [B]            1 = this sequence takes the log-space recursion
     int* canon;        // [B][Sp]        first s' with the same class as s
+    int* nxt;          // [B][Sp]        next s' > s with the same class as s, -1 if none
     int* toff;         // [B]            offset of sequence b in the concatenated targets
     int* len;          // [B]            target length clamped to [0, max_target_len] (never trust device lengths)
     int* lab;          // [B][Lp]        labels clamped to [0, C-1]
@@ -91,6 +92,7 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     const long long o_efin = take(4ll * B);
     const long long o_flag = take(4ll * B);
     const long long o_canon = take(4ll * B * Sp);
+    const long long o_nxt = take(4ll * B * Sp);
     const long long o_toff = take(4ll * B);
     const int Lp = (Sp - 1) / 2 > 0 ? (Sp - 1) / 2 : 1;          // >= max_target_len (Sp >= 2L+1)
     const int NG = (T + kGranule - 1) / kGranule;
@@ -114,6 +116,7 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     w.efin = reinterpret_cast<int*>(p + o_efin);
     w.flag = reinterpret_cast<int*>(p + o_flag);
     w.canon = reinterpret_cast<int*>(p + o_canon);
+    w.nxt = reinterpret_cast<int*>(p + o_nxt);
     w.toff = reinterpret_cast<int*>(p + o_toff);
     w.len = reinterpret_cast<int*>(p + o_len);
     w.lab = reinterpret_cast<int*>(p + o_lab);
@@ -195,6 +198,12 @@ __global__ void ctc_prep_kernel(const int32_t* __restrict__ targets, const int32
             if (cq == c) { first = q; break; }
         }
         w.canon[(long long)b * Sp + s] = first;
+        int next = -1;
+        for (int q = s + ((c == 0) ? 2 : 1); q < S; q += ((c == 0) ? 2 : 1)) {
+            const int cq = (q & 1) ? lab[q >> 1] : 0;
+            if (cq == c) { next = q; break; }
+        }
+        w.nxt[(long long)b * Sp + s] = next;
     }
 }
 
@@ -300,9 +309,16 @@ constexpr int kRebaseDiff = 900;                     // adopt the left neighbour
 constexpr int kScanChunkStates = 32;                 // steps per staged chunk x states per lane
 constexpr int kScanStageDoubles = 3 * kScanChunkStates * 32;     // 3 chunks in flight = 24 KB
 
+// Progress counters are polled with RELAXED gpu-scope loads (served by the L2, the point of coherence): an acquire load
+// keeps every later memory operation of the warp - the cp.async of the next chunk, the alpha stores - behind its own L2
+// round trip, once per granule, on the critical path of a latency-bound recursion (measured: the overlapped call 1.38 ms
+// against 0.57 ms for the same kernels back to back). Ordering comes from the producer (stores, __threadfence, atomicAdd:
+// the row is performed at the L2 before the counter moves) and, on this side, from the dependency chain counter value ->
+// warp-uniform branch -> cp.async.cg / ld.global.cg of the row, all of which read the L2 and none of which can be issued
+// before the counter value has arrived.
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -779,7 +795,8 @@ __device__ __forceinline__ void ctc_occupancy(long long row, int b, int S, int S
             float o = 0.f;
             if (ok) {
                 const int x = xa + xb - xp - xf + (ea[s / kscan] >> 1) + (eb[(S - 1 - s) / kscan] >> 1) - efin;
-                o = (x < -140) ? 0.f : ldexpf((float)(ma * mb / (mp * mf)), min(x, 8));
+                // mantissas are in [1,2): single precision is plenty for a value compared at 1e-5
+                o = (x < -140) ? 0.f : ldexpf(__fdividef((float)ma * (float)mb, (float)mp * (float)mf), min(x, 8));
             }
             occ[s] = o;
         }
@@ -848,253 +865,196 @@ ctc_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
 
 
 // ================================================================ overlapped path: rows / fix kernels
-constexpr int kRowsMaxWarps = 8;
+constexpr int kRowThreads = 128;
 
-// per-warp shared-memory buffer of the rows kernel (bytes) and where the row is staged inside it.
-//   fp32 rows: staged at offset 0 (element 0 at byte 16 - head), exp() values overwrite the row in place.
-//   bf16 rows: exp() values are fp32 - the body element i goes to byte 32 + 4 i - and the bf16 row is staged in the upper
-//   part of the same buffer (body element i at stage_off + 16 + 2 i) so that the expansion runs in place: an iteration of
-//   the warp converts 128 elements (reads 256 B, writes 512 B), and stage_off >= 2C + 288 keeps every write below the bytes
-//   later iterations still have to read (a __syncwarp between an iteration's loads and its stores covers the last ones).
-__host__ __device__ inline int rows_stage_off(int C, int elem_size) {
-    return elem_size == 4 ? 0 : ((2 * C + 15) / 16 * 16 + 576);
-}
-__host__ __device__ inline int rows_buf_bytes(int C, int elem_size) {
-    const int body = (C * elem_size + 15) / 16 * 16;
-    return rows_stage_off(C, elem_size) + 16 + body + 16 + (elem_size == 4 ? 0 : 64);
-}
+template <typename T> struct RowVec;                                   // a 16-byte vector of logits kept in registers
+template <> struct RowVec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void unpack(const uint4& q, float (&o)[4]) {
+        o[0] = __uint_as_float(q.x); o[1] = __uint_as_float(q.y); o[2] = __uint_as_float(q.z); o[3] = __uint_as_float(q.w);
+    }
+};
+template <> struct RowVec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void unpack(const uint4& q, float (&o)[8]) {
+        o[0] = bf16_lo(q.x); o[1] = bf16_hi(q.x); o[2] = bf16_lo(q.y); o[3] = bf16_hi(q.y);
+        o[4] = bf16_lo(q.z); o[5] = bf16_hi(q.z); o[6] = bf16_lo(q.w); o[7] = bf16_hi(q.w);
+    }
+};
 
-__device__ __forceinline__ float bf16_bits_to_float(unsigned short h) { return __uint_as_float(static_cast<uint32_t>(h) << 16); }
-
-// One warp per logits row (see the header of this file). Grid: persistent CTAs of `nw` warps, rows dealt in the order
-// (t = 0, all b), (t = T-1, all b), (t = 1, all b), (t = T-2, all b), ... so that both recursions are fed from their starts.
-template <typename T, bool GRAD>
-__global__ void __launch_bounds__(kRowsMaxWarps * 32)
+// Four warps per logits row, the row in REGISTERS (NV 16-byte vectors per thread, all loads issued at once: a row's whole
+// 15-30 KB is in flight, several rows per SM, no staging buffer):
+//   max, exp and sum from the registers (two 128-thread barriers) -> log-sum-exp; the label gather for the recursion (plain,
+//   mirrored, log; scattered 2/4-byte reads that hit L2) and the row's progress counter (release); then the dense part of
+//   the gradient softmax * scale from the same registers. DRAM traffic: logits once, gradient once.
+// Rows are dealt in the order (t = 0, all b), (t = T-1, all b), (t = 1, all b), ... so that both recursions are fed from
+// their starts; blocks are dispatched in index order.
+// Measured and dropped: the row staged in a warp-private shared-memory buffer by bulk copy, one warp per row (6 warps per SM
+// cannot hide their own latencies: the whole call 1.53 ms at B = 16 against 0.74 ms for the sequential passes); one warp per
+// row with two passes from global memory, the second an L2 hit (0.32 ms for this kernel at B = 16, 3.0 TB/s: DRAM 55 %
+// busy, no eligible warp 68 % of the cycles - a warp waits a full DRAM round trip per batch of four loads).
+template <typename T, int NV, bool GRAD>
+__global__ void __launch_bounds__(kRowThreads)
 ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t,
                 long long stride_b, const int32_t* __restrict__ ilen, int Sp, const float* __restrict__ lse_in,
-                float grad_scale, int buf_bytes, int stage_off, CtcWs w) {
-    constexpr int ES = (int)sizeof(T);
-    constexpr bool BF = ES == 2;
-    extern __shared__ __align__(128) unsigned char rows_smem[];        // [nw][buf_bytes], then [nw][Sp] floats
-    __shared__ __align__(8) uint64_t bars[kRowsMaxWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    unsigned char* buf = rows_smem + (size_t)warp * buf_bytes;
-    float* xg = reinterpret_cast<float*>(rows_smem + (size_t)nw * buf_bytes) + (size_t)warp * Sp;
-    unsigned char* stage = buf + stage_off;
-    uint64_t* bar = &bars[warp];
-    if (lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-    __syncwarp();
-    const int row_bytes = C * ES;
-    const int nk = (Tn + 1) / 2;
-    const long long total = (long long)nk * 2 * Bn;
-    const long long tw = (long long)gridDim.x * nw;
-    uint32_t phase = 0;
-    for (long long v = (long long)blockIdx.x * nw + warp; v < total; v += tw) {
-        const int k = (int)(v / (2 * Bn));
-        const int r = (int)(v - (long long)k * 2 * Bn);
-        int t, b;
-        if (r < Bn) { t = k; b = r; }
-        else { t = Tn - 1 - k; b = r - Bn; if (t == k) continue; }     // odd T: the middle row belongs to the first half
-        const long long row = (long long)b * Tn + t;
-        const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
-        T* g = GRAD ? grad + (long long)t * stride_t + (long long)b * stride_b : nullptr;
-        const bool live = t < ilen[b];
-        if (live) {
-            const RowGeom rg = row_geom(p, row_bytes);
-            warp_stage_row<ES>(stage, rg, row_bytes, bar, lane);
-            const int L = w.len[b], S = 2 * L + 1;
-            const int* tg = w.lab + (long long)b * w.Lp;
-            const int nhead = rg.head_bytes / ES;
-            const int nvec = rg.body_bytes >> 4;                         // 16-byte vectors of the aligned interior
-            const int tail0 = nhead + nvec * (16 / ES);
-            const int sc = lane < nhead ? lane : tail0 + (lane - nhead); // the head / tail element this lane carries
-            const bool has_sc = lane < 16 && sc < C;
-            const unsigned char* e0 = stage + 16 - rg.head_bytes;        // element 0 of the staged row
-            const unsigned char* body = stage + 16;
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            __syncwarp();                                                // head / tail elements stored by the first lanes
-            // ---- raw logits of the blank-interleaved labels (before anything is overwritten)
-            for (int q = lane; q < S; q += 32) {
+                float grad_scale, CtcWs w) {
+    constexpr int V = RowVec<T>::N;
+    __shared__ float w_m[4], w_s[4];
+    __shared__ int s_small;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long v = blockIdx.x;
+    const int k = (int)(v / (2 * Bn));
+    const int r = (int)(v - (long long)k * 2 * Bn);
+    int t, b;
+    if (r < Bn) { t = k; b = r; }
+    else { t = Tn - 1 - k; b = r - Bn; if (t == k) return; }           // odd T: the middle row belongs to the first half
+    const long long row = (long long)b * Tn + t;
+    const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+    T* g = GRAD ? grad + (long long)t * stride_t + (long long)b * stride_b : nullptr;
+    int* prog = &w.prog[(long long)b * w.NG + t / kGranule];
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > C) head = C;
+    const int nvec = (C - head) / V;
+    const int tail0 = head + nvec * V;
+    const T* pv = p + head;
+
+    if (t >= ilen[b]) {
+        // beyond the input length of this sequence: zero gradient, nothing for the scans
+        if (GRAD) {
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(g);
+            int gh = (int)(((16 - (ga & 15)) & 15) / sizeof(T));
+            if (gh > C) gh = C;
+            const int gn = (C - gh) / V;
+            if (tid < gh) Ld<T>::st_one(g + tid, 0.f);
+            for (int vi = tid; vi < gn; vi += kRowThreads) *reinterpret_cast<uint4*>(g + gh + (long long)vi * V) = make_uint4(0u, 0u, 0u, 0u);
+            if (gh + gn * V + tid < C) Ld<T>::st_one(g + gh + gn * V + tid, 0.f);
+        }
+        if (tid == 0) atomicAdd(prog, 1);
+        return;
+    }
+    // ---- the whole row into registers
+    uint4 xq[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int vi = tid + i * kRowThreads;
+        xq[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (vi < nvec) xq[i] = ld_nc_v4(pv + (long long)vi * V);
+    }
+    const int sc = tid < head ? tid : tail0 + (tid - head);            // scalar element in front of / behind the interior
+    const bool has_sc = tid < 2 * V && sc < C;
+    float x_sc = 0.f;
+    if (has_sc) x_sc = Ld<T>::one(p + sc);
+    if (tid == 0) s_small = 0;
+
+    const int L = w.len[b], S = 2 * L + 1;
+    const float scale = grad_scale / ((float)max(L, 1) * (float)Bn);
+    float lse, mul;
+    if (lse_in != nullptr) {
+        lse = lse_in[row];            // log-sum-exp already produced by the classifier epilogue
+        mul = scale;
+        __syncthreads();              // s_small initialised
+    } else {
+        // ---- maximum
+        float m = has_sc ? x_sc : -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (tid + i * kRowThreads < nvec) {
+                float x[V];
+                RowVec<T>::unpack(xq[i], x);
+                float a = fmaxf(x[0], x[1]);
+#pragma unroll
+                for (int j = 2; j < V; j += 2) a = fmaxf(a, fmaxf(x[j], x[j + 1]));
+                m = fmaxf(m, a);
+            }
+        }
+        m = warp_max(m);
+        if (lane == 0) w_m[warp] = m;
+        __syncthreads();
+        m = fmaxf(fmaxf(w_m[0], w_m[1]), fmaxf(w_m[2], w_m[3]));
+        // ---- sum of exp(x - m)
+        float s0 = 0.f, s1 = 0.f;
+        if (has_sc) s0 = ex2_fast((x_sc - m) * kLog2e);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (tid + i * kRowThreads < nvec) {
+                float x[V];
+                RowVec<T>::unpack(xq[i], x);
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < V; j += 2) acc += ex2_fast((x[j] - m) * kLog2e) + ex2_fast((x[j + 1] - m) * kLog2e);
+                if (i & 1) s1 += acc; else s0 += acc;
+            }
+        }
+        const float ws = warp_sum(s0 + s1);
+        if (lane == 0) w_s[warp] = ws;
+        __syncthreads();
+        const float sum = (w_s[0] + w_s[1]) + (w_s[2] + w_s[3]);
+        lse = m + logf(sum);
+        mul = scale;
+    }
+    if (tid == 0) w.lse[row] = lse;
+    // ---- label probabilities for the recursion (plain and mirrored), log-probs for the log-space fallback
+    {
+        const int* tg = w.lab + (long long)b * w.Lp;
+        float* dst = w.lpg + row * Sp;
+        double* dpr = w.pg + row * Sp;
+        double* dpm = w.pgr + row * Sp;
+        bool small = false;
+        for (int q = tid; q < Sp; q += kRowThreads) {
+            float lp = 0.f;
+            double pr = 0.0;
+            if (q < S) {
                 const int c = (q & 1) ? tg[q >> 1] : 0;
-                xg[q] = BF ? bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(e0 + 2 * c))
-                           : *reinterpret_cast<const float*>(e0 + 4 * c);
-            }
-            float x_sc = 0.f;
-            if (has_sc) x_sc = BF ? bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(e0 + 2 * sc))
-                                  : *reinterpret_cast<const float*>(e0 + 4 * sc);
-            float lse, mul;                                               // gradient = value * mul
-            const float scale = grad_scale / ((float)max(L, 1) * (float)Bn);
-            const bool given = lse_in != nullptr;
-            float m = 0.f;
-            if (!given) {
-                // ---- pass 1: maximum
-                m = has_sc ? x_sc : -INFINITY;
-                if (BF) {
-                    __nv_bfloat162 mm = __float2bfloat162_rn(-INFINITY);
-#pragma unroll 4
-                    for (int vi = lane; vi < nvec; vi += 32) {
-                        const uint4 q = *reinterpret_cast<const uint4*>(body + (vi << 4));
-                        const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.x), *reinterpret_cast<const __nv_bfloat162*>(&q.y));
-                        const __nv_bfloat162 c2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.z), *reinterpret_cast<const __nv_bfloat162*>(&q.w));
-                        mm = __hmax2(mm, __hmax2(a, c2));
-                    }
-                    m = fmaxf(m, fmaxf(__low2float(mm), __high2float(mm)));
-                } else {
-#pragma unroll 4
-                    for (int vi = lane; vi < nvec; vi += 32) {
-                        const float4 q = *reinterpret_cast<const float4*>(body + (vi << 4));
-                        m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
-                    }
-                }
-                m = warp_max(m);
-                __syncwarp();                                             // all gather / edge reads precede the overwrites
-                // ---- pass 2: e = exp(x - m) kept in shared memory (fp32), sum
-                float sum = 0.f;
-                float e_sc = 0.f;
-                if (has_sc) {
-                    e_sc = ex2_fast((x_sc - m) * kLog2e); sum = e_sc;
-                    if (!BF) *reinterpret_cast<float*>(stage + 16 - rg.head_bytes + 4 * sc) = e_sc;
-                }
-                if (BF) {
-                    const int nunit = nvec * 2;                           // 4-element units: 8 B in, 16 B out, conflict-free
-                    const int niter = (nunit + 31) >> 5;
-                    for (int it = 0; it < niter; ++it) {
-                        const int u = (it << 5) + lane;
-                        uint2 q = make_uint2(0u, 0u);
-                        if (u < nunit) q = *reinterpret_cast<const uint2*>(body + (u << 3));
-                        __syncwarp();                                    // every lane has its input before anybody overwrites
-                        if (u < nunit) {
-                            float4 e;
-                            e.x = ex2_fast((bf16_lo(q.x) - m) * kLog2e); e.y = ex2_fast((bf16_hi(q.x) - m) * kLog2e);
-                            e.z = ex2_fast((bf16_lo(q.y) - m) * kLog2e); e.w = ex2_fast((bf16_hi(q.y) - m) * kLog2e);
-                            sum += (e.x + e.y) + (e.z + e.w);
-                            *reinterpret_cast<float4*>(buf + 32 + (u << 4)) = e;
-                        }
-                    }
-                    __syncwarp();
-                    if (has_sc) {                                         // head: float index 8 - nhead + j; tail: 8 + 8 nvec + i
-                        const int fi = lane < nhead ? 8 - nhead + lane : 8 + nvec * 8 + (lane - nhead);
-                        *reinterpret_cast<float*>(buf + 4 * fi) = e_sc;
-                    }
-                } else {
-#pragma unroll 2
-                    for (int vi = lane; vi < nvec; vi += 32) {
-                        float4 q = *reinterpret_cast<const float4*>(body + (vi << 4));
-                        q.x = ex2_fast((q.x - m) * kLog2e); q.y = ex2_fast((q.y - m) * kLog2e);
-                        q.z = ex2_fast((q.z - m) * kLog2e); q.w = ex2_fast((q.w - m) * kLog2e);
-                        sum += (q.x + q.y) + (q.z + q.w);
-                        *reinterpret_cast<float4*>(buf + 16 + (vi << 4)) = q;
-                    }
-                }
-                sum = warp_sum(sum);
-                lse = m + logf(sum);
-                mul = scale / sum;
-                x_sc = e_sc;                                              // what the gradient pass multiplies
+                lp = Ld<T>::one(p + c) - lse;
+                pr = (double)expf(lp);
+                small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);
+                small |= !(lp == lp);
+                dpm[S - 1 - q] = pr;
             } else {
-                lse = lse_in[row];
-                mul = scale;
+                dpm[q] = 0.0;
             }
-            if (lane == 0) w.lse[row] = lse;
-            // ---- label probabilities for the recursion (plain and mirrored), log-probs for the log-space fallback
-            {
-                float* dst = w.lpg + row * Sp;
-                double* dpr = w.pg + row * Sp;
-                double* dpm = w.pgr + row * Sp;
-                bool small = false;
-                for (int q = lane; q < Sp; q += 32) {
-                    float lp = 0.f;
-                    double pr = 0.0;
-                    if (q < S) {
-                        lp = xg[q] - lse;
-                        pr = (double)expf(lp);
-                        small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);
-                        small |= !(lp == lp);
-                        dpm[S - 1 - q] = pr;
-                    } else {
-                        dpm[q] = 0.0;
-                    }
-                    dst[q] = lp;
-                    dpr[q] = pr;
-                }
-                if (__any_sync(0xffffffffu, small) && lane == 0) w.flag[b] = 1;
-            }
-            // ---- pass 3: dense part of the gradient, softmax * scale (the label classes are corrected by ctc_fix_kernel)
-            if (GRAD) {
-                const bool same_align = ((reinterpret_cast<uintptr_t>(g) & 15) == (reinterpret_cast<uintptr_t>(p) & 15));
-                unsigned char* gb = reinterpret_cast<unsigned char*>(g);
-                if (same_align) {
-                    if (BF) {
-                        const int nunit = nvec * 2;
-                        unsigned char* gbody = gb + rg.head_bytes;
-                        if (!given) {
-#pragma unroll 4
-                            for (int u = lane; u < nunit; u += 32) {
-                                const float4 e = *reinterpret_cast<const float4*>(buf + 32 + (u << 4));
-                                *reinterpret_cast<uint2*>(gbody + (u << 3)) = make_uint2(pack_bf16x2(e.x * mul, e.y * mul), pack_bf16x2(e.z * mul, e.w * mul));
-                            }
-                        } else {
-#pragma unroll 4
-                            for (int u = lane; u < nunit; u += 32) {
-                                const uint2 q = *reinterpret_cast<const uint2*>(body + (u << 3));
-                                const float a0 = ex2_fast((bf16_lo(q.x) - lse) * kLog2e) * mul, a1 = ex2_fast((bf16_hi(q.x) - lse) * kLog2e) * mul;
-                                const float a2 = ex2_fast((bf16_lo(q.y) - lse) * kLog2e) * mul, a3 = ex2_fast((bf16_hi(q.y) - lse) * kLog2e) * mul;
-                                *reinterpret_cast<uint2*>(gbody + (u << 3)) = make_uint2(pack_bf16x2(a0, a1), pack_bf16x2(a2, a3));
-                            }
-                        }
-                    } else {
-                        unsigned char* gbody = gb + rg.head_bytes;
-#pragma unroll 4
-                        for (int vi = lane; vi < nvec; vi += 32) {
-                            float4 q = *reinterpret_cast<const float4*>(body + (vi << 4));     // e (in place) or the raw logits
-                            if (given) {
-                                q.x = ex2_fast((q.x - lse) * kLog2e); q.y = ex2_fast((q.y - lse) * kLog2e);
-                                q.z = ex2_fast((q.z - lse) * kLog2e); q.w = ex2_fast((q.w - lse) * kLog2e);
-                            }
-                            q.x *= mul; q.y *= mul; q.z *= mul; q.w *= mul;
-                            *reinterpret_cast<float4*>(gbody + (vi << 4)) = q;
-                        }
-                    }
-                    if (has_sc) {
-                        const float val = (given ? ex2_fast((x_sc - lse) * kLog2e) : x_sc) * mul;
-                        Ld<T>::st_one(g + sc, val);
-                    }
-                } else {
-                    // gradient row aligned differently from the logits row: element-wise stores
-                    for (int j = lane; j < C; j += 32) {
-                        float val;
-                        if (given) {
-                            const float x = BF ? bf16_bits_to_float(*reinterpret_cast<const unsigned short*>(e0 + 2 * j))
-                                               : *reinterpret_cast<const float*>(e0 + 4 * j);
-                            val = ex2_fast((x - lse) * kLog2e);
-                        } else if (BF) {
-                            val = *reinterpret_cast<const float*>(buf + 4 * (8 - nhead + j));
-                        } else {
-                            val = *reinterpret_cast<const float*>(e0 + 4 * j);
-                        }
-                        Ld<T>::st_one(g + j, val * mul);
-                    }
-                }
-            }
-        } else if (GRAD) {
-            // beyond the input length of this sequence: zero gradient
-            const RowGeom gg = row_geom(g, row_bytes);
-            unsigned char* gb = reinterpret_cast<unsigned char*>(g);
-            const int nvec = gg.body_bytes >> 4;
-            for (int vi = lane; vi < nvec; vi += 32) *reinterpret_cast<uint4*>(gb + gg.head_bytes + (vi << 4)) = make_uint4(0u, 0u, 0u, 0u);
-            const int nhead = gg.head_bytes / ES;
-            const int tail0 = nhead + nvec * (16 / ES);
-            const int sc = lane < nhead ? lane : tail0 + (lane - nhead);
-            if (lane < 16 && sc < C) Ld<T>::st_one(g + sc, 0.f);
+            dst[q] = lp;
+            dpr[q] = pr;
         }
-        // ---- this row's probabilities are in place: publish (release) for the scans
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence();
-            atomicAdd(&w.prog[(long long)b * w.NG + t / kGranule], 1);
+        if (small) s_small = 1;
+    }
+    // ---- publish (release) for the scans before the gradient pass, whose stores the fence would otherwise wait for
+    __syncthreads();
+    if (tid == 0) {
+        if (s_small) w.flag[b] = 1;
+        __threadfence();
+        atomicAdd(prog, 1);
+    }
+    if (!GRAD) return;
+    // ---- dense part of the gradient from the registers, softmax * scale (label classes: ctc_fix_kernel)
+    const float nl = -lse * kLog2e;
+    const bool same_align = ((reinterpret_cast<uintptr_t>(g) & 15) == (addr & 15));
+    if (has_sc) Ld<T>::st_one(g + sc, ex2_fast(fmaf(x_sc, kLog2e, nl)) * mul);
+    if (same_align) {
+        T* gv = g + head;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vi = tid + i * kRowThreads;
+            if (vi < nvec) {
+                float x[V];
+                RowVec<T>::unpack(xq[i], x);
+#pragma unroll
+                for (int j = 0; j < V; ++j) x[j] = ex2_fast(fmaf(x[j], kLog2e, nl)) * mul;
+                Ld<T>::st_vec(gv + (long long)vi * V, x);
+            }
         }
-        fence_proxy_async();                  // the next bulk copy (async proxy) overwrites what this warp just read / wrote
-        __syncwarp();
+    } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vi = tid + i * kRowThreads;
+            if (vi < nvec) {
+                float x[V];
+                RowVec<T>::unpack(xq[i], x);
+#pragma unroll
+                for (int j = 0; j < V; ++j) Ld<T>::st_one(g + head + (long long)vi * V + j, ex2_fast(fmaf(x[j], kLog2e, nl)) * mul);
+            }
+        }
     }
 }
 
@@ -1133,15 +1093,22 @@ ctc_fix_kernel(T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t, 
     ctc_occupancy(row, b, S, Sp, Sa, kscan, ll, w, occ, lane, 32);
     __syncwarp();
     const int* canon = w.canon + (long long)b * Sp;
+    const int* nxt = w.nxt + (long long)b * Sp;
     const int* tg = w.lab + (long long)b * w.Lp;
     const float* lpr = w.lpg + row * Sp;                                 // log-softmax at the label classes
-    for (int s = lane; s < S; s += 32) {
-        if (canon[s] != s) continue;
+    // blank (every even state): a fixed tree over the warp
+    {
         float acc = 0.f;
-        for (int q = s; q < S; q += ((s & 1) ? 1 : 2))
-            if (canon[q] == s) acc += occ[q];
-        const int c = (s & 1) ? tg[s >> 1] : 0;
-        Ld<T>::st_one(g + c, (__expf(lpr[s]) - acc) * scale);
+        for (int s = 2 * lane; s < S; s += 64) acc += occ[s];
+        acc = warp_sum(acc);
+        if (lane == 0) Ld<T>::st_one(g, (__expf(lpr[0]) - acc) * scale);
+    }
+    // labels (odd states): the first state of a class walks the chain of its repeats, in state order
+    for (int s = 2 * lane + 1; s < S; s += 64) {
+        if (canon[s] != s) continue;
+        float acc = occ[s];
+        for (int q = nxt[s]; q >= 0; q = nxt[q]) acc += occ[q];
+        Ld<T>::st_one(g + tg[s >> 1], (__expf(lpr[s]) - acc) * scale);
     }
 }
 
@@ -1163,7 +1130,10 @@ static int ctc_side(CtcSide** out) {
     {
         std::lock_guard<std::mutex> guard(create_mu);
         if (sd.helper == nullptr) {
-            HCTR_CUDA(cudaStreamCreateWithFlags(&sd.helper, cudaStreamNonBlocking));
+            // highest priority: the 2*B latency-bound scan warps must get their SM slots ahead of the rows kernel's blocks
+            int prio_lo = 0, prio_hi = 0;
+            HCTR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            HCTR_CUDA(cudaStreamCreateWithPriority(&sd.helper, cudaStreamNonBlocking, prio_hi));
             HCTR_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
             HCTR_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
         }
@@ -1172,55 +1142,54 @@ static int ctc_side(CtcSide** out) {
     return HCTR_OK;
 }
 
-struct RowsPlan { int warps, buf_bytes, stage_off, grid; size_t smem; };
-// warps per CTA: as many per-warp row buffers as fit beside one scan CTA (24.6 KB of static shared memory) on the SM
-static int rows_plan(int C, int esz, int Sp, long long rows, RowsPlan* p) {
-    int dev = 0, smem_sm = 0, smem_optin = 0, sms = 0;
-    HCTR_CUDA(cudaGetDevice(&dev));
-    HCTR_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    HCTR_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    HCTR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    p->buf_bytes = rows_buf_bytes(C, esz);
-    p->stage_off = rows_stage_off(C, esz);
-    const int per_warp = p->buf_bytes + Sp * 4;
-    const int scan_cta = kScanStageDoubles * 8 + 1024 + 1024;         // its static shared memory + the per-CTA reservation
-    int budget = smem_sm - scan_cta - 1024 - 256;                      // our own reservation and static barriers
-    if (budget > smem_optin - 256) budget = smem_optin - 256;
-    int warps = budget / per_warp;
-    if (warps > kRowsMaxWarps) warps = kRowsMaxWarps;
-    p->warps = warps;
-    p->smem = (size_t)(warps > 0 ? warps : 0) * per_warp;
-    long long ctas = warps > 0 ? (rows + warps - 1) / warps : 0;
-    p->grid = (int)(ctas < sms ? ctas : sms);
-    return HCTR_OK;
+// vectors per thread the row needs; 0 = the row does not fit the registers of four warps (sequential passes instead)
+static int rows_nv(int C, int esz) {
+    const int V = 16 / esz;
+    const int need = (C / V + kRowThreads - 1) / kRowThreads;
+    return need <= 4 ? 4 : need <= 8 ? 8 : need <= 16 ? 16 : 0;
 }
 
-template <typename T, bool GRAD>
-static int launch_rows_t(const RowsPlan& p, const void* logits, void* grad, int T_, int B, int C, long long stride_t,
-                         long long stride_b, const int32_t* ilen, int Sp, const float* row_lse, float grad_scale,
-                         const CtcWs& w, cudaStream_t s) {
-    auto kern = ctc_rows_kernel<T, GRAD>;
-    static PerDeviceOnce once;
-    int dev;
-    if (once.need(dev)) {
-        int optin = 0;
-        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 256));
-        once.mark(dev);
+// Loads the kernel before the scan is in flight: CUDA loads functions lazily, and loading may wait for the device to drain -
+// which never happens while a scan kernel spins on rows this very kernel is supposed to produce.
+template <typename T, int NV, bool GRAD>
+static int rows_call(bool launch, const void* logits, void* grad, int T_, int B, int C, long long stride_t, long long stride_b,
+                     const int32_t* ilen, int Sp, const float* row_lse, float grad_scale, const CtcWs* w, cudaStream_t s) {
+    auto kern = ctc_rows_kernel<T, NV, GRAD>;
+    if (!launch) {
+        static PerDeviceOnce once;
+        int dev;
+        if (once.need(dev)) {
+            cudaFuncAttributes fa;
+            HCTR_CUDA(cudaFuncGetAttributes(&fa, kern));
+            once.mark(dev);
+        }
+        return HCTR_OK;
     }
-    kern<<<p.grid, p.warps * 32, p.smem, s>>>(static_cast<const T*>(logits), static_cast<T*>(grad), T_, B, C, stride_t, stride_b,
-                                              ilen, Sp, row_lse, grad_scale, p.buf_bytes, p.stage_off, w);
+    const long long total = (long long)((T_ + 1) / 2) * 2 * B;
+    HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "ctc_loss: too many rows");
+    kern<<<(unsigned)total, kRowThreads, 0, s>>>(static_cast<const T*>(logits), static_cast<T*>(grad), T_, B, C, stride_t, stride_b,
+                                                 ilen, Sp, row_lse, grad_scale, *w);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }
-static int launch_rows(const RowsPlan& p, const void* logits, void* grad, int dtype, int T_, int B, int C, long long stride_t,
-                       long long stride_b, const int32_t* ilen, int Sp, const float* row_lse, float grad_scale,
-                       const CtcWs& w, cudaStream_t s) {
+template <typename T, bool GRAD>
+static int rows_call_nv(int nv, bool launch, const void* logits, void* grad, int T_, int B, int C, long long stride_t,
+                        long long stride_b, const int32_t* ilen, int Sp, const float* row_lse, float grad_scale, const CtcWs* w,
+                        cudaStream_t s) {
+    switch (nv) {
+        case 4:  return rows_call<T, 4, GRAD>(launch, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
+        case 8:  return rows_call<T, 8, GRAD>(launch, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
+        default: return rows_call<T, 16, GRAD>(launch, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
+    }
+}
+static int rows_dispatch(bool launch, int nv, const void* logits, void* grad, int dtype, bool want_grad, int T_, int B, int C,
+                         long long stride_t, long long stride_b, const int32_t* ilen, int Sp, const float* row_lse,
+                         float grad_scale, const CtcWs* w, cudaStream_t s) {
     if (dtype == HCTR_F32)
-        return grad ? launch_rows_t<float, true>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s)
-                    : launch_rows_t<float, false>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
-    return grad ? launch_rows_t<__nv_bfloat16, true>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s)
-                : launch_rows_t<__nv_bfloat16, false>(p, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
+        return want_grad ? rows_call_nv<float, true>(nv, launch, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s)
+                         : rows_call_nv<float, false>(nv, launch, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
+    return want_grad ? rows_call_nv<__nv_bfloat16, true>(nv, launch, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s)
+                     : rows_call_nv<__nv_bfloat16, false>(nv, launch, logits, grad, T_, B, C, stride_t, stride_b, ilen, Sp, row_lse, grad_scale, w, s);
 }
 
 }  // namespace hctr
@@ -1278,31 +1247,76 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     const int blocksV = (int)((rows + 7) / 8);
     const int esz = dtype == HCTR_F32 ? 4 : 2;
 
-    // ---- overlapped path: does a row fit a per-warp buffer, with room left on the SM for a scan CTA?
-    RowsPlan plan;
-    bool overlap = !overlap_off && kscan != 0 && !debug_force_log && 2ll * B <= 4096;
-    if (overlap) {
-        int rc = rows_plan(C, esz, Sp, rows, &plan);
+    // ---- the one-pass rows kernel needs the row in the registers of four warps; the overlapped schedule needs the scans'
+    //      2*B one-warp CTAs all resident beside it ("2": the same kernels back to back on one stream, e.g. under ncu)
+    const int nv = rows_nv(C, esz);
+    const bool rows_path = !overlap_off && kscan != 0 && !debug_force_log && nv != 0;
+    // Default: rows -> scans -> fix back to back on the caller's stream. HCTR_CTC_OVERLAP=1 opts into the overlapped schedule
+    // (scans on a helper stream, fed through the progress counters): measured SLOWER on B200 at every batch size tried -
+    // B=16: 1.12 ms against 0.57 ms (the scan warps share their schedulers with the rows kernel's warps and the recursion
+    // runs 3.5x slower, 1.09 ms instead of 0.29 ms), B=64: 1.81 against 1.45 ms (rows kernel 17 % slower, scan tail 0.15 ms).
+    const bool want_overlap = ov && ov[0] == '1';
+    const bool serial = rows_path && (!want_overlap || 2ll * B > 2048);
+    const bool overlap = rows_path;
+    if (serial) {
+        int rc = rows_dispatch(true, nv, logits, grad, dtype, grad != nullptr, T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse,
+                               grad_scale, &w, s);
         if (rc) return rc;
-        overlap = plan.warps >= 2;
-    }
-    if (overlap) {
+        if (ov && ov[0] == '3') {
+            ctc_scan_kernel<4, true><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w);
+        } else
+        switch (kscan) {
+            case 4:  ctc_scan_kernel<4, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
+            case 8:  ctc_scan_kernel<8, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
+            default: ctc_scan_kernel<16, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
+        }
+        HCTR_CUDA(cudaGetLastError());
+    } else if (overlap) {
         CtcSide* side = nullptr;
         int rc = ctc_side(&side);
+        if (rc) return rc;
+        rc = rows_dispatch(false, nv, logits, grad, dtype, grad != nullptr, T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse,
+                           grad_scale, &w, s);                       // load the function before the scan is in flight
         if (rc) return rc;
         std::lock_guard<std::mutex> guard(side->mu);                 // one enqueue at a time per device (shared helper stream)
         // fork: the scans only need the prep kernel
         HCTR_CUDA(cudaEventRecord(side->fork, s));
         HCTR_CUDA(cudaStreamWaitEvent(side->helper, side->fork, 0));
+        const char* od = getenv("HCTR_CTC_ROWS_FIRST");
+        const bool rows_first = od && od[0] == '1';
+        const bool timing = getenv("HCTR_CTC_TIMING") != nullptr;    // diagnostics: per-kernel times of the overlapped schedule
+        cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (timing) { for (int i = 0; i < 4; ++i) cudaEventCreate(&tev[i]); cudaEventRecord(tev[2], side->helper); }
+        if (timing && rows_first) cudaEventRecord(tev[0], s);
+        if (rows_first) {
+            rc = rows_dispatch(true, nv, logits, grad, dtype, grad != nullptr, T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse,
+                               grad_scale, &w, s);
+            if (rc) return rc;
+        }
         switch (kscan) {
             case 4:  ctc_scan_kernel<4, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
             case 8:  ctc_scan_kernel<8, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
             default: ctc_scan_kernel<16, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
         }
         HCTR_CUDA(cudaGetLastError());
+        if (timing) cudaEventRecord(tev[3], side->helper);
         HCTR_CUDA(cudaEventRecord(side->join, side->helper));
-        rc = launch_rows(plan, logits, grad, dtype, T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse, grad_scale, w, s);
-        if (rc) return rc;
+        if (!rows_first) {
+            if (timing) cudaEventRecord(tev[0], s);
+            rc = rows_dispatch(true, nv, logits, grad, dtype, grad != nullptr, T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse,
+                               grad_scale, &w, s);
+            if (rc) return rc;
+        }
+        if (timing) {
+            cudaEventRecord(tev[1], s);
+            cudaEventSynchronize(tev[1]); cudaEventSynchronize(tev[3]);
+            float rows_ms = 0.f, scan_ms = 0.f, lead_ms = 0.f, tail_ms = 0.f;
+            cudaEventElapsedTime(&rows_ms, tev[0], tev[1]); cudaEventElapsedTime(&scan_ms, tev[2], tev[3]);
+            cudaEventElapsedTime(&lead_ms, tev[2], tev[0]); cudaEventElapsedTime(&tail_ms, tev[1], tev[3]);
+            fprintf(stderr, "hctr ctc timing: rows %.3f ms, scan %.3f ms, scan start -> rows start %.3f ms, rows end -> scan end %.3f ms\n",
+                    rows_ms, scan_ms, lead_ms, tail_ms);
+            for (int i = 0; i < 4; ++i) cudaEventDestroy(tev[i]);
+        }
         HCTR_CUDA(cudaStreamWaitEvent(s, side->join, 0));           // join
     } else {
         const long long blocksA = (rows + kLseWarps - 1) / kLseWarps;

@@ -1,12 +1,5 @@
-// Warp-per-row staging of logits rows in shared memory (used by the CTC-loss row pass and the log-softmax/top-k pass).
-//
-// A row of C logits (fp32: 29.5 KB at C = 7375, bf16: 14.75 KB) is pulled into a per-warp shared-memory buffer by the
-// bulk-copy engine (cp.async.bulk global -> shared, completion on a per-warp mbarrier), then one warp makes all its
-// passes over the shared copy: HBM is read exactly once per row, and a warp needs no block barrier at all - the per-row
-// bookkeeping of a 256-thread CTA per row (four block barriers, shared-memory hand-overs, idle lanes in the ranking)
-// was the larger half of the instructions of the first top-k kernel. Rows need not be 16-byte aligned (C = 7375 floats
-// contiguous): the bulk copy moves the 16-byte-aligned interior [lo, hi) of the row, the < 16-byte head and tail go through
-// registers of the first lanes.
+// Helpers shared by the row-wise codec kernels (log-softmax / top-k, CTC loss): bulk copy of a row's aligned interior,
+// row geometry for rows that are not 16-byte aligned (C = 7375 floats contiguous), warp reductions, exp2 on the MUFU pipe.
 #pragma once
 #include "common.cuh"
 
@@ -32,28 +25,6 @@ __device__ __forceinline__ RowGeom row_geom(const void* row_ptr, int row_bytes) 
     if (hi > lo) { r.head_bytes = (int)(lo - a); r.body_bytes = (int)(hi - lo); }
     else { r.head_bytes = 0; r.body_bytes = 0; }
     return r;
-}
-
-// One warp stages one row into `stage` (16-byte aligned; needs 16 + round16(row_bytes) + 16 bytes): lane 0 arms the
-// barrier and starts the bulk copy of the interior, lanes < 16 carry the head / tail elements (ES = element size).
-// The caller guarantees that nobody still reads the buffer (single buffer per warp) and has issued
-// fence.proxy.async + __syncwarp() after its last generic-proxy access to it.
-template <int ES>
-__device__ __forceinline__ void warp_stage_row(unsigned char* stage, const RowGeom& r, int row_bytes, uint64_t* bar, int lane) {
-    if (lane == 0) {
-        if (r.body_bytes > 0) {
-            mbar_arrive_expect_tx(bar, (uint32_t)r.body_bytes);
-            bulk_g2s(stage + 16, r.a0 + r.head_bytes, (uint32_t)r.body_bytes, bar);
-        } else {
-            mbar_arrive(bar);
-        }
-    }
-    const int nhead = r.head_bytes / ES;
-    const int off = lane < nhead ? lane * ES : r.head_bytes + r.body_bytes + (lane - nhead) * ES;
-    if (lane < 16 && off < row_bytes) {
-        if (ES == 4) *reinterpret_cast<uint32_t*>(stage + 16 - r.head_bytes + off) = __ldg(reinterpret_cast<const uint32_t*>(r.a0 + off));
-        else         *reinterpret_cast<unsigned short*>(stage + 16 - r.head_bytes + off) = __ldg(reinterpret_cast<const unsigned short*>(r.a0 + off));
-    }
 }
 
 // exp2 on the MUFU pipe; ex2.approx.ftz flushes results below 2^-126 to zero, which is what a sum of exponentials wants
