@@ -17,9 +17,13 @@
 
 namespace hctr {
 
-constexpr int kSkMaxC = 128;                // candidates per step the device path supports
+// Candidates per step: the reference takes every class with p > 0.001 (utils/ctc_codec.py:144), i.e. at most 999. The
+// common case (<= 128) keeps the candidate tables small and the dict entries of a step in shared memory; a step with more
+// makes the call report HCTR_ERR_UNSUPPORTED for that sequence, and the caller repeats the call with max_candidates = 1024:
+// same kernels, 8 KB of candidate table per row and the dict entries of a step in the global workspace.
+constexpr int kSkMaxC = 128;
+constexpr int kSkBigC = 1024;
 constexpr int kSkMaxBeam = 16;
-constexpr int kSkMaxGen = kSkMaxBeam * (kSkMaxC + 1);
 constexpr int kSkThreads = 128;
 constexpr int kPruneThreads = 256;
 
@@ -44,8 +48,8 @@ template <> struct SkLoad<__nv_bfloat16> {
     }
 };
 
-// per row outputs: meta[row] = {count, top1}, blank_lp[row], cand_idx[row][kSkMaxC] (ascending), cand_lp[row][kSkMaxC]
-template <typename T>
+// per row outputs: meta[row] = {count, top1}, blank_lp[row], cand_idx[row][MAXC] (ascending), cand_lp[row][MAXC]
+template <typename T, int MAXC>
 __global__ void __launch_bounds__(kPruneThreads)
 ctc_prune_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
                             int2* __restrict__ meta, float* __restrict__ blank_lp, int32_t* __restrict__ cand_idx,
@@ -56,8 +60,8 @@ ctc_prune_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C,
     __shared__ int redi[8];
     __shared__ float s_max, s_logs;
     __shared__ int s_top1, s_n;
-    __shared__ int c_i[kSkMaxC];
-    __shared__ float c_v[kSkMaxC];
+    __shared__ int c_i[MAXC];
+    __shared__ float c_v[MAXC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long row = blockIdx.x;                              // row = t*B + b
     const int t = (int)(row / Bn), b = (int)(row - (long long)t * Bn);
@@ -112,19 +116,19 @@ ctc_prune_logsoftmax_kernel(const T* __restrict__ logits, int Tn, int Bn, int C,
         const float lp = (rowbuf[c] - m) - logs;                   // scipy: (x - max) - log(sum(exp(x - max)))
         if ((double)lp > thresh) {
             const int slot = atomicAdd(&s_n, 1);
-            if (slot < kSkMaxC) { c_i[slot] = c; c_v[slot] = lp; }
+            if (slot < MAXC) { c_i[slot] = c; c_v[slot] = lp; }
         }
     }
     __syncthreads();
     const int n = s_n;
     if (tid == 0) { meta[row] = make_int2(n, s_top1); blank_lp[row] = (rowbuf[0] - m) - logs; }
-    if (n <= kSkMaxC) {
+    if (n <= MAXC) {
         // index order: rank by counting (indices are distinct)
         for (int e = tid; e < n; e += kPruneThreads) {
             int rank = 0;
             for (int f = 0; f < n; ++f) rank += c_i[f] < c_i[e];
-            cand_idx[row * kSkMaxC + rank] = c_i[e];
-            cand_lp[row * kSkMaxC + rank] = c_v[e];
+            cand_idx[row * MAXC + rank] = c_i[e];
+            cand_lp[row * MAXC + rank] = c_v[e];
         }
     }
 }
@@ -161,27 +165,30 @@ struct SkKept {
     double pb[kSkMaxBeam], pnb[kSkMaxBeam], lmsum[kSkMaxBeam];
 };
 
+template <int MAXC>
 __global__ void __launch_bounds__(kSkThreads)
 ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ blank_lp, const int32_t* __restrict__ cand_idx,
                      const float* __restrict__ cand_lp, int Tn, int Bn, int C, int beam_size, double lm_penalty,
                      double len_bonus, const double* __restrict__ lm_table, const hctr_ngram_lm ng_lm, int32_t* __restrict__ out_idx,
                      int32_t* __restrict__ out_len, int32_t* __restrict__ status, unsigned char* __restrict__ workspace,
-                     long long ws_per_seq) {
+                     long long ws_per_seq, unsigned char* __restrict__ entry_ws, long long entry_ws_per_seq) {
     __shared__ SkKept kept[2];
     __shared__ double Pj[kSkMaxBeam];
     __shared__ int canon[kSkMaxBeam], parentc[kSkMaxBeam], ent_of_canon[kSkMaxBeam];
-    __shared__ short new_ent[kSkMaxBeam][kSkMaxC];
-    __shared__ int cand[kSkMaxC];
-    __shared__ double candp[kSkMaxC];
-    // dict entries of one step (dynamic shared memory, beam_size * (kSkMaxC + 1) slots)
+    __shared__ int cand[MAXC];
+    __shared__ double candp[MAXC];
+    // dict entries of one step, beam_size * (MAXC + 1) slots, and the new-entry map [kSkMaxBeam][MAXC]: dynamic shared memory,
+    // or (entry_ws != nullptr, the 1024-candidate variant) this sequence's slice of the global workspace
     extern __shared__ double sk_dyn[];
-    const int gen_cap = beam_size * (kSkMaxC + 1);
-    double* e_pb = sk_dyn;
+    const int gen_cap = beam_size * (MAXC + 1);
+    double* e_base = entry_ws ? reinterpret_cast<double*>(entry_ws + (long long)blockIdx.x * entry_ws_per_seq) : sk_dyn;
+    double* e_pb = e_base;
     double* e_pnb = e_pb + gen_cap;
     double* e_tot = e_pnb + gen_cap;
     int* e_chr = reinterpret_cast<int*>(e_tot + gen_cap);
     short* e_kind = reinterpret_cast<short*>(e_chr + gen_cap);
     short* e_src = e_kind + gen_cap;
+    short (*new_ent)[MAXC] = reinterpret_cast<short (*)[MAXC]>(e_src + gen_cap);
     __shared__ int s_ngen, s_ng, s_fail;
 
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -220,18 +227,18 @@ ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ bl
     for (int t = 0; t < end_step; ++t) {
         const long long row = (long long)t * Bn + b;
         const int nc = meta[row].x;
-        if (nc > kSkMaxC) {                               // more candidates than the device path holds
+        if (nc > MAXC) {                               // more candidates than the device path holds
             if (tid == 0) { status[b] = HCTR_ERR_UNSUPPORTED; out_len[b] = 0; }
             return;
         }
         SkKept& K = kept[cur_buf];
         if (nc == 1) {
             // ---------------- in-place fast path (:147-171), one thread per kept beam
-            const int pidx = cand_idx[row * kSkMaxC];
+            const int pidx = cand_idx[row * MAXC];
             if (pidx >= unknown) continue;                // :150-151 (block-uniform)
             if (tid < nkept) {
                 const int j = tid;
-                const double p = (double)cand_lp[row * kSkMaxC], p0 = (double)blank_lp[row];
+                const double p = (double)cand_lp[row * MAXC], p0 = (double)blank_lp[row];
                 const double pr = sk_logaddexp(K.pb[j], K.pnb[j]);
                 bool extend = false;
                 if (pidx == 0) {
@@ -269,7 +276,7 @@ ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ bl
         SkKept& Kn = kept[cur_buf ^ 1];
         while (gptr < ng && g_time[gptr] <= t) ++gptr;
         int nsuf = ng - gptr; if (nsuf > 4) nsuf = 4;
-        if (tid < nc) { cand[tid] = cand_idx[row * kSkMaxC + tid]; candp[tid] = (double)cand_lp[row * kSkMaxC + tid]; }
+        for (int i = tid; i < nc; i += kSkThreads) { cand[i] = cand_idx[row * MAXC + i]; candp[i] = (double)cand_lp[row * MAXC + i]; }
         if (tid < nkept) {
             Pj[tid] = sk_logaddexp(K.pb[tid], K.pnb[tid]);
             int cn = tid;                                  // first beam with the same string
@@ -278,7 +285,7 @@ ctc_skip_beam_kernel(const int2* __restrict__ meta, const float* __restrict__ bl
             canon[tid] = cn;
             ent_of_canon[tid] = -1;
         }
-        for (int i = tid; i < kSkMaxBeam * kSkMaxC; i += kSkThreads) new_ent[i / kSkMaxC][i % kSkMaxC] = -1;
+        for (int i = tid; i < kSkMaxBeam * MAXC; i += kSkThreads) new_ent[i / MAXC][i % MAXC] = -1;
         __syncthreads();
         if (tid < nkept) {
             int pk = -1;                                   // canonical beam whose string is this one minus its last char
@@ -425,34 +432,92 @@ static long long sk_ws_per_seq(int T) {
     return (bytes + 15) & ~15ll;
 }
 
+static size_t sk_entry_bytes(int beam_size, int maxc) {
+    return (size_t)beam_size * (maxc + 1) * (3 * sizeof(double) + sizeof(int) + 2 * sizeof(short)) + (size_t)kSkMaxBeam * maxc * sizeof(short) + 64;
+}
+
+template <int MAXC>
+static int sk_launch(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b, int beam_size,
+                     double lm_penalty, double len_bonus, const double* lm_table, const hctr_ngram_lm& lm, int32_t* out_idx,
+                     int32_t* out_len, int32_t* status, void* workspace, cudaStream_t s) {
+    const long long rows = (long long)T * B;
+    const size_t smem = (size_t)C * sizeof(float);
+    char* base = static_cast<char*>(workspace);
+    int2* meta = reinterpret_cast<int2*>(base);
+    float* blank = reinterpret_cast<float*>(base + rows * 8);
+    int32_t* cidx = reinterpret_cast<int32_t*>(base + rows * 12);
+    float* clp = reinterpret_cast<float*>(base + rows * 12 + rows * MAXC * 4);
+    long long tables = rows * (8 + 4 + (long long)MAXC * 8);
+    tables = (tables + 255) & ~255ll;
+    unsigned char* seq_ws = reinterpret_cast<unsigned char*>(base + tables);
+    const long long seq_bytes = (sk_ws_per_seq(T) * B + 255) & ~255ll;
+    const bool global_entries = MAXC > kSkMaxC;
+    unsigned char* entry_ws = global_entries ? seq_ws + seq_bytes : nullptr;
+    const long long entry_per_seq = ((long long)sk_entry_bytes(kSkMaxBeam, MAXC) + 255) & ~255ll;
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_prune_logsoftmax_kernel<float, MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_prune_logsoftmax_kernel<__nv_bfloat16, MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        if (!global_entries)
+            HCTR_CUDA(cudaFuncSetAttribute(ctc_skip_beam_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sk_entry_bytes(kSkMaxBeam, MAXC)));
+        once.mark(dev);
+    }
+    if (dtype == HCTR_F32)
+        ctc_prune_logsoftmax_kernel<float, MAXC><<<(int)rows, kPruneThreads, smem, s>>>(static_cast<const float*>(logits), T, B, C, stride_t,
+                                                                                         stride_b, meta, blank, cidx, clp);
+    else
+        ctc_prune_logsoftmax_kernel<__nv_bfloat16, MAXC><<<(int)rows, kPruneThreads, smem, s>>>(
+            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, meta, blank, cidx, clp);
+    HCTR_CUDA(cudaGetLastError());
+    const size_t dyn = global_entries ? 0 : sk_entry_bytes(beam_size, MAXC);
+    ctc_skip_beam_kernel<MAXC><<<B, kSkThreads, dyn, s>>>(meta, blank, cidx, clp, T, B, C, beam_size, lm_penalty, len_bonus, lm_table, lm,
+                                                          out_idx, out_len, status, seq_ws, sk_ws_per_seq(T), entry_ws, entry_per_seq);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+
 }  // namespace hctr
 
 using namespace hctr;
 
 extern "C" {
 
-int hctr_ctc_skip_max_candidates(void) { return kSkMaxC; }
+int hctr_ctc_skip_max_candidates(void) { return kSkBigC; }
 
-long long hctr_ctc_skip_workspace_bytes(int T, int B) {
+long long hctr_ctc_skip_workspace_bytes_ex(int T, int B, int max_candidates) {
     if (T <= 0 || B <= 0) return 0;
-    // per-row candidate tables + per-sequence greedy list and prefix trie
+    const int maxc = max_candidates > kSkMaxC ? kSkBigC : kSkMaxC;
+    // per-row candidate tables + per-sequence greedy list and prefix trie (+ per-sequence dict entries for the large variant)
     const long long rows = (long long)T * B;
-    long long tables = rows * (8 + 4 + kSkMaxC * 8);
+    long long tables = rows * (8 + 4 + (long long)maxc * 8);
     tables = (tables + 255) & ~255ll;
-    return tables + sk_ws_per_seq(T) * B + 256;
+    long long entries = 0;
+    if (maxc > kSkMaxC) entries = (((long long)sk_entry_bytes(kSkMaxBeam, maxc) + 255) & ~255ll) * B;
+    return tables + ((sk_ws_per_seq(T) * B + 255) & ~255ll) + entries + 256;
 }
+long long hctr_ctc_skip_workspace_bytes(int T, int B) { return hctr_ctc_skip_workspace_bytes_ex(T, B, kSkMaxC); }
 
 int hctr_ctc_skip_beam_search(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                               int beam_size, double lm_penalty, double len_bonus, const double* lm_table, int32_t* out_idx,
                               int32_t* out_len, int32_t* status, void* workspace, long long workspace_bytes, void* stream) {
-    return hctr_ctc_skip_beam_search_lm(logits, dtype, T, B, C, stride_t, stride_b, beam_size, lm_penalty, len_bonus, lm_table,
-                                        nullptr, out_idx, out_len, status, workspace, workspace_bytes, stream);
+    return hctr_ctc_skip_beam_search_ex(logits, dtype, T, B, C, stride_t, stride_b, beam_size, lm_penalty, len_bonus, lm_table,
+                                        nullptr, kSkMaxC, out_idx, out_len, status, workspace, workspace_bytes, stream);
 }
 
 int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                                  int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
                                  const hctr_ngram_lm* ngram, int32_t* out_idx, int32_t* out_len, int32_t* status,
                                  void* workspace, long long workspace_bytes, void* stream) {
+    return hctr_ctc_skip_beam_search_ex(logits, dtype, T, B, C, stride_t, stride_b, beam_size, lm_penalty, len_bonus, lm_table,
+                                        ngram, kSkMaxC, out_idx, out_len, status, workspace, workspace_bytes, stream);
+}
+
+int hctr_ctc_skip_beam_search_ex(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
+                                 int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                 const hctr_ngram_lm* ngram, int max_candidates, int32_t* out_idx, int32_t* out_len,
+                                 int32_t* status, void* workspace, long long workspace_bytes, void* stream) {
     HCTR_CHECK(!(ngram && lm_table), HCTR_ERR_INVALID, "skip beam: pass either a unigram table or an n-gram model");
     hctr_ngram_lm lm;
     memset(&lm, 0, sizeof(lm));
@@ -466,6 +531,7 @@ int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, in
     HCTR_CHECK(dtype == HCTR_F32 || dtype == HCTR_BF16, HCTR_ERR_INVALID, "skip beam: bad dtype");
     HCTR_CHECK(beam_size >= 1 && beam_size <= kSkMaxBeam, HCTR_ERR_INVALID, "skip beam: beam size must be in [1,%d]", kSkMaxBeam);
     HCTR_CHECK(T >= 0 && B >= 0 && C > 1, HCTR_ERR_INVALID, "skip beam: bad shape");
+    HCTR_CHECK(max_candidates == kSkMaxC || max_candidates == kSkBigC, HCTR_ERR_INVALID, "skip beam: max_candidates must be %d or %d", kSkMaxC, kSkBigC);
     if (B == 0) return HCTR_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (T == 0) {
@@ -474,42 +540,17 @@ int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, in
         return HCTR_OK;
     }
     HCTR_CHECK(logits != nullptr, HCTR_ERR_INVALID, "skip beam: null logits");
-    const long long need = hctr_ctc_skip_workspace_bytes(T, B);
+    const long long need = hctr_ctc_skip_workspace_bytes_ex(T, B, max_candidates);
     HCTR_CHECK(workspace && workspace_bytes >= need, HCTR_ERR_INVALID, "skip beam: workspace too small (%lld < %lld)", workspace_bytes, need);
     HCTR_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, HCTR_ERR_INVALID, "skip beam: workspace must be 256-byte aligned");
     const long long rows = (long long)T * B;
     HCTR_CHECK(rows < (1ll << 31) && (long long)T * kSkMaxBeam + 1 < (1ll << 31), HCTR_ERR_INVALID, "skip beam: too large");
-    const size_t smem = (size_t)C * sizeof(float);
-    HCTR_CHECK(smem <= 160 * 1024, HCTR_ERR_INVALID, "skip beam: %d classes do not fit the shared-memory row buffer", C);
-    char* base = static_cast<char*>(workspace);
-    int2* meta = reinterpret_cast<int2*>(base);
-    float* blank = reinterpret_cast<float*>(base + rows * 8);
-    int32_t* cidx = reinterpret_cast<int32_t*>(base + rows * 12);
-    float* clp = reinterpret_cast<float*>(base + rows * 12 + rows * kSkMaxC * 4);
-    long long tables = rows * (8 + 4 + kSkMaxC * 8);
-    tables = (tables + 255) & ~255ll;
-    unsigned char* seq_ws = reinterpret_cast<unsigned char*>(base + tables);
-    static PerDeviceOnce once;
-    int dev;
-    if (once.need(dev)) {
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_prune_logsoftmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_prune_logsoftmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_skip_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kSkMaxBeam * (kSkMaxC + 1) * 32));
-        once.mark(dev);
-    }
-    if (dtype == HCTR_F32)
-        ctc_prune_logsoftmax_kernel<float><<<(int)rows, kPruneThreads, smem, s>>>(static_cast<const float*>(logits), T, B, C, stride_t,
-                                                                                   stride_b, meta, blank, cidx, clp);
-    else
-        ctc_prune_logsoftmax_kernel<__nv_bfloat16><<<(int)rows, kPruneThreads, smem, s>>>(
-            static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, meta, blank, cidx, clp);
-    HCTR_CUDA(cudaGetLastError());
-    const size_t dyn = (size_t)beam_size * (kSkMaxC + 1) * (3 * sizeof(double) + sizeof(int) + 2 * sizeof(short));
-    ctc_skip_beam_kernel<<<B, kSkThreads, dyn, s>>>(meta, blank, cidx, clp, T, B, C, beam_size, lm_penalty, len_bonus, lm_table, lm,
-                                                    out_idx, out_len, status, seq_ws, sk_ws_per_seq(T));
-    HCTR_CUDA(cudaGetLastError());
-    return HCTR_OK;
+    HCTR_CHECK((size_t)C * sizeof(float) <= 160 * 1024, HCTR_ERR_INVALID, "skip beam: %d classes do not fit the shared-memory row buffer", C);
+    if (max_candidates == kSkBigC)
+        return sk_launch<kSkBigC>(logits, dtype, T, B, C, stride_t, stride_b, beam_size, lm_penalty, len_bonus, lm_table, lm, out_idx,
+                                  out_len, status, workspace, s);
+    return sk_launch<kSkMaxC>(logits, dtype, T, B, C, stride_t, stride_b, beam_size, lm_penalty, len_bonus, lm_table, lm, out_idx,
+                              out_len, status, workspace, s);
 }
 
 }  // extern "C"

@@ -53,6 +53,8 @@ SIGNATURES = {
     "hctr_ctc_skip_beam_search_lm": (_I, [_P, _I, _I, _I, _I, _L, _L, _I, c_double, c_double, _P, _P, _P, _P, _P, _P, _L, _P]),
     "hctr_ctc_skip_workspace_bytes": (_L, [_I, _I]),
     "hctr_ctc_skip_max_candidates": (_I, []),
+    "hctr_ctc_skip_workspace_bytes_ex": (_L, [_I, _I, _I]),
+    "hctr_ctc_skip_beam_search_ex": (_I, [_P, _I, _I, _I, _I, _L, _L, _I, c_double, c_double, _P, _P, _I, _P, _P, _P, _P, _L, _P]),
     "hctr_ctc_loss_fwd_bwd": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _I, _P, _P, _P, _P, c_float, _P, _L, _P]),
     "hctr_ctc_loss_workspace_bytes": (_L, [_I, _I, _I]),
     "hctr_ctc_loss_flag_offset": (_L, [_I, _I, _I]),

@@ -190,29 +190,34 @@ class ctc_codec(object):
             table = None
             if self.lm_table is not None:
                 table = torch.from_numpy(np.ascontiguousarray(self.lm_table, dtype=np.float64)).to(dev)
-            nb = lib.hctr_ctc_skip_workspace_bytes(T, B)
-            ws = torch.empty((max(nb, 8) + 256,), dtype=torch.uint8, device=dev)
-            off = (-ws.data_ptr()) % 256
             ngram = getattr(self, "ngram", None)
+            lm_ref = None
             if ngram is not None and hasattr(ngram, "struct"):
                 import ctypes
                 lm = ngram.struct(dev)
-                nat.check(lib.hctr_ctc_skip_beam_search_lm(
+                lm_ref = ctypes.byref(lm)
+                table = None
+
+            def run(max_candidates):
+                nb = lib.hctr_ctc_skip_workspace_bytes_ex(T, B, max_candidates)
+                ws = torch.empty((max(nb, 8) + 256,), dtype=torch.uint8, device=dev)
+                off = (-ws.data_ptr()) % 256
+                nat.check(lib.hctr_ctc_skip_beam_search_ex(
                     nat.ptr(logits), self._dtype_code(nat, logits), T, B, C, logits.stride(0), logits.stride(1),
-                    int(self.beam_size), float(self.lm_panelty), float(self.len_bonus), None, ctypes.byref(lm), nat.ptr(idx),
-                    nat.ptr(ln), nat.ptr(status), nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()), "ctc_skip_beam_search_lm")
-            else:
-                nat.check(lib.hctr_ctc_skip_beam_search(
-                    nat.ptr(logits), self._dtype_code(nat, logits), T, B, C, logits.stride(0), logits.stride(1),
-                    int(self.beam_size), float(self.lm_panelty), float(self.len_bonus), nat.ptr(table), nat.ptr(idx), nat.ptr(ln),
-                    nat.ptr(status), nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()), "ctc_skip_beam_search")
-            st = status.cpu()
+                    int(self.beam_size), float(self.lm_panelty), float(self.len_bonus), nat.ptr(table), lm_ref, max_candidates,
+                    nat.ptr(idx), nat.ptr(ln), nat.ptr(status), nat.c_void_p(ws.data_ptr() + off), nb, nat.stream_ptr()),
+                    "ctc_skip_beam_search")
+                return status.cpu()
+
+            st = run(128)
+            if T > 0 and bool((st == nat.HCTR_ERR_UNSUPPORTED).any()):
+                # a step with more than 128 classes above the 0.001 prune threshold (the reference takes up to 999,
+                # utils/ctc_codec.py:144): repeat with the large candidate tables
+                st = run(lib.hctr_ctc_skip_max_candidates())
             if T == 0 or bool((st == nat.HCTR_ERR_INDEX).any()) or bool((st == -1).any()):
                 raise IndexError("list index out of range")     # reference: utils/ctc_codec.py:139,179
             if bool((st != 0).any()):
-                raise NotImplementedError("hctr_b200: a time step has more than %d classes above the 0.001 prune "
-                                          "threshold; the device skip-search holds at most that many candidates"
-                                          % lib.hctr_ctc_skip_max_candidates())
+                raise RuntimeError("hctr_b200: skip search failed with status %s" % sorted(set(st.tolist())))
         return idx, ln
 
     def beam_search_indices(self, logits):

@@ -173,7 +173,7 @@ int hctr_ctc_prefix_beam_search_lm(const int32_t* topk_idx, const float* topk_lo
  * in index order; a single candidate takes the reference's in-place fast path (quirks included), otherwise a
  * duplicate-aware context beam search runs over the candidates. Fused log-softmax/prune pre-pass + one CTA per sequence.
  * status[b]: 0 ok; HCTR_ERR_INDEX where the reference raises IndexError (empty greedy path :139, or a step without any
- * candidate :179); HCTR_ERR_UNSUPPORTED if a step has more than hctr_ctc_skip_max_candidates() candidates. */
+ * candidate :179); HCTR_ERR_UNSUPPORTED if a step has more than 128 candidates (see hctr_ctc_skip_beam_search_ex below). */
 int hctr_ctc_skip_beam_search(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                               int beam_size, double lm_penalty, double len_bonus, const double* lm_table, int32_t* out_idx,
                               int32_t* out_len, int32_t* status, void* workspace, long long workspace_bytes, void* stream);
@@ -183,7 +183,18 @@ int hctr_ctc_skip_beam_search_lm(const void* logits, int dtype, int T, int B, in
                                  const hctr_ngram_lm* ngram, int32_t* out_idx, int32_t* out_len, int32_t* status,
                                  void* workspace, long long workspace_bytes, void* stream);
 long long hctr_ctc_skip_workspace_bytes(int T, int B);
+/* Candidates per step: the reference takes every class with p > 0.001 (utils/ctc_codec.py:144), at most 999. The entry points
+ * above hold up to 128 per step (small candidate tables, a step's dict entries in shared memory) and report
+ * HCTR_ERR_UNSUPPORTED in status[b] for a sequence that needs more; the caller then repeats the call through
+ * hctr_ctc_skip_beam_search_ex with max_candidates = hctr_ctc_skip_max_candidates() (= 1024: 8 KB of candidate table per
+ * row, dict entries in the workspace) and a workspace of hctr_ctc_skip_workspace_bytes_ex(T, B, max_candidates).
+ * max_candidates must be 128 or 1024; ngram may be NULL. */
 int hctr_ctc_skip_max_candidates(void);
+long long hctr_ctc_skip_workspace_bytes_ex(int T, int B, int max_candidates);
+int hctr_ctc_skip_beam_search_ex(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
+                                 int beam_size, double lm_penalty, double len_bonus, const double* lm_table,
+                                 const hctr_ngram_lm* ngram, int max_candidates, int32_t* out_idx, int32_t* out_len,
+                                 int32_t* status, void* workspace, long long workspace_bytes, void* stream);
 
 /* CTCLoss(blank=0, reduction='mean', zero_infinity=True) on log_softmax(logits) and its gradient wrt the
  * logits (main.py:205,406-409,426). logits element (t,b,c) at logits[t*stride_t + b*stride_b + c];

@@ -229,7 +229,8 @@ def _skip_inputs(g, case):
     return synth.peakier(x, boost), C
 
 
-SKIP_CASES = [(c, s) for c in ("small", "mid", "wide", "flat") for s in ("zero_b0", "zero_b58", "tab_p2")]
+# "big": up to 144 classes above the prune threshold in one step -> the call is repeated with the 1024-candidate tables
+SKIP_CASES = [(c, s) for c in ("small", "mid", "wide", "flat", "big") for s in ("zero_b0", "zero_b58", "tab_p2")]
 
 
 @pytest.mark.parametrize("case,setting", SKIP_CASES)
@@ -243,13 +244,23 @@ def test_skip_search_golden(golden, case, setting):
     assert c.decode(x) == list(g["%s_%s_text" % (case, setting)])
 
 
-def test_skip_search_candidate_overflow_and_errors(golden):
-    g = golden("beam_skip")
-    x, C = _skip_inputs(g, "big")                          # up to 144 classes above the prune threshold in one step
+def test_skip_search_many_candidates_and_errors(golden):
+    """A nearly flat distribution: several hundred classes above the 0.001 prune threshold at every step (the reference takes
+    up to 999, utils/ctc_codec.py:144). Device (1024-candidate variant) vs the oracle restatement of __cbs_skip__."""
+    from oracle.codec import CodecTables
+    T, B, C = 24, 2, 900
+    rs = np.random.RandomState(12)
+    x = (0.3 * rs.randn(T, B, C)).astype(np.float32)       # p ~ 1/900 each: about half the classes pass the threshold
+    x[np.arange(0, T, 3), :, 7] += 6.0                     # a non-empty greedy path
+    x[np.arange(1, T, 3), :, 0] += 6.0
+    lp = oracle.log_softmax(x)
+    counts = (lp > np.log(0.001)).sum(axis=2)
+    assert counts.max() > 300 and counts.min() >= 1
     c = _codec(C)
-    c.set_beam_search(skip_search=True, use_tfm_pred=False)
-    with pytest.raises(NotImplementedError):
-        c.decode(x)
+    c.set_beam_search(skip_search=True, use_tfm_pred=False, lm_panelty=2.0, len_bonus=0.0)
+    idx, ln, st = oracle.beam_search_skip(x, 10, 2.0, 0.0, None)
+    assert (st == 0).all()
+    assert c.decode(x) == CodecTables(synth.charset(C - 2)).to_text(idx, ln)
     flat = np.zeros((6, 1, 2000), np.float32)              # uniform over 2000 classes: nothing above 0.001 -> reference IndexError
     flat[:, 0, 5] = 0.5
     c2 = _codec(2000)
