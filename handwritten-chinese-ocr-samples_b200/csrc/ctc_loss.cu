@@ -64,6 +64,7 @@ struct CtcWs {
     int* lab;          // [B][Lp]        labels clamped to [0, C-1]
     int* prog;         // [B][NG]        rows of granule g (8 time steps) whose label probabilities are in place
     int* err;          // [4]            bit 0: a length / label was out of range; bit 1: the scan timed out waiting for rows
+    unsigned long long* dbg;   // [B][2][8]  HCTR_CTC_TIMING diagnostics of the polling scan: start, end, ns waiting, polls, quarter marks
     int Lp, NG;
 };
 constexpr int kGranule = 8;          // time steps per progress counter
@@ -100,6 +101,7 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     const long long o_lab = take(4ll * B * Lp);
     const long long o_prog = take(4ll * B * NG);
     const long long o_err = take(16);
+    const long long o_dbg = take(128ll * B);
     if (total) *total = off;
     CtcWs w;
     char* p = static_cast<char*>(base);
@@ -122,6 +124,7 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     w.lab = reinterpret_cast<int*>(p + o_lab);
     w.prog = reinterpret_cast<int*>(p + o_prog);
     w.err = reinterpret_cast<int*>(p + o_err);
+    w.dbg = reinterpret_cast<unsigned long long*>(p + o_dbg);
     w.Lp = Lp; w.NG = NG;
     return w;
 }
@@ -396,6 +399,8 @@ ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restr
     int gnext = rev ? (Tb - 1) / kGranule : 0;        // next granule to acquire: upwards for alpha, downwards for beta
     int pend = 0;                                     // lane 0: prefetched counter of granule gnext
     bool timed_out = false;
+    unsigned long long dbg_t0 = 0, dbg_wait = 0, dbg_polls = 0;
+    if (POLL && lane == 0) dbg_t0 = global_timer_ns();
     if (POLL && lane == 0) pend = ld_acquire_gpu(prog + gnext);
     auto ensure = [&](int i_hi) {                     // warp-uniform: rows of steps 0..i_hi are complete on return
         while (ready <= i_hi && !timed_out) {
@@ -408,8 +413,10 @@ ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restr
                     do {
                         __nanosleep(100);
                         cnt = ld_acquire_gpu(prog + gnext);
+                        ++dbg_polls;
                         if (cnt < target && global_timer_ns() - t0 > kScanWaitLimitNs) { ok = 0; break; }
                     } while (cnt < target);
+                    dbg_wait += global_timer_ns() - t0;
                 }
             }
             ok = __shfl_sync(0xffffffffu, ok, 0);     // the other lanes' reads are ordered after lane 0's acquire
@@ -472,6 +479,8 @@ ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restr
     for (int c = 0; c < nchunks; ++c) {
         issue(slot == 0 ? 2 : slot - 1);
         if (POLL && timed_out) break;                 // warp-uniform
+        if (POLL && lane == 0 && (c == nchunks / 4 || c == nchunks / 2 || c == 3 * nchunks / 4))
+            w.dbg[((long long)b * 2 + (rev ? 1 : 0)) * 8 + 4 + (c == nchunks / 4 ? 0 : c == nchunks / 2 ? 1 : 2)] = global_timer_ns();
         cp_async_wait<2>();                           // chunk c has landed (each lane reads only what it copied itself)
         const double2* buf = reinterpret_cast<const double2*>(stage) + slot * (kScanChunkStates * 16) + lane;
         slot = slot == 2 ? 0 : slot + 1;
@@ -555,6 +564,12 @@ ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restr
         }
     }
     cp_async_wait<0>();
+    if (POLL && lane == 0) {
+        unsigned long long* d = w.dbg + ((long long)b * 2 + (rev ? 1 : 0)) * 8;
+        d[0] = dbg_t0; d[1] = global_timer_ns(); d[2] = dbg_wait; d[3] = dbg_polls;
+        unsigned smid; asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        d[7] = smid;
+    }
     if (POLL && timed_out) {
         // the rows never arrived (protocol bug, or the two kernels could not run concurrently): report, do not hang
         if (lane == 0) {
@@ -957,15 +972,29 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     } else {
         // ---- maximum
         float m = has_sc ? x_sc : -INFINITY;
+        if (V == 8) {
+            // bf16 rows stay packed: 4 HMNMX2 per 8 elements, two independent chains
+            __nv_bfloat162 a0 = __float2bfloat162_rn(-INFINITY), a1 = a0;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            if (tid + i * kRowThreads < nvec) {
-                float x[V];
-                RowVec<T>::unpack(xq[i], x);
-                float a = fmaxf(x[0], x[1]);
+            for (int i = 0; i < NV; ++i) {
+                if (tid + i * kRowThreads < nvec) {
+                    a0 = __hmax2(a0, __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&xq[i].x), *reinterpret_cast<const __nv_bfloat162*>(&xq[i].y)));
+                    a1 = __hmax2(a1, __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&xq[i].z), *reinterpret_cast<const __nv_bfloat162*>(&xq[i].w)));
+                }
+            }
+            a0 = __hmax2(a0, a1);
+            m = fmaxf(m, fmaxf(__low2float(a0), __high2float(a0)));
+        } else {
 #pragma unroll
-                for (int j = 2; j < V; j += 2) a = fmaxf(a, fmaxf(x[j], x[j + 1]));
-                m = fmaxf(m, a);
+            for (int i = 0; i < NV; ++i) {
+                if (tid + i * kRowThreads < nvec) {
+                    float x[V];
+                    RowVec<T>::unpack(xq[i], x);
+                    float a = fmaxf(x[0], x[1]);
+#pragma unroll
+                    for (int j = 2; j < V; j += 2) a = fmaxf(a, fmaxf(x[j], x[j + 1]));
+                    m = fmaxf(m, a);
+                }
             }
         }
         m = warp_max(m);
@@ -1134,6 +1163,9 @@ static int ctc_side(CtcSide** out) {
             int prio_lo = 0, prio_hi = 0;
             HCTR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             HCTR_CUDA(cudaStreamCreateWithPriority(&sd.helper, cudaStreamNonBlocking, prio_hi));
+            HCTR_CUDA(cudaFuncSetAttribute(ctc_scan_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            HCTR_CUDA(cudaFuncSetAttribute(ctc_scan_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            HCTR_CUDA(cudaFuncSetAttribute(ctc_scan_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
             HCTR_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
             HCTR_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
         }
@@ -1251,11 +1283,12 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     //      2*B one-warp CTAs all resident beside it ("2": the same kernels back to back on one stream, e.g. under ncu)
     const int nv = rows_nv(C, esz);
     const bool rows_path = !overlap_off && kscan != 0 && !debug_force_log && nv != 0;
-    // Default: rows -> scans -> fix back to back on the caller's stream. HCTR_CTC_OVERLAP=1 opts into the overlapped schedule
-    // (scans on a helper stream, fed through the progress counters): measured SLOWER on B200 at every batch size tried -
-    // B=16: 1.12 ms against 0.57 ms (the scan warps share their schedulers with the rows kernel's warps and the recursion
-    // runs 3.5x slower, 1.09 ms instead of 0.29 ms), B=64: 1.81 against 1.45 ms (rows kernel 17 % slower, scan tail 0.15 ms).
-    const bool want_overlap = ov && ov[0] == '1';
+    // Schedule. Serial: rows -> scans -> fix back to back on the caller's stream. Overlapped: the scans run on a helper stream
+    // underneath the rows kernel, fed through the progress counters; when the rows kernel ends each scan still has the
+    // second half of its steps to go (the rows were dealt from both ends), so the gain is at most half a scan (0.12 ms) minus
+    // the cost of sharing the SMs. Measured (T=2048, C=7375, bf16; serial / overlapped): B=2 0.30 / 0.34 ms, B=16 0.57 / 0.50,
+    // B=64 1.45 / 1.51 (rows kernel 17 % slower beside 128 scan CTAs). HCTR_CTC_OVERLAP=1 / 2 force overlapped / serial.
+    const bool want_overlap = ov ? ov[0] == '1' : (B >= 8 && B <= 32);
     const bool serial = rows_path && (!want_overlap || 2ll * B > 2048);
     const bool overlap = rows_path;
     if (serial) {
@@ -1293,10 +1326,14 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
                                grad_scale, &w, s);
             if (rc) return rc;
         }
+        // One scan CTA per SM, enforced by an unused dynamic shared-memory request: launched beside a kernel that fills the
+        // GPU, the one-warp CTAs are otherwise packed eight to an SM - on the few SMs that free up first - and, one warp per
+        // CTA, onto the same scheduler of it: the recursion then runs 4x slower (measured: 32 scan CTAs on SMs 0, 6, 32, 64).
+        const size_t spread = 112 * 1024;
         switch (kscan) {
-            case 4:  ctc_scan_kernel<4, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
-            case 8:  ctc_scan_kernel<8, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
-            default: ctc_scan_kernel<16, true><<<gridB, 32, 0, side->helper>>>(input_lengths, T, Sp, nll, w); break;
+            case 4:  ctc_scan_kernel<4, true><<<gridB, 32, spread, side->helper>>>(input_lengths, T, Sp, nll, w); break;
+            case 8:  ctc_scan_kernel<8, true><<<gridB, 32, spread, side->helper>>>(input_lengths, T, Sp, nll, w); break;
+            default: ctc_scan_kernel<16, true><<<gridB, 32, spread, side->helper>>>(input_lengths, T, Sp, nll, w); break;
         }
         HCTR_CUDA(cudaGetLastError());
         if (timing) cudaEventRecord(tev[3], side->helper);
@@ -1316,6 +1353,20 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
             fprintf(stderr, "hctr ctc timing: rows %.3f ms, scan %.3f ms, scan start -> rows start %.3f ms, rows end -> scan end %.3f ms\n",
                     rows_ms, scan_ms, lead_ms, tail_ms);
             for (int i = 0; i < 4; ++i) cudaEventDestroy(tev[i]);
+            {
+                unsigned long long all[16 * 2 * 8];
+                const int nb = B < 16 ? B : 16;
+                cudaMemcpy(all, w.dbg, sizeof(unsigned long long) * nb * 16, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "   scan CTA -> SM:");
+                for (int q = 0; q < nb * 2; ++q) fprintf(stderr, " %llu", all[q * 8 + 7]);
+                fprintf(stderr, "\n");
+            }
+            unsigned long long hd[32];
+            cudaMemcpy(hd, w.dbg, sizeof(hd), cudaMemcpyDeviceToHost);           // sequences 0 and 1, both directions
+            for (int q = 0; q < 4; ++q)
+                fprintf(stderr, "   scan b=%d %s: lifetime %.3f ms (quarters at %.3f %.3f %.3f), waiting %.3f ms in %llu polls\n", q / 2,
+                        (q & 1) ? "beta " : "alpha", (hd[q * 8 + 1] - hd[q * 8]) * 1e-6, (hd[q * 8 + 4] - hd[q * 8]) * 1e-6,
+                        (hd[q * 8 + 5] - hd[q * 8]) * 1e-6, (hd[q * 8 + 6] - hd[q * 8]) * 1e-6, hd[q * 8 + 2] * 1e-6, hd[q * 8 + 3]);
         }
         HCTR_CUDA(cudaStreamWaitEvent(s, side->join, 0));           // join
     } else {
