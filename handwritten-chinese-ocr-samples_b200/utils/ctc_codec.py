@@ -172,8 +172,15 @@ class ctc_codec(object):
                 # turned into a device hash table and queried inside the beam-search kernel
                 self.ngram = _core().ngram_lm.NgramLM.from_arpa(ngram_path, self)
             else:
-                raise NotImplementedError("hctr_b200: KenLM binary files are not read; pass the ARPA file lmplz wrote "
-                                          "(*.arpa) or a per-class unigram table (*.npy)")
+                # build_binary's output hashes its n-grams (probing) or bit-packs them (trie) and cannot be turned back into
+                # n-grams without the library; the ARPA file it was made FROM holds the same model (third-party/README.md:
+                # `lmplz -o 5 <text >text.arpa` then `build_binary text.arpa text.bin`) - point ngram_path at that file
+                arpa = os.path.splitext(ngram_path)[0] + ".arpa"
+                if os.path.exists(arpa):
+                    self.ngram = _core().ngram_lm.NgramLM.from_arpa(arpa, self)
+                else:
+                    raise NotImplementedError("hctr_b200: KenLM binary files are not read; pass the ARPA file build_binary was "
+                                              "given (looked for %s) or a per-class unigram table (*.npy)" % arpa)
 
     def skip_search_indices(self, logits):
         """__cbs_skip__ on the device (reference: utils/ctc_codec.py:124-181)."""

@@ -344,6 +344,12 @@ def test_set_beam_search_reads_an_arpa_file(tmp_path):
     assert len(out) == 2 and all(isinstance(t, str) for t in out)
     with pytest.raises(NotImplementedError):
         c.set_beam_search(ngram_path="model.bin", use_tfm_pred=False)
+    # a KenLM binary next to the ARPA file it was built from (third-party/README.md:40-42): the ARPA file is read instead
+    (tmp_path / "lm.bin").write_bytes(b"mmap lm http://kheafield.com/code format version 5\n\0")
+    c2 = _codec(C)
+    c2.set_beam_search(ngram_path=str(tmp_path / "lm.bin"), use_tfm_pred=False)
+    assert c2.ngram is not None and c2.ngram.order == 3
+    assert c2.decode(torch.from_numpy(x).cuda()) == out
 
 
 @pytest.mark.parametrize("case", ["small", "mid", "flat"])
