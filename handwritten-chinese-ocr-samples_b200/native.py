@@ -79,6 +79,7 @@ SIGNATURES = {
     "hctr_stem_wgrad_workspace_bytes": (_L, [_I, _I, _I]),
     "hctr_sgd_clip_step": (_I, [_P, _P, _P, _L, c_float, c_float, c_float, c_float, c_float, _I, _P, _P, _P]),
     "hctr_sgd_workspace_bytes": (_L, []),
+    "hctr_pack_weights": (_I, [_P, _I, _L, _P]),
     "hctr_edit_distance": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "hctr_normalize_pad": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "hctr_resize_area_u8": (_I, [_P, _I, _I, _L, _P, _I, _I, _L, _P]),
@@ -88,6 +89,14 @@ SIGNATURES = {
 TESTING_SIGNATURES = {
     "hctr_testing_set_conv_variant": (_I, [_I, _I]),
 }
+
+
+
+class PackDesc(ctypes.Structure):
+    """hctr_pack_desc of include/hctr_b200.h."""
+    _fields_ = [("src", c_void_p), ("dst_fwd", c_void_p), ("dst_bwd", c_void_p), ("cout", c_int), ("cin", c_int),
+                ("taps", c_int), ("bwd_mode", c_int), ("bwd_pitch", c_longlong), ("tile_start", c_longlong)]
+
 
 _lib = None
 

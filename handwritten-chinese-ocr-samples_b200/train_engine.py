@@ -37,6 +37,8 @@ class TrainEngine(object):
         self._ones = {}
         self._zeros = {}
         self._tracked = {}            # id(bn) -> host copy of num_batches_tracked (only for momentum=None modules)
+        self._pack = None             # packed bf16 weight operands of every tensor-core layer (rebuilt when parameters move)
+        self._bn_seen = []            # BatchNorm modules of the running forward (their counters are bumped in one op)
 
     def _batches_tracked(self, bn):
         n = self._tracked.get(id(bn))
@@ -64,6 +66,71 @@ class TrainEngine(object):
     def _ws(nbytes, dev):
         return torch.empty((max(int(nbytes), 16),), dtype=torch.uint8, device=dev)
 
+    # ------------------------------------------------------------------ weight operands: one pack launch per step
+    def _packed_layers(self):
+        m = self.model
+        cnn = m.cnn
+        convs = [cnn.conv0_2]
+        for stage in range(1, 5):
+            for unit in getattr(cnn, "block%d" % stage):
+                convs += [unit.conv1, unit.conv2]
+                if unit.downsample is not None:
+                    convs.append(unit.downsample[0])
+            convs.append(getattr(cnn, "conv%d" % stage))
+        return convs
+
+    def pack_weights(self):
+        """bf16 operand layouts of all 32 tensor-core convolutions and the classifier (forward [Cout][tap][Cin]; data
+        gradient [Cin][tap][Cout], classifier [tap][Cin][pitch]) from the current fp32 parameters: ONE kernel over a
+        descriptor table (hctr_pack_weights). The optimizer rewrites every parameter each step, so this runs per forward;
+        the table and the two arenas are rebuilt only when a parameter's storage moves."""
+        import ctypes
+        m = self.model
+        lin = m.linear
+        convs = self._packed_layers()
+        key = tuple(c.weight.data_ptr() for c in convs) + (lin.weight.data_ptr(),)
+        pk = self._pack
+        if pk is None or pk["key"] != key:
+            dev = lin.weight.device
+            n, d = lin.weight.shape
+            hf = 4
+            cf = d // hf
+            pitch = (n + 7) // 8 * 8
+            items = [(c.weight, c.weight.shape[0], c.weight.shape[1], c.weight.shape[2] * c.weight.shape[3], 0, 0) for c in convs]
+            items.append((lin.weight, n, cf, hf, 1, pitch))
+            fwd_total = sum(co * ci * t for _, co, ci, t, _, _ in items)
+            bwd_total = sum((t * ci * p) if mode == 1 else (co * ci * t) for _, co, ci, t, mode, p in items)
+            fwd = torch.empty((fwd_total,), dtype=torch.bfloat16, device=dev)
+            bwd = torch.zeros((bwd_total,), dtype=torch.bfloat16, device=dev)     # classifier pad columns stay zero
+            descs = (nat.PackDesc * len(items))()
+            views_f, views_b = {}, {}
+            fo = bo = tiles = 0
+            for i, (w, co, ci, t, mode, p) in enumerate(items):
+                nf = co * ci * t
+                nb = t * ci * p if mode == 1 else nf
+                descs[i].src = w.data_ptr()
+                descs[i].dst_fwd = fwd.data_ptr() + 2 * fo
+                descs[i].dst_bwd = bwd.data_ptr() + 2 * bo
+                descs[i].cout, descs[i].cin, descs[i].taps, descs[i].bwd_mode = co, ci, t, mode
+                descs[i].bwd_pitch = p
+                descs[i].tile_start = tiles
+                tiles += ((co + 31) // 32) * ((ci + 31) // 32)
+                if mode == 1:
+                    views_f[id(w)] = fwd[fo:fo + nf].view(co, t * ci)
+                    views_b[id(w)] = bwd[bo:bo + nb].view(t * ci, p)
+                else:
+                    k = int(round(t ** 0.5))
+                    views_f[id(w)] = fwd[fo:fo + nf].view(co, k, k, ci)
+                    views_b[id(w)] = bwd[bo:bo + nb].view(ci, k, k, co)
+                fo += nf
+                bo += nb
+            raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+            pk = {"key": key, "fwd": fwd, "bwd": bwd, "descs": raw, "n": len(items), "tiles": tiles, "vf": views_f, "vb": views_b,
+                  "pitch": pitch}
+            self._pack = pk
+        nat.check(self.lib.hctr_pack_weights(nat.ptr(pk["descs"]), pk["n"], pk["tiles"], nat.stream_ptr()), "pack_weights")
+        return pk
+
     # ------------------------------------------------------------------ one conv + BN (+SE, +residual) unit
     def unit_forward(self, name, x, conv, bn, B, H, W, relu, pool, drop_p, seed, se=None, res=None, stem=False):
         lib, st, dev = self.lib, nat.stream_ptr(), conv.weight.device
@@ -75,7 +142,7 @@ class TrainEngine(object):
             nat.check(lib.hctr_stem_conv_fwd(nat.ptr(x), nat.ptr(w), nat.ptr(self.ones(cout, dev)), nat.ptr(bias), nat.ptr(z),
                                              B, H, W, 0, st), "stem")
         else:
-            w = conv.weight.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+            w = self._pack["vf"][id(conv.weight)]
             nat.check(lib.hctr_conv_bn_act_fwd(nat.ptr(x), nat.ptr(w), nat.ptr(self.ones(cout, dev)), nat.ptr(bias), nat.ptr(z),
                                                B, H, W, cin, cout, k, 0, 0, st), "conv")
         slices = lib.hctr_stat_slices(B, H, W)
@@ -97,7 +164,7 @@ class TrainEngine(object):
                                              nat.ptr(bn.running_var) if track else None, nat.ptr(stats[0]), nat.ptr(stats[1]),
                                              nat.ptr(stats[2]), nat.ptr(stats[3]), nat.ptr(line_sum), st), "bn_finalize")
         if track:
-            bn.num_batches_tracked += 1
+            self._bn_seen.append(bn)
             if id(bn) in self._tracked:
                 self._tracked[id(bn)] += 1
         m = self.model
@@ -169,7 +236,7 @@ class TrainEngine(object):
                   "conv_wgrad")
         dx = None
         if need_dx:
-            wt = conv.weight.detach().permute(1, 2, 3, 0).contiguous().to(torch.bfloat16)       # [Cin][kh][kw][Cout]
+            wt = self._pack["vb"][id(conv.weight)]                                               # [Cin][kh][kw][Cout]
             dx = torch.empty((B, H, W, s.cin), dtype=torch.bfloat16, device=dev)
             nat.check(lib.hctr_conv_dgrad(nat.ptr(dz), nat.ptr(wt), nat.ptr(self.ones(s.cin, dev)), nat.ptr(self.zeros(s.cin, dev)),
                                           nat.ptr(add), nat.ptr(dx), B, H, W, C, s.cin, s.ksize, st), "conv_dgrad")
@@ -183,6 +250,8 @@ class TrainEngine(object):
         B, _, H, W = x.shape
         ctx = {"units": {}, "B": B, "W": W, "x": x}
         k = [0]
+        pk = self.pack_weights()
+        self._bn_seen = []
 
         def seed():
             k[0] += 1
@@ -218,7 +287,7 @@ class TrainEngine(object):
         pitch = (n + 7) // 8 * 8
         lin = m.linear
         cf = lin.weight.shape[1] // H
-        wk = (lin.weight.detach().reshape(n, cf, H).permute(0, 2, 1).contiguous().to(torch.bfloat16).reshape(n, H * cf))
+        wk = pk["vf"][id(lin.weight)]                       # [n][h*cf + c]: the reference's flatten gives d = c*4 + h
         logits = torch.empty((B, W, pitch), dtype=torch.bfloat16, device=x.device)
         # classifier GEMM fused with log_softmax: the epilogue also yields the row log-sum-exp the CTC loss needs
         row_lse = torch.empty((B, W), dtype=torch.float32, device=x.device)
@@ -229,6 +298,10 @@ class TrainEngine(object):
                                                    nat.stream_ptr()), "classifier_lse")
         ctx["feat"], ctx["Hf"], ctx["cf"], ctx["pitch"], ctx["wk"] = a, H, cf, pitch, wk
         ctx["row_lse"] = row_lse
+        counters = [bn.num_batches_tracked for bn in self._bn_seen if bn.num_batches_tracked is not None]
+        if counters:
+            torch._foreach_add_(counters, 1)                # 33 counters, one launch
+        self._bn_seen = []
         return logits, ctx
 
     def backward(self, ctx, dlogits, grads, on_stage_done=None):
@@ -251,8 +324,7 @@ class TrainEngine(object):
         nb = lib.hctr_colsum_workspace_bytes(B * W, n)
         ws2 = self._ws(nb, dev)
         nat.check(lib.hctr_colsum_bf16(nat.ptr(dlogits), B * W, n, pitch, nat.ptr(grads["linear.bias"]), nat.ptr(ws2), nb, st), "colsum")
-        wt = torch.zeros((Hf * cf, pitch), dtype=torch.bfloat16, device=dev)
-        wt[:, :n] = ctx["wk"].t()
+        wt = self._pack["vb"][id(m.linear.weight)]            # [h*cf + c][pitch], packed with the forward operands
         d = torch.empty((B, Hf, W, cf), dtype=torch.bfloat16, device=dev)
         nat.check(lib.hctr_classifier_dgrad(nat.ptr(dlogits), pitch, nat.ptr(wt), nat.ptr(self.ones(cf, dev)),
                                             nat.ptr(self.zeros(cf, dev)), nat.ptr(d), B, Hf, W, cf, n, st), "classifier_dgrad")

@@ -285,6 +285,22 @@ int hctr_sgd_clip_step(float* params, const float* grads, float* momentum_buf, l
                        float* workspace, void* stream);
 long long hctr_sgd_workspace_bytes(void);
 
+/* All weight operands of a training step in one launch (the optimizer rewrites every parameter each step): fp32 parameters
+ * in the reference layout - conv OIHW [Cout][Cin][kh*kw], nn.Linear [N][Cf*Hf] read as Cout = N, Cin = Cf, taps = Hf
+ * (models/handwritten_ctr_model.py:37-40,169) - to the bf16 layouts hctr_conv_bn_act_fwd / hctr_classifier_fwd (dst_fwd:
+ * [Cout][taps][Cin]) and hctr_conv_dgrad / hctr_classifier_dgrad (dst_bwd, may be NULL: bwd_mode 0 = [Cin][taps][Cout],
+ * bwd_mode 1 = [taps][Cin][bwd_pitch], columns >= Cout untouched) read. taps <= 9. The descriptor array lives in DEVICE
+ * memory; tile_start = running sum of ceil(cout/32)*ceil(cin/32) over the preceding descriptors, total_tiles = that sum. */
+typedef struct hctr_pack_desc {
+    const float* src;
+    void* dst_fwd;
+    void* dst_bwd;
+    int cout, cin, taps, bwd_mode;
+    long long bwd_pitch;
+    long long tile_start;
+} hctr_pack_desc;
+int hctr_pack_weights(const hctr_pack_desc* descs_device, int ndesc, long long total_tiles, void* stream);
+
 /* ---- input pipeline (next to the path: utils/dataset.py:78-93 NormalizePAD, test.py:170-186) ----------------- */
 
 /* pixels: uint8 grayscale lines of height H, line b stored row-major [H][widths[b]] at pixels + offsets[b] (device);

@@ -226,3 +226,37 @@ def test_stem_wgrad_and_fused_sgd():
     nat.check(lib.hctr_sgd_clip_step(nat.ptr(pm), nat.ptr(gs), nat.ptr(buf2), n, 1.0, 5.0, 1e-3, 0.9, 1e-4, 1,
                                      nat.ptr(normo), nat.ptr(ws), S()))
     assert torch.equal(pm, p_before) and buf2.abs().max().item() == 0.0
+
+
+def test_pack_weights_matches_torch_layouts():
+    """hctr_pack_weights: every operand layout of a step in one launch vs the torch permutes it replaces."""
+    import ctypes
+    nat = _nat(); lib = nat.lib()
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 64, 3), (128, 64, 1), (256, 128, 3), (96, 160, 3)]            # (Cout, Cin, k); the last one is ragged (tiles of 32)
+    ws = [torch.randn(co, ci, k, k, generator=g).cuda() for co, ci, k in shapes]
+    n, cf, hf = 7375, 512, 4
+    lw = torch.randn(n, cf * hf, generator=g).cuda()
+    pitch = 7376
+    items = [(w, w.shape[0], w.shape[1], w.shape[2] * w.shape[3], 0, 0) for w in ws] + [(lw, n, cf, hf, 1, pitch)]
+    descs = (nat.PackDesc * len(items))()
+    outs, tiles = [], 0
+    for i, (w, co, ci, t, mode, p) in enumerate(items):
+        f = torch.full((co * ci * t,), float("nan"), dtype=torch.bfloat16, device="cuda")
+        b = torch.zeros((t * ci * p if mode else co * ci * t,), dtype=torch.bfloat16, device="cuda")
+        outs.append((f, b))
+        descs[i].src, descs[i].dst_fwd, descs[i].dst_bwd = w.data_ptr(), f.data_ptr(), b.data_ptr()
+        descs[i].cout, descs[i].cin, descs[i].taps, descs[i].bwd_mode, descs[i].bwd_pitch, descs[i].tile_start = co, ci, t, mode, p, tiles
+        tiles += ((co + 31) // 32) * ((ci + 31) // 32)
+    raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).cuda()
+    nat.check(lib.hctr_pack_weights(nat.ptr(raw), len(items), tiles, nat.stream_ptr()))
+    torch.cuda.synchronize()
+    for (w, co, ci, t, mode, p), (f, b) in zip(items, outs):
+        if mode == 0:
+            k = int(round(t ** 0.5))
+            assert torch.equal(f.view(co, k, k, ci), w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+            assert torch.equal(b.view(ci, k, k, co), w.permute(1, 2, 3, 0).contiguous().to(torch.bfloat16))
+        else:
+            wk = w.reshape(co, ci, t).permute(0, 2, 1).contiguous().to(torch.bfloat16).reshape(co, t * ci)      # k = h*Cf + c
+            assert torch.equal(f.view(co, t * ci), wk)
+            assert torch.equal(b.view(t * ci, p)[:, :co], wk.t()) and b.view(t * ci, p)[:, co:].abs().max().item() == 0.0
