@@ -73,7 +73,9 @@ def codec_legs(nat, codec, dev, peaks):
         ms = _timeit(lambda: nat.check(lib.hctr_ctc_topk_logsoftmax(nat.ptr(xt), code, T, B, C, xt.stride(0), xt.stride(1), k,
                                                                     nat.ptr(ti), nat.ptr(tp), nat.ptr(lse), nat.stream_ptr())), 10, 3)
         nbytes = float(T) * B * C * xt.element_size()
-        out["roofline_topk"][name] = {"kernel": "ctc_topk_warp_kernel<%s>" % name, "bound": "hbm", "ms": ms,
+        kern = "ctc_topk_logsoftmax_kernel<float,128> (one 128-thread CTA per row, bulk-copied row in shared memory)" if name == "f32" \
+            else "ctc_topk_warp_kernel<bf16> (one warp per row, second pass from L2)"
+        out["roofline_topk"][name] = {"kernel": kern, "bound": "hbm", "ms": ms,
                                       "achieved": nbytes / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": nbytes, "traffic": None,
                                       "l2": "%.2f GB tensor >> L2" % (nbytes / 1e9)}
@@ -125,7 +127,8 @@ def ctc_loss_legs(nat, dev, peaks):
         moved = 2.0 * es * T * B * C                                     # the one-pass row kernel: logits read once, gradient written once
         foff = lib.hctr_ctc_loss_flag_offset(T, B, maxl)
         flags = ws[off + foff: off + foff + 4 * B].clone().view(torch.int32).cpu().numpy()
-        res[name] = {"kernel": "ctc_rows_kernel + ctc_scan_kernel (overlapped) + ctc_fix_kernel", "bound": "hbm", "ms": ms,
+        res[name] = {"kernel": "ctc_prep + ctc_rows_kernel (one pass, row in registers) + ctc_scan_kernel x2 (%s) + verify + ctc_fix_kernel"
+                               % ("overlapped with the rows kernel" if 8 <= B <= 32 else "after the rows kernel"), "bound": "hbm", "ms": ms,
                      "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / peaks["hbm_gbs"],
                      "algorithmic_bytes": alg, "bytes_moved_by_design": moved, "frac_on_bytes_moved": moved / ms / 1e6 / peaks["hbm_gbs"],
                      "traffic": None, "loss": float(loss.item()), "log_space_fallbacks": int(flags.sum()),

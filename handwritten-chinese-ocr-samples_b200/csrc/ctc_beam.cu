@@ -87,7 +87,6 @@ template <> struct LoadVec<__nv_bfloat16> {
 // on registers, no staging) executes a third fewer instructions but needs 221 registers - 8 warps per SM - and a fully
 // unrolled 2000-instruction body per row: 27 % issue-active (fixed-latency and instruction-fetch stalls), 1.9 ms against
 // 1.2 ms for this kernel on the config-5 tensor.
-constexpr int kTopkThreads = 256;
 constexpr int kMaxCand = 512;
 constexpr int kTopkEdge = 16;          // head + tail elements of a row that do not belong to the aligned interior (< 16 B each)
 
@@ -109,15 +108,21 @@ __device__ __forceinline__ TopkRow topk_row(const T* logits, unsigned t, unsigne
     return r;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kTopkThreads)
+// THREADS = 256 (round 1: two row buffers per CTA, three CTAs per SM) or 128 (round 2 default: ONE row buffer per CTA, seven
+// CTAs per SM at C = 7375 fp32 - the other CTAs' bulk copies are in flight while one reduces). Half the threads per row double
+// every thread's share of the row (58 instead of 29 elements), so the per-row bookkeeping - barriers, ranking, staging
+// protocol - weighs half as much per element. Config-5 tensor, fp32: 1.00 ms (0.59 of the HBM peak) -> 0.79 ms (0.75);
+// 64 threads per row: 1.00 ms; 128 threads with two buffers (three CTAs per SM): 1.19 ms.
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn, int C, long long stride_t, long long stride_b,
                            int k, int nbuf, int buf_bytes, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp,
                            float* __restrict__ lse_out) {
     constexpr int V = LoadVec<T>::N;
     extern __shared__ __align__(128) unsigned char rowbufs[];      // [nbuf][buf_bytes]
     __shared__ __align__(8) uint64_t full_bar[2];
-    __shared__ float gmax[16], red_sum[8];
+    __shared__ float gmax[16], red_sum[THREADS / 32];
+    constexpr int GRP = THREADS / 16;                 // lanes per group: 16 group maxima bound the k-th largest element
     __shared__ float s_tau, s_m;
     __shared__ int s_ncand[2];
     __shared__ float cand_v[kMaxCand];
@@ -189,25 +194,38 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
 
         // ---- pass 1: per-thread max
         float tmax = has_sc ? LoadVec<T>::one_smem(rb + sc) : -INFINITY;
+        if (sizeof(T) == 2) {
+            // bf16 rows stay packed: 4 HMNMX2 per 8 elements, two independent chains
+            __nv_bfloat162 a0 = __float2bfloat162_rn(-INFINITY), a1 = a0;
 #pragma unroll 2
-        for (int vi = tid; vi < nvec; vi += kTopkThreads) {
-            float x[V];
-            LoadVec<T>::load_smem(buf + 16 + (vi << 4), x);
+            for (int vi = tid; vi < nvec; vi += THREADS) {
+                const uint4 q = *reinterpret_cast<const uint4*>(buf + 16 + (vi << 4));
+                a0 = __hmax2(a0, __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.x), *reinterpret_cast<const __nv_bfloat162*>(&q.y)));
+                a1 = __hmax2(a1, __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.z), *reinterpret_cast<const __nv_bfloat162*>(&q.w)));
+            }
+            a0 = __hmax2(a0, a1);
+            tmax = fmaxf(tmax, fmaxf(__low2float(a0), __high2float(a0)));
+        } else {
+#pragma unroll 2
+            for (int vi = tid; vi < nvec; vi += THREADS) {
+                float x[V];
+                LoadVec<T>::load_smem(buf + 16 + (vi << 4), x);
 #pragma unroll
-            for (int j = 0; j < V; j += 2) tmax = fmaxf(tmax, fmaxf(x[j], x[j + 1]));
+                for (int j = 0; j < V; j += 2) tmax = fmaxf(tmax, fmaxf(x[j], x[j + 1]));
+            }
         }
         float hmax = tmax;                                           // maximum of this half-warp
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-        if ((lane & 15) == 0) gmax[tid >> 4] = hmax;
+        for (int o = GRP / 2; o > 0; o >>= 1) hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+        if ((tid & (GRP - 1)) == 0) gmax[tid / GRP] = hmax;
         if (tid == 0) s_ncand[(it + 1) & 1] = 0;
         __syncthreads();
         // rank the 16 half-warp maxima (value desc, index asc; a permutation of 0..15): warp w ranks values 2w and 2w+1,
         // lane l compares value 2w + (l >> 4) with value l & 15, a ballot counts; tau = the kk-th largest, m = the largest
-        {
-            const int vi = 2 * warp + (lane >> 4);
-            const float gv = gmax[vi], o = gmax[lane & 15];
-            const bool ahead = o > gv || (o == gv && (lane & 15) < vi);
+        for (int pr = tid; pr < 256; pr += THREADS) {     // pair (value vi, other value pr & 15); a half-warp ranks one value
+            const int vi = pr >> 4;
+            const float gv = gmax[vi], o = gmax[pr & 15];
+            const bool ahead = o > gv || (o == gv && (pr & 15) < vi);
             const unsigned bal = __ballot_sync(0xffffffffu, ahead);
             const int grank = __popc(lane < 16 ? (bal & 0xffffu) : (bal >> 16));
             if ((lane & 15) == 0) {
@@ -229,7 +247,7 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
             }
         }
 #pragma unroll 2
-        for (int vi = tid; vi < nvec; vi += kTopkThreads) {
+        for (int vi = tid; vi < nvec; vi += THREADS) {
             float x[V];
             LoadVec<T>::load_smem(buf + 16 + (vi << 4), x);
             float vmax = fmaxf(x[0], x[1]);
@@ -253,13 +271,13 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
         __syncthreads();
         float sacc = 0.f;
 #pragma unroll
-        for (int i = 0; i < kTopkThreads / 32; ++i) sacc += red_sum[i];          // fixed order
+        for (int i = 0; i < THREADS / 32; ++i) sacc += red_sum[i];          // fixed order
         const float logs = logf(sacc);
         if (tid == 0) lse_out[row] = m + logs;
         const int ncand = s_ncand[it & 1];
         if (ncand <= kMaxCand) {
             // ---- rank by counting: exact order (value desc, index asc), independent of the collection order
-            for (int e = tid; e < ncand; e += kTopkThreads) {
+            for (int e = tid; e < ncand; e += THREADS) {
                 const float v = cand_v[e]; const int ci = cand_i[e];
                 int rank = 0;
                 for (int f = 0; f < ncand; ++f) rank += cand_better(cand_v[f], cand_i[f], v, ci) ? 1 : 0;
@@ -275,7 +293,7 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
             float lv = INFINITY; int li = -1;
             for (int r = 0; r < k; ++r) {
                 float bv = -INFINITY; int bi = 0x7fffffff;
-                for (int c = tid; c < C; c += kTopkThreads) {
+                for (int c = tid; c < C; c += THREADS) {
                     const float x = LoadVec<T>::one_smem(rb + c);
                     // eligible: strictly after (lv, li) in the (value desc, index asc) order
                     const bool elig = (x < lv) || (x == lv && c > li);
@@ -291,7 +309,7 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
                 if (lane == 0) { bv_s[warp] = bv; bi_s[warp] = bi; }
                 __syncthreads();
                 float v = bv_s[0]; int i2 = bi_s[0];
-                for (int q = 1; q < kTopkThreads / 32; ++q) if (cand_better(bv_s[q], bi_s[q], v, i2)) { v = bv_s[q]; i2 = bi_s[q]; }
+                for (int q = 1; q < THREADS / 32; ++q) if (cand_better(bv_s[q], bi_s[q], v, i2)) { v = bv_s[q]; i2 = bi_s[q]; }
                 lv = v; li = i2;
                 if (tid == 0) {
                     topk_idx[row * k + r] = i2;
@@ -830,8 +848,10 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     static PerDeviceOnce once;                     // value = SM count of the device
     int dev, num_sms;
     if (once.need(dev)) {
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<__nv_bfloat16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HCTR_CUDA(cudaFuncSetAttribute(ctc_topk_logsoftmax_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         HCTR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         once.mark(dev, num_sms);
     } else {
@@ -872,19 +892,24 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
         }
     }
     const int buf_bytes = (int)(((size_t)C * esz + 32 + 127) & ~size_t(127));        // row + 16 bytes of misalignment either side
-    const int nbuf = 2 * (size_t)buf_bytes <= 200 * 1024 ? 2 : 1;
+    // 128 threads per row (the default): one row buffer per CTA and as many CTAs as the shared memory holds (7 at C = 7375
+    // fp32) - the other CTAs' copies are in flight while one reduces; 256 threads: two buffers per CTA (round 1).
+    int threads = 128;
+    if (const char* e = getenv("HCTR_TOPK_THREADS")) { if (atoi(e) == 256) threads = 256; }       // A/B measurements
+    int nbuf = (threads == 256 && 2 * (size_t)buf_bytes <= 200 * 1024) ? 2 : 1;
+    if (const char* e = getenv("HCTR_TOPK_NBUF")) { const int v = atoi(e); if ((v == 1 || v == 2) && (size_t)v * buf_bytes <= 200 * 1024) nbuf = v; }
     const size_t smem = (size_t)nbuf * buf_bytes;
-    // persistent grid: as many CTAs as fit (shared memory: two row buffers + ~5 KB static each), at most 8 per SM
-    long long per_sm = (220 * 1024) / (long long)(smem + 6 * 1024);
+    long long per_sm = (224 * 1024) / (long long)(smem + 6 * 1024);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    const long long per_sm_cap = threads == 256 ? 8 : 12;
+    if (per_sm > per_sm_cap) per_sm = per_sm_cap;
     const long long grid = rows < per_sm * num_sms ? rows : per_sm * num_sms;
-    if (dtype == HCTR_F32)
-        ctc_topk_logsoftmax_kernel<float><<<(int)grid, kTopkThreads, smem, s>>>(
-            static_cast<const float*>(logits), rows, B, C, stride_t, stride_b, k, nbuf, buf_bytes, topk_idx, topk_logp, lse);
-    else
-        ctc_topk_logsoftmax_kernel<__nv_bfloat16><<<(int)grid, kTopkThreads, smem, s>>>(
-            static_cast<const __nv_bfloat16*>(logits), rows, B, C, stride_t, stride_b, k, nbuf, buf_bytes, topk_idx, topk_logp, lse);
+#define HCTR_TOPK_LAUNCH(TT, TH)                                                                                          \
+    ctc_topk_logsoftmax_kernel<TT, TH><<<(int)grid, TH, smem, s>>>(static_cast<const TT*>(logits), rows, B, C, stride_t,   \
+                                                                   stride_b, k, nbuf, buf_bytes, topk_idx, topk_logp, lse)
+    if (dtype == HCTR_F32) { if (threads == 256) HCTR_TOPK_LAUNCH(float, 256); else HCTR_TOPK_LAUNCH(float, 128); }
+    else { if (threads == 256) HCTR_TOPK_LAUNCH(__nv_bfloat16, 256); else HCTR_TOPK_LAUNCH(__nv_bfloat16, 128); }
+#undef HCTR_TOPK_LAUNCH
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }

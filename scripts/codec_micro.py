@@ -18,16 +18,18 @@ for dt, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
     xt = x if dt == torch.float32 else x.to(dt)
     code = nat.HCTR_F32 if dt == torch.float32 else nat.HCTR_BF16
     res = {}
-    for mode in ("1", "0"):
-        os.environ["HCTR_TOPK_WARP"] = mode
-        os.environ.pop("HCTR_TOPK_CTAS", None)
-        if mode.startswith("c"):
-            os.environ["HCTR_TOPK_CTAS"] = mode[1:]
+    for label, env in (("warp", {"HCTR_TOPK_WARP": "1"}), ("cta256", {"HCTR_TOPK_WARP": "0", "HCTR_TOPK_THREADS": "256"}),
+                       ("cta128", {"HCTR_TOPK_WARP": "0", "HCTR_TOPK_THREADS": "128"}),
+                       ("default", {})):
+        for k2 in ("HCTR_TOPK_WARP", "HCTR_TOPK_THREADS", "HCTR_TOPK_NBUF"):
+            os.environ.pop(k2, None)
+        os.environ.update(env)
         ms = bx._timeit(lambda: nat.check(lib.hctr_ctc_topk_logsoftmax(nat.ptr(xt), code, T, B, C, xt.stride(0), xt.stride(1), k,
                                                                        nat.ptr(ti), nat.ptr(tp), nat.ptr(lse), nat.stream_ptr())), 10, 3)
-        res[{"1": "warp", "0": "cta"}[mode]] = {"ms": ms, "frac_hbm": T * B * C * xt.element_size() / ms / 1e6 / HBM, "chk": int(ti.sum().item())}
+        res[label] = {"ms": ms, "frac_hbm": T * B * C * xt.element_size() / ms / 1e6 / HBM, "chk": int(ti.sum().item())}
+    for k2 in ("HCTR_TOPK_WARP", "HCTR_TOPK_THREADS", "HCTR_TOPK_NBUF"):
+        os.environ.pop(k2, None)
     out["topk_" + name] = res
-os.environ.pop("HCTR_TOPK_WARP", None)
 del x
 peaks = {"hbm_gbs": HBM}
 os.environ.pop("HCTR_TOPK_CTAS", None)
