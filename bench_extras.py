@@ -60,6 +60,17 @@ def beam_logits_device(T, B, C, seed, dev, period=8):
     return x
 
 
+def _ncu_traffic(key):
+    """DRAM read+write bytes per launch from the committed ncu --set full captures (profiles/ncu_traffic.json), or None."""
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)[key]["dram_bytes_per_launch"]
+    except Exception:                   # noqa: BLE001
+        return None
+
+
 def codec_legs(nat, codec, dev, peaks):
     lib = nat.lib()
     T, B, C, k = 512, 256, NUM_CLASSES, 10
@@ -77,7 +88,9 @@ def codec_legs(nat, codec, dev, peaks):
             else "ctc_topk_warp_kernel<bf16> (one warp per row, second pass from L2)"
         out["roofline_topk"][name] = {"kernel": kern, "bound": "hbm", "ms": ms,
                                       "achieved": nbytes / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                      "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": nbytes, "traffic": None,
+                                      "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": nbytes,
+                                      "traffic": _ncu_traffic("r2_ctc_topk_logsoftmax_f32_T512_B256_C7375" if name == "f32"
+                                                              else "r2_ctc_topk_warp_bf16_T512_B256_C7375"),
                                       "l2": "%.2f GB tensor >> L2" % (nbytes / 1e9)}
     codec.set_beam_search(use_tfm_pred=False, lm_panelty=2.0, len_bonus=5.8, beam_size=10, search_depth=10)
     codec.lm_table = None
@@ -131,7 +144,9 @@ def ctc_loss_legs(nat, dev, peaks):
                                % ("overlapped with the rows kernel" if 8 <= B <= 32 else "after the rows kernel"), "bound": "hbm", "ms": ms,
                      "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / peaks["hbm_gbs"],
                      "algorithmic_bytes": alg, "bytes_moved_by_design": moved, "frac_on_bytes_moved": moved / ms / 1e6 / peaks["hbm_gbs"],
-                     "traffic": None, "loss": float(loss.item()), "log_space_fallbacks": int(flags.sum()),
+                     "traffic": (_ncu_traffic("r2_ctc_rows_bf16_T2048_B16_C7375") + _ncu_traffic("r2_ctc_fix_bf16_T2048_B16")
+                                 + _ncu_traffic("r2_ctc_scan_T2048_B16")) if name == "B16_bf16" and _ncu_traffic("r2_ctc_scan_T2048_B16") else None,
+                     "loss": float(loss.item()), "log_space_fallbacks": int(flags.sum()),
                      "l2": "rotating %d buffer set(s) of %.0f MB" % (nrot, per / 1e6)}
         del bufs, grads, ws
     return res

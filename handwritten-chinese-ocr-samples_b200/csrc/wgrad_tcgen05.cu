@@ -187,17 +187,36 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-// out[m][n][tap] (OIHW fp32, the reference's parameter layout) = sum over splits, fixed order
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int ntaps, int M, int N,
-                                    float* __restrict__ out, int out_tap_major) {
-    const long long total = (long long)ntaps * M * N;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += partial[(size_t)sp * total + i];
-        const int n = (int)(i % N); long long r = i / N;
-        const int m = (int)(r % M); const int tap = (int)(r / M);
-        if (out_tap_major) out[i] = s;                                       // [tap][M][N]
-        else out[((size_t)m * N + n) * ntaps + tap] = s;                     // [M][N][tap] == OIHW
+// out[m][n][tap] (OIHW fp32, the reference's parameter layout) = sum over splits, fixed order. One thread per (m, n): the
+// reads of every (split, tap) plane are coalesced across the warp and independent (splits * ntaps loads in flight), and the
+// thread's ntaps results are one contiguous run of the OIHW tensor - a warp writes 32 * ntaps consecutive floats. (The first
+// version walked (tap, m, n) and wrote single floats 4 * ntaps bytes apart: eight times the sector traffic; 23 us per
+// launch at 2 lines per GPU, 66 launches per step.)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int ntaps, int M, int N, float* __restrict__ out,
+                    int out_tap_major) {
+    const long long plane = (long long)M * N;
+    const long long total = (long long)ntaps * plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.x * blockDim.x) {
+        float s[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) s[t] = 0.f;
+        for (int sp = 0; sp < splits; ++sp) {
+            const float* src = partial + (size_t)sp * total + i;
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (t < ntaps) s[t] += __ldg(src + (size_t)t * plane);
+        }
+        if (out_tap_major) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (t < ntaps) out[(size_t)t * plane + i] = s[t];            // [tap][M][N]
+        } else {
+            float* dst = out + (size_t)i * ntaps;                            // [M][N][tap] == OIHW
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (t < ntaps) dst[t] = s[t];
+        }
     }
 }
 
@@ -320,8 +339,9 @@ static int wgrad_run(const void* grad_out, long long g_pitch, const void* x, lon
         else rc = launch_wgrad<64, 1, 4>(tg, tx, p, s);
     }
     if (rc) return rc;
-    const long long total = (long long)ntaps * M * N;
-    int blocks = (int)((total + 255) / 256);
+    HCTR_CHECK(ntaps <= 9, HCTR_ERR_INVALID, "wgrad: at most 9 taps");
+    const long long plane = (long long)M * N;
+    int blocks = (int)((plane + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(p.partial, p.splits, ntaps, M, N, dw, tap_major_out);
     HCTR_CUDA(cudaGetLastError());
