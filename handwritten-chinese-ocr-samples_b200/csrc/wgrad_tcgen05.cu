@@ -288,12 +288,20 @@ static int wgrad_plan(int B, int H, int W, int M, int N, int ntaps, WgradParams&
     p.m_tiles = (M + num_sub * 128 - 1) / (num_sub * 128);
     p.n_tiles = (N + block_n - 1) / block_n;
     const int base_items = ntaps * p.m_tiles * p.n_tiles;
-    // enough work items for ~3 waves of 148 CTAs, but at least 16 K blocks per item
-    int splits = (3 * 148 + base_items - 1) / base_items;
-    const int max_splits = (p.kblocks_total + 15) / 16;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    if (splits > 64) splits = 64;
+    // Split K so that the work items fill whole waves of the 148 persistent CTAs with as few splits as possible: every split
+    // writes and the reduction re-reads a full fp32 copy of dW (9.4 MB for 512x512x9), which at small batches costs more
+    // than an idle tail (13 splits at 2 lines per GPU = 122 MB per layer and a 49 us reduction behind a 200 us GEMM).
+    // cost(s) = waves(s) * (K blocks per item + per-item overhead) + s * (traffic of one partial copy, in K-block times)
+    const int max_splits = (p.kblocks_total + 15) / 16 > 64 ? 64 : (p.kblocks_total + 15) / 16;
+    int splits = 1;
+    double best = 1e30;
+    for (int s = 1; s <= (max_splits < 1 ? 1 : max_splits); ++s) {
+        const int per = (p.kblocks_total + s - 1) / s;
+        const int items = base_items * ((p.kblocks_total + per - 1) / per);
+        const int waves = (items + 147) / 148;
+        const double cost = (double)waves * (per + 6.0) + 5.0 * s;
+        if (cost < best - 1e-9) { best = cost; splits = s; }
+    }
     p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
     p.splits = (p.kblocks_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
     p.total_items = base_items * p.splits;
