@@ -329,7 +329,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-constexpr unsigned long long kScanWaitLimitNs = 4000000000ull;    // a protocol bug must end the kernel, not hang the GPU
+constexpr unsigned long long kScanWaitLimitNs = 1000000000ull;    // a protocol bug must end the kernel, not hang the GPU
 
 __device__ __forceinline__ double pow2_clamped(int x) {          // 2^x, exact, x clamped to the normal range
     x = max(-1022, min(1023, x));
@@ -1283,12 +1283,14 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     //      2*B one-warp CTAs all resident beside it ("2": the same kernels back to back on one stream, e.g. under ncu)
     const int nv = rows_nv(C, esz);
     const bool rows_path = !overlap_off && kscan != 0 && !debug_force_log && nv != 0;
-    // Schedule. Serial: rows -> scans -> fix back to back on the caller's stream. Overlapped: the scans run on a helper stream
-    // underneath the rows kernel, fed through the progress counters; when the rows kernel ends each scan still has the
-    // second half of its steps to go (the rows were dealt from both ends), so the gain is at most half a scan (0.12 ms) minus
-    // the cost of sharing the SMs. Measured (T=2048, C=7375, bf16; serial / overlapped): B=2 0.30 / 0.34 ms, B=16 0.57 / 0.50,
-    // B=64 1.45 / 1.51 (rows kernel 17 % slower beside 128 scan CTAs). HCTR_CTC_OVERLAP=1 / 2 force overlapped / serial.
-    const bool want_overlap = ov ? ov[0] == '1' : (B >= 8 && B <= 32);
+    // Schedule. Default: rows -> scans -> fix back to back on the caller's stream. HCTR_CTC_OVERLAP=1 opts into the overlapped
+    // schedule: the scans run on a helper stream underneath the rows kernel, fed through the progress counters; when the rows
+    // kernel ends each scan still has the second half of its steps to go (the rows were dealt from both ends), so the gain is
+    // at most half a scan (0.12 ms) minus the cost of sharing the SMs. Measured (T=2048, C=7375, bf16; serial / overlapped):
+    // B=2 0.30 / 0.34 ms, B=16 0.56 / 0.49, B=64 1.42 / 1.47. It stays opt-in because it needs the two kernels to really run
+    // at the same time: under a tool that serialises kernels (ncu, compute-sanitizer) the scans wait for rows that cannot
+    // start, give up after kScanWaitLimitNs and the loss comes out NaN.
+    const bool want_overlap = ov && ov[0] == '1';
     const bool serial = rows_path && (!want_overlap || 2ll * B > 2048);
     const bool overlap = rows_path;
     if (serial) {
