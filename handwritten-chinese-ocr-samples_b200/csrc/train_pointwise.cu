@@ -462,15 +462,34 @@ train_bwd_apply_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, co
         *reinterpret_cast<float4*>(Qv) = __ldg(reinterpret_cast<const float4*>(Q + (size_t)b * p.C + c0));
         *reinterpret_cast<float4*>(Qv + 4) = __ldg(reinterpret_cast<const float4*>(Q + (size_t)b * p.C + c0 + 4));
         const size_t ibase = (size_t)row * rowlen;
-        for (int j = j0 + threadIdx.x; j < j1; j += 256) {
-            const int w = j >> p.vshift;
-            float zv[8], d[8], o[8];
-            bwd_dpre(p, dout, b, h, w, c0, keep_scale, zv, d);
+        const int Ho = p.pool ? p.H / 2 : p.H;
+        const size_t obase = ((size_t)b * Ho + (p.pool ? (h >> 1) : h)) * rowlen;    // the row of dout this input row reads
+        // two vectors per thread and iteration, all four 16-byte loads issued before the first use: the pass is latency-bound
+        // (one vector per iteration kept 16-32 KB in flight per SM; DRAM 46 % busy)
+        for (int j = j0 + threadIdx.x; j < j1; j += 512) {
+            const bool two = j + 256 < j1;
+            const size_t i0 = ibase + j, i1 = i0 + 256;
+            const uint4 zq0 = ld_nc_v4(p.z + i0 * 8);
+            const uint4 gq0 = ld_nc_v4(dout + (obase + j) * 8);
+            const uint32_t m0 = p.mask[i0];
+            uint4 zq1 = zq0, gq1 = gq0;
+            uint32_t m1 = 0u;
+            if (two) { zq1 = ld_nc_v4(p.z + i1 * 8); gq1 = ld_nc_v4(dout + (obase + j + 256) * 8); m1 = p.mask[i1]; }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = fmaf(Pv[q], d[q], fmaf(Rv[q], zv[q], Qv[q]));
-            const size_t i = ibase + j;
-            *reinterpret_cast<uint4*>(dz + i * 8) = pack8(o);
-            if (dres) *reinterpret_cast<uint4*>(dres + i * 8) = pack8(d);
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                float zv[8], g[8], d[8], o[8];
+                unpack8(u ? zq1 : zq0, zv);
+                unpack8(u ? gq1 : gq0, g);
+                const uint32_t m = u ? m1 : m0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[q] = ((m >> q) & 1u) ? g[q] * keep_scale : 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) o[q] = fmaf(Pv[q], d[q], fmaf(Rv[q], zv[q], Qv[q]));
+                const size_t i = u ? i1 : i0;
+                *reinterpret_cast<uint4*>(dz + i * 8) = pack8(o);
+                if (dres) *reinterpret_cast<uint4*>(dres + i * 8) = pack8(d);
+            }
         }
     }
 }
