@@ -389,7 +389,29 @@ ctc_topk_warp_kernel(const T* __restrict__ logits, long long rows, int Bn, int C
 
     // ---- pass 1: per-lane maximum
     float lm = fmaxf(x_h, x_t);
-    {
+    if (sizeof(T) == 2) {
+        // bf16 rows stay packed: 4 HMNMX2 per 8 elements, four independent chains (the kernel is issue-bound: 12 instructions
+        // per element with the rows unpacked to fp32 in both passes)
+        const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+        __nv_bfloat162 a[4] = {ninf, ninf, ninf, ninf};
+        int vi = lane;
+        for (; vi + 96 < nvec; vi += 128) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = ld_nc_v4(pv + (long long)(vi + 32 * u) * V);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                a[u] = __hmax2(a[u], __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q[u].x), *reinterpret_cast<const __nv_bfloat162*>(&q[u].y)),
+                                             __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q[u].z), *reinterpret_cast<const __nv_bfloat162*>(&q[u].w))));
+        }
+        for (; vi < nvec; vi += 32) {
+            const uint4 q = ld_nc_v4(pv + (long long)vi * V);
+            a[0] = __hmax2(a[0], __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.x), *reinterpret_cast<const __nv_bfloat162*>(&q.y)),
+                                         __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q.z), *reinterpret_cast<const __nv_bfloat162*>(&q.w))));
+        }
+        const __nv_bfloat162 t2 = __hmax2(__hmax2(a[0], a[1]), __hmax2(a[2], a[3]));
+        lm = fmaxf(lm, fmaxf(__low2float(t2), __high2float(t2)));
+    } else {
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         int vi = lane;
         for (; vi + 96 < nvec; vi += 128) {
@@ -432,6 +454,7 @@ ctc_topk_warp_kernel(const T* __restrict__ logits, long long rows, int Bn, int C
         if (slot < kWarpMaxCand) { cand_v[warp][slot] = x; cand_i[warp][slot] = idx; }
     };
     float sum = 0.f;
+    const float nml = -m * kLog2e;                      // exp(x - m) = 2^(x*log2e - m*log2e): one FFMA + one MUFU per element
     if (lane < head) { sum += exp_neg_fast(x_h - m); if (x_h >= tau) push(x_h, lane); }
     if (tail0 + lane < C) { sum += exp_neg_fast(x_t - m); if (x_t >= tau) push(x_t, tail0 + lane); }
     {
@@ -444,11 +467,11 @@ ctc_topk_warp_kernel(const T* __restrict__ logits, long long rows, int Bn, int C
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float vmax = fmaxf(x[u][0], x[u][1]);
-                float acc = exp_neg_fast(x[u][0] - m) + exp_neg_fast(x[u][1] - m);
+                float acc = ex2_fast(fmaf(x[u][0], kLog2e, nml)) + ex2_fast(fmaf(x[u][1], kLog2e, nml));
 #pragma unroll
                 for (int j = 2; j < V; j += 2) {
                     vmax = fmaxf(vmax, fmaxf(x[u][j], x[u][j + 1]));
-                    acc += exp_neg_fast(x[u][j] - m) + exp_neg_fast(x[u][j + 1] - m);
+                    acc += ex2_fast(fmaf(x[u][j], kLog2e, nml)) + ex2_fast(fmaf(x[u][j + 1], kLog2e, nml));
                 }
                 s4[u] += acc;
                 if (!(vmax < tau)) {

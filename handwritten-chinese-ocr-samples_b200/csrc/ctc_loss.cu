@@ -963,8 +963,16 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     if (tid == 0) s_small = 0;
 
     const int L = w.len[b], S = 2 * L + 1;
+    // the raw logit of this thread's first label state, fetched while the row is in flight (its two dependent round trips -
+    // label, then logit - would otherwise sit behind the log-sum-exp on the CTA's critical path)
+    float xg0 = 0.f;
+    if (tid < S) {
+        const int c = (tid & 1) ? w.lab[(long long)b * w.Lp + (tid >> 1)] : 0;
+        xg0 = Ld<T>::one(p + c);
+    }
     const float scale = grad_scale / ((float)max(L, 1) * (float)Bn);
-    float lse, mul;
+    float lse, mul, inv_sum = 0.f, m_row = 0.f;
+    bool have_e = false;               // x_sc (and, for fp32 rows, the registers) hold exp(x - m_row) instead of x
     if (lse_in != nullptr) {
         lse = lse_in[row];            // log-sum-exp already produced by the classifier epilogue
         mul = scale;
@@ -1003,7 +1011,7 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
         m = fmaxf(fmaxf(w_m[0], w_m[1]), fmaxf(w_m[2], w_m[3]));
         // ---- sum of exp(x - m)
         float s0 = 0.f, s1 = 0.f;
-        if (has_sc) s0 = ex2_fast((x_sc - m) * kLog2e);
+        if (has_sc) { x_sc = ex2_fast((x_sc - m) * kLog2e); s0 = x_sc; }      // from here on x_sc = exp(x - m)
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             if (tid + i * kRowThreads < nvec) {
@@ -1011,8 +1019,10 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
                 RowVec<T>::unpack(xq[i], x);
                 float acc = 0.f;
 #pragma unroll
-                for (int j = 0; j < V; j += 2) acc += ex2_fast((x[j] - m) * kLog2e) + ex2_fast((x[j + 1] - m) * kLog2e);
+                for (int j = 0; j < V; ++j) { x[j] = ex2_fast((x[j] - m) * kLog2e); acc += x[j]; }
                 if (i & 1) s1 += acc; else s0 += acc;
+                if (V == 4)          // fp32 rows: exp(x - m) replaces x in the registers, the gradient pass only scales it
+                    xq[i] = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3 % V]));
             }
         }
         const float ws = warp_sum(s0 + s1);
@@ -1021,6 +1031,9 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
         const float sum = (w_s[0] + w_s[1]) + (w_s[2] + w_s[3]);
         lse = m + logf(sum);
         mul = scale;
+        have_e = true;
+        inv_sum = 1.f / sum;
+        m_row = m;
     }
     if (tid == 0) w.lse[row] = lse;
     // ---- label probabilities for the recursion (plain and mirrored), log-probs for the log-space fallback
@@ -1034,8 +1047,12 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
             float lp = 0.f;
             double pr = 0.0;
             if (q < S) {
-                const int c = (q & 1) ? tg[q >> 1] : 0;
-                lp = Ld<T>::one(p + c) - lse;
+                float xc = xg0;
+                if (q != tid) {
+                    const int c = (q & 1) ? tg[q >> 1] : 0;
+                    xc = Ld<T>::one(p + c);
+                }
+                lp = xc - lse;
                 pr = (double)expf(lp);
                 small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);
                 small |= !(lp == lp);
@@ -1059,7 +1076,10 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
     // ---- dense part of the gradient from the registers, softmax * scale (label classes: ctc_fix_kernel)
     const float nl = -lse * kLog2e;
     const bool same_align = ((reinterpret_cast<uintptr_t>(g) & 15) == (addr & 15));
-    if (has_sc) Ld<T>::st_one(g + sc, ex2_fast(fmaf(x_sc, kLog2e, nl)) * mul);
+    const bool scaled = have_e && V == 4;          // registers hold exp(x - m): softmax = e / sum
+    const float emul = mul * inv_sum;
+    (void)m_row;
+    if (has_sc) Ld<T>::st_one(g + sc, have_e ? x_sc * emul : ex2_fast(fmaf(x_sc, kLog2e, nl)) * mul);
     if (same_align) {
         T* gv = g + head;
 #pragma unroll
@@ -1069,7 +1089,7 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
                 float x[V];
                 RowVec<T>::unpack(xq[i], x);
 #pragma unroll
-                for (int j = 0; j < V; ++j) x[j] = ex2_fast(fmaf(x[j], kLog2e, nl)) * mul;
+                for (int j = 0; j < V; ++j) x[j] = scaled ? x[j] * emul : ex2_fast(fmaf(x[j], kLog2e, nl)) * mul;
                 Ld<T>::st_vec(gv + (long long)vi * V, x);
             }
         }
@@ -1081,7 +1101,8 @@ ctc_rows_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int 
                 float x[V];
                 RowVec<T>::unpack(xq[i], x);
 #pragma unroll
-                for (int j = 0; j < V; ++j) Ld<T>::st_one(g + head + (long long)vi * V + j, ex2_fast(fmaf(x[j], kLog2e, nl)) * mul);
+                for (int j = 0; j < V; ++j)
+                    Ld<T>::st_one(g + head + (long long)vi * V + j, scaled ? x[j] * emul : ex2_fast(fmaf(x[j], kLog2e, nl)) * mul);
             }
         }
     }
