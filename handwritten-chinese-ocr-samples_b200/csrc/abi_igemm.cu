@@ -104,7 +104,14 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
         once.mark(dev);
     }
     int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    kern<<<grid, kIgemmThreads, L::kTotal, stream>>>(tmA, tmB, p);
+    IgemmParams q = p;
+    // whole (line, span) columns per CTA when a column has several tiles and the columns balance (<= 4 % idle tail);
+    // HCTR_IGEMM_COLS=0 turns it off (A/B measurements)
+    static const bool cols_off = getenv("HCTR_IGEMM_COLS") && getenv("HCTR_IGEMM_COLS")[0] == '0';
+    const long long ncols = (long long)p.B * p.w_tiles;
+    const long long padded = (ncols + grid - 1) / grid * grid;
+    q.col_mode = (!cols_off && EPI == EPI_CONV && p.h_tiles > 1 && padded * 100 <= ncols * 104) ? 1 : 0;
+    kern<<<grid, kIgemmThreads, L::kTotal, stream>>>(tmA, tmB, q);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }

@@ -80,6 +80,39 @@ struct IgemmSmem {
     static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + 1024 /*alignment slack*/;
 };
 
+// The i-th tile of persistent CTA `cta`. Two orders (as in the CTA-pair kernel, igemm2_tcgen05.cuh):
+//   p.col_mode == 0: tiles dealt round-robin, channel tile fastest, then the 128-px span, the row pair, the line
+//   p.col_mode == 1: whole (line, span) columns dealt round-robin; inside a column the row pairs top to bottom, channel tile
+//                    fastest: a CTA streams every input row of its column once (the halo rows of one tile are the rows of the
+//                    next) and no two CTAs - in particular no two dies - read the same rows. Round-robin tiles read the
+//                    input of a 128->128 launch 1.37x from DRAM (profiles/r1_ncu_thin128.txt).
+struct CtaTile { int n_tile, w_tile, h_tile, b; };
+__device__ __forceinline__ int cta_tile_count(const IgemmParams& p, int cta, int nctas) {
+    if (!p.col_mode) return (p.total_tiles - cta + nctas - 1) / nctas;
+    const int ncols = p.B * p.w_tiles;
+    return ((ncols - cta + nctas - 1) / nctas) * (p.h_tiles * p.n_tiles);
+}
+__device__ __forceinline__ CtaTile cta_tile(const IgemmParams& p, int cta, int nctas, int i) {
+    CtaTile t;
+    if (!p.col_mode) {
+        const int tile = cta + i * nctas;
+        t.n_tile = tile % p.n_tiles;
+        int m = tile / p.n_tiles;
+        t.w_tile = m % p.w_tiles; m /= p.w_tiles;
+        t.h_tile = m % p.h_tiles;
+        t.b = m / p.h_tiles;
+    } else {
+        const int per_col = p.h_tiles * p.n_tiles;
+        const int col = cta + (i / per_col) * nctas;
+        const int r = i % per_col;
+        t.n_tile = r % p.n_tiles;
+        t.h_tile = r / p.n_tiles;
+        t.w_tile = col % p.w_tiles;
+        t.b = col / p.w_tiles;
+    }
+    return t;
+}
+
 template <int BLOCK_N, int NUM_SUB, int STAGES, int ACC_STAGES, int EPI, int KWF = 0>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -121,17 +154,15 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     const int kblocks = (KWF ? 3 : p.ntaps) * p.cin_chunks;      // KWF: one K block = (kh, chunk) = three taps
     const int sub_rows = p.sub_dh ? NUM_SUB : 1;     // input rows covered by one tile
     const int sub_cols = p.sub_dw ? NUM_SUB : 1;     // 128-px spans covered by one tile
+    const int my_tiles = cta_tile_count(p, blockIdx.x, gridDim.x);
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.n_tiles;
-                int m = tile / p.n_tiles;
-                const int w_tile = m % p.w_tiles; m /= p.w_tiles;
-                const int h_tile = m % p.h_tiles;
-                const int b = m / p.h_tiles;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const CtaTile tl = cta_tile(p, blockIdx.x, gridDim.x, ti);
+                const int n_tile = tl.n_tile, w_tile = tl.w_tile, h_tile = tl.h_tile, b = tl.b;
                 const int h0 = h_tile * sub_rows;
                 const int w0 = w_tile * sub_cols * kTileM;
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -170,7 +201,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int ti = 0; ti < my_tiles; ++ti) {
             mbar_wait(&acc_empty[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_base = tmem_base + acc * kAccCols;
@@ -220,12 +251,9 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         const int half = (warp - 2) >> 2;               // which half of the accumulator columns this warp drains
         const int pix = quad * 32 + lane;               // pixel within the 128-px sub-tile
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int n_tile = tile % p.n_tiles;
-            int m = tile / p.n_tiles;
-            const int w_tile = m % p.w_tiles; m /= p.w_tiles;
-            const int h_tile = m % p.h_tiles;
-            const int b = m / p.h_tiles;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const CtaTile tl = cta_tile(p, blockIdx.x, gridDim.x, ti);
+            const int n_tile = tl.n_tile, w_tile = tl.w_tile, h_tile = tl.h_tile, b = tl.b;
             const int h0 = h_tile * sub_rows;
             const int w0 = w_tile * sub_cols * kTileM;
 
