@@ -289,7 +289,7 @@ long long hctr_sgd_workspace_bytes(void);
  * in the reference layout - conv OIHW [Cout][Cin][kh*kw], nn.Linear [N][Cf*Hf] read as Cout = N, Cin = Cf, taps = Hf
  * (models/handwritten_ctr_model.py:37-40,169) - to the bf16 layouts hctr_conv_bn_act_fwd / hctr_classifier_fwd (dst_fwd:
  * [Cout][taps][Cin]) and hctr_conv_dgrad / hctr_classifier_dgrad (dst_bwd, may be NULL: bwd_mode 0 = [Cin][taps][Cout],
- * bwd_mode 1 = [taps][Cin][bwd_pitch], columns >= Cout untouched) read. taps <= 9. The descriptor array lives in DEVICE
+ * bwd_mode 1 = [taps][Cin][bwd_pitch], columns >= Cout untouched) read. taps is 1, 4 or 9. The descriptor array lives in DEVICE
  * memory; tile_start = running sum of ceil(cout/32)*ceil(cin/32) over the preceding descriptors, total_tiles = that sum. */
 typedef struct hctr_pack_desc {
     const float* src;
