@@ -416,6 +416,17 @@ int hctr_classifier_dgrad(const void* dlogits, long long pitch, const void* w_t,
     return HCTR_OK;
 }
 
+// Column tile of the classifier GEMM: 256 (one TMEM accumulator stage: the epilogue - 1.9 GB of logits at B=64 - is not
+// overlapped with the next tile's main loop) or 128 (two stages; twice the activation re-reads). HCTR_CLS_N picks (A/B).
+static int cls_block_n() {
+    static int n = 0;
+    if (n == 0) {
+        const char* e = getenv("HCTR_CLS_N");
+        n = (e && atoi(e) == 128) ? 128 : 256;
+    }
+    return n;
+}
+
 static int classifier_launch(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
                              long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, float2* lse_partial,
                              void* stream) {
@@ -436,7 +447,8 @@ static int classifier_launch(const void* feat, const void* w_packed, const float
     p.N = num_classes;
     p.w_tiles = (W + 2 * kTileM - 1) / (2 * kTileM);
     p.h_tiles = 1;
-    p.n_tiles = (num_classes + 255) / 256;
+    const int block_n = cls_block_n();
+    p.n_tiles = (num_classes + block_n - 1) / block_n;
     p.shift = bias; p.out = logits;
     p.out_H = 1;
     p.out_dtype = out_dtype; p.out_pitch = out_pitch;
@@ -448,8 +460,9 @@ static int classifier_launch(const void* feat, const void* w_packed, const float
     CUtensorMap tmA, tmB;
     int rc = make_act_map(&tmA, feat, B, Hf, W, Cf);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, w_packed, num_classes, Hf * Cf, 256);
+    rc = make_weight_map(&tmB, w_packed, num_classes, Hf * Cf, block_n);
     if (rc) return rc;
+    if (block_n == 128) return launch_igemm<128, 2, 4, 2, EPI_LINEAR>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
     return launch_igemm<256, 2, 3, 1, EPI_LINEAR>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -460,7 +473,7 @@ int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bia
 }
 
 long long hctr_classifier_lse_workspace_bytes(int B, int W, int num_classes) {
-    return (long long)B * W * ((num_classes + 255) / 256) * 2 * (long long)sizeof(float2);
+    return (long long)B * W * ((num_classes + 127) / 128) * 2 * (long long)sizeof(float2);      // sized for the 128-column tile
 }
 
 int hctr_classifier_lse_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
@@ -473,7 +486,7 @@ int hctr_classifier_lse_fwd(const void* feat, const void* w_packed, const float*
                                static_cast<float2*>(workspace), stream);
     if (rc) return rc;
     const long long rows = (long long)B * W;
-    const int slots = ((num_classes + 255) / 256) * 2;
+    const int slots = ((num_classes + cls_block_n() - 1) / cls_block_n()) * 2;
     lse_combine_kernel<<<(int)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float2*>(workspace), rows, slots, row_lse);
     HCTR_CUDA(cudaGetLastError());
