@@ -75,8 +75,9 @@ template <> struct LoadVec<__nv_bfloat16> {
 // The kernel is bound by instruction issue, not by latency (first persistent version: 38 instructions per element, 56 %
 // issue-active with 24 warps/SM, slower than HBM allows), so the two passes work on 16-byte shared-memory vectors and
 // everything per row is kept short:
-//   pass 1  per-thread maximum (ld.shared.v4 + a max tree); maxima of the 16 half-warps -> shared memory
-//   bound   the k-th largest of the 16 half-warp maxima is a valid lower bound tau for the k-th largest element of the
+//   pass 1  per-thread maximum (ld.shared.v4 + a max tree); maxima of 16 thread groups (half-warps at 256 threads per row,
+//           quarter-warps at 128) -> shared memory
+//   bound   the k-th largest of the 16 group maxima is a valid lower bound tau for the k-th largest element of the
 //           row (k distinct elements are >= it; ~15 elements of a random row reach it); each warp ranks two of the 16 values
 //           (one compare per lane + a ballot); the row maximum falls out of the same ranking
 //   pass 2  sum exp(x - max) and collect the few elements >= tau (one compare per vector on its maximum)
@@ -220,8 +221,8 @@ ctc_topk_logsoftmax_kernel(const T* __restrict__ logits, long long rows, int Bn,
         if ((tid & (GRP - 1)) == 0) gmax[tid / GRP] = hmax;
         if (tid == 0) s_ncand[(it + 1) & 1] = 0;
         __syncthreads();
-        // rank the 16 half-warp maxima (value desc, index asc; a permutation of 0..15): warp w ranks values 2w and 2w+1,
-        // lane l compares value 2w + (l >> 4) with value l & 15, a ballot counts; tau = the kk-th largest, m = the largest
+        // rank the 16 group maxima (value desc, index asc; a permutation of 0..15): pair pr = (value pr >> 4, other value
+        // pr & 15), so a half-warp ranks one value with one compare per lane and a ballot; tau = the kk-th largest, m = the largest
         for (int pr = tid; pr < 256; pr += THREADS) {     // pair (value vi, other value pr & 15); a half-warp ranks one value
             const int vi = pr >> 4;
             const float gv = gmax[vi], o = gmax[pr & 15];
