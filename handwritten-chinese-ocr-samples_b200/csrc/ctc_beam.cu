@@ -533,6 +533,251 @@ ctc_topk_warp_kernel(const T* __restrict__ logits, long long rows, int Bn, int C
     }
 }
 
+// ---------------------------------------------------------------------------------------------- top-k, one warp per row, one read
+// Round 2, after the measurement in scripts/topk_ramp.py: the two-pass warp kernel above keeps 4736 rows in flight (32 warps
+// on each of 148 SMs) - 70 MB of bf16 rows - and its second pass hits the L2 only on a quiet device: with ANY other touched
+// allocation alive (0.25 GB is enough) and always under ncu the re-read misses (L2 hit rate 9 %, DRAM traffic 2x the tensor)
+// and the kernel falls from 0.43 to 0.57 ms. This kernel reads every byte once and needs no L2 residency at all: the warp
+// walks its row in CHUNKS of kChunkVec 16-byte vectors per lane held in registers, and does both passes on a chunk while it
+// is there:
+//   max     per-vector and per-lane maxima of the chunk (bf16 rows packed, HMNMX2); the lane's RUNNING maximum over all
+//           chunks so far; one redux.sync gives the row maximum so far, m
+//   rescale the running sum of exponentials is kept relative to m; when a chunk raises m the four partial sums are
+//           multiplied by 2^((m_old - m_new) log2 e) - one warp-uniform branch per chunk (online log-sum-exp at chunk, not
+//           element, granularity: the per-element work is the FFMA + MUFU + FADD of the two-pass kernel)
+//   bound   tau = the k-th largest RUNNING lane maximum (k distinct elements of the row reach it, so it never exceeds the
+//           k-th largest element; it only grows). Refreshed after chunks 0, 1, 3, 7, ... and once more at the end
+//   mark    a lane whose chunk maximum reaches tau notes WHICH of its vectors do (vector index -> the warp's list, one shared-
+//           memory atomic per lane and chunk). Nothing per element: the first version pushed the elements themselves from inside the loop, and since a warp step
+//           covers 256 elements, 4 out of 5 steps had some lane on that 170-instruction path - 20 issue slots per element,
+//           0.56 ms for bf16 rows. Every element of the final top k is >= the final tau >= the tau of its own chunk, so
+//           its vector is in the list
+//   collect after the row: the elements >= the FINAL tau of the ~50 listed vectors become the candidates (~13). The list keeps
+//           the vectors' 16 bytes next to their indices: re-reading them from global memory cost fp32 rows 7 % more DRAM
+//           traffic (a 32-byte sector per entry, and 140 MB of rows in flight do not stay in the L2)
+//   rank    by counting, exactly as in the kernels above.
+// An exact k-round arg-max over the row (re-read from global memory) covers lists that overflow (ascending or constant rows).
+constexpr int kChunkVec = 8;
+constexpr int kChunkMaxList = 192;     // vectors that may hold a candidate, per row (index + 16 bytes of data each)
+constexpr int kChunkMaxCand = 128;     // elements >= the final tau, per row
+
+__device__ __forceinline__ float order_key_to_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+template <typename T>
+__global__ void __launch_bounds__(kTopkWarps * 32, 4)
+ctc_topk_chunk_kernel(const T* __restrict__ logits, long long rows, int Bn, int C, long long stride_t, long long stride_b,
+                      int k, int32_t* __restrict__ topk_idx, float* __restrict__ topk_logp, float* __restrict__ lse_out) {
+    constexpr int V = LoadVec<T>::N;
+    constexpr unsigned kFull = 0xffffffffu;
+    __shared__ uint4 list_q[kTopkWarps][kChunkMaxList];
+    __shared__ int list_v[kTopkWarps][kChunkMaxList];
+    __shared__ float cand_v[kTopkWarps][kChunkMaxCand];
+    __shared__ int cand_i[kTopkWarps][kChunkMaxCand];
+    __shared__ int nlist_s[kTopkWarps], ncand_s[kTopkWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * kTopkWarps + warp;
+    if (lane == 0) { nlist_s[warp] = 0; ncand_s[warp] = 0; }
+    __syncwarp();
+    if (row >= rows) return;
+    const unsigned t = (unsigned)row / (unsigned)Bn, b = (unsigned)row - t * (unsigned)Bn;     // rows < 2^31 (checked by the caller)
+    const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > C) head = C;
+    const int nvec = (C - head) / V;
+    const int tail0 = head + nvec * V;
+    const T* pv = p + head;
+    const int kk = k < 32 ? k : 32;
+    float x_h = -INFINITY, x_t = -INFINITY;
+    if (lane < head) x_h = LoadVec<T>::one(p + lane);
+    if (tail0 + lane < C) x_t = LoadVec<T>::one(p + tail0 + lane);
+
+    auto push = [&](float x, int idx) {
+        const int slot = atomicAdd(&ncand_s[warp], 1);
+        if (slot < kChunkMaxCand) { cand_v[warp][slot] = x; cand_i[warp][slot] = idx; }
+    };
+    // tau <- max(tau, kk-th largest running lane maximum). The keys are made distinct (low five bits <- 31 - lane, the result
+    // floored to a multiple of 32 in key order: at most 32 fp32 ulps low, nothing for bf16 rows), so a round is redux + compare
+    auto refresh_tau = [&](float lmax, float tau) {
+        int key = (float_order_key(lmax) & ~31) | (31 - lane);
+        const int dead = (int)0x80000000;
+        int mx = __reduce_max_sync(kFull, key);
+        for (int r = 1; r < kk; ++r) {
+            if (key == mx) key = dead;                                      // one lane leaves per round
+            mx = __reduce_max_sync(kFull, key);
+        }
+        return fmaxf(tau, order_key_to_float(mx & ~31));
+    };
+    auto unpack = [](const uint4& q, float (&x)[V]) {
+        if (sizeof(T) == 2) {
+            x[0] = bf16_lo(q.x); x[1] = bf16_hi(q.x); x[2] = bf16_lo(q.y); x[3] = bf16_hi(q.y);
+            x[V - 4] = bf16_lo(q.z); x[V - 3] = bf16_hi(q.z); x[V - 2] = bf16_lo(q.w); x[V - 1] = bf16_hi(q.w);
+        } else {
+            x[0] = __uint_as_float(q.x); x[1] = __uint_as_float(q.y); x[2] = __uint_as_float(q.z); x[3] = __uint_as_float(q.w);
+        }
+    };
+
+    const uint32_t ninf_w = sizeof(T) == 2 ? 0xFF80FF80u : 0xFF800000u;
+    float lmax = fmaxf(x_h, x_t);                                           // running lane maximum (the lane's own elements)
+    float m = -INFINITY, tau = -INFINITY;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    int chunk = 0;
+    for (int base = 0; base < nvec; base += 32 * kChunkVec, ++chunk) {
+        uint4 q[kChunkVec];
+        if (base + 32 * kChunkVec <= nvec) {
+#pragma unroll
+            for (int u = 0; u < kChunkVec; ++u) q[u] = ld_nc_v4(pv + (long long)(base + 32 * u + lane) * V);
+        } else {
+#pragma unroll
+            for (int u = 0; u < kChunkVec; ++u) {
+                const int vi = base + 32 * u + lane;
+                q[u] = make_uint4(ninf_w, ninf_w, ninf_w, ninf_w);
+                if (vi < nvec) q[u] = ld_nc_v4(pv + (long long)vi * V);
+            }
+        }
+        // ---- maxima: per vector (kept for the marking), per lane
+        uint32_t vmx[kChunkVec];
+        float cm;
+        if (sizeof(T) == 2) {
+            __nv_bfloat162 a[kChunkVec];
+#pragma unroll
+            for (int u = 0; u < kChunkVec; ++u) {
+                a[u] = __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q[u].x), *reinterpret_cast<const __nv_bfloat162*>(&q[u].y)),
+                               __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q[u].z), *reinterpret_cast<const __nv_bfloat162*>(&q[u].w)));
+                vmx[u] = *reinterpret_cast<const uint32_t*>(&a[u]);
+            }
+#pragma unroll
+            for (int w = kChunkVec / 2; w > 0; w >>= 1) {
+#pragma unroll
+                for (int u = 0; u < w; ++u) a[u] = __hmax2(a[u], a[u + w]);
+            }
+            cm = fmaxf(__low2float(a[0]), __high2float(a[0]));
+        } else {
+            float a[kChunkVec];
+#pragma unroll
+            for (int u = 0; u < kChunkVec; ++u) {
+                a[u] = fmaxf(fmaxf(__uint_as_float(q[u].x), __uint_as_float(q[u].y)), fmaxf(__uint_as_float(q[u].z), __uint_as_float(q[u].w)));
+                vmx[u] = __float_as_uint(a[u]);
+            }
+#pragma unroll
+            for (int w = kChunkVec / 2; w > 0; w >>= 1) {
+#pragma unroll
+                for (int u = 0; u < w; ++u) a[u] = fmaxf(a[u], a[u + w]);
+            }
+            cm = a[0];
+        }
+        lmax = fmaxf(lmax, cm);
+        // ---- row maximum so far; tau after chunks 0, 1, 3, 7, ...
+        const int mx = __reduce_max_sync(kFull, float_order_key(lmax));
+        const float m_new = order_key_to_float(mx);
+        if ((chunk & (chunk + 1)) == 0) tau = refresh_tau(lmax, tau);
+        if (m_new > m) {                                                    // warp-uniform
+            const float sc = ex2_fast((m - m_new) * kLog2e);                // m = -inf: 0
+            s4[0] *= sc; s4[1] *= sc; s4[2] *= sc; s4[3] *= sc;
+            m = m_new;
+        }
+        // ---- mark the vectors that may hold one of the top k: only the (about three) lanes whose chunk maximum reaches tau
+        if (!(cm < tau)) {
+            const __nv_bfloat162 tau2 = __float2bfloat162_rn(tau);          // exact: tau is an element of a bf16 row (or -inf)
+            const int nvalid = nvec - base - lane;                          // vector u of this lane exists iff 32 u < nvalid
+            unsigned msk = 0;
+#pragma unroll
+            for (int u = 0; u < kChunkVec; ++u) {
+                bool hit;
+                if (sizeof(T) == 2) hit = !__hblt2(*reinterpret_cast<const __nv_bfloat162*>(&vmx[u]), tau2);   // some half >= tau (or NaN)
+                else hit = !(__uint_as_float(vmx[u]) < tau);
+                if (hit && 32 * u < nvalid) msk |= 1u << u;
+            }
+            int slot = atomicAdd(&nlist_s[warp], __popc(msk));
+#pragma unroll
+            for (int u = 0; u < kChunkVec; ++u) {
+                if (msk >> u & 1u) {
+                    if (slot < kChunkMaxList) { list_v[warp][slot] = base + 32 * u + lane; list_q[warp][slot] = q[u]; }
+                    ++slot;
+                }
+            }
+        }
+        // ---- sum of exponentials, from the registers
+        const float nml = m > -INFINITY ? -m * kLog2e : 0.f;                // all -inf so far: every term is 2^-inf = 0
+        const int rem = nvec - base;                                        // warp-uniform: vector step u has data iff 32 u < rem
+#pragma unroll
+        for (int u = 0; u < kChunkVec; ++u) {
+            if (32 * u >= rem) break;
+            float x[V];
+            unpack(q[u], x);
+            float acc = ex2_fast(fmaf(x[0], kLog2e, nml)) + ex2_fast(fmaf(x[1], kLog2e, nml));
+#pragma unroll
+            for (int j = 2; j < V; j += 2) acc += ex2_fast(fmaf(x[j], kLog2e, nml)) + ex2_fast(fmaf(x[j + 1], kLog2e, nml));
+            s4[u & 3] += acc;
+        }
+    }
+    // ---- final maximum and bound, unless the last chunk has just refreshed them (also covers rows with no aligned interior)
+    if (chunk == 0 || ((chunk - 1) & chunk) != 0) {
+        const int mx = __reduce_max_sync(kFull, float_order_key(lmax));
+        const float m_new = order_key_to_float(mx);
+        tau = refresh_tau(lmax, tau);
+        if (m_new > m) {
+            const float sc = ex2_fast((m - m_new) * kLog2e);
+            s4[0] *= sc; s4[1] *= sc; s4[2] *= sc; s4[3] *= sc;
+            m = m_new;
+        }
+    }
+    // ---- the scalars in front of / behind the interior; candidates out of the marked vectors
+    float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    if (lane < head) { sum += exp_neg_fast(x_h - m); if (x_h >= tau) push(x_h, lane); }
+    if (tail0 + lane < C) { sum += exp_neg_fast(x_t - m); if (x_t >= tau) push(x_t, tail0 + lane); }
+    sum = warp_sum(sum);                                                    // (its shuffles also order the list writes)
+    const float logs = logf(sum);
+    if (lane == 0) lse_out[row] = m + logs;
+    __syncwarp();
+    const int nlist = nlist_s[warp];
+    if (nlist <= kChunkMaxList) {
+        for (int e = lane; e < nlist; e += 32) {
+            const int vi = list_v[warp][e];
+            float x[V];
+            unpack(list_q[warp][e], x);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (x[j] >= tau) push(x[j], head + vi * V + j);
+        }
+    }
+    __syncwarp();                                                           // candidate list complete
+    const int ncand = ncand_s[warp];
+    int32_t* oi = topk_idx + row * k;
+    float* op = topk_logp + row * k;
+    if (nlist <= kChunkMaxList && ncand <= kChunkMaxCand) {
+        // ---- rank by counting: exact order (value desc, index asc), independent of the collection order
+        for (int e = lane; e < ncand; e += 32) {
+            const float v = cand_v[warp][e]; const int ci = cand_i[warp][e];
+            int rank = 0;
+            for (int f = 0; f < ncand; ++f) rank += cand_better(cand_v[warp][f], cand_i[warp][f], v, ci) ? 1 : 0;
+            if (rank < k) {
+                oi[rank] = ci;
+                op[rank] = (v - m) - logs;                                   // scipy: (x - max) - log(sum(exp(x - max)))
+            }
+        }
+    } else {
+        // ---- exact fallback: k rounds of warp arg-best with exclusion of what was already emitted
+        float lv = INFINITY; int li = -1;
+        for (int r = 0; r < k; ++r) {
+            float bv = -INFINITY; int bi = 0x7fffffff;
+            for (int c = lane; c < C; c += 32) {
+                const float x = LoadVec<T>::one(p + c);
+                const bool elig = (x < lv) || (x == lv && c > li);
+                if (elig && cand_better(x, c, bv, bi)) { bv = x; bi = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(kFull, bv, o);
+                const int ov_i = __shfl_xor_sync(kFull, bi, o);
+                if (cand_better(ov, ov_i, bv, bi)) { bv = ov; bi = ov_i; }
+            }
+            lv = bv; li = bi;
+            if (lane == 0) { oi[r] = bi; op[r] = (bv - m) - logs; }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- beam search
 __device__ __forceinline__ double logaddexp_np(double x, double y) {
     // numpy npy_logaddexp for doubles:  x == y -> x + ln 2;  d = x - y;  d > 0 -> x + log1p(exp(-d));  d <= 0 -> y + log1p(exp(d));
@@ -881,7 +1126,23 @@ int hctr_ctc_topk_logsoftmax(const void* logits, int dtype, int T, int B, int C,
     } else {
         num_sms = once.get(dev);
     }
-    // ---- one warp per row (two passes, the second from L2): bf16 rows, and rows too large for the shared-memory kernel
+    // ---- one warp per row, the row read once in register chunks
+    {
+        const char* cv = getenv("HCTR_TOPK_CHUNK");                       // "0": off (A/B against the kernels below)
+        const bool use_chunk = cv ? cv[0] != '0' : true;
+        if (use_chunk) {
+            const long long blocks = (rows + kTopkWarps - 1) / kTopkWarps;
+            if (dtype == HCTR_F32)
+                ctc_topk_chunk_kernel<float><<<(int)blocks, kTopkWarps * 32, 0, s>>>(
+                    static_cast<const float*>(logits), rows, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
+            else
+                ctc_topk_chunk_kernel<__nv_bfloat16><<<(int)blocks, kTopkWarps * 32, 0, s>>>(
+                    static_cast<const __nv_bfloat16*>(logits), rows, B, C, stride_t, stride_b, k, topk_idx, topk_logp, lse);
+            HCTR_CUDA(cudaGetLastError());
+            return HCTR_OK;
+        }
+    }
+    // ---- one warp per row (two passes, the second from L2): rows too large for the shared-memory kernel
     {
         const char* wv = getenv("HCTR_TOPK_WARP");                        // "0" / "1": force the CTA-per-row / warp-per-row kernel
         const bool fits_smem = (size_t)C * 4 <= 160 * 1024;

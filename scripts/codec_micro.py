@@ -18,16 +18,25 @@ for dt, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
     xt = x if dt == torch.float32 else x.to(dt)
     code = nat.HCTR_F32 if dt == torch.float32 else nat.HCTR_BF16
     res = {}
-    for label, env in (("warp", {"HCTR_TOPK_WARP": "1"}), ("cta256", {"HCTR_TOPK_WARP": "0", "HCTR_TOPK_THREADS": "256"}),
-                       ("cta128", {"HCTR_TOPK_WARP": "0", "HCTR_TOPK_THREADS": "128"}),
+    keys = ("HCTR_TOPK_WARP", "HCTR_TOPK_THREADS", "HCTR_TOPK_NBUF", "HCTR_TOPK_CHUNK")
+    base = None
+    for label, env in (("chunk", {"HCTR_TOPK_CHUNK": "1"}), ("warp", {"HCTR_TOPK_CHUNK": "0", "HCTR_TOPK_WARP": "1"}),
+                       ("cta256", {"HCTR_TOPK_CHUNK": "0", "HCTR_TOPK_WARP": "0", "HCTR_TOPK_THREADS": "256"}),
+                       ("cta128", {"HCTR_TOPK_CHUNK": "0", "HCTR_TOPK_WARP": "0", "HCTR_TOPK_THREADS": "128"}),
                        ("default", {})):
-        for k2 in ("HCTR_TOPK_WARP", "HCTR_TOPK_THREADS", "HCTR_TOPK_NBUF"):
+        for k2 in keys:
             os.environ.pop(k2, None)
         os.environ.update(env)
+        ti.zero_(); tp.zero_(); lse.zero_()
         ms = bx._timeit(lambda: nat.check(lib.hctr_ctc_topk_logsoftmax(nat.ptr(xt), code, T, B, C, xt.stride(0), xt.stride(1), k,
-                                                                       nat.ptr(ti), nat.ptr(tp), nat.ptr(lse), nat.stream_ptr())), 10, 3)
+                                                                       nat.ptr(ti), nat.ptr(tp), nat.ptr(lse), nat.stream_ptr())), 20, 5)
         res[label] = {"ms": ms, "frac_hbm": T * B * C * xt.element_size() / ms / 1e6 / HBM, "chk": int(ti.sum().item())}
-    for k2 in ("HCTR_TOPK_WARP", "HCTR_TOPK_THREADS", "HCTR_TOPK_NBUF"):
+        if base is None:
+            base = (ti.clone(), tp.clone(), lse.clone())
+        else:       # every variant must give the same candidates; log-probs to rounding
+            res[label]["idx_equal_to_chunk"] = bool(torch.equal(ti, base[0]))
+            res[label]["max_abs_dlogp"] = float((tp - base[1]).abs().max()); res[label]["max_abs_dlse"] = float((lse - base[2]).abs().max())
+    for k2 in keys:
         os.environ.pop(k2, None)
     out["topk_" + name] = res
 del x
