@@ -71,6 +71,14 @@ def _ncu_traffic(key):
         return None
 
 
+def _ctc_traffic():
+    """DRAM bytes of one split-schedule call at B=16 bf16: the four captured kernels summed, or None if one is missing."""
+    keys = ("r2_ctc_lse_chunk_bf16_T2048_B16_C7375", "r2_ctc_dense_grad_bf16_T2048_B16_C7375", "r2_ctc_fix_bf16_T2048_B16",
+            "r2_ctc_scan_T2048_B16")
+    vals = [_ncu_traffic(k) for k in keys]
+    return None if any(v is None for v in vals) else float(sum(vals))
+
+
 def codec_legs(nat, codec, dev, peaks):
     lib = nat.lib()
     T, B, C, k = 512, 256, NUM_CLASSES, 10
@@ -84,13 +92,14 @@ def codec_legs(nat, codec, dev, peaks):
         ms = _timeit(lambda: nat.check(lib.hctr_ctc_topk_logsoftmax(nat.ptr(xt), code, T, B, C, xt.stride(0), xt.stride(1), k,
                                                                     nat.ptr(ti), nat.ptr(tp), nat.ptr(lse), nat.stream_ptr())), 20, 10)
         nbytes = float(T) * B * C * xt.element_size()
-        kern = "ctc_topk_logsoftmax_kernel<float,128> (one 128-thread CTA per row, bulk-copied row in shared memory)" if name == "f32" \
-            else "ctc_topk_warp_kernel<bf16> (one warp per row, second pass from L2)"
+        kern = "ctc_topk_chunk_kernel<%s> (one warp per row, the row read once in register chunks: online log-sum-exp + marking of " \
+               "the vectors that reach the running top-k bound)" % ("float" if name == "f32" else "bf16")
         out["roofline_topk"][name] = {"kernel": kern, "bound": "hbm", "ms": ms,
                                       "achieved": nbytes / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": nbytes / ms / 1e6 / peaks["hbm_gbs"], "algorithmic_bytes": nbytes,
-                                      "traffic": _ncu_traffic("r2_ctc_topk_logsoftmax_f32_T512_B256_C7375" if name == "f32"
-                                                              else "r2_ctc_topk_warp_bf16_T512_B256_C7375"),
+                                      "traffic": _ncu_traffic("r2_ctc_topk_chunk_f32_T512_B256_C7375" if name == "f32"
+                                                              else "r2_ctc_topk_chunk_bf16_T512_B256_C7375"),
+                                      "peak_note": "peak = the copy-measured HBM figure; a read-only stream can exceed it",
                                       "l2": "%.2f GB tensor >> L2" % (nbytes / 1e9)}
     codec.set_beam_search(use_tfm_pred=False, lm_panelty=2.0, len_bonus=5.8, beam_size=10, search_depth=10)
     codec.lm_table = None
@@ -136,24 +145,25 @@ def ctc_loss_legs(nat, dev, peaks):
                                                 nat.ptr(il), maxl, None, nat.ptr(nll), nat.ptr(loss), nat.ptr(grads[i]), 1.0,
                                                 nat.c_void_p(ws.data_ptr() + off), wsb, nat.stream_ptr()))
         ms = _timeit(run, 20, 10)                                        # (short kernels: warm the clocks up first)
-        ms_overlapped = None
-        if 8 <= B <= 32:                                                 # the opt-in schedule: scans underneath the rows kernel
-            os.environ["HCTR_CTC_OVERLAP"] = "1"
-            try:
-                ms_overlapped = _timeit(run, 20, 10)
-            finally:
-                os.environ.pop("HCTR_CTC_OVERLAP", None)
+        ms_rows = None                                                   # the other schedule, for comparison
+        os.environ["HCTR_CTC_OVERLAP"] = "2" if B <= 24 else "4"
+        try:
+            ms_rows = _timeit(run, 20, 10)
+        finally:
+            os.environ.pop("HCTR_CTC_OVERLAP", None)
+        split = B <= 24                                                  # csrc/ctc_loss.cu split_by_default
         alg = 3.0 * es * T * B * C                                       # (2*s_in + s_out) * T*B*C
-        moved = 2.0 * es * T * B * C                                     # the one-pass row kernel: logits read once, gradient written once
+        moved = 2.0 * es * T * B * C                                     # the one-pass rows kernel: logits read once, gradient written once
         foff = lib.hctr_ctc_loss_flag_offset(T, B, maxl)
         flags = ws[off + foff: off + foff + 4 * B].clone().view(torch.int32).cpu().numpy()
-        res[name] = {"kernel": "ctc_prep + ctc_rows_kernel (one pass, row in registers) + ctc_scan_kernel x2 + verify + ctc_fix_kernel",
-                     "bound": "hbm", "ms": ms, "ms_overlapped_schedule_opt_in": ms_overlapped,
-                     "frac_overlapped_schedule_opt_in": (alg / ms_overlapped / 1e6 / peaks["hbm_gbs"]) if ms_overlapped else None,
+        res[name] = {"kernel": ("split schedule: ctc_prep + ctc_lse_chunk_kernel (one read: log-sum-exp + label gather) -> [ctc_scan_kernel x2 "
+                                "on SMs of their own || ctc_dense_grad_kernel on a helper stream] -> verify + ctc_fix_kernel") if split else
+                               "ctc_prep + ctc_rows_kernel (one pass, row in registers) + ctc_scan_kernel x2 + verify + ctc_fix_kernel",
+                     "bound": "hbm", "ms": ms,
+                     "ms_other_schedule": ms_rows, "other_schedule": "one-pass rows kernel, back to back" if split else "split",
                      "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / peaks["hbm_gbs"],
-                     "algorithmic_bytes": alg, "bytes_moved_by_design": moved, "frac_on_bytes_moved": moved / ms / 1e6 / peaks["hbm_gbs"],
-                     "traffic": (_ncu_traffic("r2_ctc_rows_bf16_T2048_B16_C7375") + _ncu_traffic("r2_ctc_fix_bf16_T2048_B16")
-                                 + _ncu_traffic("r2_ctc_scan_T2048_B16")) if name == "B16_bf16" and _ncu_traffic("r2_ctc_scan_T2048_B16") else None,
+                     "algorithmic_bytes": alg, "bytes_moved_by_design": alg if split else moved,
+                     "traffic": _ctc_traffic() if name == "B16_bf16" else None,
                      "loss": float(loss.item()), "log_space_fallbacks": int(flags.sum()),
                      "l2": "rotating %d buffer set(s) of %.0f MB" % (nrot, per / 1e6)}
         del bufs, grads, ws

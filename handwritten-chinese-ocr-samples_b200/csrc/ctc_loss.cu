@@ -300,6 +300,202 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
     if (__any_sync(0xffffffffu, small) && lane == 0) w.flag[b] = 1;
 }
 
+// ---------------------------------------------------------------- split schedule: pass A' (log-sum-exp + gather, one read)
+// Round 2, second half. The schedule "A' -> [scans || softmax*scale] -> fix": the scans (2*B one-warp CTAs, 0.24 ms of pure
+// latency at T = 2048 whatever B is) need nothing but the log-sum-exp and the label probabilities of every row, and the dense
+// part of the gradient needs nothing from the scans - so the dense part runs on a helper stream UNDERNEATH them, by plain
+// stream fork / join: no progress counters, no polling, correct under tools that serialise kernels. It costs one more read
+// of the logits than the one-pass rows kernel ((2*s_in + s_out) * T*B*C bytes, SURVEY 8d's figure), and both of its passes
+// are simpler kernels that run closer to the HBM peak than the rows kernel's 65 %.
+//   A'  one warp per row, the row read ONCE in register chunks of kLseChunkVec 16-byte vectors per lane (the top-k kernel's
+//       scheme, ctc_beam.cu): per chunk the lane's packed maximum, a lane-private online rescale of its sum when the maximum
+//       grows (predicated, no cross-lane traffic), FFMA + ex2 + FADD per element; one warp reduction at the end; then the
+//       label gather of ctc_lse_gather_kernel (the labels' logits were read microseconds ago: L2 hits).
+constexpr int kLseChunkVec = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kLseWarps * 32, 4)
+ctc_lse_chunk_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
+                     const int32_t* __restrict__ ilen, int Sp, const float* __restrict__ lse_in, CtcWs w) {
+    constexpr int V = Ld<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * kLseWarps + (threadIdx.x >> 5);     // row = b*T + t
+    if (row >= (long long)Tn * Bn) return;
+    const int b = (int)((unsigned)row / (unsigned)Tn), t = (int)((unsigned)row - (unsigned)b * (unsigned)Tn);
+    if (t >= ilen[b]) return;
+    const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+    float lse;
+    if (lse_in != nullptr) {
+        lse = lse_in[row];            // log-sum-exp already produced by the classifier epilogue: only gather the labels
+    } else {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+        int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+        if (head > C) head = C;
+        const int nvec = (C - head) / V;
+        const int tail0 = head + nvec * V;
+        const T* pv = p + head;
+        float x_h = -INFINITY, x_t = -INFINITY;
+        if (lane < head) x_h = Ld<T>::one(p + lane);
+        if (tail0 + lane < C) x_t = Ld<T>::one(p + tail0 + lane);
+        const uint32_t ninf_w = sizeof(T) == 2 ? 0xFF80FF80u : 0xFF800000u;
+        float m = -INFINITY;                                                 // lane-private running maximum
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};                                  // lane-private sums of exp(x - m)
+        for (int base = 0; base < nvec; base += 32 * kLseChunkVec) {
+            uint4 q[kLseChunkVec];
+            if (base + 32 * kLseChunkVec <= nvec) {
+#pragma unroll
+                for (int u = 0; u < kLseChunkVec; ++u) q[u] = ld_nc_v4(pv + (long long)(base + 32 * u + lane) * V);
+            } else {
+#pragma unroll
+                for (int u = 0; u < kLseChunkVec; ++u) {
+                    const int vi = base + 32 * u + lane;
+                    q[u] = make_uint4(ninf_w, ninf_w, ninf_w, ninf_w);
+                    if (vi < nvec) q[u] = ld_nc_v4(pv + (long long)vi * V);
+                }
+            }
+            float cm;
+            if (sizeof(T) == 2) {
+                __nv_bfloat162 a[kLseChunkVec];
+#pragma unroll
+                for (int u = 0; u < kLseChunkVec; ++u)
+                    a[u] = __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q[u].x), *reinterpret_cast<const __nv_bfloat162*>(&q[u].y)),
+                                   __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&q[u].z), *reinterpret_cast<const __nv_bfloat162*>(&q[u].w)));
+#pragma unroll
+                for (int h = kLseChunkVec / 2; h > 0; h >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < h; ++u) a[u] = __hmax2(a[u], a[u + h]);
+                }
+                cm = fmaxf(__low2float(a[0]), __high2float(a[0]));
+            } else {
+                float a[kLseChunkVec];
+#pragma unroll
+                for (int u = 0; u < kLseChunkVec; ++u)
+                    a[u] = fmaxf(fmaxf(__uint_as_float(q[u].x), __uint_as_float(q[u].y)), fmaxf(__uint_as_float(q[u].z), __uint_as_float(q[u].w)));
+#pragma unroll
+                for (int h = kLseChunkVec / 2; h > 0; h >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < h; ++u) a[u] = fmaxf(a[u], a[u + h]);
+                }
+                cm = a[0];
+            }
+            if (cm > m) {                                                    // (m = -inf: the sums are still zero)
+                const float sc = ex2_fast((m - cm) * kLog2e);
+                s4[0] *= sc; s4[1] *= sc; s4[2] *= sc; s4[3] *= sc;
+                m = cm;
+            }
+            const float nml = m > -INFINITY ? -m * kLog2e : 0.f;            // nothing but -inf so far: every term is 2^-inf = 0
+            const int rem = nvec - base;                                     // warp-uniform: vector step u has data iff 32 u < rem
+#pragma unroll
+            for (int u = 0; u < kLseChunkVec; ++u) {
+                if (32 * u >= rem) break;
+                float x[V];
+                if (sizeof(T) == 2) {
+                    x[0] = bf16_lo(q[u].x); x[1] = bf16_hi(q[u].x); x[2] = bf16_lo(q[u].y); x[3] = bf16_hi(q[u].y);
+                    x[V - 4] = bf16_lo(q[u].z); x[V - 3] = bf16_hi(q[u].z); x[V - 2] = bf16_lo(q[u].w); x[V - 1] = bf16_hi(q[u].w);
+                } else {
+                    x[0] = __uint_as_float(q[u].x); x[1] = __uint_as_float(q[u].y); x[2] = __uint_as_float(q[u].z); x[3] = __uint_as_float(q[u].w);
+                }
+                float acc = ex2_fast(fmaf(x[0], kLog2e, nml)) + ex2_fast(fmaf(x[1], kLog2e, nml));
+#pragma unroll
+                for (int j = 2; j < V; j += 2) acc += ex2_fast(fmaf(x[j], kLog2e, nml)) + ex2_fast(fmaf(x[j + 1], kLog2e, nml));
+                s4[u & 3] += acc;
+            }
+        }
+        // ---- the scalars in front of / behind the interior, then across the warp
+        const float xs = fmaxf(x_h, x_t);
+        float ssum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        if (xs > m) { ssum *= ex2_fast((m - xs) * kLog2e); m = xs; }
+        if (m > -INFINITY) ssum += ex2_fast((x_h - m) * kLog2e) + ex2_fast((x_t - m) * kLog2e);
+        const float mm = warp_max(m);
+        ssum = warp_sum(m > -INFINITY ? ssum * ex2_fast((m - mm) * kLog2e) : 0.f);
+        lse = mm + logf(ssum);
+    }
+    if (lane == 0) w.lse[row] = lse;
+    const int L = w.len[b], S = 2 * L + 1;
+    const int* tg = w.lab + (long long)b * w.Lp;
+    float* dst = w.lpg + row * Sp;
+    double* dpr = w.pg + row * Sp;
+    double* dpm = w.pgr + row * Sp;
+    bool small = false;
+    for (int q = lane; q < Sp; q += 32) {
+        float lp = 0.f;
+        double pr = 0.0;
+        if (q < S) {
+            const int c = (q & 1) ? tg[q >> 1] : 0;
+            lp = Ld<T>::one(p + c) - lse;
+            pr = (double)expf(lp);
+            small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);       // exp(-inf) = 0 is exact in linear space
+            small |= !(lp == lp);                                        // NaN: let the log-space path propagate it
+            dpm[S - 1 - q] = pr;
+        } else {
+            dpm[q] = 0.0;
+        }
+        dst[q] = lp;
+        dpr[q] = pr;
+    }
+    if (__any_sync(0xffffffffu, small) && lane == 0) w.flag[b] = 1;
+}
+
+// ---------------------------------------------------------------- split schedule: the dense part of the gradient
+// grad = softmax * scale = 2^(x log2 e - lse log2 e) * scale for every class (the label classes are corrected by
+// ctc_fix_kernel once the scans are done), zeros for the rows beyond a sequence's input length. A pure stream: one warp per
+// row, four 16-byte loads in flight per lane, FFMA + ex2 + FMUL per element. Runs on the helper stream beside the scans.
+constexpr int kDenseWarps = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kDenseWarps * 32)
+ctc_dense_grad_kernel(const T* __restrict__ logits, T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t,
+                      long long stride_b, const int32_t* __restrict__ ilen, float grad_scale, CtcWs w) {
+    constexpr int V = Ld<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * kDenseWarps + (threadIdx.x >> 5);   // row = b*T + t
+    if (row >= (long long)Tn * Bn) return;
+    const int b = (int)((unsigned)row / (unsigned)Tn), t = (int)((unsigned)row - (unsigned)b * (unsigned)Tn);
+    const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+    T* g = grad + (long long)t * stride_t + (long long)b * stride_b;
+    const bool live = t < ilen[b];
+    const float scale = grad_scale / ((float)max(w.len[b], 1) * (float)Bn);
+    const float nl = live ? -w.lse[row] * kLog2e : 0.f;
+    const float mul = live ? scale : 0.f;
+    auto val = [&](float x) { return live ? ex2_fast(fmaf(x, kLog2e, nl)) * mul : 0.f; };
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    if ((reinterpret_cast<uintptr_t>(g) & 15) != (addr & 15)) {                        // never with equal strides and aligned bases
+        for (int c = lane; c < C; c += 32) Ld<T>::st_one(g + c, val(live ? Ld<T>::one(p + c) : 0.f));
+        return;
+    }
+    int head = (int)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > C) head = C;
+    const int nvec = (C - head) / V;
+    const int tail0 = head + nvec * V;
+    if (lane < head) Ld<T>::st_one(g + lane, val(live ? Ld<T>::one(p + lane) : 0.f));
+    if (tail0 + lane < C) Ld<T>::st_one(g + tail0 + lane, val(live ? Ld<T>::one(p + tail0 + lane) : 0.f));
+    const T* pv = p + head;
+    T* gv = g + head;
+    if (!live) {
+        for (int vi = lane; vi < nvec; vi += 32) *reinterpret_cast<uint4*>(gv + (long long)vi * V) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    int vi = lane;
+    for (; vi + 96 < nvec; vi += 128) {
+        float x[4][V];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Ld<T>::vec(pv + (long long)(vi + 32 * u) * V, x[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) x[u][j] = ex2_fast(fmaf(x[u][j], kLog2e, nl)) * mul;
+            Ld<T>::st_vec(gv + (long long)(vi + 32 * u) * V, x[u]);
+        }
+    }
+    for (; vi < nvec; vi += 32) {
+        float x[V];
+        Ld<T>::vec(pv + (long long)vi * V, x);
+#pragma unroll
+        for (int j = 0; j < V; ++j) x[j] = ex2_fast(fmaf(x[j], kLog2e, nl)) * mul;
+        Ld<T>::st_vec(gv + (long long)vi * V, x);
+    }
+}
+
 // ---------------------------------------------------------------- pass B (fast): scaled linear recursion, one warp
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -310,7 +506,7 @@ constexpr int kTinyExp = -760;                       // a state this far below i
 constexpr int kTinyHi = (1023 + kTinyExp) << 20;     // high word of 2^kTinyExp
 constexpr int kRebaseDiff = 900;                     // adopt the left neighbour's exponent when it is this far above ours
 constexpr int kScanChunkStates = 32;                 // steps per staged chunk x states per lane
-constexpr int kScanStageDoubles = 3 * kScanChunkStates * 32;     // 3 chunks in flight = 24 KB
+constexpr int kScanChunkBytes = kScanChunkStates * 32 * 8;       // one staged chunk = 8 KB; NST chunks in flight
 
 // Progress counters are polled with RELAXED gpu-scope loads (served by the L2, the point of coherence): an acquire load
 // keeps every later memory operation of the warp - the cp.async of the next chunk, the alpha stores - behind its own L2
@@ -345,14 +541,16 @@ __device__ __forceinline__ double pow2_clamped(int x) {          // 2^x, exact, 
 // POLL (overlapped path): the label probabilities are being produced by ctc_rows_kernel while this kernel runs; before
 // the rows of a granule are staged, lane 0 acquires the granule's progress counter (prefetched one granule ahead so the
 // L2 round trip is off the recursion's critical path) and the warp synchronises on the answer.
-template <int K, bool POLL>
+// NST = staged chunks in flight (dynamic shared memory, NST * 8 KB): 3 (24 steps ahead at K = 4, enough on a quiet device);
+// kScanDeepStages when the dense gradient pass streams beside the scans and a DRAM round trip takes several microseconds.
+template <int K, bool POLL, int NST>
 __global__ void __launch_bounds__(32)
 ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restrict__ nll_out, CtcWs w) {
     constexpr int CH = kScanChunkStates / K;          // steps per staged chunk (even)
     constexpr int SA = 32 * K;                        // alpha/beta row pitch: every lane's states exist in memory
     constexpr int KP = K / 2;                         // 16-byte pairs of states per lane
     static_assert(CH % 2 == 0 && K % 4 == 0, "pairs of steps, 32-byte aligned runs of states");
-    __shared__ __align__(16) double stage[kScanStageDoubles];
+    extern __shared__ __align__(16) double stage[];                   // [NST][kScanChunkStates * 32]
     __shared__ double fin_v[2];
     __shared__ int fin_e[2];
     const int b = blockIdx.x, lane = threadIdx.x;
@@ -443,7 +641,7 @@ ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restr
             ensure(hi);
             istaged = hi;
         }
-        const uint32_t dst = stage_u32 + slot * (kScanChunkStates * 32 * 8);
+        const uint32_t dst = stage_u32 + slot * kScanChunkBytes;
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             if (ileft > 0) { isrc += istride; --ileft; }
@@ -455,8 +653,8 @@ ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restr
         cp_async_commit();
     };
     if (POLL) ensure(0);
-    issue(0);
-    issue(1);
+#pragma unroll 1
+    for (int i = 0; i < NST - 1; ++i) issue(i);
 
     // ---- i = 0
     double v[K];
@@ -477,13 +675,13 @@ ctc_scan_kernel(const int32_t* __restrict__ ilen, int Tn, int Sp, float* __restr
     int d_next = 0, d_after = 0;                      // rescale exponents for the next two exponent steps
     int slot = 0;
     for (int c = 0; c < nchunks; ++c) {
-        issue(slot == 0 ? 2 : slot - 1);
+        issue(slot == 0 ? NST - 1 : slot - 1);
         if (POLL && timed_out) break;                 // warp-uniform
         if (POLL && lane == 0 && (c == nchunks / 4 || c == nchunks / 2 || c == 3 * nchunks / 4))
             w.dbg[((long long)b * 2 + (rev ? 1 : 0)) * 8 + 4 + (c == nchunks / 4 ? 0 : c == nchunks / 2 ? 1 : 2)] = global_timer_ns();
-        cp_async_wait<2>();                           // chunk c has landed (each lane reads only what it copied itself)
+        cp_async_wait<NST - 1>();                     // chunk c has landed (each lane reads only what it copied itself)
         const double2* buf = reinterpret_cast<const double2*>(stage) + slot * (kScanChunkStates * 16) + lane;
-        slot = slot == 2 ? 0 : slot + 1;
+        slot = slot == NST - 1 ? 0 : slot + 1;
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
             const int i = 1 + c * CH + u;
@@ -1184,15 +1382,50 @@ static int ctc_side(CtcSide** out) {
             int prio_lo = 0, prio_hi = 0;
             HCTR_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             HCTR_CUDA(cudaStreamCreateWithPriority(&sd.helper, cudaStreamNonBlocking, prio_hi));
-            HCTR_CUDA(cudaFuncSetAttribute(ctc_scan_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            HCTR_CUDA(cudaFuncSetAttribute(ctc_scan_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            HCTR_CUDA(cudaFuncSetAttribute(ctc_scan_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
             HCTR_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
             HCTR_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
         }
     }
     *out = &sd;
     return HCTR_OK;
+}
+
+// One launch site for the scans: K states per lane, NST staged chunks (NST * 8 KB of dynamic shared memory, or more when the
+// caller asks for a whole SM's worth to keep the one-warp CTAs one to an SM).
+constexpr int kScanStages = 3;
+constexpr int kScanDeepStages = 12;
+constexpr size_t kScanExclusiveSmem = 226 * 1024;      // + static + 1 KB reserved = the SM's 228 KB
+constexpr int kSplitMaxScanCtas = 48;                     // SMs the split schedule may take away from the dense pass
+template <int K, bool POLL, int NST>
+static int scan_launch_k(dim3 grid, size_t min_smem, cudaStream_t st, const int32_t* ilen, int T, int Sp, float* nll, const CtcWs& w) {
+    auto kern = ctc_scan_kernel<K, POLL, NST>;
+    static PerDeviceOnce once;
+    int dev;
+    if (once.need(dev)) {
+        HCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanExclusiveSmem));
+        once.mark(dev);
+    }
+    size_t smem = (size_t)NST * kScanChunkBytes;
+    if (smem < min_smem) smem = min_smem;
+    kern<<<grid, 32, smem, st>>>(ilen, T, Sp, nll, w);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}
+template <bool POLL, int NST>
+static int scan_launch(int kscan, dim3 grid, size_t min_smem, cudaStream_t st, const int32_t* ilen, int T, int Sp, float* nll,
+                       const CtcWs& w) {
+    switch (kscan) {
+        case 4:  return scan_launch_k<4, POLL, NST>(grid, min_smem, st, ilen, T, Sp, nll, w);
+        case 8:  return scan_launch_k<8, POLL, NST>(grid, min_smem, st, ilen, T, Sp, nll, w);
+        case 16: return scan_launch_k<16, POLL, NST>(grid, min_smem, st, ilen, T, Sp, nll, w);
+        default: return HCTR_OK;                      // too many states: the log-space recursion only
+    }
+}
+
+// The split schedule is the default when a gradient is wanted, the scans' 2*B one-warp CTAs can each have an SM to themselves
+// without starving the dense pass (B <= 24), and the logits are large enough for the dense pass to be worth hiding.
+static bool split_by_default(int T, int B, int C, int esz, bool want_grad) {
+    return want_grad && 2 * B <= kSplitMaxScanCtas && (long long)T * B * C * esz >= (32ll << 20);
 }
 
 // vectors per thread the row needs; 0 = the row does not fit the registers of four warps (sequential passes instead)
@@ -1312,21 +1545,76 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     // at the same time: under a tool that serialises kernels (ncu, compute-sanitizer) the scans wait for rows that cannot
     // start, give up after kScanWaitLimitNs and the loss comes out NaN.
     const bool want_overlap = ov && ov[0] == '1';
-    const bool serial = rows_path && (!want_overlap || 2ll * B > 2048);
-    const bool overlap = rows_path;
-    if (serial) {
+    // The split schedule (see ctc_lse_chunk_kernel): A' -> [scans || dense gradient on the helper stream] -> fix. "4" forces it,
+    // "2" forces the one-pass rows kernel back to back with the scans.
+    const bool split = kscan != 0 && !debug_force_log && !overlap_off && !want_overlap && !(ov && (ov[0] == '2' || ov[0] == '3')) &&
+                       ((ov && ov[0] == '4') || split_by_default(T, B, C, esz, grad != nullptr));
+    const bool serial = !split && rows_path && (!want_overlap || 2ll * B > 2048);
+    const bool overlap = rows_path || split;                          // the gradient's label classes are ctc_fix_kernel's
+    CtcSide* split_side = nullptr;
+    if (split) {
+        const long long blocksA = (rows + kLseWarps - 1) / kLseWarps;
+        if (dtype == HCTR_F32)
+            ctc_lse_chunk_kernel<float><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
+                static_cast<const float*>(logits), T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse, w);
+        else
+            ctc_lse_chunk_kernel<__nv_bfloat16><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
+                static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse, w);
+        HCTR_CUDA(cudaGetLastError());
+        if (grad != nullptr) {
+            int rc = ctc_side(&split_side);
+            if (rc) return rc;
+            split_side->mu.lock();                                    // one enqueue at a time per device (shared helper stream)
+            cudaError_t e = cudaEventRecord(split_side->fork, s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(split_side->helper, split_side->fork, 0);
+            if (e != cudaSuccess) { split_side->mu.unlock(); HCTR_CUDA(e); }
+        }
+        // the scans first: their 2*B one-warp CTAs take their SM slots on an idle device, the dense pass fills in around them
+        const bool timing = grad != nullptr && getenv("HCTR_CTC_TIMING") != nullptr;     // diagnostics: scan / dense pass times
+        cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (timing) { for (int i = 0; i < 4; ++i) cudaEventCreate(&tev[i]); cudaEventRecord(tev[0], s); }
+        {
+            // Beside the dense pass each scan CTA asks for (nearly) a whole SM's shared memory, and the dense kernel for a token
+            // 4 KB, so that no dense CTA can share an SM with a scan: co-resident, the dense warps keep the SM's load/store
+            // queue full and every shared-memory read, cp.async and store of the scan waits in it - measured, the scans then
+            // advance at 15 % of their speed until the dense pass is over (0.38 ms instead of 0.24; 0.28 with the SM to
+            // themselves and kScanDeepStages chunks staged ahead, which covers the longer DRAM round trips of a busy device).
+            const int rc = grad != nullptr ? scan_launch<false, kScanDeepStages>(kscan, gridB, kScanExclusiveSmem, s, input_lengths, T, Sp, nll, w)
+                                           : scan_launch<false, kScanStages>(kscan, gridB, 0, s, input_lengths, T, Sp, nll, w);
+            if (rc) { if (split_side) split_side->mu.unlock(); return rc; }
+        }
+        if (timing) { cudaEventRecord(tev[1], s); cudaEventRecord(tev[2], split_side->helper); }
+        if (grad != nullptr) {
+            const long long blocksD = (rows + kDenseWarps - 1) / kDenseWarps;
+            if (dtype == HCTR_F32)
+                ctc_dense_grad_kernel<float><<<(int)blocksD, kDenseWarps * 32, 4096, split_side->helper>>>(
+                    static_cast<const float*>(logits), static_cast<float*>(grad), T, B, C, stride_t, stride_b, input_lengths, grad_scale, w);
+            else
+                ctc_dense_grad_kernel<__nv_bfloat16><<<(int)blocksD, kDenseWarps * 32, 4096, split_side->helper>>>(
+                    static_cast<const __nv_bfloat16*>(logits), static_cast<__nv_bfloat16*>(grad), T, B, C, stride_t, stride_b,
+                    input_lengths, grad_scale, w);
+            cudaError_t e = cudaGetLastError();
+            if (timing) {
+                cudaEventRecord(tev[3], split_side->helper);
+                cudaEventSynchronize(tev[1]); cudaEventSynchronize(tev[3]);
+                float scan_ms = 0.f, dense_ms = 0.f;
+                cudaEventElapsedTime(&scan_ms, tev[0], tev[1]); cudaEventElapsedTime(&dense_ms, tev[2], tev[3]);
+                fprintf(stderr, "hctr ctc timing (split): scans %.3f ms, dense gradient pass %.3f ms\n", scan_ms, dense_ms);
+                for (int i = 0; i < 4; ++i) cudaEventDestroy(tev[i]);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(split_side->join, split_side->helper);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, split_side->join, 0);    // join: everything after this on s follows the dense pass
+            split_side->mu.unlock();
+            HCTR_CUDA(e);
+        }
+        HCTR_CUDA(cudaGetLastError());
+    } else if (serial) {
         int rc = rows_dispatch(true, nv, logits, grad, dtype, grad != nullptr, T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse,
                                grad_scale, &w, s);
         if (rc) return rc;
-        if (ov && ov[0] == '3') {
-            ctc_scan_kernel<4, true><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w);
-        } else
-        switch (kscan) {
-            case 4:  ctc_scan_kernel<4, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
-            case 8:  ctc_scan_kernel<8, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
-            default: ctc_scan_kernel<16, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
-        }
-        HCTR_CUDA(cudaGetLastError());
+        rc = (ov && ov[0] == '3') ? scan_launch<true, kScanStages>(kscan, gridB, 0, s, input_lengths, T, Sp, nll, w)
+                                  : scan_launch<false, kScanStages>(kscan, gridB, 0, s, input_lengths, T, Sp, nll, w);
+        if (rc) return rc;
     } else if (overlap) {
         CtcSide* side = nullptr;
         int rc = ctc_side(&side);
@@ -1353,12 +1641,8 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
         // GPU, the one-warp CTAs are otherwise packed eight to an SM - on the few SMs that free up first - and, one warp per
         // CTA, onto the same scheduler of it: the recursion then runs 4x slower (measured: 32 scan CTAs on SMs 0, 6, 32, 64).
         const size_t spread = 112 * 1024;
-        switch (kscan) {
-            case 4:  ctc_scan_kernel<4, true><<<gridB, 32, spread, side->helper>>>(input_lengths, T, Sp, nll, w); break;
-            case 8:  ctc_scan_kernel<8, true><<<gridB, 32, spread, side->helper>>>(input_lengths, T, Sp, nll, w); break;
-            default: ctc_scan_kernel<16, true><<<gridB, 32, spread, side->helper>>>(input_lengths, T, Sp, nll, w); break;
-        }
-        HCTR_CUDA(cudaGetLastError());
+        rc = scan_launch<true, kScanStages>(kscan, gridB, spread, side->helper, input_lengths, T, Sp, nll, w);
+        if (rc) return rc;
         if (timing) cudaEventRecord(tev[3], side->helper);
         HCTR_CUDA(cudaEventRecord(side->join, side->helper));
         if (!rows_first) {
@@ -1402,13 +1686,10 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
                 static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, targets, target_lengths, input_lengths, Sp, row_lse, w);
         HCTR_CUDA(cudaGetLastError());
         // one warp per (sequence, direction); the beta recursion is only needed for the gradient
-        switch (kscan) {
-            case 4:  ctc_scan_kernel<4, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
-            case 8:  ctc_scan_kernel<8, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
-            case 16: ctc_scan_kernel<16, false><<<gridB, 32, 0, s>>>(input_lengths, T, Sp, nll, w); break;
-            default: break;
+        {
+            const int rc = scan_launch<false, kScanStages>(kscan, gridB, 0, s, input_lengths, T, Sp, nll, w);
+            if (rc) return rc;
         }
-        HCTR_CUDA(cudaGetLastError());
     }
     switch (kscan) {
         case 4:  ctc_scan_verify_kernel<4><<<blocksV, 256, 0, s>>>(target_lengths, input_lengths, T, B, Sp, have_beta, w); break;

@@ -42,13 +42,13 @@ for dt, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
 del x
 peaks = {"hbm_gbs": HBM}
 os.environ.pop("HCTR_TOPK_CTAS", None)
-for mode in ("", "1", "0"):
+for mode in ("", "4", "2", "1", "0"):
     os.environ["HCTR_CTC_OVERLAP"] = mode
     os.environ.pop("HCTR_CTC_ROWS_CTAS", None)
     if mode.startswith("c"):
         os.environ["HCTR_CTC_ROWS_CTAS"] = mode[1:]
     r = bx.ctc_loss_legs(nat, dev, peaks)
-    out[{"": "ctc_default_rows_scan_fix", "1": "ctc_overlapped_schedule", "0": "ctc_round1_passes"}[mode]] = {k2: {"ms": v["ms"], "frac": v["frac"], "loss": v["loss"]} for k2, v in r.items()}
+    out[{"": "ctc_default", "4": "ctc_split_schedule", "2": "ctc_rows_scan_fix", "1": "ctc_overlapped_schedule", "0": "ctc_round1_passes"}[mode]] = {k2: {"ms": v["ms"], "frac": v["frac"], "loss": v["loss"]} for k2, v in r.items()}
 print(json.dumps(out, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "codec_micro.json"), "w"), indent=1)

@@ -197,10 +197,11 @@ def test_ctc_loss_only_no_gradient():
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("T,B,C,lo,hi", [(2048, 4, 7375, 20, 60), (257, 3, 101, 1, 9), (64, 2, 37, 0, 3), (1, 2, 11, 0, 1)])
 def test_ctc_loss_overlapped_and_sequential_paths_agree(monkeypatch, dtype, T, B, C, lo, hi):
-    """Round 2: the default path reads every logits row once (lse + label gather + dense gradient, the row in the registers
-    of four warps), then runs the alpha/beta scans and a sparse fix-up; HCTR_CTC_OVERLAP=1 overlaps the scans with the row
-    pass on a helper stream, fed through progress counters; HCTR_CTC_OVERLAP=0 runs round 1's three sequential passes.
-    Same loss, same gradient for all three, for contiguous and model-layout (pitched, permuted) logits, with ragged input
+    """Round 2: the default (split) schedule reads every logits row once for the log-sum-exp and the label gather, then runs
+    the alpha/beta scans with the dense part of the gradient on a helper stream underneath them, then a sparse fix-up;
+    HCTR_CTC_OVERLAP=2 is the one-pass rows kernel (lse + gather + dense gradient, the row in the registers of four warps)
+    back to back with the scans, =1 overlaps those two through progress counters, =0 runs round 1's three sequential passes.
+    Same loss, same gradient for all of them, for contiguous and model-layout (pitched, permuted) logits, with ragged input
     lengths, odd T, and T = 1."""
     from hctr_b200.ctc_loss import CTCLoss
     x = synth.ctc_like_logits(T, B, C, 7 + T)
@@ -209,7 +210,7 @@ def test_ctc_loss_overlapped_and_sequential_paths_agree(monkeypatch, dtype, T, B
     if T > 8:
         il[-1] = T - 5
     results = []
-    for mode in ("", "1", "0"):
+    for mode in ("", "4", "2", "1", "0"):           # default, split, one-pass rows back to back, overlapped, round-1 passes
         monkeypatch.setenv("HCTR_CTC_OVERLAP", mode)
         for layout in ("contiguous", "model"):
             if layout == "contiguous":
@@ -234,8 +235,10 @@ def test_ctc_loss_overlapped_and_sequential_paths_agree(monkeypatch, dtype, T, B
     for loss, g in results:
         assert abs(loss - oloss) <= 1e-4 * abs(oloss) + 1e-6, (loss, oloss)
         assert np.abs(g.numpy() - ograd).max() <= gate
-    assert abs(results[0][0] - results[2][0]) <= 1e-6 * abs(oloss) + 1e-7          # default vs overlapped schedule
-    assert abs(results[0][0] - results[4][0]) <= 1e-5 * abs(oloss) + 1e-6          # default vs round-1 passes
+    assert abs(results[0][0] - results[2][0]) <= 1e-6 * abs(oloss) + 1e-7          # default vs forced split schedule
+    assert abs(results[0][0] - results[4][0]) <= 1e-5 * abs(oloss) + 1e-6          # default vs one-pass rows kernel
+    assert abs(results[4][0] - results[6][0]) <= 1e-6 * abs(oloss) + 1e-7          # rows kernel: back to back vs overlapped
+    assert abs(results[0][0] - results[8][0]) <= 1e-5 * abs(oloss) + 1e-6          # default vs round-1 passes
 
 
 def test_ctc_loss_bad_lengths_and_labels_do_not_touch_memory_out_of_bounds():
