@@ -161,6 +161,66 @@ def test_topk_logsoftmax_strided_views_and_constant_rows():
     assert np.allclose(tp[0, 0], -np.log(777.0), rtol=1e-6)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_topk_logsoftmax_adversarial_rows(dtype):
+    """Rows that defeat the running top-k bound of the one-read kernel: ascending rows (every vector of every chunk reaches the
+    bound of the chunks before it: the marked-vector list overflows -> exact fallback), descending rows (the first chunk holds
+    the whole top k), a late spike after a flat start, -inf-padded rows, rows whose top k sit in one lane's vectors, heavy ties.
+    Exact indices for any of them (value desc, index asc)."""
+    T, B, C, k = 9, 2, 7375, 10
+    rng = np.random.default_rng(11)
+    x = np.zeros((T, B, C), dtype=np.float32)
+    ramp = np.linspace(-8.0, 8.0, C, dtype=np.float32)
+    x[0] = ramp                                        # ascending
+    x[1] = ramp[::-1]                                  # descending
+    x[2] = -3.0; x[2, :, C - 5:] = np.arange(5, dtype=np.float32)[None, :] + 4.0     # flat, spike in the last vector
+    x[3] = rng.standard_normal((B, C)).astype(np.float32); x[3, :, 100:] = -np.inf    # mostly -inf
+    x[4] = rng.standard_normal((B, C)).astype(np.float32); x[4, :, :4096] = -np.inf   # the first chunks are all -inf
+    x[5] = rng.standard_normal((B, C)).astype(np.float32)
+    x[5, :, 8 * 32 * 3: 8 * 32 * 3 + 16] += 20.0       # 16 large elements in two adjacent vectors of one lane pair
+    x[6] = np.round(rng.standard_normal((B, C)) * 2).astype(np.float32)               # heavy ties (few distinct values)
+    x[7] = rng.standard_normal((B, C)).astype(np.float32) * 30.0                       # large dynamic range
+    x[8] = ramp; x[8, :, ::2] = ramp[::-1][::2]        # interleaved up / down
+    xt = torch.from_numpy(x).cuda().to(dtype)
+    xf = xt.float().cpu().numpy()
+    ti, tp, lse = _run_topk(xt, k)
+    want = oracle.topk(xf, k)
+    assert np.array_equal(ti, want)
+    m = xf.max(axis=2)
+    ref_lse = m + np.log(np.exp((xf - m[..., None]).astype(np.float64)).sum(axis=2))
+    assert np.abs(lse - ref_lse).max() <= 1e-5 * max(1.0, np.abs(ref_lse).max())
+    ref = np.take_along_axis(xf, want, 2).astype(np.float64) - ref_lse[..., None]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(tp), fin)
+    assert np.abs(tp[fin] - ref[fin]).max() <= 4e-6 * max(1.0, np.abs(ref[fin]).max())
+
+
+def test_topk_logsoftmax_kernel_variants_agree(monkeypatch):
+    """The default one-read chunk kernel against the kernels it replaced (CTA per row, two-pass warp per row), misaligned rows
+    and every search depth: identical indices, log-probs to rounding."""
+    T, B, C = 23, 3, 7375
+    rng = np.random.default_rng(3)
+    base = torch.from_numpy((2.5 * rng.standard_normal((T, B, C + 1))).astype(np.float32)).cuda()
+    for dtype in (torch.float32, torch.bfloat16):
+        buf = base.to(dtype)
+        view = buf[:, :, 1:]                                      # rows start 1 element off the 16-byte grid
+        for k in (1, 5, 10, 16):
+            res = {}
+            for name, env in (("chunk", {}), ("cta", {"HCTR_TOPK_CHUNK": "0", "HCTR_TOPK_WARP": "0"}),
+                              ("warp", {"HCTR_TOPK_CHUNK": "0", "HCTR_TOPK_WARP": "1"})):
+                for key in ("HCTR_TOPK_CHUNK", "HCTR_TOPK_WARP"):
+                    monkeypatch.delenv(key, raising=False)
+                for key, val in env.items():
+                    monkeypatch.setenv(key, val)
+                res[name] = _run_topk(view, k)
+            for name in ("cta", "warp"):
+                assert np.array_equal(res["chunk"][0], res[name][0]), (dtype, k, name)
+                assert np.abs(res["chunk"][1] - res[name][1]).max() <= 4e-6
+                assert np.abs(res["chunk"][2] - res[name][2]).max() <= 4e-6
+            xf = view.float().cpu().numpy()
+            assert np.array_equal(res["chunk"][0], oracle.topk(xf, k))
+
+
 BEAM_CASES = [(c, s) for c in ("small", "mid", "wide") for s in ("zero_b0", "zero_b58", "tab_p2", "tab_p08")]
 
 
