@@ -220,6 +220,22 @@ __global__ void lse_combine_kernel(const float2* __restrict__ partial, long long
     lse[r] = m + logf(s);
 }
 
+// arg-max fix-up of the classifier's per-(row, half-tile) partials, in class order: numpy.argmax over the row
+__global__ void argmax_combine_kernel(const int2* __restrict__ partial, long long rows, int slots, int32_t* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int2* p = partial + r * slots;
+    float bv = 0.f;
+    int bi = -1;
+    for (int i = 0; i < slots; ++i) {
+        const int2 q = p[i];
+        if (q.y < 0) continue;                                  // a half-tile beyond the last class
+        const float x = __int_as_float(q.x);
+        if (bi < 0 || x > bv || (x != x && bv == bv)) { bv = x; bi = q.y; }
+    }
+    out[r] = bi < 0 ? 0 : bi;
+}
+
 }  // namespace hctr
 
 using namespace hctr;
@@ -429,8 +445,8 @@ static int cls_block_n() {
 
 static int classifier_launch(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
                              long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, float2* lse_partial,
-                             void* stream) {
-    HCTR_CHECK(feat && w_packed && bias && logits, HCTR_ERR_INVALID, "classifier: null pointer");
+                             int2* argmax_partial, void* stream) {
+    HCTR_CHECK(feat && w_packed && bias && (logits || (argmax_partial && !lse_partial)), HCTR_ERR_INVALID, "classifier: null pointer");
     HCTR_CHECK(B > 0 && W > 0 && Hf > 0 && Hf <= kMaxTaps, HCTR_ERR_INVALID, "classifier: bad shape B=%d Hf=%d W=%d", B, Hf, W);
     HCTR_CHECK(Cf % 64 == 0 && Cf >= 64, HCTR_ERR_INVALID, "classifier: feature channels must be a multiple of 64 (got %d)", Cf);
     HCTR_CHECK(num_classes > 0 && out_pitch >= num_classes, HCTR_ERR_INVALID, "classifier: pitch %lld < classes %d", out_pitch, num_classes);
@@ -453,6 +469,7 @@ static int classifier_launch(const void* feat, const void* w_packed, const float
     p.out_H = 1;
     p.out_dtype = out_dtype; p.out_pitch = out_pitch;
     p.lse_partial = lse_partial;
+    p.argmax_partial = argmax_partial;
     const long long total = (long long)B * p.w_tiles * p.n_tiles;
     HCTR_CHECK(total < (1ll << 31), HCTR_ERR_INVALID, "classifier: too many tiles");
     p.total_tiles = (int)total;
@@ -469,7 +486,7 @@ static int classifier_launch(const void* feat, const void* w_packed, const float
 
 int hctr_classifier_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
                         long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, void* stream) {
-    return classifier_launch(feat, w_packed, bias, logits, out_dtype, out_pitch, B, Hf, W, Cf, num_classes, nullptr, stream);
+    return classifier_launch(feat, w_packed, bias, logits, out_dtype, out_pitch, B, Hf, W, Cf, num_classes, nullptr, nullptr, stream);
 }
 
 long long hctr_classifier_lse_workspace_bytes(int B, int W, int num_classes) {
@@ -483,7 +500,7 @@ int hctr_classifier_lse_fwd(const void* feat, const void* w_packed, const float*
     HCTR_CHECK(workspace_bytes >= hctr_classifier_lse_workspace_bytes(B, W, num_classes), HCTR_ERR_INVALID, "classifier_lse: workspace too small");
     HCTR_CHECK(aligned16(workspace), HCTR_ERR_INVALID, "classifier_lse: workspace alignment");
     int rc = classifier_launch(feat, w_packed, bias, logits, out_dtype, out_pitch, B, Hf, W, Cf, num_classes,
-                               static_cast<float2*>(workspace), stream);
+                               static_cast<float2*>(workspace), nullptr, stream);
     if (rc) return rc;
     const long long rows = (long long)B * W;
     const int slots = ((num_classes + cls_block_n() - 1) / cls_block_n()) * 2;
@@ -491,6 +508,28 @@ int hctr_classifier_lse_fwd(const void* feat, const void* w_packed, const float*
         static_cast<const float2*>(workspace), rows, slots, row_lse);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
+}
+
+long long hctr_classifier_greedy_workspace_bytes(int B, int W, int num_classes) {
+    return (long long)B * W * ((num_classes + 127) / 128) * 2 * (long long)sizeof(int2);        // sized for the 128-column tile
+}
+
+int hctr_classifier_greedy_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                               long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, int32_t* argmax_bt,
+                               int32_t* out_idx, int32_t* out_len, void* workspace, long long workspace_bytes, void* stream) {
+    HCTR_CHECK(argmax_bt && out_idx && out_len && workspace, HCTR_ERR_INVALID, "classifier_greedy: null pointer");
+    HCTR_CHECK(workspace_bytes >= hctr_classifier_greedy_workspace_bytes(B, W, num_classes), HCTR_ERR_INVALID,
+               "classifier_greedy: workspace too small");
+    HCTR_CHECK(aligned16(workspace), HCTR_ERR_INVALID, "classifier_greedy: workspace alignment");
+    int rc = classifier_launch(feat, w_packed, bias, logits, out_dtype, out_pitch, B, Hf, W, Cf, num_classes, nullptr,
+                               static_cast<int2*>(workspace), stream);
+    if (rc) return rc;
+    const long long rows = (long long)B * W;
+    const int slots = ((num_classes + cls_block_n() - 1) / cls_block_n()) * 2;
+    argmax_combine_kernel<<<(int)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const int2*>(workspace), rows, slots, argmax_bt);
+    HCTR_CUDA(cudaGetLastError());
+    return hctr_ctc_collapse(argmax_bt, W, B, num_classes, out_idx, out_len, stream);
 }
 
 }  // extern "C"

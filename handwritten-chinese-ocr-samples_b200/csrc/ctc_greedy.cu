@@ -221,3 +221,18 @@ extern "C" int hctr_ctc_greedy_decode(const void* logits, int dtype, int T, int 
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }
+
+extern "C" int hctr_ctc_collapse(const int32_t* argmax_bt, int T, int B, int C, int32_t* out_idx, int32_t* out_len, void* stream) {
+    HCTR_CHECK(T >= 0 && B >= 0 && C > 0, HCTR_ERR_INVALID, "collapse: bad shape T=%d B=%d C=%d", T, B, C);
+    if (B == 0) return HCTR_OK;
+    HCTR_CHECK(out_len != nullptr, HCTR_ERR_INVALID, "collapse: null output");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (T == 0) {
+        HCTR_CUDA(cudaMemsetAsync(out_len, 0, sizeof(int32_t) * B, s));
+        return HCTR_OK;
+    }
+    HCTR_CHECK(argmax_bt != nullptr && out_idx != nullptr, HCTR_ERR_INVALID, "collapse: null pointer");
+    ctc_collapse_kernel<<<B, 256, 0, s>>>(argmax_bt, T, C - 1, out_idx, out_len);
+    HCTR_CUDA(cudaGetLastError());
+    return HCTR_OK;
+}

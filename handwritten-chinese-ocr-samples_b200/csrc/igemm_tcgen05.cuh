@@ -58,6 +58,9 @@ struct IgemmParams {
     long long out_pitch;      // EPI_LINEAR: elements between consecutive (b,w) rows
     float2* lse_partial;      // EPI_LINEAR: optional [B*W][n_tiles*2] (max, sum exp(x-max)) per (row, column half-tile) of the
                               // logits as stored (log_softmax fused into the classifier epilogue; combined by lse_combine)
+    int2* argmax_partial;     // EPI_LINEAR: optional [B*W][n_tiles*2] (bits of the largest stored value, its class) per (row,
+                              //   column half-tile): greedy decoding without ever reading - or, with out == nullptr, writing -
+                              //   the logits (numpy argmax semantics: first maximum, the first NaN beats everything)
 };
 
 // KWF ("kw-fused", 3x3 convs only): one A box of 136 pixels (w0-1 .. w0+134) per (kh, 64-channel chunk) serves the three
@@ -298,8 +301,10 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
 
             float run_m[NUM_SUB], run_s[NUM_SUB];
+            float best_v[NUM_SUB];
+            int best_i[NUM_SUB];
 #pragma unroll
-            for (int s = 0; s < NUM_SUB; ++s) { run_m[s] = -3.0e38f; run_s[s] = 0.f; }
+            for (int s = 0; s < NUM_SUB; ++s) { run_m[s] = -3.0e38f; run_s[s] = 0.f; best_v[s] = -INFINITY; best_i[s] = -1; }
 #pragma unroll 1
             for (int ck = 0; ck < kWarpChunks; ++ck) {
                 const int c0 = half * (BLOCK_N / 2) + ck * 32;
@@ -439,6 +444,17 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                         const int w = w0 + s * p.sub_dw * kTileM + pix;
                         if (w >= p.W) continue;
                         const size_t row = static_cast<size_t>(b) * p.W + w;
+                        if (p.argmax_partial) {
+                            // first maximum of the values as they are (or would be) stored; a NaN, once met, stays
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = v[s][j] + __ldg(p.shift + min(n0 + j, p.N - 1));
+                                if (p.out_dtype != HCTR_F32) x = __bfloat162float(__float2bfloat16_rn(x));
+                                const bool take = (n0 + j < p.N) && (best_i[s] < 0 || x > best_v[s] || (x != x && best_v[s] == best_v[s]));
+                                if (take) { best_v[s] = x; best_i[s] = n0 + j; }
+                            }
+                        }
+                        if (p.out == nullptr) continue;                  // arg-max only: the logits are never written
                         if (p.lse_partial) {
                             // online (max, sum exp) over this thread's row: the row of D lives in one TMEM lane, so the
                             // softmax statistics need no cross-thread traffic. Values are taken as they will be stored.
@@ -494,6 +510,15 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                 }
             }
             if constexpr (EPI == EPI_LINEAR) {
+                if (p.argmax_partial) {
+#pragma unroll
+                    for (int s = 0; s < NUM_SUB; ++s) {
+                        const int w = w0 + s * p.sub_dw * kTileM + pix;
+                        if (w < p.W)
+                            p.argmax_partial[(static_cast<size_t>(b) * p.W + w) * (p.n_tiles * 2) + n_tile * 2 + half] =
+                                make_int2(__float_as_int(best_v[s]), best_i[s]);
+                    }
+                }
                 if (p.lse_partial) {
 #pragma unroll
                     for (int s = 0; s < NUM_SUB; ++s) {

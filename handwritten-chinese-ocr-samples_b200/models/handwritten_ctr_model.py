@@ -180,7 +180,7 @@ class hctr_model(nn.Module):
         return self._plan
 
     # -------------------------------------------------------------------------------- forward
-    def forward(self, input):
+    def _check_input(self, input):
         if not input.is_cuda:
             raise RuntimeError("hctr_b200: input must be a CUDA tensor on an sm_100a device (no CPU fallback)")
         if input.dim() != 4 or input.shape[1] != 1:
@@ -192,11 +192,27 @@ class hctr_model(nn.Module):
                                                       self.linear.in_features))
         if self.linear.weight.device != input.device:
             raise RuntimeError("hctr_b200: input is on %s but parameters are on %s" % (input.device, self.linear.weight.device))
+
+    def forward(self, input):
+        self._check_input(input)
         with torch.cuda.device(input.device):
             x = input.detach().float().contiguous()
             if self.training:
                 return self._forward_train(x)
             return self._forward_eval(x)
+
+    def greedy_decode(self, input, return_argmax=False):
+        """eval() forward fused with greedy CTC decoding: what `codec.decode(model(input))` computes in the reference
+        (test.py greedy path; models/handwritten_ctr_model.py:171-178 + utils/ctc_codec.py:70-99), with the arg-max taken in the
+        classifier's epilogue, so the [W,B,C] logits are never written to memory. Returns (int32 [B,W] label indices, int32 [B]
+        lengths) on the device - feed them to `ctc_codec.indices_to_text`. Bit-identical to
+        `codec.greedy_indices(model(input))` with the same `logits_dtype` (the epilogue compares the values as they would have
+        been stored)."""
+        if self.training:
+            raise RuntimeError("hctr_b200: greedy_decode() is an eval()-mode path")
+        self._check_input(input)
+        with torch.cuda.device(input.device):
+            return self._forward_eval(input.detach().float().contiguous(), greedy=True, return_argmax=return_argmax)
 
     # -------------------------------------------------------------------------------- train mode
     def _engine(self):
@@ -250,7 +266,7 @@ class hctr_model(nn.Module):
                      B, H, W, spec.cin, spec.cout, spec.ksize, int(relu), int(pool), nat.stream_ptr())
         return y
 
-    def _forward_eval(self, x):
+    def _forward_eval(self, x, greedy=False, return_argmax=False):
         nat = _core().native
         lib = nat.lib()
         plan = self._get_plan()
@@ -269,6 +285,8 @@ class hctr_model(nn.Module):
                 a = self._residual_unit(nat, lib, a, u, B, H, W, st, dev)
             a = self._conv(nat, a, tail, B, H, W, relu=True, pool=True)
             H //= 2
+        if greedy:
+            return self._classify_greedy(nat, a, plan, B, H, W, return_argmax)
         return self._classify(nat, a, plan, B, H, W)
 
     def _residual_unit(self, nat, lib, a, u, B, H, W, st, dev):
@@ -320,14 +338,36 @@ class hctr_model(nn.Module):
                      B, H, W, c2.cin, c2.cout, c2.ksize, 1, st)
         return out
 
-    def _classify(self, nat, feat, plan, B, Hf, W):
+    def _logits_layout(self, nat):
         n = self.noutput
         if self.logits_dtype == torch.bfloat16:
-            code, pitch = nat.HCTR_BF16, (n + 7) // 8 * 8        # 16-byte aligned rows
-        elif self.logits_dtype == torch.float32:
-            code, pitch = nat.HCTR_F32, (n + 3) // 4 * 4
-        else:
-            raise ValueError("logits_dtype must be torch.float32 or torch.bfloat16")
+            return nat.HCTR_BF16, (n + 7) // 8 * 8               # 16-byte aligned rows
+        if self.logits_dtype == torch.float32:
+            return nat.HCTR_F32, (n + 3) // 4 * 4
+        raise ValueError("logits_dtype must be torch.float32 or torch.bfloat16")
+
+    def _classify_greedy(self, nat, feat, plan, B, Hf, W, return_argmax):
+        """Classifier GEMM with the arg-max in its epilogue + collapse; the logits are never written (K7c)."""
+        n = self.noutput
+        code, pitch = self._logits_layout(nat)
+        dev = feat.device
+        lib = nat.lib()
+        raw = torch.empty((B, W), dtype=torch.int32, device=dev)
+        idx = torch.zeros((B, W), dtype=torch.int32, device=dev)
+        ln = torch.zeros((B,), dtype=torch.int32, device=dev)
+        wsb = lib.hctr_classifier_greedy_workspace_bytes(B, W, n)
+        ws = torch.empty((wsb + 16,), dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 16
+        self._launch(nat, "classifier_greedy", 2.0 * B * W * n * Hf * plan.cf, 2.0 * feat.numel() + 2.0 * plan.cls_w.numel() + wsb,
+                     lib.hctr_classifier_greedy_fwd, nat.ptr(feat), nat.ptr(plan.cls_w), nat.ptr(plan.cls_b), None, code, pitch,
+                     B, Hf, W, plan.cf, n, nat.ptr(raw), nat.ptr(idx), nat.ptr(ln), nat.c_void_p(ws.data_ptr() + off), wsb,
+                     nat.stream_ptr())
+        self.launch_count += 2                      # + the arg-max fix-up and the collapse kernel
+        return (idx, ln, raw) if return_argmax else (idx, ln)
+
+    def _classify(self, nat, feat, plan, B, Hf, W):
+        n = self.noutput
+        code, pitch = self._logits_layout(nat)
         logits = torch.empty((B, W, pitch), dtype=self.logits_dtype, device=feat.device)
         self._launch(nat, "classifier", 2.0 * B * W * n * Hf * plan.cf,
                      2.0 * feat.numel() + logits.numel() * logits.element_size() + 2.0 * plan.cls_w.numel(),

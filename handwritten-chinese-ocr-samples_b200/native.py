@@ -43,7 +43,10 @@ SIGNATURES = {
     "hctr_classifier_fwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _P]),
     "hctr_classifier_lse_fwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _P, _P, _L, _P]),
     "hctr_classifier_lse_workspace_bytes": (_L, [_I, _I, _I]),
+    "hctr_classifier_greedy_fwd": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _L, _P]),
+    "hctr_classifier_greedy_workspace_bytes": (_L, [_I, _I, _I]),
     "hctr_ctc_greedy_decode": (_I, [_P, _I, _I, _I, _I, _L, _L, _P, _P, _P, _P]),
+    "hctr_ctc_collapse": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "hctr_ctc_topk_logsoftmax": (_I, [_P, _I, _I, _I, _I, _L, _L, _I, _P, _P, _P, _P]),
     "hctr_ctc_prefix_beam_search": (_I, [_P, _P, _I, _I, _I, _I, _I, c_double, c_double, _P, _P, _P, _P, _P, _L, _P]),
     "hctr_ctc_beam_workspace_bytes": (_L, [_I, _I, _I]),

@@ -125,7 +125,10 @@ def recognize_lines(model, codec, images, rank=0, world=1, multiple=256, column_
             else:
                 lines = {i: resize_line(images[i], resize_height, resize_rule, device=device) for i in idx}
                 x = make_batch(lines, idx, wb, device)
-            texts = codec.decode(model(x))
+            if codec.use_beam_search or model.training or len(codec.characters) != model.noutput:
+                texts = codec.decode(model(x))
+            else:                       # greedy: the arg-max runs in the classifier epilogue, the logits are never written
+                texts = codec.indices_to_text(*model.greedy_decode(x))
             for i, t in zip(idx, texts):
                 result[i] = t
     return result

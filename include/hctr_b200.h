@@ -116,6 +116,19 @@ int hctr_classifier_lse_fwd(const void* feat, const void* w_packed, const float*
                             void* workspace, long long workspace_bytes, void* stream);
 long long hctr_classifier_lse_workspace_bytes(int B, int W, int num_classes);
 
+/* The same classifier GEMM fused with greedy decoding (hctr_model.forward :172-176 followed by
+ * ctc_codec.decode -> __greedy_search__, utils/ctc_codec.py:63-99): the epilogue keeps the first maximum per logits row
+ * and column half-tile of the values AS THEY ARE STORED in out_dtype (numpy.argmax semantics: ties -> lowest index, the first
+ * NaN beats everything), a fix-up kernel combines them into argmax_bt int32 [B][W], then blank / unknown / repeats are
+ * dropped exactly as hctr_ctc_greedy_decode does: out_idx int32 [B][W], out_len int32 [B]. logits may be NULL: the 1.93 GB
+ * of bf16 logits of a 64-line batch are then never written (nor read back by the arg-max pass); out_dtype still says how a
+ * value would have been rounded, so the result equals hctr_classifier_fwd + hctr_ctc_greedy_decode bit for bit.
+ * workspace: hctr_classifier_greedy_workspace_bytes(B, W, num_classes), 16-byte aligned. */
+int hctr_classifier_greedy_fwd(const void* feat, const void* w_packed, const float* bias, void* logits, int out_dtype,
+                               long long out_pitch, int B, int Hf, int W, int Cf, int num_classes, int32_t* argmax_bt,
+                               int32_t* out_idx, int32_t* out_len, void* workspace, long long workspace_bytes, void* stream);
+long long hctr_classifier_greedy_workspace_bytes(int B, int W, int num_classes);
+
 /* ---- CTC codec ------------------------------------------------------------------------------ */
 
 /* ctc_codec.__greedy_search__ (utils/ctc_codec.py:70-99): per (t,b) argmax over C (ties -> lowest index,
@@ -125,6 +138,9 @@ long long hctr_classifier_lse_workspace_bytes(int B, int W, int num_classes);
  * out_len: int32 [B]. */
 int hctr_ctc_greedy_decode(const void* logits, int dtype, int T, int B, int C, long long stride_t, long long stride_b,
                            int32_t* argmax_out, int32_t* out_idx, int32_t* out_len, void* stream);
+
+/* The second half of hctr_ctc_greedy_decode alone: argmax_bt int32 [B][T] raw per-step classes -> out_idx / out_len. */
+int hctr_ctc_collapse(const int32_t* argmax_bt, int T, int B, int C, int32_t* out_idx, int32_t* out_len, void* stream);
 
 /* log_softmax over C (scipy.special.log_softmax, utils/ctc_codec.py:65) fused with the per-step top-k
  * (np.argsort flip, :186). topk_idx: int32 [T][B][k] descending by log-prob (ties -> lower index first);

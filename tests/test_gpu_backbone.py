@@ -317,6 +317,93 @@ def test_classifier_fused_log_softmax(dtype):
     assert torch.equal(plain, out)                      # the fused epilogue stores the same logits
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("W,N", [(300, 7375), (77, 101), (129, 257)])
+def test_classifier_fused_greedy_decode(dtype, W, N):
+    """Classifier GEMM fused with greedy decoding: arg-max in the epilogue + collapse, logits never written ==
+    hctr_classifier_fwd followed by hctr_ctc_greedy_decode on the stored logits, bit for bit - ragged W, class counts that end
+    inside a half-tile, duplicated classes (ties -> lowest index), feature rows of NaN (first NaN = class 0), and with the
+    logits written as well."""
+    nat = _nat()
+    lib = nat.lib()
+    B = 3
+    g = torch.Generator().manual_seed(W + N)
+    feat = torch.randn(B, 4, W, 512, generator=g).cuda().to(torch.bfloat16)
+    feat[1, :, 5] = float("nan")                                       # every logit of (b=1, w=5) is NaN
+    w = (torch.randn(N, 2048, generator=g) / 20).cuda().to(torch.bfloat16)
+    bias = torch.randn(N, generator=g).cuda()
+    w[N // 2] = w[3]; bias[N // 2] = bias[3]                           # exact ties between class 3 and class N/2
+    w[N - 1] = w[3]; bias[N - 1] = bias[3]
+    bias[0] += 1.5                                                     # blanks win now and then
+    code = nat.HCTR_F32 if dtype == torch.float32 else nat.HCTR_BF16
+    pitch = (N + 7) // 8 * 8
+    plain = torch.zeros((B, W, pitch), dtype=dtype, device="cuda")
+    nat.check(lib.hctr_classifier_fwd(nat.ptr(feat), nat.ptr(w), nat.ptr(bias), nat.ptr(plain), code, pitch, B, 4, W, 512, N,
+                                      nat.stream_ptr()))
+    view = plain[:, :, :N].permute(1, 0, 2)                            # [T,B,C]
+    raw0 = torch.empty((B, W), dtype=torch.int32, device="cuda"); idx0 = torch.zeros_like(raw0)
+    ln0 = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    nat.check(lib.hctr_ctc_greedy_decode(nat.ptr(view), code, W, B, N, view.stride(0), view.stride(1), nat.ptr(raw0), nat.ptr(idx0),
+                                         nat.ptr(ln0), nat.stream_ptr()))
+    nb = lib.hctr_classifier_greedy_workspace_bytes(B, W, N)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    for write_logits in (False, True):
+        out = torch.zeros_like(plain)
+        raw = torch.full((B, W), -7, dtype=torch.int32, device="cuda"); idx = torch.zeros_like(raw)
+        ln = torch.zeros((B,), dtype=torch.int32, device="cuda")
+        nat.check(lib.hctr_classifier_greedy_fwd(nat.ptr(feat), nat.ptr(w), nat.ptr(bias), nat.ptr(out) if write_logits else None,
+                                                 code, pitch, B, 4, W, 512, N, nat.ptr(raw), nat.ptr(idx), nat.ptr(ln), nat.ptr(ws),
+                                                 nb, nat.stream_ptr()))
+        assert torch.equal(raw, raw0)
+        assert torch.equal(ln, ln0)
+        for b in range(B):
+            assert torch.equal(idx[b, :ln[b]], idx0[b, :ln0[b]])
+        if write_logits:
+            assert torch.equal(out.view(torch.int16 if dtype == torch.bfloat16 else torch.int32),
+                               plain.view(torch.int16 if dtype == torch.bfloat16 else torch.int32))       # NaNs included
+        else:
+            assert out.abs().sum().item() == 0
+    assert raw0[1, 5].item() == 0                                      # numpy: the first NaN
+    assert int((raw0 == N // 2).sum().item()) == 0 and int((raw0 == N - 1).sum().item()) == 0          # ties -> class 3
+    assert len(torch.unique(raw0)) > 5
+
+
+def test_model_greedy_decode_equals_decode_of_logits():
+    """hctr_model.greedy_decode(x) == codec.greedy_indices(model(x)) (raw arg-max, labels, lengths) for both logits dtypes,
+    BN-calibrated weights (a varied arg-max path), ragged width; and the pipeline's transcripts agree with codec.decode."""
+    from hctr_b200.models.handwritten_ctr_model import hctr_model
+    from hctr_b200.utils.ctc_codec import ctc_codec
+    from hctr_b200.pipeline import recognize_lines
+    C = 101
+    torch.manual_seed(21)
+    ref = hctr_model(C)
+    x = torch.from_numpy(synth.text_lines(3, 264, 5))
+    sd = hctr_forward.calibrate_bn({k: v.clone() for k, v in ref.state_dict().items()}, x)
+    ref.load_state_dict(sd)
+    m = ref.cuda().eval()
+    codec = ctc_codec(synth.charset(C - 2))
+    xd = x.cuda()
+    for dt in (torch.float32, torch.bfloat16):
+        m.logits_dtype = dt
+        with torch.no_grad():
+            idx0, ln0, raw0 = codec.greedy_indices(m(xd), return_argmax=True)
+            idx, ln, raw = m.greedy_decode(xd, return_argmax=True)
+        assert torch.equal(raw, raw0) and torch.equal(ln, ln0) and torch.equal(idx, idx0)
+        assert codec.indices_to_text(idx, ln) == codec.decode(m(xd))
+    assert len(torch.unique(raw0)) > 1
+    images = [((synth.text_lines(1, w, 40 + i)[0, 0] * 0.5 + 0.5) * 255).round().astype(np.uint8) for i, w in enumerate((130, 264, 300))]
+    got = recognize_lines(m, codec, images)
+    from hctr_b200.pipeline import make_batch
+    for i, im in enumerate(images):
+        wb = (im.shape[1] + 255) // 256 * 256
+        with torch.no_grad():
+            want = codec.decode(m(make_batch(images, [i], wb, xd.device)))[0]
+        assert got[i] == want
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.greedy_decode(xd)
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 8, 200, 128), (2, 4, 300, 256), (1, 6, 129, 512)])
 def test_se_gate_from_conv_input(B, H, W, C):
     """The SE gate computed BEFORE conv2 from sums of conv2's input (mean of a conv output is linear in the input) equals
