@@ -84,49 +84,70 @@ chan_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ psum,
     }
 }
 
+// Partial sums of two [B][slices][C] arrays over the slices `part, part + workers, ...` of lines b0 .. b0+LB-1 for channel c.
+// All 2*LB*U loads of a step are issued before the first use, from clamped (always valid) addresses, and masked afterwards:
+// written with `if (b0 + k < B)` around each load the compiler emits a branch per line and one round trip per load (measured:
+// 0.9 us per loop iteration, 18-21 us for the 2-block launches of the 64-channel layers).
+template <int LB, int U>
+__device__ __forceinline__ void slice_partials(const float* __restrict__ a0, const float* __restrict__ a1, int b0, int B,
+                                               int slices, int C, int c, int part, int workers, float (&x)[LB], float (&y)[LB]) {
+#pragma unroll
+    for (int k = 0; k < LB; ++k) { x[k] = 0.f; y[k] = 0.f; }
+    size_t base[LB];
+#pragma unroll
+    for (int k = 0; k < LB; ++k) base[k] = (size_t)min(b0 + k, B - 1) * slices * C + c;
+    for (int i = part; i < slices; i += U * workers) {
+        float v[U][LB], w[U][LB];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = min(i + u * workers, slices - 1);
+#pragma unroll
+            for (int k = 0; k < LB; ++k) { v[u][k] = a0[base[k] + (size_t)s * C]; w[u][k] = a1[base[k] + (size_t)s * C]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = i + u * workers < slices;
+#pragma unroll
+            for (int k = 0; k < LB; ++k) { x[k] += ok ? v[u][k] : 0.f; y[k] += ok ? w[u][k] : 0.f; }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- BN batch statistics -> scale/shift (+running stats)
-// One block = 32 channels x 8 partial workers; the workers split the slices of a line, their partials are combined in a
-// fixed order. line_sum[b][c] = sum over (h,w) of z (used by the SE squeeze and by the backward).
-__global__ void __launch_bounds__(256)
+// One block = 32 channels (lanes) x 32 workers (warps); the workers split the slices of a line, their partials are combined
+// in a fixed order. line_sum[b][c] = sum over (h,w) of z (used by the SE squeeze and by the backward).
+// The first version had 8 workers per channel and C/32 blocks in all: at 2 lines per GPU a thread walked 32-73 dependent
+// L2 round trips and the 33 launches of a step cost 0.48 ms (17-19 us each); 32 workers and four loads in flight per
+// array leave two to five round trips.
+constexpr int kFinWorkers = 32;
+
+__global__ void __launch_bounds__(32 * kFinWorkers)
 bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int B, int slices,
                    int C, int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, float momentum, float* __restrict__ running_mean,
                    float* __restrict__ running_var, float* __restrict__ mean_out,
                    float* __restrict__ invstd_out, float* __restrict__ scale_out,
                    float* __restrict__ shift_out, float* __restrict__ line_sum) {
-    constexpr int LB = 4;                                  // lines reduced per round: LB*2 independent loads per iteration
-    __shared__ float ps[LB][8][32];
-    __shared__ double pq[LB][8][32];
+    constexpr int LB = 2;                                  // lines reduced per round
+    __shared__ float ps[LB][kFinWorkers][32];
+    __shared__ double pq[LB][kFinWorkers][32];
     __shared__ float lt[LB][32];
     __shared__ double lu[LB][32];
     const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     double s = 0.0, q = 0.0;
     for (int b0 = 0; b0 < B; b0 += LB) {
-        float ls[LB];
-        double lq[LB];
+        float ls[LB], lq[LB];
+        // per-worker partials in fp32 (a worker adds at most slices/32 values), the cross-worker and cross-line sums of the
+        // squares in fp64 below
+        slice_partials<LB, 4>(psum, psq, b0, B, slices, C, min(c, C - 1), part, kFinWorkers, ls, lq);
 #pragma unroll
-        for (int k = 0; k < LB; ++k) { ls[k] = 0.f; lq[k] = 0.0; }
-        if (c < C) {
-#pragma unroll 2
-            for (int i = part; i < slices; i += 8) {
-#pragma unroll
-                for (int k = 0; k < LB; ++k) {
-                    if (b0 + k < B) {
-                        const size_t o = ((size_t)(b0 + k) * slices + i) * C + c;
-                        ls[k] += psum[o];
-                        lq[k] += (double)psq[o];
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < LB; ++k) { ps[k][part][lane] = ls[k]; pq[k][part][lane] = lq[k]; }
+        for (int k = 0; k < LB; ++k) { ps[k][part][lane] = ls[k]; pq[k][part][lane] = (double)lq[k]; }
         __syncthreads();
-        if (part < LB && b0 + part < B && c < C) {           // warp k combines the 8 partials of line b0+k, fixed order
+        if (part < LB && b0 + part < B && c < C) {           // warp k combines the partials of line b0+k, fixed order
             float t = 0.f; double u = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { t += ps[part][k][lane]; u += pq[part][k][lane]; }
+            for (int k = 0; k < kFinWorkers; ++k) { t += ps[part][k][lane]; u += pq[part][k][lane]; }
             if (line_sum) line_sum[(size_t)(b0 + part) * C + c] = t;
             lt[part][lane] = t; lu[part][lane] = u;
         }
@@ -339,32 +360,37 @@ train_bwd_reduce_kernel(ApplyParams p, const __nv_bfloat16* __restrict__ dout, f
     }
 }
 
-// Combine the per-slice partial sums of every (b,c) item into slice 0, in a fixed order (64 items x 4 workers per block).
-__global__ void __launch_bounds__(256)
+// Combine the per-slice partial sums of every (b,c) item into slice 0, in a fixed order: one block = 32 items (lanes) x 32
+// workers (warps). Only the SE layers need this pass (their finalize reads the totals of ALL channels); the other layers
+// reduce inside the finalize kernel. (First version: 64 items x 4 workers, 64-146 dependent loads per thread, 13-26 us.)
+__global__ void __launch_bounds__(32 * kFinWorkers)
 bwd_slice_reduce_kernel(float* __restrict__ pA2, float* __restrict__ pA3, int slices, int B, int C) {
-    __shared__ float s2[4][64], s3[4][64];
-    const int li = threadIdx.x & 63, part = threadIdx.x >> 6;
-    const int item = blockIdx.x * 64 + li;
+    __shared__ float s2[kFinWorkers][32], s3[kFinWorkers][32];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int item = blockIdx.x * 32 + lane;                // C % 32 == 0: the 32 items of a block share their line
     const int items = B * C;
     float x = 0.f, y = 0.f;
     size_t o0 = 0;
     if (item < items) {
         const int b = item / C, c = item - b * C;
         o0 = ((size_t)b * slices) * C + c;
-        for (int s = part; s < slices; s += 4) { x += pA2[o0 + (size_t)s * C]; y += pA3[o0 + (size_t)s * C]; }
+#pragma unroll 4
+        for (int s = part; s < slices; s += kFinWorkers) { x += pA2[o0 + (size_t)s * C]; y += pA3[o0 + (size_t)s * C]; }
     }
-    s2[part][li] = x; s3[part][li] = y;
+    s2[part][lane] = x; s3[part][lane] = y;
     __syncthreads();
-    if (part == 0 && item < items) {
-        pA2[o0] = (s2[0][li] + s2[1][li]) + (s2[2][li] + s2[3][li]);
-        pA3[o0] = (s3[0][li] + s3[1][li]) + (s3[2][li] + s3[3][li]);
+    if (part < 2 && item < items) {
+        const float (*src)[32] = part ? s3 : s2;
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < kFinWorkers; ++k) t += src[k][lane];
+        (part ? pA3 : pA2)[o0] = t;
     }
 }
 
-// BN (+SE) backward on [B,C]-sized data. One block, threads over channels; the SE FC backward is done by the
-// same block (C <= 512, Cr <= 32).
+// BN (+SE) backward on [B,C]-sized data.
 struct BwdFinalizeParams {
-    const float* pA2; const float* pA3; int slices;       // slice 0 holds the totals (bwd_slice_reduce_kernel ran first)
+    const float* pA2; const float* pA3; int slices;       // SE layers: slice 0 holds the totals (bwd_slice_reduce_kernel ran first)
     int B, C, HW;
     const float* gamma; const float* mean; const float* invstd; const float* scale; const float* shift;
     const float* line_sum;       // [B][C] sum_hw z (forward)
@@ -380,88 +406,153 @@ struct BwdFinalizeParams {
     float* R;                    // [C]
 };
 
-__global__ void __launch_bounds__(512)
+// One block per 32 channels (the first version was ONE block for the layer: 47 us for a 512-channel SE layer, 6 us otherwise,
+// behind a 13-26 us slice reduction). Everything after the slice sums is local to a channel except the SE hidden-layer
+// gradient da[b][r] = sum_c W2[c][r] du[b][c], which every block recomputes from the [B][C] totals (B*Cr*C MACs: microseconds)
+// instead of exchanging partials. Layers without a gate reduce their own channels' slices here: one launch per layer.
+// shared memory: A2o, A3o, dmo [B][32] | t1, t2 [B][32] doubles | sc [2][32] doubles | red [2*LB][32][32] (no gate)
+//                or du [B][C], da [B][Cr], pda [<=1024] (gate)
+__global__ void __launch_bounds__(32 * kFinWorkers)
 train_bwd_finalize_kernel(BwdFinalizeParams p) {
-    extern __shared__ float sm[];
-    // layout: A2[B*C], A3[B*C], dm[B*C], du[B*C], da[B*Cr]
-    float* A2 = sm; float* A3 = A2 + p.B * p.C; float* dm = A3 + p.B * p.C; float* du = dm + p.B * p.C;
-    float* da = du + p.B * p.C;
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    const int B = p.B, C = p.C, Cr = p.Cr;
+    double* t1 = reinterpret_cast<double*>(fin_smem);
+    double* t2 = t1 + B * 32;
+    double* sc = t2 + B * 32;                               // S1[32], R[32]
+    float* A2o = reinterpret_cast<float*>(sc + 64);
+    float* A3o = A2o + B * 32;
+    float* dmo = A3o + B * 32;
+    float* extra = dmo + B * 32;
     const int tid = threadIdx.x, nt = blockDim.x;
-    // the per-slice partials were already combined into slice 0 by bwd_slice_reduce_kernel (many blocks)
-    for (int i = tid; i < p.B * p.C; i += nt) {
-        const int b = i / p.C, c = i - b * p.C;
-        const size_t o = ((size_t)b * p.slices) * p.C + c;
-        A2[i] = p.pA2[o]; A3[i] = p.pA3[o]; dm[i] = 0.f;
-    }
-    __syncthreads();
-    if (p.gate) {
-        // dgate[b,c] = sum_hw d_pre * bn(z) = scale*A3 + shift*A2 ; du = dgate * g (1-g)
-        for (int i = tid; i < p.B * p.C; i += nt) {
-            const int c = i % p.C;
-            const float dg = p.scale[c] * A3[i] + p.shift[c] * A2[i];
+    const int lane = tid & 31, part = tid >> 5;
+    const int c0 = blockIdx.x * 32;
+    const int c = c0 + lane;
+
+    if (!p.gate) {
+        // slice sums of this block's 32 channels, LB lines per round, fixed-order combine
+        constexpr int LB = 4;
+        float (*red)[kFinWorkers][32] = reinterpret_cast<float (*)[kFinWorkers][32]>(extra);     // [2*LB]
+        for (int b0 = 0; b0 < B; b0 += LB) {
+            float x[LB], y[LB];
+            slice_partials<LB, 2>(p.pA2, p.pA3, b0, B, p.slices, C, c, part, kFinWorkers, x, y);
+#pragma unroll
+            for (int k = 0; k < LB; ++k) { red[k][part][lane] = x[k]; red[LB + k][part][lane] = y[k]; }
+            __syncthreads();
+            if (part < 2 * LB) {
+                const int k = part < LB ? part : part - LB;
+                if (b0 + k < B) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kFinWorkers; ++w) t += red[part][w][lane];
+                    (part < LB ? A2o : A3o)[(b0 + k) * 32 + lane] = t;
+                }
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < B * 32; i += nt) dmo[i] = 0.f;
+        __syncthreads();
+    } else {
+        float* du = extra; float* da = du + (size_t)B * C; float* pda = da + B * Cr;
+        // dgate[b,c] = sum_hw d_pre * bn(z) = scale*A3 + shift*A2 ; du = dgate * g (1-g)     (all channels)
+        for (int i = tid; i < B * C; i += nt) {
+            const int b = i / C, cc = i - b * C;
+            const size_t o = ((size_t)b * p.slices) * C + cc;
+            const float a2 = p.pA2[o], a3 = p.pA3[o];
+            const float dg = p.scale[cc] * a3 + p.shift[cc] * a2;
             const float g = p.gate[i];
             du[i] = dg * g * (1.f - g);
+            if (cc >= c0 && cc < c0 + 32) { A2o[b * 32 + cc - c0] = a2; A3o[b * 32 + cc - c0] = a3; }
         }
         __syncthreads();
-        // dW2[c][r] = sum_b du[b,c] * hidden[b,r]
-        for (int i = tid; i < p.C * p.Cr; i += nt) {
-            const int c = i / p.Cr, r = i - c * p.Cr;
-            float s = 0.f;
-            for (int b = 0; b < p.B; ++b) s = fmaf(du[b * p.C + c], p.se_hidden[b * p.Cr + r], s);
-            p.dw2[i] = s;
+        // da[b,r] = [hidden>0] * sum_c W2[c][r] du[b,c]: item = (b, r), the channel range split over nt/items chunks
+        const int items = B * Cr;
+        for (int i0 = 0; i0 < items; i0 += nt) {
+            const int n_here = min(items - i0, nt);
+            int chunks = nt / n_here;
+            if (chunks > C) chunks = C;
+            const int per = (C + chunks - 1) / chunks;
+            const int ch = tid / n_here, li = tid - ch * n_here;
+            if (ch < chunks) {
+                const int it = i0 + li, b = it / Cr, r = it - b * Cr;
+                const int ca = ch * per, cb = min(C, ca + per);
+                float s = 0.f;
+                for (int cc = ca; cc < cb; ++cc) s = fmaf(__ldg(p.w2 + (size_t)cc * Cr + r), du[b * C + cc], s);
+                pda[ch * n_here + li] = s;
+            }
+            __syncthreads();
+            if (tid < n_here) {
+                float s = 0.f;
+                for (int k = 0; k < chunks; ++k) s += pda[k * n_here + tid];
+                da[i0 + tid] = p.se_hidden[i0 + tid] > 0.f ? s : 0.f;
+            }
+            __syncthreads();
         }
-        // da[b,r] = [hidden>0] * sum_c W2[c][r] du[b,c]
-        for (int i = tid; i < p.B * p.Cr; i += nt) {
-            const int b = i / p.Cr, r = i - b * p.Cr;
+        // own channels: dW2[c][r] = sum_b du[b,c] * hidden[b,r]
+        for (int i = tid; i < 32 * Cr; i += nt) {
+            const int cl = i / Cr, r = i - cl * Cr;
             float s = 0.f;
-            for (int c = 0; c < p.C; ++c) s = fmaf(p.w2[c * p.Cr + r], du[b * p.C + c], s);
-            da[i] = p.se_hidden[i] > 0.f ? s : 0.f;
+            for (int b = 0; b < B; ++b) s = fmaf(du[b * C + c0 + cl], p.se_hidden[b * Cr + r], s);
+            p.dw2[(size_t)(c0 + cl) * Cr + r] = s;
         }
-        __syncthreads();
         // dW1[r][c] = sum_b da[b,r] m[b,c] ; dm[b,c] = sum_r W1[r][c] da[b,r]
-        for (int i = tid; i < p.Cr * p.C; i += nt) {
-            const int r = i / p.C, c = i - r * p.C;
+        for (int i = tid; i < Cr * 32; i += nt) {
+            const int r = i >> 5, cl = i & 31;
             float s = 0.f;
-            for (int b = 0; b < p.B; ++b) s = fmaf(da[b * p.Cr + r], p.se_mean[b * p.C + c], s);
-            p.dw1[i] = s;
+            for (int b = 0; b < B; ++b) s = fmaf(da[b * Cr + r], p.se_mean[(size_t)b * C + c0 + cl], s);
+            p.dw1[(size_t)r * C + c0 + cl] = s;
         }
-        for (int i = tid; i < p.B * p.C; i += nt) {
-            const int b = i / p.C, c = i - b * p.C;
+        for (int i = tid; i < B * 32; i += nt) {
+            const int b = i >> 5, cl = i & 31;
             float s = 0.f;
-            for (int r = 0; r < p.Cr; ++r) s = fmaf(p.w1[r * p.C + c], da[b * p.Cr + r], s);
-            dm[i] = s;
+            for (int r = 0; r < Cr; ++r) s = fmaf(p.w1[(size_t)r * C + c0 + cl], da[b * Cr + r], s);
+            dmo[i] = s;
         }
         __syncthreads();
     }
-    const double n = (double)p.B * (double)p.HW;
-    for (int c = tid; c < p.C; c += nt) {
-        const double mu = p.mean[c], is = p.invstd[c];
+
+    // per-(b, channel) terms in fp64, summed over the lines in line order by one thread per channel
+    const double n = (double)B * (double)p.HW;
+    const double mu = p.mean[c], is = p.invstd[c];
+    for (int i = tid; i < B * 32; i += nt) {
+        const int b = i >> 5;                               // i & 31 == lane
+        const size_t gi = (size_t)b * C + c;
+        const double g = p.gate ? (double)p.gate[gi] : 1.0;
+        const double a2 = A2o[i], a3 = A3o[i];
+        const double dmb = dmo[i];
+        const double x1 = ((double)p.line_sum[gi] - (double)p.HW * mu) * is;     // sum_hw xhat
+        t1[i] = g * a2 + dmb;
+        t2[i] = g * (a3 - mu * a2) * is + dmb / (double)p.HW * x1;
+    }
+    __syncthreads();
+    const double gis = (double)p.gamma[c] * is;
+    if (part == 0) {
         double S1 = 0.0, S2 = 0.0;
-        for (int b = 0; b < p.B; ++b) {
-            const int i = b * p.C + c;
-            const double g = p.gate ? (double)p.gate[i] : 1.0;
-            const double a2 = A2[i], a3 = A3[i];
-            const double dmb = dm[i];
-            const double x1 = ((double)p.line_sum[i] - (double)p.HW * mu) * is;     // sum_hw xhat
-            S1 += g * a2 + dmb;
-            S2 += g * (a3 - mu * a2) * is + dmb / (double)p.HW * x1;
-        }
+        for (int b = 0; b < B; ++b) { S1 += t1[b * 32 + lane]; S2 += t2[b * 32 + lane]; }
         p.dgamma[c] = (float)S2;
         p.dbeta[c] = (float)S1;
-        const double gi = (double)p.gamma[c] * is;
-        const double R = -gi * is * S2 / n;
+        const double R = -gis * is * S2 / n;
         p.R[c] = (float)R;
-        double dbias = 0.0;
-        for (int b = 0; b < p.B; ++b) {
-            const int i = b * p.C + c;
-            const double g = p.gate ? (double)p.gate[i] : 1.0;
-            const double Pv = gi * g;
-            const double Qv = gi * ((double)dm[i] / (double)p.HW - S1 / n) - R * mu;
-            p.P[i] = (float)Pv;
-            p.Q[i] = (float)Qv;
-            dbias += Pv * (double)A2[i] + Qv * (double)p.HW + R * (double)p.line_sum[i];
+        sc[lane] = S1; sc[32 + lane] = R;
+    }
+    __syncthreads();
+    {
+        const double S1 = sc[lane], R = sc[32 + lane];
+        for (int i = tid; i < B * 32; i += nt) {
+            const int b = i >> 5;
+            const size_t gi = (size_t)b * C + c;
+            const double g = p.gate ? (double)p.gate[gi] : 1.0;
+            const double Pv = gis * g;
+            const double Qv = gis * ((double)dmo[i] / (double)p.HW - S1 / n) - R * mu;
+            p.P[gi] = (float)Pv;
+            p.Q[gi] = (float)Qv;
+            t1[i] = Pv * (double)A2o[i] + Qv * (double)p.HW + R * (double)p.line_sum[gi];
         }
-        if (p.dbias) p.dbias[c] = (float)dbias;
+    }
+    __syncthreads();
+    if (part == 0 && p.dbias) {
+        double dbias = 0.0;
+        for (int b = 0; b < B; ++b) dbias += t1[b * 32 + lane];
+        p.dbias[c] = (float)dbias;
     }
 }
 
@@ -588,7 +679,7 @@ int hctr_bn_finalize_train(const float* psum, const float* psq, int B, int slice
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                            float* mean, float* invstd, float* scale, float* shift, float* line_sum, void* stream) {
     HCTR_CHECK(psum && psq && gamma && beta && mean && invstd && scale && shift, HCTR_ERR_INVALID, "bn_finalize: null pointer");
-    bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_finalize_kernel<<<(C + 31) / 32, 32 * kFinWorkers, 0, static_cast<cudaStream_t>(stream)>>>(
         psum, psq, B, slices, C, HW, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, line_sum);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
@@ -677,18 +768,22 @@ int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int 
     p.gamma = gamma; p.mean = mean; p.invstd = invstd; p.scale = scale; p.shift = shift; p.line_sum = line_sum;
     p.gate = gate; p.se_hidden = se_hidden; p.se_mean = se_mean; p.w1 = w1; p.w2 = w2; p.Cr = gate ? Cr : 0;
     p.dw1 = dw1; p.dw2 = dw2; p.dgamma = dgamma; p.dbeta = dbeta; p.dbias = dbias; p.P = P; p.Q = Q; p.R = R;
-    const size_t smem = ((size_t)4 * B * C + (size_t)B * (gate ? Cr : 0)) * sizeof(float);
-    HCTR_CHECK(smem <= 200 * 1024, HCTR_ERR_INVALID, "train_bwd_finalize: B*C too large for one block (%zu bytes)", smem);
+    HCTR_CHECK(C % 32 == 0, HCTR_ERR_INVALID, "train_bwd_finalize: C must be a multiple of 32 (C=%d)", C);
+    const size_t smem = (size_t)(2 * B * 32 + 64) * sizeof(double) + (size_t)3 * B * 32 * sizeof(float) +
+                        (gate ? ((size_t)B * C + (size_t)B * Cr + 1024) : (size_t)8 * kFinWorkers * 32) * sizeof(float);
+    HCTR_CHECK(smem <= 200 * 1024, HCTR_ERR_INVALID, "train_bwd_finalize: B*C too large for a block's shared memory (%zu bytes)", smem);
     static PerDeviceOnce once;
     int dev;
     if (once.need(dev)) {
         HCTR_CUDA(cudaFuncSetAttribute(train_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         once.mark(dev);
     }
-    bwd_slice_reduce_kernel<<<(B * C + 63) / 64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        const_cast<float*>(pA2), const_cast<float*>(pA3), slices, B, C);
-    HCTR_CUDA(cudaGetLastError());
-    train_bwd_finalize_kernel<<<1, 512, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    if (gate) {
+        bwd_slice_reduce_kernel<<<(B * C + 31) / 32, 32 * kFinWorkers, 0, static_cast<cudaStream_t>(stream)>>>(
+            const_cast<float*>(pA2), const_cast<float*>(pA3), slices, B, C);
+        HCTR_CUDA(cudaGetLastError());
+    }
+    train_bwd_finalize_kernel<<<C / 32, 32 * kFinWorkers, smem, static_cast<cudaStream_t>(stream)>>>(p);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }

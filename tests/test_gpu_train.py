@@ -147,11 +147,14 @@ def test_fused_train_step_matches_reference_loop():
         gn = torch.nn.utils.clip_grad_norm_(ma.parameters(), max_norm=5.0)
         opt.step()
         lb = ts.step(x, tg, tl)
-        # step 0 runs the same kernels on identical weights; later steps start from weights that differ in the last
-        # fp32 bits (fused vs torch SGD), which flips bf16 roundings of weights/activations: bf16-level agreement only
+        # step 0 runs the same forward kernels on identical weights (same loss); its gradients agree only to bf16 level: the
+        # fused step takes the rows' log-sum-exp from the classifier epilogue, the CTCLoss module reduces the stored logits
+        # itself - one ulp between the two flips bf16 roundings of the logits gradient, and the flips grow to ~1 % in the
+        # earliest layers (with the same log-sum-exp source the two paths are bit-identical; measured). Later steps also
+        # start from weights that differ in the last fp32 bits (fused vs torch SGD).
         tol = 1e-5 if step == 0 else 3e-2
         assert abs(la.item() - lb.item()) <= tol * abs(la.item()) + 1e-5, (step, la.item(), lb.item())
-        assert abs(ts.norm[0].item() - gn.item()) <= (1e-4 if step == 0 else 0.1) * gn.item(), (step, ts.norm[0].item(), gn.item())
+        assert abs(ts.norm[0].item() - gn.item()) <= (2e-3 if step == 0 else 0.1) * gn.item(), (step, ts.norm[0].item(), gn.item())
     for (ka, pa), (kb, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         assert ka == kb
         assert (pa - pb).abs().max().item() <= 5e-3 * max(1.0, pa.abs().max().item()), ka

@@ -66,7 +66,9 @@ def test_conv_wgrad_and_dgrad(B, H, W, Cin, Cout, k):
 @pytest.mark.parametrize("B,H,W,C,gate,res,relu,pool", [(2, 8, 200, 64, 0, 0, 1, 1), (2, 8, 136, 128, 0, 0, 1, 0),
                                                          (2, 8, 136, 128, 1, 1, 1, 0), (3, 4, 300, 256, 1, 1, 1, 0),
                                                          (2, 4, 130, 512, 1, 1, 1, 0), (2, 4, 130, 512, 0, 0, 1, 1),
-                                                         (2, 4, 100, 256, 0, 0, 0, 0), (16, 2, 64, 512, 1, 1, 1, 0)])
+                                                         (2, 4, 100, 256, 0, 0, 0, 0), (16, 2, 64, 512, 1, 1, 1, 0),
+                                                         (2, 16, 520, 256, 1, 1, 1, 0), (2, 32, 512, 64, 0, 0, 1, 1),
+                                                         (5, 8, 264, 128, 0, 1, 1, 0), (33, 2, 40, 64, 1, 0, 1, 0)])
 def test_bn_se_act_unit_forward_backward(B, H, W, C, gate, res, relu, pool):
     """BatchNorm(train) [+SE] [+residual] [+ReLU] [+(2,1) pool]: forward, running stats, dz, dres, dgamma, dbeta, SE grads."""
     nat = _nat(); lib = nat.lib(); S = nat.stream_ptr
