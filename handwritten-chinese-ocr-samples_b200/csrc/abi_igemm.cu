@@ -256,7 +256,8 @@ int hctr_device_supported(int device) {
 
 static int conv_launch(const void* x, const void* w_packed, const float* scale, const float* shift, const void* add,
                        void* y, int B, int H, int W, int Cin, int Cout, int ksize, int relu, int pool, int flip,
-                       void* stream, float* se_partial = nullptr, int sum_stored = 0, const float* gate = nullptr) {
+                       void* stream, float* se_partial = nullptr, int sum_stored = 0, const float* gate = nullptr,
+                       float* sq_partial = nullptr) {
     HCTR_CHECK(x && w_packed && scale && shift && y, HCTR_ERR_INVALID, "conv: null pointer");
     HCTR_CHECK(ksize == 1 || ksize == 3, HCTR_ERR_INVALID, "conv: ksize must be 1 or 3 (got %d)", ksize);
     HCTR_CHECK(B > 0 && H > 0 && W > 0, HCTR_ERR_INVALID, "conv: empty tensor %dx%dx%d", B, H, W);
@@ -286,6 +287,7 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     p.add = add;
     p.se_partial = se_partial;
     p.sum_stored = sum_stored;
+    p.sq_partial = sq_partial;
     p.gate = gate;
     p.N = Cout;
     p.w_tiles = (W + kTileM - 1) / kTileM;
@@ -373,6 +375,12 @@ int hctr_conv_bn_act_sum_fwd(const void* x, const void* w_packed, const float* s
                              float* partial, int B, int H, int W, int Cin, int Cout, int ksize, int relu, void* stream) {
     HCTR_CHECK(partial != nullptr, HCTR_ERR_INVALID, "conv_bn_act_sum: null partial buffer");
     return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, relu, 0, 0, stream, partial, 1);
+}
+
+int hctr_conv_stats_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, float* psum,
+                        float* psq, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {
+    HCTR_CHECK(psum != nullptr && psq != nullptr, HCTR_ERR_INVALID, "conv_stats: null partial buffer");
+    return conv_launch(x, w_packed, scale, shift, nullptr, y, B, H, W, Cin, Cout, ksize, 0, 0, 0, stream, psum, 1, nullptr, psq);
 }
 
 int hctr_conv_bn_gate_res_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, const float* gate,

@@ -376,9 +376,22 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }                                                                 \
                         }
                         HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
-#undef HCTR_BFLY
                         const size_t slot = ((static_cast<size_t>(b) * p.H + h) * p.w_tiles + w_tile) * 4 + quad;
                         if (h < p.H) p.se_partial[slot * p.N + n0 + lane] = tsum[0];
+                        if (p.sq_partial) {                          // train-mode BN: sum of squares of the same values
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = v[j];
+                                if (p.sum_stored) {
+                                    if (p.relu) x = fmaxf(x, 0.f);
+                                    x = __bfloat162float(__float2bfloat16_rn(x));
+                                }
+                                tsum[j] = ok ? x * x : 0.f;
+                            }
+                            HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
+                            if (h < p.H) p.sq_partial[slot * p.N + n0 + lane] = tsum[0];
+                        }
+#undef HCTR_BFLY
                     }
                 }
                 // pack to bf16, stage this lane's pixel row, write the chunk out as 64-byte runs

@@ -52,6 +52,8 @@ struct IgemmParams {
                               // epilogue output (the SE squeeze folded into the producing conv; deterministic)
     int sum_stored;           // 1: the sums are taken over the values as STORED (after gate/add/ReLU, rounded to bf16) -
                               // what the next convolution will read - instead of the fp32 BN output
+    float* sq_partial;        // EPI_CONV: optional, same slots as se_partial: sums of the SQUARES of the same values (train-mode
+                              // BatchNorm statistics of z = conv(x)+bias taken in the epilogue: no separate pass over z)
     const float* gate;        // EPI_CONV: optional [B][N] per-(line, channel) factor applied after BN, before `add`
                               // (the SE gate folded into the producing conv: out = relu(bn(conv)*gate + add))
     int out_dtype;            // EPI_LINEAR: HCTR_F32 | HCTR_BF16
@@ -355,9 +357,28 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             }                                                                 \
                         }
                         HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
-#undef HCTR_BFLY
                         const size_t slot = ((static_cast<size_t>(b) * p.h_tiles * p.w_tiles + static_cast<size_t>(h_tile) * p.w_tiles + w_tile) * 4 + quad);
                         p.se_partial[slot * p.N + n0 + lane] = tsum[0];
+                        if (p.sq_partial) {                          // train-mode BN: sum of squares of the same values
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float a = 0.f;
+#pragma unroll
+                                for (int s = 0; s < NUM_SUB; ++s) {
+                                    const bool ok = (w0 + s * p.sub_dw * kTileM + pix < p.W) && (h0 + s * p.sub_dh < p.out_H);
+                                    float x = v[s][j];
+                                    if (p.sum_stored) {
+                                        if (p.relu) x = fmaxf(x, 0.f);
+                                        x = __bfloat162float(__float2bfloat16_rn(x));
+                                    }
+                                    a = ok ? fmaf(x, x, a) : a;
+                                }
+                                tsum[j] = a;
+                            }
+                            HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
+                            p.sq_partial[slot * p.N + n0 + lane] = tsum[0];
+                        }
+#undef HCTR_BFLY
                     }
                     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
                     if (p.pool) {

@@ -90,12 +90,14 @@ chan_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ psum,
 // 0.9 us per loop iteration, 18-21 us for the 2-block launches of the 64-channel layers).
 template <int LB, int U>
 __device__ __forceinline__ void slice_partials(const float* __restrict__ a0, const float* __restrict__ a1, int b0, int B,
-                                               int slices, int C, int c, int part, int workers, float (&x)[LB], float (&y)[LB]) {
+                                               int slices, int C, int c, int part, int workers, float (&x)[LB], float (&y)[LB],
+                                               int line_stride = 0) {
+    if (line_stride == 0) line_stride = slices;          // slices per line in memory (>= the `slices` that are summed)
 #pragma unroll
     for (int k = 0; k < LB; ++k) { x[k] = 0.f; y[k] = 0.f; }
     size_t base[LB];
 #pragma unroll
-    for (int k = 0; k < LB; ++k) base[k] = (size_t)min(b0 + k, B - 1) * slices * C + c;
+    for (int k = 0; k < LB; ++k) base[k] = (size_t)min(b0 + k, B - 1) * line_stride * C + c;
     for (int i = part; i < slices; i += U * workers) {
         float v[U][LB], w[U][LB];
 #pragma unroll
@@ -122,7 +124,7 @@ __device__ __forceinline__ void slice_partials(const float* __restrict__ a0, con
 constexpr int kFinWorkers = 32;
 
 __global__ void __launch_bounds__(32 * kFinWorkers)
-bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int B, int slices,
+bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq, int B, int slices, int line_stride,
                    int C, int HW, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, float momentum, float* __restrict__ running_mean,
                    float* __restrict__ running_var, float* __restrict__ mean_out,
@@ -140,7 +142,7 @@ bn_finalize_kernel(const float* __restrict__ psum, const float* __restrict__ psq
         float ls[LB], lq[LB];
         // per-worker partials in fp32 (a worker adds at most slices/32 values), the cross-worker and cross-line sums of the
         // squares in fp64 below
-        slice_partials<LB, 4>(psum, psq, b0, B, slices, C, min(c, C - 1), part, kFinWorkers, ls, lq);
+        slice_partials<LB, 4>(psum, psq, b0, B, slices, C, min(c, C - 1), part, kFinWorkers, ls, lq, line_stride);
 #pragma unroll
         for (int k = 0; k < LB; ++k) { ps[k][part][lane] = ls[k]; pq[k][part][lane] = (double)lq[k]; }
         __syncthreads();
@@ -679,8 +681,17 @@ int hctr_bn_finalize_train(const float* psum, const float* psq, int B, int slice
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                            float* mean, float* invstd, float* scale, float* shift, float* line_sum, void* stream) {
     HCTR_CHECK(psum && psq && gamma && beta && mean && invstd && scale && shift, HCTR_ERR_INVALID, "bn_finalize: null pointer");
+    int used = slices;
+    if (slices > 2 * kFinWorkers) {
+        // many partials per line (the conv epilogue's per-(row, span, warp) slots, or long lines): one block per (line, 32
+        // channels) first adds a line's partials into its slice 0, in a fixed order
+        bwd_slice_reduce_kernel<<<(B * C + 31) / 32, 32 * kFinWorkers, 0, static_cast<cudaStream_t>(stream)>>>(
+            const_cast<float*>(psum), const_cast<float*>(psq), slices, B, C);
+        HCTR_CUDA(cudaGetLastError());
+        used = 1;
+    }
     bn_finalize_kernel<<<(C + 31) / 32, 32 * kFinWorkers, 0, static_cast<cudaStream_t>(stream)>>>(
-        psum, psq, B, slices, C, HW, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, line_sum);
+        psum, psq, B, used, slices, C, HW, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, line_sum);
     HCTR_CUDA(cudaGetLastError());
     return HCTR_OK;
 }

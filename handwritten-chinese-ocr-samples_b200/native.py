@@ -33,6 +33,7 @@ SIGNATURES = {
     "hctr_conv_bn_se_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hctr_conv_sum_slices": (_I, [_I, _I, _I, _I, _I]),
     "hctr_conv_bn_act_sum_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "hctr_conv_stats_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "hctr_se_gate_workspace_bytes": (_L, [_I, _I]),
     "hctr_se_gate_from_input": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "hctr_conv_bn_gate_res_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

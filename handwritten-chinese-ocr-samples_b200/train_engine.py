@@ -9,6 +9,8 @@ Per conv+BN unit:
 Parameters stay fp32 `nn.Parameter`s in the reference layout; gradients are produced in that layout (optionally straight
 into one flat buffer for the NCCL all-reduce + fused clip/SGD tail). No torch op touches an activation tensor.
 """
+import os
+
 import torch
 
 from . import native as nat
@@ -20,6 +22,9 @@ def _mix_seed(base, k):
     x = (x * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
     x ^= x >> 29
     return int(x & 0xFFFFFFFF)
+
+
+_FOLD_STATS = int(os.environ.get("HCTR_TRAIN_FOLD_STATS", "1"))
 
 
 class _Saved(object):
@@ -137,18 +142,30 @@ class TrainEngine(object):
         cout, cin, k = conv.weight.shape[0], conv.weight.shape[1], conv.weight.shape[2]
         bias = conv.bias.detach().float().contiguous() if conv.bias is not None else self.zeros(cout, dev)
         z = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=dev)
+        # BatchNorm batch statistics: taken in the conv epilogue (per-(row, span, warp) sums of z and z*z as stored) where the
+        # epilogue hides under the main loop - the CTA-pair layers, Cout >= 256 - and by a pass over z otherwise (the thin and 1x1
+        # layers' epilogues are exposed; measured). HCTR_TRAIN_FOLD_STATS=0 / 2: never / every tensor-core conv.
+        fold = (not stem) and (_FOLD_STATS == 2 or (_FOLD_STATS == 1 and k == 3 and cout >= 256 and H % 2 == 0))
         if stem:
             w = conv.weight.detach().float().reshape(cout, 9).contiguous()
             nat.check(lib.hctr_stem_conv_fwd(nat.ptr(x), nat.ptr(w), nat.ptr(self.ones(cout, dev)), nat.ptr(bias), nat.ptr(z),
                                              B, H, W, 0, st), "stem")
         else:
             w = self._pack["vf"][id(conv.weight)]
-            nat.check(lib.hctr_conv_bn_act_fwd(nat.ptr(x), nat.ptr(w), nat.ptr(self.ones(cout, dev)), nat.ptr(bias), nat.ptr(z),
-                                               B, H, W, cin, cout, k, 0, 0, st), "conv")
-        slices = lib.hctr_stat_slices(B, H, W)
-        psum = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
-        psq = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
-        nat.check(lib.hctr_chan_stats(nat.ptr(z), nat.ptr(psum), nat.ptr(psq), B, H, W, cout, st), "chan_stats")
+        if fold:
+            slices = lib.hctr_conv_sum_slices(H, W, cin, cout, k)
+            psum = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
+            psq = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
+            nat.check(lib.hctr_conv_stats_fwd(nat.ptr(x), nat.ptr(w), nat.ptr(self.ones(cout, dev)), nat.ptr(bias), nat.ptr(z),
+                                              nat.ptr(psum), nat.ptr(psq), B, H, W, cin, cout, k, st), "conv_stats")
+        else:
+            if not stem:
+                nat.check(lib.hctr_conv_bn_act_fwd(nat.ptr(x), nat.ptr(w), nat.ptr(self.ones(cout, dev)), nat.ptr(bias), nat.ptr(z),
+                                                   B, H, W, cin, cout, k, 0, 0, st), "conv")
+            slices = lib.hctr_stat_slices(B, H, W)
+            psum = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
+            psq = torch.empty((B, slices, cout), dtype=torch.float32, device=dev)
+            nat.check(lib.hctr_chan_stats(nat.ptr(z), nat.ptr(psum), nat.ptr(psq), B, H, W, cout, st), "chan_stats")
         stats = torch.empty((4, cout), dtype=torch.float32, device=dev)         # mean, invstd, scale, shift
         line_sum = torch.empty((B, cout), dtype=torch.float32, device=dev)
         track = bn.track_running_stats and bn.running_mean is not None

@@ -79,6 +79,13 @@ int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale,
 int hctr_conv_sum_slices(int H, int W, int Cin, int Cout, int ksize);
 int hctr_conv_bn_act_sum_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y,
                              float* partial, int B, int H, int W, int Cin, int Cout, int ksize, int relu, void* stream);
+/* Train-mode convolution with the BatchNorm batch statistics taken in its epilogue (nn.BatchNorm2d in train(),
+ * models/handwritten_ctr_model.py:38,40,74-92 - F.batch_norm's mean / biased variance over (B,H,W)): z = conv(x)*scale + shift
+ * (bf16 NHWC, no ReLU) plus per-(tile row, 128-px span, warp quarter) sums of z and z*z AS STORED (bf16-rounded), both
+ * fp32 [B][hctr_conv_sum_slices(H,W,Cin,Cout,ksize)][Cout] - the layout hctr_chan_stats produces with its own slice count, so
+ * hctr_bn_finalize_train(psum, psq, B, slices = hctr_conv_sum_slices(...), ...) finishes them. Replaces one full read of z. */
+int hctr_conv_stats_fwd(const void* x, const void* w_packed, const float* scale, const float* shift, void* y, float* psum,
+                        float* psq, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 long long hctr_se_gate_workspace_bytes(int B, int C);
 int hctr_se_gate_from_input(const void* t, const float* partial, int slices, const void* conv_w_packed, const float* scale,
                             const float* shift, const float* w1, const float* w2, float* gate, int B, int H, int W, int C,

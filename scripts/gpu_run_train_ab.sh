@@ -1,16 +1,12 @@
 #!/bin/bash
-# same-box A/B of the training step: the library as built vs csrc/_build/libhctr_old.so (boxes of the pool differ by 2-3 %)
+# training parity, then a same-box A/B of the training step over HCTR_TRAIN_FOLD_STATS (boxes of the pool differ by 2-3 %)
 mkdir -p gpurun_out
-L=handwritten-chinese-ocr-samples_b200/libhctr_b200.so
 timeout 600 python -m pytest tests/test_gpu_train_kernels.py tests/test_gpu_train.py -q -m gpu --timeout 300 > gpurun_out/t_pytest.log 2>&1; echo "pytest rc=$?"
-tail -n 3 gpurun_out/t_pytest.log
-cp $L /tmp/new.so
+tail -n 12 gpurun_out/t_pytest.log | cut -c1-300
 for rep in 1 2; do
-for v in new old; do
-  if [ $v = old ]; then cp handwritten-chinese-ocr-samples_b200/csrc/_build/libhctr_old.so $L; else cp /tmp/new.so $L; fi
+for v in 1 0 2; do
   for n in 2 16; do
-    timeout 300 python scripts/train_bench.py --lines-per-gpu $n --steps 10 --warmup 4 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v lines', d['lines_per_gpu'], 'ms', round(d['ms_per_step'],3))"
+    HCTR_TRAIN_FOLD_STATS=$v timeout 300 python scripts/train_bench.py --lines-per-gpu $n --steps 10 --warmup 4 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('fold=$v lines', d['lines_per_gpu'], 'ms', round(d['ms_per_step'],3), 'loss', d['loss'])"
   done
 done
 done
-cp /tmp/new.so $L

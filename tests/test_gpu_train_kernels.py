@@ -262,3 +262,42 @@ def test_pack_weights_matches_torch_layouts():
             wk = w.reshape(co, ci, t).permute(0, 2, 1).contiguous().to(torch.bfloat16).reshape(co, t * ci)      # k = h*Cf + c
             assert torch.equal(f.view(co, t * ci), wk)
             assert torch.equal(b.view(t * ci, p)[:, :co], wk.t()) and b.view(t * ci, p)[:, co:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 4, 300, 256, 512, 3), (3, 8, 136, 256, 256, 3), (2, 6, 200, 128, 128, 3),
+                                               (2, 8, 130, 64, 64, 3), (2, 4, 200, 128, 256, 1), (2, 5, 96, 64, 128, 3)])
+def test_conv_with_batch_statistics_in_the_epilogue(B, H, W, Cin, Cout, k):
+    """hctr_conv_stats_fwd: z equals hctr_conv_bn_act_fwd's bit for bit, and its per-slot sums of z and z*z, finished by
+    hctr_bn_finalize_train, give the statistics of the STORED (bf16) z - CTA-pair and single-CTA kernels, ragged widths, odd H."""
+    nat = _nat(); lib = nat.lib(); S = nat.stream_ptr
+    g = torch.Generator().manual_seed(B * 7 + W + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda().to(torch.bfloat16)
+    bias = (0.5 * torch.randn(Cout, generator=g)).cuda()
+    ones = torch.ones(Cout, device="cuda")
+    xn = x.permute(0, 2, 3, 1).contiguous(); wp = w.permute(0, 2, 3, 1).contiguous()
+    z0 = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+    nat.check(lib.hctr_conv_bn_act_fwd(nat.ptr(xn), nat.ptr(wp), nat.ptr(ones), nat.ptr(bias), nat.ptr(z0), B, H, W, Cin, Cout, k, 0, 0, S()))
+    slices = lib.hctr_conv_sum_slices(H, W, Cin, Cout, k)
+    ps = torch.full((B, slices, Cout), float("nan"), device="cuda"); pq = torch.full((B, slices, Cout), float("nan"), device="cuda")
+    z1 = torch.empty_like(z0)
+    nat.check(lib.hctr_conv_stats_fwd(nat.ptr(xn), nat.ptr(wp), nat.ptr(ones), nat.ptr(bias), nat.ptr(z1), nat.ptr(ps), nat.ptr(pq),
+                                      B, H, W, Cin, Cout, k, S()))
+    assert torch.equal(z0, z1)
+    zf = z1.double()
+    assert torch.isfinite(ps).all() and torch.isfinite(pq).all()
+    s_ref, q_ref = zf.sum(dim=(1, 2)), (zf * zf).sum(dim=(1, 2))
+    assert (ps.double().sum(dim=1) - s_ref).abs().max().item() <= 1e-5 * zf.abs().sum(dim=(1, 2)).max().item()
+    assert (pq.double().sum(dim=1) - q_ref).abs().max().item() <= 1e-5 * q_ref.max().item()
+    gamma = (torch.rand(Cout, generator=g) + 0.5).cuda(); beta = (0.2 * torch.randn(Cout, generator=g)).cuda()
+    st = torch.empty(4, Cout, device="cuda"); line = torch.empty(B, Cout, device="cuda")
+    rm = torch.zeros(Cout, device="cuda"); rv = torch.ones(Cout, device="cuda")
+    nat.check(lib.hctr_bn_finalize_train(nat.ptr(ps), nat.ptr(pq), B, slices, Cout, H * W, nat.ptr(gamma), nat.ptr(beta), 1e-5, 0.1,
+                                         nat.ptr(rm), nat.ptr(rv), nat.ptr(st[0]), nat.ptr(st[1]), nat.ptr(st[2]), nat.ptr(st[3]),
+                                         nat.ptr(line), S()))
+    zc = zf.reshape(-1, Cout)
+    mean, var = zc.mean(dim=0), zc.var(dim=0, unbiased=False)
+    _close(st[0], mean.float(), 1e-5)
+    _close(st[1], (1.0 / torch.sqrt(var + 1e-5)).float(), 1e-4)
+    _close(line, s_ref.float(), 1e-5)
+    _close(rv, (0.9 + 0.1 * zc.var(dim=0, unbiased=True)).float(), 1e-4)
