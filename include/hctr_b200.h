@@ -244,7 +244,9 @@ long long hctr_ctc_loss_flag_offset(int T, int B, int max_target_len);
 int hctr_stat_slices(int B, int H, int W);
 int hctr_chan_stats(const void* x, float* psum, float* psq, int B, int H, int W, int C, void* stream);
 /* Batch mean / biased variance -> invstd, scale = gamma*invstd, shift = beta - mean*scale; updates running stats with
- * `momentum` and the unbiased variance (pass NULL to skip); line_sum: fp32 [B][C] = sum over (h,w) (may be NULL). */
+ * `momentum` and the unbiased variance (pass NULL to skip); line_sum: fp32 [B][C] = sum over (h,w) (may be NULL).
+ * The partials are consumed: with more than 64 slices per line (the conv epilogue's slots, hctr_conv_stats_fwd) each line's
+ * partials are first added into its slice 0 in place. */
 int hctr_bn_finalize_train(const float* psum, const float* psq, int B, int slices, int C, int HW, const float* gamma,
                            const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                            float* mean, float* invstd, float* scale, float* shift, float* line_sum, void* stream);
@@ -264,7 +266,8 @@ int hctr_train_apply_fwd(const void* z, const float* scale, const float* shift, 
  * the coefficients P[B][C], Q[B][C], R[C]; apply -> dz = P*d_pre + Q + R*z, dres = d_pre. */
 int hctr_train_bwd_reduce(const void* dout, const void* z, const void* mask, float* pA2, float* pA3, int B, int H, int W,
                           int C, int pool, float drop_p, void* stream);
-/* (finalize combines the per-slice partials in place: slice 0 of pA2/pA3 is overwritten with the totals) */
+/* (finalize consumes the per-slice partials: for layers with an SE gate slice 0 of pA2/pA3 is overwritten with the totals;
+ *  C must be a multiple of 32) */
 int hctr_train_bwd_finalize(const float* pA2, const float* pA3, int slices, int B, int C, int HW, const float* gamma,
                             const float* mean, const float* invstd, const float* scale, const float* shift,
                             const float* line_sum, const float* gate, const float* se_hidden, const float* se_mean,
