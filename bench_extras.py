@@ -320,24 +320,32 @@ def gpu_library_leg(dev, width, lines=16, steps=3):
 
 def b1_latency_leg(model, codec, dev):
     """Latency of a single line through the public API (device-resident fp32 input -> strings), synchronised per call:
-    BASELINE configs[0] shape (batch 1, the five bundled widths) and one 128x2048 line."""
+    BASELINE configs[0] shape (batch 1, the five bundled widths) and one 128x2048 line. Measured twice: every call issued
+    kernel by kernel (`*_eager`), and with the shapes replayed from CUDA graphs (the default for small batches: captured on
+    the third call with a shape, hctr_model._forward_eval)."""
     import synth
     out = {}
+    prev = getattr(model, "cuda_graphs", True)
     with torch.no_grad():
         for name, widths in (("line_128x2048", [2048]), ("config1_widths_3514_908_2375_1913_488", [3514, 908, 2375, 1913, 488])):
             xs = [torch.from_numpy(synth.text_lines(1, w, 40 + i)).to(dev) for i, w in enumerate(widths)]
-            for x in xs:                                        # warm-up: plan, shapes, allocator
-                codec.decode(model(x))
-            torch.cuda.synchronize()
-            samples = []
-            for _ in range(10):
-                t0 = time.perf_counter()
-                for x in xs:
-                    codec.decode(model(x))
-                samples.append((time.perf_counter() - t0) * 1e3)
-            samples.sort()
-            out[name] = {"median_ms": samples[len(samples) // 2], "min_ms": samples[0], "calls": len(widths)}
-            # device time alone (events around the same calls, no host sync in between)
-            ms = _timeit(lambda: [codec.greedy_indices(model(x)) for x in xs], 10, 2)
-            out[name]["device_ms"] = ms
+            out[name] = {"calls": len(widths)}
+            for graphs, sfx in ((False, "_eager"), (True, "")):
+                model.cuda_graphs = graphs
+                for _ in range(4):                                  # warm-up: plan, shapes, allocator, graph capture
+                    for x in xs:
+                        codec.decode(model(x))
+                torch.cuda.synchronize()
+                samples = []
+                for _ in range(10):
+                    t0 = time.perf_counter()
+                    for x in xs:
+                        codec.decode(model(x))
+                    samples.append((time.perf_counter() - t0) * 1e3)
+                samples.sort()
+                out[name]["median_ms" + sfx] = samples[len(samples) // 2]
+                out[name]["min_ms" + sfx] = samples[0]
+                # device time alone (events around the same calls, no host sync in between)
+                out[name]["device_ms" + sfx] = _timeit(lambda: [codec.greedy_indices(model(x)) for x in xs], 10, 2)
+    model.cuda_graphs = prev
     return out

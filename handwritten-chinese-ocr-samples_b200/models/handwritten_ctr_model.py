@@ -169,8 +169,20 @@ class hctr_model(nn.Module):
     def _current_key(self):
         # torch-side changes show up as (data_ptr, _version); kernels that update parameters or running statistics through
         # raw pointers (hctr_sgd_clip_step, hctr_bn_finalize_train) bump `_param_generation` instead
-        return (self.__dict__.get("_param_generation", 0),) + tuple(
-            (t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        # (walks the modules' own parameter / buffer dicts - the module tree is fixed after construction - instead of the
+        #  recursive generators: this runs on every forward and weighs on batch-1 latency)
+        mods = self.__dict__.get("_key_modules")
+        if mods is None:
+            mods = self.__dict__["_key_modules"] = [m for m in self.modules() if m._parameters or m._buffers]
+        key = [self.__dict__.get("_param_generation", 0)]
+        for m in mods:
+            for t in m._parameters.values():
+                if t is not None:
+                    key.append(t.data_ptr()); key.append(t._version)
+            for t in m._buffers.values():
+                if t is not None:
+                    key.append(t.data_ptr()); key.append(t._version)
+        return tuple(key)
 
     def _get_plan(self):
         key = self._current_key()
@@ -266,7 +278,75 @@ class hctr_model(nn.Module):
                      B, H, W, spec.cin, spec.cout, spec.ksize, int(relu), int(pool), nat.stream_ptr())
         return y
 
+    # -------------------------------------------------------------------------------- small batches: CUDA-graph replay
+    # A single 128x2048 line is ~75 kernel launches of 10-60 us each: issued one ctypes call at a time the host is the
+    # slower side (3.3 ms per call for 2.9 ms of device time, most of that gaps). A shape that keeps coming back (batch-1
+    # serving, BASELINE configs[0]) is therefore captured ONCE into a CUDA graph - same kernels, same C-ABI calls, made on
+    # the capture stream - and replayed: one cudaGraphLaunch per forward. The graph owns a static input buffer and its
+    # intermediates (torch's graph-private pool); results are handed back as copies, so callers never see a buffer that a
+    # later call overwrites. Captured on the third call with a shape; at most `_GRAPH_SLOTS` shapes are kept (LRU).
+    # `model.cuda_graphs = False` or HCTR_CUDA_GRAPHS=0 keeps every call eager; so do kernel traces and outer captures.
+    _GRAPH_MAX_COLUMNS = 8192          # B*W up to which a forward is launch-bound enough to be worth a graph
+    _GRAPH_SLOTS = 8
+
     def _forward_eval(self, x, greedy=False, return_argmax=False):
+        B, _, _, W = x.shape
+        if (B * W > self._GRAPH_MAX_COLUMNS or not getattr(self, "cuda_graphs", True) or self.kernel_trace is not None
+                or os.environ.get("HCTR_CUDA_GRAPHS", "1") == "0" or torch.cuda.is_current_stream_capturing()):
+            return self._forward_eval_eager(x, greedy, return_argmax)
+        plan = self._get_plan()
+        cache = self.__dict__.get("_graph_cache")
+        if cache is None or cache["plan"] is not plan:
+            cache = {"plan": plan, "entries": {}, "tick": 0}        # new weights / folded BN: every captured graph is stale
+            self.__dict__["_graph_cache"] = cache
+        key = (B, W, bool(greedy), bool(return_argmax), self.logits_dtype, x.device.index, bool(getattr(self, "se_from_input", True)))
+        ent = cache["entries"].get(key)
+        if ent is None:
+            ent = cache["entries"][key] = {"seen": 0, "graph": None}
+        cache["tick"] += 1
+        ent["used"] = cache["tick"]
+        if ent["graph"] is None:
+            ent["seen"] += 1
+            if ent["seen"] < 3 or ent.get("failed"):
+                return self._forward_eval_eager(x, greedy, return_argmax)
+            try:
+                self._capture_eval_graph(cache, ent, x, greedy, return_argmax)
+            except Exception:                                            # capture is an optimisation, never a requirement
+                ent["failed"] = True
+                ent["graph"] = None
+                torch.cuda.synchronize(x.device)
+                return self._forward_eval_eager(x, greedy, return_argmax)
+        ent["x"].copy_(x)
+        ent["graph"].replay()
+        self.launch_count += ent["launches"]
+        outs = ent["outs"]
+        if isinstance(outs, tuple):
+            return tuple(self._copy_out(o) for o in outs)
+        return self._copy_out(outs)
+
+    @staticmethod
+    def _copy_out(o):
+        """A private copy of a graph-owned result with the shape AND strides of the eager result (the logits are a permuted
+        view of a padded [B,W,pitch] buffer, like the reference's `.permute(1, 0, 2)`)."""
+        if o._base is None:
+            return o.clone()
+        return o._base.clone().as_strided(o.shape, o.stride(), o.storage_offset())
+
+    def _capture_eval_graph(self, cache, ent, x, greedy, return_argmax):
+        live = [k for k, e in cache["entries"].items() if e.get("graph") is not None]
+        if len(live) >= self._GRAPH_SLOTS:                               # least recently used shape makes room
+            victim = min(live, key=lambda k: cache["entries"][k]["used"])
+            del cache["entries"][victim]
+        ent["x"] = x.clone()
+        g = torch.cuda.CUDAGraph()
+        before = self.launch_count
+        with torch.cuda.graph(g):
+            ent["outs"] = self._forward_eval_eager(ent["x"], greedy, return_argmax)
+        ent["launches"] = self.launch_count - before
+        self.launch_count = before
+        ent["graph"] = g
+
+    def _forward_eval_eager(self, x, greedy=False, return_argmax=False):
         nat = _core().native
         lib = nat.lib()
         plan = self._get_plan()

@@ -544,3 +544,44 @@ def test_full_size_lines_against_the_fp32_oracle(regime):
         assert e32.max().item() <= 1.5 * ea.max().item() and e32.mean().item() <= 1.2 * ea.mean().item(), stats
         assert ag32 >= aga - 0.03, stats
         assert ag16 >= aga - 0.05, stats
+
+
+def test_small_batch_forward_replays_a_cuda_graph_with_identical_results():
+    """Batch-1 serving: the third forward with a shape is captured into a CUDA graph and later ones replay it. Results, shapes
+    and strides equal the eager path bit for bit on fresh inputs; a second shape gets its own graph; changed weights drop the
+    captured graphs; greedy_decode takes the same route; outputs are private copies (a later call does not overwrite them)."""
+    m = _model(53, 77).cuda().eval()
+    codec_inputs = [torch.from_numpy(synth.text_lines(1, 200, 300 + i)).cuda() for i in range(6)]
+    other = [torch.from_numpy(synth.text_lines(2, 136, 400 + i)).cuda() for i in range(4)]
+    with torch.no_grad():
+        m.cuda_graphs = False
+        want = [m(x) for x in codec_inputs]
+        want_other = [m(x) for x in other]
+        want_greedy = [m.greedy_decode(x, return_argmax=True) for x in codec_inputs]
+        assert m.__dict__.get("_graph_cache") is None
+        m.cuda_graphs = True
+        got = [m(x) for x in codec_inputs]
+        cache = m.__dict__["_graph_cache"]
+        assert sum(e.get("graph") is not None for e in cache["entries"].values()) == 1
+        got_other = [m(x) for x in other]
+        got2 = [m(x) for x in codec_inputs]                               # back to the first shape: replay
+        assert sum(e.get("graph") is not None for e in cache["entries"].values()) == 2
+        got_greedy = [m.greedy_decode(x, return_argmax=True) for x in codec_inputs]
+    for a, b, c in zip(want, got, got2):
+        assert a.shape == b.shape and a.stride() == b.stride() and a.dtype == b.dtype
+        assert torch.equal(a, b) and torch.equal(a, c)
+    for a, b in zip(want_other, got_other):
+        assert a.stride() == b.stride() and torch.equal(a, b)
+    for a, b in zip(want_greedy, got_greedy):
+        assert all(torch.equal(u, v) for u, v in zip(a, b))
+    assert not torch.equal(got[4], got[5])                                # distinct inputs gave distinct, un-aliased results
+    # new weights: the plan changes, every captured graph is dropped and results follow the new weights
+    with torch.no_grad():
+        m.linear.bias.add_(0.25)
+        y_new = [m(codec_inputs[0]) for _ in range(4)]
+        m.cuda_graphs = False
+        y_ref = m(codec_inputs[0])
+    assert m.__dict__["_graph_cache"]["plan"] is m._plan
+    for y in y_new:
+        assert torch.equal(y, y_ref)
+    assert not torch.equal(y_ref, want[0])
