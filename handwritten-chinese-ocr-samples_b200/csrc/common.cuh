@@ -73,6 +73,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// the same with ReLU inside the conversion (cvt.rn.relu: negative -> +0, NaN stays NaN as in torch.relu): the epilogues'
+// separate FMNMX per element were 32 of a chunk's ~250 instructions
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// one pixel's 32 channels of a chunk -> 64 bytes of bf16 at `dst` (shared memory), ReLU folded into the conversion
+template <bool RELU>
+__device__ __forceinline__ void stage_chunk_row(const float (&v)[32], uint8_t* dst) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            pk[j] = RELU ? pack_bf16x2_relu(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]) : pack_bf16x2(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+        *reinterpret_cast<uint4*>(dst + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 

@@ -38,7 +38,10 @@ struct PairSmem {
     // (128 L2 requests per warp and chunk) into 64-byte runs (32 requests)
     static constexpr int kEpiPitch = 80;
     static constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch;
-    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + 1024 /*alignment slack*/;
+    // per epilogue warp: scale[] then shift[] of its BLOCK_N/2 columns of the current tile (broadcast 16-byte reads)
+    static constexpr int kSclBytes = kEpiWarps * (BLOCK_N / 2) * 2 * 4;
+    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + kSclBytes + 1024 /*alignment slack*/;
+    static_assert(kTotal <= 227 * 1024, "shared memory of one CTA");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -156,6 +159,7 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint64_t* acc_empty = acc_full + kPairAcc;                             // [kPairAcc]      (leader's are used)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kPairAcc);
     uint8_t* epi_base = bar_base + L::kBarBytes;                           // [kEpiWarps][32][kEpiPitch]
+    float* scl_base = reinterpret_cast<float*>(epi_base + L::kEpiBytes);   // [kEpiWarps][2][kPairBlockN/2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -310,18 +314,22 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
             }
             // per-channel epilogue factors of this tile, one column per lane, fetched before the accumulator is awaited and
-            // broadcast by shuffle below: y = acc*scale + shift (conv bias and eval-mode BN folded, fp32), times the SE gate
-            // when it is folded into the producing conv (out = relu(bn(conv) * gate[b, c] + residual))
-            float scl[kChunks], shl[kChunks];
+            // parked in the warp's shared-memory strip (read back as broadcast 16-byte loads in the chunk loop, see
+            // igemm_tcgen05.cuh): y = acc*scale + shift (conv bias and eval-mode BN folded, fp32), times the SE gate when it is
+            // folded into the producing conv (out = relu(bn(conv) * gate[b, c] + residual))
+            float* wsc = scl_base + (warp - 2) * (kPairBlockN / 2) * 2;
 #pragma unroll
             for (int ck = 0; ck < kChunks; ++ck) {
                 const int n = n_tile * kPairBlockN + half * (kPairBlockN / 2) + ck * 32 + lane;
-                scl[ck] = __ldg(p.scale + n); shl[ck] = __ldg(p.shift + n);
+                float sc_v = __ldg(p.scale + n), sh_v = __ldg(p.shift + n);
                 if (p.gate) {
                     const float gt = __ldg(p.gate + static_cast<size_t>(b) * p.N + n);
-                    scl[ck] *= gt; shl[ck] *= gt;
+                    sc_v *= gt; sh_v *= gt;
                 }
+                wsc[ck * 32 + lane] = sc_v;
+                wsc[kPairBlockN / 2 + ck * 32 + lane] = sh_v;
             }
+            __syncwarp();
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
@@ -331,9 +339,18 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int n0 = n_tile * kPairBlockN + c0;
                 float v[32];
                 tmem_ld_32x32(t_base + c0, v);
+                {
+                    const float4* sc4 = reinterpret_cast<const float4*>(wsc + ck * 32);
+                    const float4* sh4 = reinterpret_cast<const float4*>(wsc + kPairBlockN / 2 + ck * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    v[j] = fmaf(v[j], __shfl_sync(0xffffffffu, scl[ck], j), __shfl_sync(0xffffffffu, shl[ck], j));
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 a = sc4[q], c = sh4[q];
+                        v[4 * q + 0] = fmaf(v[4 * q + 0], a.x, c.x);
+                        v[4 * q + 1] = fmaf(v[4 * q + 1], a.y, c.y);
+                        v[4 * q + 2] = fmaf(v[4 * q + 2], a.z, c.z);
+                        v[4 * q + 3] = fmaf(v[4 * q + 3], a.w, c.w);
+                    }
+                }
                 if constexpr (ADD) {
                     // residual: transposed registers -> staging rows -> this lane's own pixel
 #pragma unroll
@@ -395,17 +412,8 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
                 // pack to bf16, stage this lane's pixel row, write the chunk out as 64-byte runs
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float a0 = v[8 * q + 2 * j], a1 = v[8 * q + 2 * j + 1];
-                        if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                        pk[j] = pack_bf16x2(a0, a1);
-                    }
-                    *reinterpret_cast<uint4*>(ebuf + lane * L::kEpiPitch + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                }
+                if (p.relu) stage_chunk_row<true>(v, ebuf + lane * L::kEpiPitch);
+                else        stage_chunk_row<false>(v, ebuf + lane * L::kEpiPitch);
                 __syncwarp();
                 if (h < p.H) {
 #pragma unroll

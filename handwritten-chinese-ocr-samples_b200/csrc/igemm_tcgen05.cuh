@@ -82,7 +82,11 @@ struct IgemmSmem {
     // per-pixel and the transposed access): per-thread 16-byte global stores at a 2*N-byte stride become 64-byte runs
     static constexpr int kEpiPitch = 80;
     static constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch;
-    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + 1024 /*alignment slack*/;
+    // per epilogue warp: scale[] then shift[] of the warp's BLOCK_N/2 columns of the current tile (read back as broadcast
+    // 16-byte loads in the chunk loop)
+    static constexpr int kSclBytes = kEpiWarps * (BLOCK_N / 2) * 2 * 4;
+    static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + kSclBytes + 1024 /*alignment slack*/;
+    static_assert(kTotal <= 227 * 1024, "shared memory of one CTA");
 };
 
 // The i-th tile of persistent CTA `cta`. Two orders (as in the CTA-pair kernel, igemm2_tcgen05.cuh):
@@ -139,6 +143,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     uint64_t* acc_empty = acc_full + ACC_STAGES;                           // [ACC_STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
     uint8_t* epi_base = bar_base + L::kBarBytes;                           // [kEpiWarps][32][kEpiPitch]
+    float* scl_base = reinterpret_cast<float*>(epi_base + L::kEpiBytes);   // [kEpiWarps][2][BLOCK_N/2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -280,22 +285,28 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     }
                 }
             }
-            // per-channel epilogue factors of this warp's columns, one column per lane and chunk, fetched before the wait on the
-            // accumulator and broadcast by shuffle below (vector __ldg's per chunk sat on the epilogue's critical path, which
-            // bounds the 1x1 and 64-channel layers): y = acc*scale + shift, times the SE gate when it is folded in
+            // per-channel epilogue factors of this warp's columns: y = acc*scale + shift, times the SE gate when it is folded in.
+            // One column per lane and chunk, fetched before the wait on the accumulator and parked in the warp's shared-memory
+            // strip; the chunk loop reads them back as broadcast 16-byte loads (16 LDS per 32 columns). Vector __ldg's per chunk
+            // sat on the epilogue's critical path; a shuffle broadcast per column (round 1) cost 64 of the ~300 instructions of
+            // a chunk in an epilogue that is latency-bound on its own instruction chain (profiles/r2_ncu_conv1x1_64_128.txt).
             constexpr int kWarpChunks = BLOCK_N / 2 / 32;
-            float scl[kWarpChunks], shl[kWarpChunks];
+            float* wsc = scl_base + (warp - 2) * (BLOCK_N / 2) * 2;
             if constexpr (EPI == EPI_CONV) {
 #pragma unroll
                 for (int ck = 0; ck < kWarpChunks; ++ck) {
                     const int n = n_tile * BLOCK_N + half * (BLOCK_N / 2) + ck * 32 + lane;
-                    scl[ck] = __ldg(p.scale + n); shl[ck] = __ldg(p.shift + n);
+                    float sc_v = __ldg(p.scale + n), sh_v = __ldg(p.shift + n);
                     if (p.gate) {
                         const float gt = __ldg(p.gate + static_cast<size_t>(b) * p.N + n);
-                        scl[ck] *= gt; shl[ck] *= gt;
+                        sc_v *= gt; sh_v *= gt;
                     }
+                    wsc[ck * 32 + lane] = sc_v;
+                    wsc[BLOCK_N / 2 + ck * 32 + lane] = sh_v;
                 }
+                __syncwarp();
             }
+            const uint32_t wsc_u32 = smem_u32(wsc);
             uint8_t* ebuf = epi_base + (warp - 2) * (32 * L::kEpiPitch);
             const int tr = lane >> 2, tq = lane & 3;     // transposed role: 16-byte piece tq of pixel rows tr, tr+8, tr+16, tr+24
             mbar_wait(&acc_full[acc], acc_phase);
@@ -318,14 +329,22 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
                 if constexpr (EPI == EPI_CONV) {
                     // y = acc*scale + shift  (conv bias and eval-mode BN folded, fp32; SE gate folded into both), ReLU, H-pair max
-                    float sc_l = scl[0], sh_l = shl[0];
+                    {
+                        // (32-bit shared-memory addresses: the generic pointer pair cost the N = 128 variants their last registers)
+                        const uint32_t sc_u32 = wsc_u32 + ck * 128;
 #pragma unroll
-                    for (int q = 1; q < kWarpChunks; ++q) { if (ck == q) { sc_l = scl[q]; sh_l = shl[q]; } }
+                        for (int q = 0; q < 8; ++q) {
+                            float4 a, c;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(sc_u32 + q * 16));
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(sc_u32 + (BLOCK_N / 2) * 4 + q * 16));
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sc = __shfl_sync(0xffffffffu, sc_l, j), sh = __shfl_sync(0xffffffffu, sh_l, j);
-#pragma unroll
-                        for (int s = 0; s < NUM_SUB; ++s) v[s][j] = fmaf(v[s][j], sc, sh);
+                            for (int s = 0; s < NUM_SUB; ++s) {
+                                v[s][4 * q + 0] = fmaf(v[s][4 * q + 0], a.x, c.x);
+                                v[s][4 * q + 1] = fmaf(v[s][4 * q + 1], a.y, c.y);
+                                v[s][4 * q + 2] = fmaf(v[s][4 * q + 2], a.z, c.z);
+                                v[s][4 * q + 3] = fmaf(v[s][4 * q + 3], a.w, c.w);
+                            }
+                        }
                     }
                     if (p.se_partial) {
                         // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum over this
@@ -385,17 +404,9 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                         const int ho = h_tile;
                         const int wq = w0 + quad * 32;                   // this warp's first pixel
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float a0 = fmaxf(v[0][8 * q + 2 * j], v[NUM_SUB - 1][8 * q + 2 * j]);
-                                float a1 = fmaxf(v[0][8 * q + 2 * j + 1], v[NUM_SUB - 1][8 * q + 2 * j + 1]);
-                                if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                                pk[j] = pack_bf16x2(a0, a1);
-                            }
-                            *reinterpret_cast<uint4*>(ebuf + lane * L::kEpiPitch + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        }
+                        for (int j = 0; j < 32; ++j) v[0][j] = fmaxf(v[0][j], v[NUM_SUB - 1][j]);
+                        if (p.relu) stage_chunk_row<true>(v[0], ebuf + lane * L::kEpiPitch);
+                        else        stage_chunk_row<false>(v[0], ebuf + lane * L::kEpiPitch);
                         __syncwarp();
                         if (ho < p.out_H) {
                             __nv_bfloat16* obase = out + ((static_cast<size_t>(b) * p.out_H + ho) * p.W + wq) * p.N + n0;
@@ -430,17 +441,8 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                 }
                             }
                             // pack, stage this lane's pixel row, write the chunk out as 64-byte runs
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t pk[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float a0 = v[s][8 * q + 2 * j], a1 = v[s][8 * q + 2 * j + 1];
-                                    if (p.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-                                    pk[j] = pack_bf16x2(a0, a1);
-                                }
-                                *reinterpret_cast<uint4*>(ebuf + lane * L::kEpiPitch + q * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            }
+                            if (p.relu) stage_chunk_row<true>(v[s], ebuf + lane * L::kEpiPitch);
+                            else        stage_chunk_row<false>(v[s], ebuf + lane * L::kEpiPitch);
                             __syncwarp();
                             if (h < p.out_H) {
                                 const int wq = w0 + s * p.sub_dw * kTileM + quad * 32;       // this warp's first pixel
