@@ -151,6 +151,19 @@ def ctc_loss_legs(nat, dev, peaks):
             ms_rows = _timeit(run, 20, 10)
         finally:
             os.environ.pop("HCTR_CTC_OVERLAP", None)
+        # the training step's configuration (TrainStep / train_engine): the rows' log-sum-exp comes from the classifier epilogue
+        # (hctr_classifier_lse_fwd), so the loss call only gathers the label logits, scans, and writes the gradient
+        lses = [torch.logsumexp(b_[:, :, :C].float(), dim=2).contiguous() for b_ in bufs]
+
+        def run_lse():
+            i = it[0] % nrot
+            it[0] += 1
+            nat.check(lib.hctr_ctc_loss_fwd_bwd(nat.ptr(bufs[i]), code, T, B, C, pitch, T * pitch, nat.ptr(tgt), nat.ptr(tlt),
+                                                nat.ptr(il), maxl, nat.ptr(lses[i]), nat.ptr(nll), nat.ptr(loss), nat.ptr(grads[i]), 1.0,
+                                                nat.c_void_p(ws.data_ptr() + off), wsb, nat.stream_ptr()))
+        ms_lse = _timeit(run_lse, 20, 10)
+        loss_lse = float(loss.item())
+        run()
         split = B <= 24                                                  # csrc/ctc_loss.cu split_by_default
         alg = 3.0 * es * T * B * C                                       # (2*s_in + s_out) * T*B*C
         moved = 2.0 * es * T * B * C                                     # the one-pass rows kernel: logits read once, gradient written once
@@ -164,9 +177,13 @@ def ctc_loss_legs(nat, dev, peaks):
                      "achieved": alg / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / peaks["hbm_gbs"],
                      "algorithmic_bytes": alg, "bytes_moved_by_design": alg if split else moved,
                      "traffic": _ctc_traffic() if name == "B16_bf16" else None,
+                     "ms_with_classifier_lse": ms_lse, "frac_with_classifier_lse": moved / ms_lse / 1e6 / peaks["hbm_gbs"],
+                     "with_classifier_lse": "the training step's call: row log-sum-exp taken from the classifier epilogue, frac on "
+                                            "(s_in + s_out)*T*B*C bytes (logits read once by the gradient pass, gradient written once)",
+                     "loss_with_classifier_lse": loss_lse,
                      "loss": float(loss.item()), "log_space_fallbacks": int(flags.sum()),
                      "l2": "rotating %d buffer set(s) of %.0f MB" % (nrot, per / 1e6)}
-        del bufs, grads, ws
+        del bufs, grads, ws, lses
     return res
 
 
