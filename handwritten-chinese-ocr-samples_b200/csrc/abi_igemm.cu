@@ -268,6 +268,7 @@ static int conv_launch(const void* x, const void* w_packed, const float* scale, 
     HCTR_CHECK(aligned16(x) && aligned16(w_packed) && aligned16(y) && aligned16(scale) && aligned16(shift),
                HCTR_ERR_INVALID, "conv: pointers must be 16-byte aligned");
 
+    HCTR_CHECK(!(se_partial && sum_stored && pool), HCTR_ERR_INVALID, "conv: sums of the stored tensor are not taken on pooled layers");
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     p.B = B; p.H = H; p.W = W;
@@ -367,7 +368,9 @@ int hctr_conv_bn_se_fwd(const void* x, const void* w_packed, const float* scale,
 }
 
 int hctr_conv_sum_slices(int H, int W, int Cin, int Cout, int ksize) {
-    const int rows = use_pair(H, Cin, Cout, ksize, 0) ? H : (H + 1) / 2;
+    // sums of the values as stored: one slot per (row, 128-px span, epilogue warp quarter) in either kernel; the single-CTA
+    // kernel's tiles are row pairs, so an odd H has one more (zero) row of slots
+    const int rows = use_pair(H, Cin, Cout, ksize, 0) ? H : (H + 1) / 2 * 2;
     return rows * ((W + kTileM - 1) / kTileM) * 4;
 }
 

@@ -96,6 +96,35 @@ __device__ __forceinline__ void stage_chunk_row(const float (&v)[32], uint8_t* d
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Channel sums of a staged chunk "as stored": the store loop of the conv epilogues reads the staged 32-pixel x 32-channel bf16
+// chunk back as 16-byte pieces (8 channels of one pixel row; lane = (row & 7) * 4 + piece, rows r, r+8, r+16, r+24). Adding the
+// pieces a lane holds and then the eight lanes of a piece (xor 4, 8, 16) gives the per-channel sums over the chunk's pixels in
+// 24 shuffles - against 31 shuffles + 62 selects + the separate ReLU / bf16 rounding of 32 values per lane for the
+// transpose-reduce butterfly on the fp32 registers. Lanes 0..3 end up holding channels piece*8 .. piece*8+7.
+__device__ __forceinline__ void piece_add(const uint4& q, float (&s)[8]) {
+    s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
+    s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
+}
+__device__ __forceinline__ void piece_add_sq(const uint4& q, float (&t)[8]) {
+    float x;
+    x = bf16_lo(q.x); t[0] = fmaf(x, x, t[0]); x = bf16_hi(q.x); t[1] = fmaf(x, x, t[1]);
+    x = bf16_lo(q.y); t[2] = fmaf(x, x, t[2]); x = bf16_hi(q.y); t[3] = fmaf(x, x, t[3]);
+    x = bf16_lo(q.z); t[4] = fmaf(x, x, t[4]); x = bf16_hi(q.z); t[5] = fmaf(x, x, t[5]);
+    x = bf16_lo(q.w); t[6] = fmaf(x, x, t[6]); x = bf16_hi(q.w); t[7] = fmaf(x, x, t[7]);
+}
+__device__ __forceinline__ void piece_rows_reduce(float (&s)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 4);
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 8);
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 16);
+    }
+}
+__device__ __forceinline__ void piece_store(float* dst, const float (&s)[8]) {     // dst: 32-byte aligned run of 8 floats
+    *reinterpret_cast<float4*>(dst) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(s[4], s[5], s[6], s[7]);
+}
+
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -368,21 +368,15 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     __syncwarp();
                 }
                 if constexpr (!ADD) {
-                    if (p.se_partial) {
-                        // per-channel sum over this warp's 32 pixels by a transpose-reduce butterfly; afterwards lane L holds
-                        // column n0+L. One slot per (line, row, 128-px span, warp): fixed-order final sum in the consumer.
-                        // Either the fp32 BN output (SELayer squeeze of this conv, models/handwritten_ctr_model.py:27-28) or
-                        // the values as stored (ReLU, bf16) when the NEXT conv's squeeze is derived from this tensor.
+                    if (p.se_partial && !p.sum_stored) {
+                        // per-channel sum of the fp32 BN output (SELayer squeeze of this conv, models/handwritten_ctr_model.py:
+                        // 27-28) over this warp's 32 pixels by a transpose-reduce butterfly; afterwards lane L holds column n0+L.
+                        // One slot per (line, row, 128-px span, warp): fixed-order final sum in the consumer. (Sums of the values
+                        // AS STORED - p.sum_stored, the NEXT conv's squeeze / train-mode BN statistics - come from the staged bf16
+                        // chunk in the store loop below.)
                         float tsum[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float x = v[j];
-                            if (p.sum_stored) {
-                                if (p.relu) x = fmaxf(x, 0.f);
-                                x = __bfloat162float(__float2bfloat16_rn(x));
-                            }
-                            tsum[j] = ok ? x : 0.f;
-                        }
+                        for (int j = 0; j < 32; ++j) tsum[j] = ok ? v[j] : 0.f;
 #define HCTR_BFLY(O)                                                                          \
                         {                                                                     \
                             const bool upper = (lane & (O)) != 0;                             \
@@ -393,44 +387,57 @@ igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             }                                                                 \
                         }
                         HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
+#undef HCTR_BFLY
                         const size_t slot = ((static_cast<size_t>(b) * p.H + h) * p.w_tiles + w_tile) * 4 + quad;
                         if (h < p.H) p.se_partial[slot * p.N + n0 + lane] = tsum[0];
-                        if (p.sq_partial) {                          // train-mode BN: sum of squares of the same values
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float x = v[j];
-                                if (p.sum_stored) {
-                                    if (p.relu) x = fmaxf(x, 0.f);
-                                    x = __bfloat162float(__float2bfloat16_rn(x));
-                                }
-                                tsum[j] = ok ? x * x : 0.f;
-                            }
-                            HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
-                            if (h < p.H) p.sq_partial[slot * p.N + n0 + lane] = tsum[0];
-                        }
-#undef HCTR_BFLY
                     }
                 }
                 // pack to bf16, stage this lane's pixel row, write the chunk out as 64-byte runs
                 if (p.relu) stage_chunk_row<true>(v, ebuf + lane * L::kEpiPitch);
                 else        stage_chunk_row<false>(v, ebuf + lane * L::kEpiPitch);
                 __syncwarp();
-                if (h < p.H) {
+                // (ADD == 0, p.sum_stored) channel sums / sums of squares of the chunk as stored, from the pieces read back for the
+                // stores; the plain loop is kept apart so that layers without sums pay nothing for it
+                if (ADD || !(p.se_partial && p.sum_stored)) {
+                    if (h < p.H) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = tr + 8 * i;
-                        if (wq + r < p.W) {
-                            __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + warp_off + static_cast<size_t>(r) * p.N + ck * 32 + tq * 8;
-                            const uint4 val = *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
-                            if (p.pool) {
-                                // max(relu(a), relu(b)) with the output zero-filled by the host: every operand is >= 0, so
-                                // the order of the two CTAs' reductions does not matter and bf16 max is exact
-                                asm volatile("red.relaxed.gpu.global.max.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};"
-                                             :: "l"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
-                            } else {
-                                *reinterpret_cast<uint4*>(dst) = val;
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = tr + 8 * i;
+                            if (wq + r < p.W) {
+                                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + warp_off + static_cast<size_t>(r) * p.N + ck * 32 + tq * 8;
+                                const uint4 val = *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                                if (p.pool) {
+                                    // max(relu(a), relu(b)) with the output zero-filled by the host: every operand is >= 0, so
+                                    // the order of the two CTAs' reductions does not matter and bf16 max is exact
+                                    asm volatile("red.relaxed.gpu.global.max.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+                                                 :: "l"(dst), "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+                                } else {
+                                    *reinterpret_cast<uint4*>(dst) = val;
+                                }
                             }
                         }
+                    }
+                } else {
+                    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (h < p.H) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = tr + 8 * i;
+                            if (wq + r < p.W) {
+                                __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(p.out) + warp_off + static_cast<size_t>(r) * p.N + ck * 32 + tq * 8;
+                                const uint4 val = *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                                *reinterpret_cast<uint4*>(dst) = val;                     // (never pooled: the sums are of the stored tensor)
+                                piece_add(val, cs);
+                                if (p.sq_partial) piece_add_sq(val, cq);
+                            }
+                        }
+                    }
+                    const size_t slot = ((static_cast<size_t>(b) * p.H + h) * p.w_tiles + w_tile) * 4 + quad;
+                    piece_rows_reduce(cs);
+                    if (lane < 4 && h < p.H) piece_store(p.se_partial + slot * p.N + n0 + lane * 8, cs);
+                    if (p.sq_partial) {
+                        piece_rows_reduce(cq);
+                        if (lane < 4 && h < p.H) piece_store(p.sq_partial + slot * p.N + n0 + lane * 8, cq);
                     }
                 }
                 __syncwarp();

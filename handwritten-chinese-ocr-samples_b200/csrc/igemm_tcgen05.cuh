@@ -51,7 +51,8 @@ struct IgemmParams {
     float* se_partial;        // EPI_CONV: optional [B][h_tiles*w_tiles][4][N] per-(tile, warp) channel sums of the fp32
                               // epilogue output (the SE squeeze folded into the producing conv; deterministic)
     int sum_stored;           // 1: the sums are taken over the values as STORED (after gate/add/ReLU, rounded to bf16) -
-                              // what the next convolution will read - instead of the fp32 BN output
+                              // what the next convolution will read - instead of the fp32 BN output; slots are then per
+                              // (line, row, span, warp): [B][2*h_tiles*w_tiles][4][N] (hctr_conv_sum_slices)
     float* sq_partial;        // EPI_CONV: optional, same slots as se_partial: sums of the SQUARES of the same values (train-mode
                               // BatchNorm statistics of z = conv(x)+bias taken in the epilogue: no separate pass over z)
     const float* gate;        // EPI_CONV: optional [B][N] per-(line, channel) factor applied after BN, before `add`
@@ -346,10 +347,11 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             }
                         }
                     }
-                    if (p.se_partial) {
-                        // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum over this
-                        // warp's 32 pixels x NUM_SUB rows by a transpose-reduce butterfly (31 shuffles per 32 columns);
+                    if (p.se_partial && !p.sum_stored) {
+                        // SELayer squeeze (models/handwritten_ctr_model.py:27-28) folded in: per-channel sum of the fp32 BN output
+                        // over this warp's 32 pixels x NUM_SUB rows by a transpose-reduce butterfly (31 shuffles per 32 columns);
                         // afterwards lane L holds column n0+L. Slots are per (tile, warp): fixed-order final sum.
+                        // (Sums of the values AS STORED - p.sum_stored - come from the staged bf16 chunk in the store loop below.)
                         float tsum[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -357,12 +359,7 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #pragma unroll
                             for (int s = 0; s < NUM_SUB; ++s) {
                                 const bool ok = (w0 + s * p.sub_dw * kTileM + pix < p.W) && (h0 + s * p.sub_dh < p.out_H);
-                                float x = v[s][j];
-                                if (p.sum_stored) {                  // un-pooled, no `add`: the value as it will be stored
-                                    if (p.relu) x = fmaxf(x, 0.f);
-                                    x = __bfloat162float(__float2bfloat16_rn(x));
-                                }
-                                a += ok ? x : 0.f;
+                                a += ok ? v[s][j] : 0.f;
                             }
                             tsum[j] = a;
                         }
@@ -376,28 +373,9 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             }                                                                 \
                         }
                         HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
+#undef HCTR_BFLY
                         const size_t slot = ((static_cast<size_t>(b) * p.h_tiles * p.w_tiles + static_cast<size_t>(h_tile) * p.w_tiles + w_tile) * 4 + quad);
                         p.se_partial[slot * p.N + n0 + lane] = tsum[0];
-                        if (p.sq_partial) {                          // train-mode BN: sum of squares of the same values
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                float a = 0.f;
-#pragma unroll
-                                for (int s = 0; s < NUM_SUB; ++s) {
-                                    const bool ok = (w0 + s * p.sub_dw * kTileM + pix < p.W) && (h0 + s * p.sub_dh < p.out_H);
-                                    float x = v[s][j];
-                                    if (p.sum_stored) {
-                                        if (p.relu) x = fmaxf(x, 0.f);
-                                        x = __bfloat162float(__float2bfloat16_rn(x));
-                                    }
-                                    a = ok ? fmaf(x, x, a) : a;
-                                }
-                                tsum[j] = a;
-                            }
-                            HCTR_BFLY(16) HCTR_BFLY(8) HCTR_BFLY(4) HCTR_BFLY(2) HCTR_BFLY(1)
-                            p.sq_partial[slot * p.N + n0 + lane] = tsum[0];
-                        }
-#undef HCTR_BFLY
                     }
                     __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
                     if (p.pool) {
@@ -444,17 +422,43 @@ igemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                             if (p.relu) stage_chunk_row<true>(v[s], ebuf + lane * L::kEpiPitch);
                             else        stage_chunk_row<false>(v[s], ebuf + lane * L::kEpiPitch);
                             __syncwarp();
-                            if (h < p.out_H) {
-                                const int wq = w0 + s * p.sub_dw * kTileM + quad * 32;       // this warp's first pixel
-                                const size_t woff = p.out_line_pitch
-                                    ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + wq) * p.N + n0
-                                    : ((static_cast<size_t>(b) * p.out_H + h) * p.W + wq) * p.N + n0;
+                            // With p.sum_stored: channel sums (and sums of squares) of the chunk as stored, from the pieces read
+                            // back for the stores - one slot per (line, ROW, 128-px span, warp quarter); rows beyond the tensor
+                            // write zeros. The plain loop is kept apart so that layers without sums pay nothing for it.
+                            const int wq = w0 + s * p.sub_dw * kTileM + quad * 32;           // this warp's first pixel
+                            const size_t woff = p.out_line_pitch
+                                ? static_cast<size_t>(b) * p.out_line_pitch + (static_cast<size_t>(h) * p.W + wq) * p.N + n0
+                                : ((static_cast<size_t>(b) * p.out_H + h) * p.W + wq) * p.N + n0;
+                            if (!(p.se_partial && p.sum_stored)) {
+                                if (h < p.out_H) {
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int r = tr + 8 * i;
-                                    if (wq + r < p.W)
-                                        *reinterpret_cast<uint4*>(out + woff + static_cast<size_t>(r) * p.N + tq * 8) =
-                                            *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int r = tr + 8 * i;
+                                        if (wq + r < p.W)
+                                            *reinterpret_cast<uint4*>(out + woff + static_cast<size_t>(r) * p.N + tq * 8) =
+                                                *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                                    }
+                                }
+                            } else {
+                                float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                if (h < p.out_H) {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int r = tr + 8 * i;
+                                        if (wq + r < p.W) {
+                                            const uint4 val = *reinterpret_cast<const uint4*>(ebuf + r * L::kEpiPitch + tq * 16);
+                                            *reinterpret_cast<uint4*>(out + woff + static_cast<size_t>(r) * p.N + tq * 8) = val;
+                                            piece_add(val, cs);
+                                            if (p.sq_partial) piece_add_sq(val, cq);
+                                        }
+                                    }
+                                }
+                                const size_t slot = ((static_cast<size_t>(b) * (2 * p.h_tiles) + h) * p.w_tiles + w_tile) * 4 + quad;
+                                piece_rows_reduce(cs);
+                                if (lane < 4) piece_store(p.se_partial + slot * p.N + n0 + lane * 8, cs);
+                                if (p.sq_partial) {
+                                    piece_rows_reduce(cq);
+                                    if (lane < 4) piece_store(p.sq_partial + slot * p.N + n0 + lane * 8, cq);
                                 }
                             }
                             __syncwarp();
