@@ -169,8 +169,10 @@ def ctc_loss_legs(nat, dev, peaks):
         moved = 2.0 * es * T * B * C                                     # the one-pass rows kernel: logits read once, gradient written once
         foff = lib.hctr_ctc_loss_flag_offset(T, B, maxl)
         flags = ws[off + foff: off + foff + 4 * B].clone().view(torch.int32).cpu().numpy()
-        res[name] = {"kernel": ("split schedule: ctc_prep + ctc_lse_chunk_kernel (one read: log-sum-exp + label gather) -> [ctc_scan_kernel x2 "
-                                "on SMs of their own || ctc_dense_grad_kernel on a helper stream] -> verify + ctc_fix_kernel") if split else
+        res[name] = {"kernel": ("split schedule, relative form: ctc_prep + ctc_gather_rel_kernel (label logits relative to the row's largest "
+                                "label logit: no log-sum-exp needed) -> [ctc_scan_kernel x2 on SMs of their own || ctc_lse_chunk_kernel "
+                                "(one read: log-sum-exp) + ctc_dense_grad_kernel on a helper stream] -> verify + nll correction + "
+                                "ctc_fix_kernel") if split else
                                "ctc_prep + ctc_rows_kernel (one pass, row in registers) + ctc_scan_kernel x2 + verify + ctc_fix_kernel",
                      "bound": "hbm", "ms": ms,
                      "ms_other_schedule": ms_rows, "other_schedule": "one-pass rows kernel, back to back" if split else "split",

@@ -46,6 +46,8 @@ namespace hctr {
 
 struct CtcWs {
     float* lse;        // [B][T]
+    float* ref;        // [B][T]         relative schedule: the row's reference logit (max over the label set); lpg / pg / pgr
+                       //                are then relative to it instead of to the log-sum-exp
     float* lpg;        // [B][T][Sp]     log-prob of l'_s at (t,b) (log-space fallback)
     double* pg;        // [B][T][Sp]     probability of l'_s at (t,b), zero beyond S (scaled linear recursion)
     double* pgr;       // [B][T][Sp]     the same row mirrored: pgr[q] = pg[S-1-q] (what the beta scan reads front to back)
@@ -81,6 +83,7 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     long long off = 0;
     auto take = [&](long long bytes) { long long o = off; off = align_up(off + bytes, 256); return o; };
     const long long o_lse = take(4ll * B * T);
+    const long long o_ref = take(4ll * B * T);
     const long long o_lpg = take(4ll * B * T * Sp);
     const long long o_pg = take(8ll * B * T * Sp);
     const long long o_pgr = take(8ll * B * T * Sp + 64);
@@ -106,6 +109,7 @@ static CtcWs carve(void* base, int T, int B, int Sp, int Sa, long long* total) {
     CtcWs w;
     char* p = static_cast<char*>(base);
     w.lse = reinterpret_cast<float*>(p + o_lse);
+    w.ref = reinterpret_cast<float*>(p + o_ref);
     w.lpg = reinterpret_cast<float*>(p + o_lpg);
     w.pg = reinterpret_cast<double*>(p + o_pg);
     w.pgr = reinterpret_cast<double*>(p + o_pgr);
@@ -313,7 +317,7 @@ ctc_lse_gather_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long 
 //       label gather of ctc_lse_gather_kernel (the labels' logits were read microseconds ago: L2 hits).
 constexpr int kLseChunkVec = 8;
 
-template <typename T>
+template <typename T, bool GATHER = true>
 __global__ void __launch_bounds__(kLseWarps * 32, 4)
 ctc_lse_chunk_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long long stride_t, long long stride_b,
                      const int32_t* __restrict__ ilen, int Sp, const float* __restrict__ lse_in, CtcWs w) {
@@ -411,6 +415,7 @@ ctc_lse_chunk_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long l
         lse = mm + logf(ssum);
     }
     if (lane == 0) w.lse[row] = lse;
+    if (!GATHER) return;                              // relative schedule: the labels were gathered before the scans started
     const int L = w.len[b], S = 2 * L + 1;
     const int* tg = w.lab + (long long)b * w.Lp;
     float* dst = w.lpg + row * Sp;
@@ -434,6 +439,86 @@ ctc_lse_chunk_kernel(const T* __restrict__ logits, int Tn, int Bn, int C, long l
         dpr[q] = pr;
     }
     if (__any_sync(0xffffffffu, small) && lane == 0) w.flag[b] = 1;
+}
+
+// ---------------------------------------------------------------- relative schedule: label gather without the log-sum-exp
+// Every alignment path takes exactly one emission per time step, so the recursions do not need NORMALISED label probabilities:
+// with p'_t(s) = exp(x_t(l'_s) - r_t) for ANY per-row reference r_t, alpha', beta' and the likelihood L' all carry the same
+// factor prod_t exp(lse_t - r_t), the state occupancy alpha' beta' / (p' L') is unchanged, and
+//     log L = log L' + sum_t (r_t - lse_t).
+// With r_t = the largest logit of the row's label set (blank and labels) the gather needs a few dozen scattered reads per row
+// instead of the whole row, p' <= 1 with equality somewhere (the block-floating-point scan's assumptions hold as before), and
+// the scans can start at once - the full-row log-sum-exp pass and the dense gradient pass both run underneath them on the
+// helper stream. One warp per row; lpg / pg / pgr hold the relative values, w.ref the reference.
+template <typename T>
+__global__ void __launch_bounds__(kLseWarps * 32)
+ctc_gather_rel_kernel(const T* __restrict__ logits, int Tn, int Bn, long long stride_t, long long stride_b,
+                      const int32_t* __restrict__ ilen, int Sp, CtcWs w) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * kLseWarps + (threadIdx.x >> 5);     // row = b*T + t
+    if (row >= (long long)Tn * Bn) return;
+    const int b = (int)((unsigned)row / (unsigned)Tn), t = (int)((unsigned)row - (unsigned)b * (unsigned)Tn);
+    if (t >= ilen[b]) return;
+    const T* p = logits + (long long)t * stride_t + (long long)b * stride_b;
+    const int L = w.len[b], S = 2 * L + 1;
+    const int* tg = w.lab + (long long)b * w.Lp;
+    float m = -INFINITY;
+    bool nan = false;
+    for (int q = lane; q < S; q += 32) {
+        const float x = Ld<T>::one(p + ((q & 1) ? tg[q >> 1] : 0));
+        nan |= !(x == x);
+        m = fmaxf(m, x);
+    }
+    m = warp_max(m);
+    if (lane == 0) w.ref[row] = m;
+    float* dst = w.lpg + row * Sp;
+    double* dpr = w.pg + row * Sp;
+    double* dpm = w.pgr + row * Sp;
+    bool small = nan;                                                    // NaN: let the log-space path propagate it
+    for (int q = lane; q < Sp; q += 32) {
+        float lp = 0.f;
+        double pr = 0.0;
+        if (q < S) {
+            const float x = Ld<T>::one(p + ((q & 1) ? tg[q >> 1] : 0));
+            lp = (m == -INFINITY) ? -INFINITY : x - m;                   // every label impossible: all zeros, L' = 0
+            pr = (double)expf(lp);
+            small |= (lp < kMinLinearLogProb) && (lp > -INFINITY);       // exp(-inf) = 0 is exact in linear space
+            small |= !(lp == lp);
+            dpm[S - 1 - q] = pr;
+        } else {
+            dpm[q] = 0.0;
+        }
+        dst[q] = lp;
+        dpr[q] = pr;
+    }
+    if (__any_sync(0xffffffffu, small) && lane == 0) w.flag[b] = 1;
+}
+
+// nll_b = -(log L'_b + sum_t (ref_t - lse_t)) for the relative schedule; runs after the scans / the log-space fallback wrote
+// nll_b = -log L'_b and w.ll[b] = log L'_b (which stays relative: the gradient kernels use it with the relative tables).
+__global__ void __launch_bounds__(256)
+ctc_nll_rel_kernel(const int32_t* __restrict__ ilen, int Tn, float* __restrict__ nll_out, CtcWs w) {
+    __shared__ double part[256];
+    const int b = blockIdx.x;
+    const int Tb = min(ilen[b], Tn);
+    const float* lse = w.lse + (long long)b * Tn;
+    const float* ref = w.ref + (long long)b * Tn;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < Tb; t += 256) acc += (double)lse[t] - (double)ref[t];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double ll = w.ll[b];
+        if (ll > -INFINITY && Tb > 0) {                                  // (-inf: nll stays 0, zero_infinity; NaN propagates)
+            float n = (float)(-ll + part[0]);
+            if (!(n < INFINITY) && n == n) n = 0.f;
+            nll_out[b] = n;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- split schedule: the dense part of the gradient
@@ -1314,7 +1399,7 @@ constexpr int kFixWarps = 8;
 template <typename T>
 __global__ void __launch_bounds__(kFixWarps * 32)
 ctc_fix_kernel(T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t, long long stride_b,
-               const int32_t* __restrict__ ilen, int Sp, int Sa, int kscan, float grad_scale, CtcWs w) {
+               const int32_t* __restrict__ ilen, int Sp, int Sa, int kscan, float grad_scale, int relative, CtcWs w) {
     extern __shared__ float fix_occ[];                                  // [kFixWarps][Sp]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long row = (long long)blockIdx.x * kFixWarps + warp;     // row = b*T + t
@@ -1343,20 +1428,21 @@ ctc_fix_kernel(T* __restrict__ grad, int Tn, int Bn, int C, long long stride_t, 
     const int* canon = w.canon + (long long)b * Sp;
     const int* nxt = w.nxt + (long long)b * Sp;
     const int* tg = w.lab + (long long)b * w.Lp;
-    const float* lpr = w.lpg + row * Sp;                                 // log-softmax at the label classes
+    const float* lpr = w.lpg + row * Sp;                                 // log-softmax at the label classes ...
+    const float corr = relative ? w.ref[row] - w.lse[row] : 0.f;         // ... relative to the row's reference in the relative schedule
     // blank (every even state): a fixed tree over the warp
     {
         float acc = 0.f;
         for (int s = 2 * lane; s < S; s += 64) acc += occ[s];
         acc = warp_sum(acc);
-        if (lane == 0) Ld<T>::st_one(g, (__expf(lpr[0]) - acc) * scale);
+        if (lane == 0) Ld<T>::st_one(g, (__expf(lpr[0] + corr) - acc) * scale);
     }
     // labels (odd states): the first state of a class walks the chain of its repeats, in state order
     for (int s = 2 * lane + 1; s < S; s += 64) {
         if (canon[s] != s) continue;
         float acc = occ[s];
         for (int q = nxt[s]; q >= 0; q = nxt[q]) acc += occ[q];
-        Ld<T>::st_one(g + tg[s >> 1], (__expf(lpr[s]) - acc) * scale);
+        Ld<T>::st_one(g + tg[s >> 1], (__expf(lpr[s] + corr) - acc) * scale);
     }
 }
 
@@ -1548,13 +1634,24 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
     // The split schedule (see ctc_lse_chunk_kernel): A' -> [scans || dense gradient on the helper stream] -> fix. "4" forces it,
     // "2" forces the one-pass rows kernel back to back with the scans.
     const bool split = kscan != 0 && !debug_force_log && !overlap_off && !want_overlap && !(ov && (ov[0] == '2' || ov[0] == '3')) &&
-                       ((ov && ov[0] == '4') || split_by_default(T, B, C, esz, grad != nullptr));
+                       ((ov && (ov[0] == '4' || ov[0] == '5')) || split_by_default(T, B, C, esz, grad != nullptr));
+    // The relative form of the split schedule (ctc_gather_rel_kernel): the scans start right after a sparse label gather and the
+    // full-row log-sum-exp pass joins the dense gradient pass on the helper stream underneath them. Used when the caller has
+    // no row log-sum-exp to offer (with one, the gather-only form of pass A' is just as short); "5" forces it, "4" the other.
+    const bool relative = split && grad != nullptr && ((ov && ov[0] == '5') || (row_lse == nullptr && !(ov && ov[0] == '4')));
     const bool serial = !split && rows_path && (!want_overlap || 2ll * B > 2048);
     const bool overlap = rows_path || split;                          // the gradient's label classes are ctc_fix_kernel's
     CtcSide* split_side = nullptr;
     if (split) {
         const long long blocksA = (rows + kLseWarps - 1) / kLseWarps;
-        if (dtype == HCTR_F32)
+        if (relative) {
+            if (dtype == HCTR_F32)
+                ctc_gather_rel_kernel<float><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
+                    static_cast<const float*>(logits), T, B, stride_t, stride_b, input_lengths, Sp, w);
+            else
+                ctc_gather_rel_kernel<__nv_bfloat16><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
+                    static_cast<const __nv_bfloat16*>(logits), T, B, stride_t, stride_b, input_lengths, Sp, w);
+        } else if (dtype == HCTR_F32)
             ctc_lse_chunk_kernel<float><<<(int)blocksA, kLseWarps * 32, 0, s>>>(
                 static_cast<const float*>(logits), T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse, w);
         else
@@ -1585,6 +1682,16 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
         }
         if (timing) { cudaEventRecord(tev[1], s); cudaEventRecord(tev[2], split_side->helper); }
         if (grad != nullptr) {
+            if (relative) {
+                // the rows' log-sum-exp (given, or one read of every row), on the helper stream beside the scans; like the dense
+                // kernel it asks for a token 4 KB of shared memory so that none of its CTAs can share an SM with a scan
+                if (dtype == HCTR_F32)
+                    ctc_lse_chunk_kernel<float, false><<<(int)blocksA, kLseWarps * 32, 4096, split_side->helper>>>(
+                        static_cast<const float*>(logits), T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse, w);
+                else
+                    ctc_lse_chunk_kernel<__nv_bfloat16, false><<<(int)blocksA, kLseWarps * 32, 4096, split_side->helper>>>(
+                        static_cast<const __nv_bfloat16*>(logits), T, B, C, stride_t, stride_b, input_lengths, Sp, row_lse, w);
+            }
             const long long blocksD = (rows + kDenseWarps - 1) / kDenseWarps;
             if (dtype == HCTR_F32)
                 ctc_dense_grad_kernel<float><<<(int)blocksD, kDenseWarps * 32, 4096, split_side->helper>>>(
@@ -1705,6 +1812,10 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
         ctc_alpha_beta_log_kernel<<<gridB, threads, smB, s>>>(targets, target_lengths, input_lengths, T, Sp, Sa, nll, w);
         HCTR_CUDA(cudaGetLastError());
     }
+    if (relative) {
+        ctc_nll_rel_kernel<<<B, 256, 0, s>>>(input_lengths, T, nll, w);
+        HCTR_CUDA(cudaGetLastError());
+    }
     ctc_mean_loss_kernel<<<1, 32, 0, s>>>(nll, w.len, w.err, B, loss);
     HCTR_CUDA(cudaGetLastError());
     if (grad != nullptr) {
@@ -1713,10 +1824,11 @@ int hctr_ctc_loss_fwd_bwd(const void* logits, int dtype, int T, int B, int C, lo
             const int blocksF = (int)((rows + kFixWarps - 1) / kFixWarps);
             if (dtype == HCTR_F32)
                 ctc_fix_kernel<float><<<blocksF, kFixWarps * 32, smF, s>>>(static_cast<float*>(grad), T, B, C, stride_t, stride_b,
-                                                                         input_lengths, Sp, Sa, kscan, grad_scale, w);
+                                                                         input_lengths, Sp, Sa, kscan, grad_scale, relative ? 1 : 0, w);
             else
                 ctc_fix_kernel<__nv_bfloat16><<<blocksF, kFixWarps * 32, smF, s>>>(static_cast<__nv_bfloat16*>(grad), T, B, C, stride_t,
-                                                                                 stride_b, input_lengths, Sp, Sa, kscan, grad_scale, w);
+                                                                                 stride_b, input_lengths, Sp, Sa, kscan, grad_scale,
+                                                                                 relative ? 1 : 0, w);
         } else {
             const size_t smC = (size_t)Sp * sizeof(float);
             if (dtype == HCTR_F32)

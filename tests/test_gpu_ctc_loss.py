@@ -197,7 +197,7 @@ def test_ctc_loss_only_no_gradient():
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("T,B,C,lo,hi", [(2048, 4, 7375, 20, 60), (257, 3, 101, 1, 9), (64, 2, 37, 0, 3), (1, 2, 11, 0, 1)])
 def test_ctc_loss_overlapped_and_sequential_paths_agree(monkeypatch, dtype, T, B, C, lo, hi):
-    """Round 2: the default (split) schedule reads every logits row once for the log-sum-exp and the label gather, then runs
+    """Round 2: the split schedule reads every logits row once for the log-sum-exp and the label gather, then runs
     the alpha/beta scans with the dense part of the gradient on a helper stream underneath them, then a sparse fix-up;
     HCTR_CTC_OVERLAP=2 is the one-pass rows kernel (lse + gather + dense gradient, the row in the registers of four warps)
     back to back with the scans, =1 overlaps those two through progress counters, =0 runs round 1's three sequential passes.
@@ -210,7 +210,9 @@ def test_ctc_loss_overlapped_and_sequential_paths_agree(monkeypatch, dtype, T, B
     if T > 8:
         il[-1] = T - 5
     results = []
-    for mode in ("", "4", "2", "1", "0"):           # default, split, one-pass rows back to back, overlapped, round-1 passes
+    # default, split (normalised tables), one-pass rows back to back, overlapped, round-1 passes, split in its relative form
+    # (label gather relative to the row's largest label logit, log-sum-exp pass beside the scans; the default for large calls)
+    for mode in ("", "4", "2", "1", "0", "5"):
         monkeypatch.setenv("HCTR_CTC_OVERLAP", mode)
         for layout in ("contiguous", "model"):
             if layout == "contiguous":
@@ -239,6 +241,8 @@ def test_ctc_loss_overlapped_and_sequential_paths_agree(monkeypatch, dtype, T, B
     assert abs(results[0][0] - results[4][0]) <= 1e-5 * abs(oloss) + 1e-6          # default vs one-pass rows kernel
     assert abs(results[4][0] - results[6][0]) <= 1e-6 * abs(oloss) + 1e-7          # rows kernel: back to back vs overlapped
     assert abs(results[0][0] - results[8][0]) <= 1e-5 * abs(oloss) + 1e-6          # default vs round-1 passes
+    assert abs(results[2][0] - results[10][0]) <= 1e-6 * abs(oloss) + 1e-7         # split: normalised vs relative label tables
+    assert np.abs(results[2][1].numpy() - results[10][1].numpy()).max() <= (2e-6 if dtype == torch.float32 else gate)
 
 
 def test_ctc_loss_bad_lengths_and_labels_do_not_touch_memory_out_of_bounds():
