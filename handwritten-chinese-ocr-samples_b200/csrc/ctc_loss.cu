@@ -34,6 +34,13 @@
 //   fix   (ctc_fix_kernel): one warp per row subtracts the occupancy at the <= L+1 distinct label classes (a few dozen
 //         2-byte read-modify-writes per row; blank = a fixed warp tree, repeated labels = a precomputed chain).
 // HCTR_CTC_OVERLAP=0 keeps the round-1 sequential passes A/B/C (also the fallback for rows that do not fit).
+//
+// Round 2 - the SPLIT schedules (default with a gradient and B <= 24; ctc_lse_chunk_kernel / ctc_gather_rel_kernel below):
+//   a sparse label gather -> [scans on SMs of their own || log-sum-exp pass + dense gradient pass on a helper stream] ->
+//   verify -> [log-space fallback] -> fix. In the RELATIVE form the label tables are relative to the row's largest label
+//   logit instead of to the log-sum-exp (the recursions do not need normalised probabilities: every path takes one emission
+//   per step, so the factor prod_t exp(lse_t - ref_t) cancels in the occupancy and is added back to the loss at the end);
+//   with the classifier's row log-sum-exp passed in (the training step) the normalised form needs no full-row pass either.
 #include <cfloat>
 #include <cstdlib>
 #include <mutex>
