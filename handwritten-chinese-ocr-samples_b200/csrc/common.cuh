@@ -96,6 +96,22 @@ __device__ __forceinline__ void stage_chunk_row(const float (&v)[32], uint8_t* d
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Packed fp32 pairs (Blackwell FFMA2: two IEEE fp32 fused multiply-adds per instruction, each lane rounded exactly like fmaf;
+// an operand built from the same scalar twice becomes the instruction's broadcast form, no move)
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // Channel sums of a staged chunk "as stored": the store loop of the conv epilogues reads the staged 32-pixel x 32-channel bf16
 // chunk back as 16-byte pieces (8 channels of one pixel row; lane = (row & 7) * 4 + piece, rows r, r+8, r+16, r+24). Adding the
 // pieces a lane holds and then the eight lanes of a piece (xor 4, 8, 16) gives the per-channel sums over the chunk's pixels in
