@@ -585,3 +585,24 @@ def test_small_batch_forward_replays_a_cuda_graph_with_identical_results():
     for y in y_new:
         assert torch.equal(y, y_ref)
     assert not torch.equal(y_ref, want[0])
+
+
+def test_cuda_graph_cache_keeps_at_most_eight_shapes():
+    """More recurring small shapes than graph slots: the least recently used graph is dropped, results stay those of the eager
+    path, and a shape whose graph was dropped is simply captured again."""
+    m = _model(29, 78).cuda().eval()
+    widths = [64 + 8 * i for i in range(11)]
+    xs = [torch.from_numpy(synth.text_lines(1, w, 500 + w)).cuda() for w in widths]
+    with torch.no_grad():
+        m.cuda_graphs = False
+        want = [m(x) for x in xs]
+        m.cuda_graphs = True
+        for _ in range(4):
+            got = [m(x) for x in xs]
+        cache = m.__dict__["_graph_cache"]
+        live = [k for k, e in cache["entries"].items() if e.get("graph") is not None]
+        assert 1 <= len(live) <= m._GRAPH_SLOTS
+        for a, b in zip(want, got):
+            assert a.stride() == b.stride() and torch.equal(a, b)
+        again = [m(xs[0]) for _ in range(4)]                     # the oldest shape: evicted above, captured again here
+    assert all(torch.equal(want[0], y) for y in again)
