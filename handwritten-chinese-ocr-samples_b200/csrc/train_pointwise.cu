@@ -249,13 +249,6 @@ train_apply_fwd_kernel(ApplyParams p, __nv_bfloat16* __restrict__ out) {
                 const int j = jb + 256 * u;
                 if (j >= j1) break;
                 const size_t i = obase + j;
-                uint32_t keep = 0xffu;                                   // dropout keep bits of the 8 output elements
-                if (p.drop_p > 0.f) {
-                    const uint32_t base = drop_base(i, p.seed);
-                    keep = 0u;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) keep |= drop_keep(base, q, thresh) ? (1u << q) : 0u;
-                }
                 float v[8], e[8];
                 unpack8(zq[u], e);
 #pragma unroll
@@ -272,6 +265,13 @@ train_apply_fwd_kernel(ApplyParams p, __nv_bfloat16* __restrict__ out) {
                 }
                 const size_t mi = zoff[u] >> 3;                           // mask byte of this input-resolution vector
                 if (p.pool) {
+                    uint32_t keep = 0xffu;                               // dropout keep bits of the 8 output elements
+                    if (p.drop_p > 0.f) {
+                        const uint32_t base = drop_base(i, p.seed);
+                        keep = 0u;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) keep |= drop_keep(base, q, thresh) ? (1u << q) : 0u;
+                    }
                     float v1[8];
                     unpack8(sq[u], e);
 #pragma unroll
@@ -291,18 +291,45 @@ train_apply_fwd_kernel(ApplyParams p, __nv_bfloat16* __restrict__ out) {
                         p.mask[mi] = (uint8_t)(m0 & keep);
                         p.mask[mi + (size_t)p.W * vpp] = (uint8_t)(m1 & keep);
                     }
+                    if (p.drop_p > 0.f) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[q] = ((keep >> q) & 1u) ? v[q] * keep_scale : 0.f;
+                    }
                 } else {
+                    // ReLU and dropout are ONE decision per element: it passes iff it is positive and kept - one predicate
+                    // (the integer compare chained onto the float one), one keep-bit, one select. Decided separately (ReLU
+                    // mask + maximum, keep bits, then bit tests and selects) the pass spent ~10 integer-pipe instructions per
+                    // element on them and was instruction-bound: ALU pipe 52 %, DRAM 43 % busy
+                    // (profiles/r2_ncu_train_apply_fwd_kernel_B16_512ch.txt).
                     uint32_t m0 = 0xffu;
-                    if (p.relu) {
+                    if (p.drop_p > 0.f) {
+                        const uint32_t base = drop_base(i, p.seed);
+                        m0 = 0u;
+                        if (p.relu) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const bool pass = v[q] > 0.f && drop_keep(base, q, thresh);
+                                m0 |= pass ? (1u << q) : 0u;
+                                v[q] = pass ? v[q] * keep_scale : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const bool pass = drop_keep(base, q, thresh);
+                                m0 |= pass ? (1u << q) : 0u;
+                                v[q] = pass ? v[q] * keep_scale : 0.f;
+                            }
+                        }
+                    } else if (p.relu) {
                         m0 = 0u;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) { if (v[q] > 0.f) m0 |= 1u << q; v[q] = fmaxf(v[q], 0.f); }
+                        for (int q = 0; q < 8; ++q) {
+                            const bool pass = v[q] > 0.f;
+                            m0 |= pass ? (1u << q) : 0u;
+                            v[q] = pass ? v[q] : 0.f;
+                        }
                     }
-                    if (p.mask) p.mask[mi] = (uint8_t)(m0 & keep);
-                }
-                if (p.drop_p > 0.f) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q] = ((keep >> q) & 1u) ? v[q] * keep_scale : 0.f;
+                    if (p.mask) p.mask[mi] = (uint8_t)m0;
                 }
                 *reinterpret_cast<uint4*>(out + i * 8) = pack8(v);
             }
