@@ -65,7 +65,10 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_const
                               : (NUM_SUB * BLOCK_N <= 256) ? 256 : 512;
     static_assert(NUM_SUB * BLOCK_N <= 512, "TMEM");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1 KB alignment by POINTER arithmetic on the __shared__ array: rounding the address as an integer and casting it back made
+    // every later access through `smem` a generic LD/ST (the compiler no longer knew the address space) - 495 generic loads and
+    // 380 generic stores in the conv kernels' epilogues, long-scoreboard stalls at the staged stores (ncu source view)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;
